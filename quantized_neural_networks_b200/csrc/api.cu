@@ -1,0 +1,656 @@
+// api.cu -- C ABI of libgpfq (include/gpfq.h): context, workspaces, host<->device staging, method choice.
+#include <stdarg.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+// kernels / stages implemented in the other translation units
+int dense_gram_path(gpfq_ctx *, const float *, const float *, int64_t, int64_t, int64_t, const float *, int64_t,
+                    int64_t, int64_t, const double *, const int *, int, double *, int64_t, int64_t, gpfq_stats *);
+int dense_stream_path(gpfq_ctx *, const float *, const float *, int64_t, int64_t, int64_t, const float *, int64_t,
+                      int64_t, int64_t, const double *, const int *, int, double *, int64_t, int64_t, gpfq_stats *);
+int dense_gram_only(gpfq_ctx *, const float *, const float *, int64_t, int64_t, int64_t, double *, double *);
+int conv_supported_kk(int kk);
+int conv_pick_chunks(gpfq_ctx *, int64_t, int, int64_t *);
+int conv_gram_stage(gpfq_ctx *, int, ConvPtrs, bool, int64_t, int, int, int64_t, double *);
+int conv_finalize_stage(gpfq_ctx *, const double *, int, int, int, bool, double *);
+int conv_sweep_stage(gpfq_ctx *, int, const double *, const float *, double *, int64_t, int64_t, int64_t, int,
+                     const double *, const int *, int);
+int im2col_stage(gpfq_ctx *, const float *, int64_t, int, int, int64_t, int64_t, int, int, int, int, int, int, int,
+                 int, int, int, int, float *, int64_t);
+int msq_stage(gpfq_ctx *, const void *, int, int64_t, const double *, int, double *);
+
+// ---------------------------------------------------------------------------------------------
+int gpfq_fail(gpfq_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+int gpfq_ws(gpfq_ctx *ctx, int slot, size_t bytes, void **out) {
+    DevBuf &b = ctx->ws[slot];
+    if (bytes == 0) bytes = 16;
+    if (b.cap < bytes) {
+        if (b.p) {
+            // pending kernels may still read the old buffer
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
+            CUDA_TRY(ctx, cudaFree(b.p));
+            b.p = nullptr;
+            b.cap = 0;
+        }
+        size_t cap = (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+        cudaError_t e = cudaMalloc(&b.p, cap);
+        if (e != cudaSuccess) {
+            b.p = nullptr;
+            cudaGetLastError();
+            return gpfq_fail(ctx, GPFQ_ERR_OOM, "cudaMalloc of %zu bytes (workspace %d) failed: %s", cap, slot,
+                             cudaGetErrorString(e));
+        }
+        b.cap = cap;
+    }
+    *out = b.p;
+    return GPFQ_OK;
+}
+
+int gpfq_pinned(gpfq_ctx *ctx, int slot, size_t bytes, void **out) {
+    DevBuf &b = ctx->pinned[slot];
+    if (bytes == 0) bytes = 16;
+    if (b.cap < bytes) {
+        if (b.p) {
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            CUDA_TRY(ctx, cudaFreeHost(b.p));
+            b.p = nullptr;
+            b.cap = 0;
+        }
+        cudaError_t e = cudaMallocHost(&b.p, bytes);
+        if (e != cudaSuccess) {
+            b.p = nullptr;
+            cudaGetLastError();
+            return gpfq_fail(ctx, GPFQ_ERR_OOM, "cudaMallocHost of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        }
+        b.cap = bytes;
+    }
+    *out = b.p;
+    return GPFQ_OK;
+}
+
+extern "C" int gpfq_version(void) { return GPFQ_VERSION; }
+
+extern "C" int gpfq_create(int device, gpfq_ctx **out) {
+    if (!out) return GPFQ_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return GPFQ_ERR_UNSUPPORTED;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return GPFQ_ERR_CUDA;
+    if (prop.major != 10) return GPFQ_ERR_UNSUPPORTED;  // built for sm_100a only
+    if (cudaSetDevice(device) != cudaSuccess) return GPFQ_ERR_CUDA;
+    gpfq_ctx *ctx = new gpfq_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; ok && i < 8; ++i) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
+    for (int i = 0; ok && i < 4; ++i) ok = cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+        delete ctx;
+        return GPFQ_ERR_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return GPFQ_OK;
+}
+
+extern "C" int gpfq_trim(gpfq_ctx *ctx) {
+    if (!ctx) return GPFQ_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->copy_stream);
+    for (auto &b : ctx->ws) {
+        if (b.p) cudaFree(b.p);
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    for (auto &b : ctx->pinned) {
+        if (b.p) cudaFreeHost(b.p);
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    ctx->alph_cache.clear();
+    ctx->alph_used = 0;
+    return GPFQ_OK;
+}
+
+extern "C" void gpfq_destroy(gpfq_ctx *ctx) {
+    if (!ctx) return;
+    gpfq_trim(ctx);
+    for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
+    for (auto &e : ctx->ev_copy) if (e) cudaEventDestroy(e);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+}
+
+extern "C" const char *gpfq_last_error(const gpfq_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int gpfq_set_stream(gpfq_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return GPFQ_ERR_ARG;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return GPFQ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// alphabets: validate, flatten to device (levels + prefix offsets)
+// ---------------------------------------------------------------------------------------------
+struct Alphabets {
+    const double *d_levels = nullptr;
+    const int *d_koff = nullptr;
+    std::vector<int> h_koff;
+};
+
+static int upload_alphabets(gpfq_ctx *ctx, const double *alphabets, const int32_t *K, int n_alph, Alphabets *out) {
+    if (!alphabets || !K || n_alph < 1 || n_alph > 1024) return gpfq_fail(ctx, GPFQ_ERR_ARG, "bad alphabet arguments");
+    out->h_koff.assign(n_alph + 1, 0);
+    for (int a = 0; a < n_alph; ++a) {
+        if (K[a] < 1 || K[a] > GPFQ_MAX_K)
+            return gpfq_fail(ctx, GPFQ_ERR_ARG, "alphabet %d has %d levels (supported: 1..%d)", a, K[a], GPFQ_MAX_K);
+        out->h_koff[a + 1] = out->h_koff[a] + K[a];
+    }
+    const size_t nlev = out->h_koff[n_alph];
+    const size_t lev_bytes = nlev * sizeof(double);
+    const size_t bytes = (lev_bytes + (n_alph + 1) * sizeof(int) + 15) & ~(size_t)15;
+    std::vector<char> blob(bytes, 0);
+    memcpy(blob.data(), alphabets, lev_bytes);
+    memcpy(blob.data() + lev_bytes, out->h_koff.data(), (n_alph + 1) * sizeof(int));
+    const size_t cap = (size_t)1 << 20;
+    char *d = nullptr;
+    GPFQ_TRY(gpfq_ws(ctx, WS_ALPH, cap, (void **)&d));
+    const AlphEntry *hit = nullptr;
+    for (const auto &e : ctx->alph_cache)
+        if (e.blob.size() == bytes && memcmp(e.blob.data(), blob.data(), bytes) == 0) { hit = &e; break; }
+    if (!hit) {
+        if (bytes > cap) return gpfq_fail(ctx, GPFQ_ERR_ARG, "alphabet table too large");
+        if (ctx->alph_used + bytes > cap || ctx->alph_cache.size() >= 256) {
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // kernels may still read the old entries
+            ctx->alph_cache.clear();
+            ctx->alph_used = 0;
+        }
+        ctx->alph_cache.emplace_back();
+        AlphEntry &e = ctx->alph_cache.back();
+        e.blob.swap(blob);
+        e.off = ctx->alph_used;
+        ctx->alph_used += bytes;
+        CUDA_TRY(ctx, cudaMemcpyAsync(d + e.off, e.blob.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
+        hit = &e;
+    }
+    out->d_levels = reinterpret_cast<const double *>(d + hit->off);
+    out->d_koff = reinterpret_cast<const int *>(d + hit->off + lev_bytes);
+    return GPFQ_OK;
+}
+
+static float ev_ms(cudaEvent_t a, cudaEvent_t b) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) { cudaGetLastError(); return 0.f; }
+    return ms;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Dense
+// ---------------------------------------------------------------------------------------------
+static int choose_dense_method(gpfq_ctx *ctx, uint32_t flags, int64_t N0, int64_t m, int64_t nj, bool same, int n_alph) {
+    const uint32_t want = flags & GPFQ_METHOD_MASK;
+    if (want == GPFQ_METHOD_STREAM) return GPFQ_METHOD_STREAM;
+    if (want == GPFQ_METHOD_GRAM) return GPFQ_METHOD_GRAM;
+    // Cost table (DESIGN.md "method choice"; constants fitted to B200 measurements, profiles/):
+    //   streaming: ~3 fp64 MACs per (sample, direction, neuron), walked once per alphabet
+    //   Gram+sweep: (1 or 1/2) m N0^2 MACs once + N0^2 nj MACs and 2 launches per 32 directions per alphabet
+    const double stream_rate = 2.0e12, gram_rate = 9.0e12, sweep_rate = 4.0e12, launch_s = 6e-6;
+    const bool u_fits = (size_t)m * sizeof(double) + 8192 <= ctx->smem_optin;
+    double t_stream = 3.0 * (double)m * N0 * nj * n_alph / stream_rate * (u_fits ? 1.0 : 6.0);
+    double t_gram = (same ? 0.5 : 1.0) * (double)m * N0 * N0 / gram_rate +
+                    n_alph * ((double)N0 * N0 * nj / sweep_rate) + 2.0 * (N0 / 32.0) * launch_s;
+    const double gram_bytes = (same ? 1.0 : 2.0) * 8.0 * N0 * N0;
+    if (gram_bytes > 48e9) return GPFQ_METHOD_STREAM;
+    return t_gram < t_stream ? GPFQ_METHOD_GRAM : GPFQ_METHOD_STREAM;
+}
+
+extern "C" int gpfq_dense_layer(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx, int64_t N0, int64_t m,
+                                const float *W, int64_t ldw, int64_t N1, int64_t j0, int64_t j1,
+                                const double *alphabets, const int32_t *K, int32_t n_alph, double *Q_out,
+                                int64_t ldq, uint32_t flags, gpfq_stats *stats) {
+    if (!ctx) return GPFQ_ERR_ARG;
+    ctx->err.clear();
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (!X || !W || !Q_out) return gpfq_fail(ctx, GPFQ_ERR_ARG, "NULL X, W or Q_out");
+    if (N0 < 1 || m < 1 || N1 < 1 || ldx < m || ldw < N1 || ldq < N1 || j0 < 0 || j1 > N1 || j0 > j1)
+        return gpfq_fail(ctx, GPFQ_ERR_ARG, "bad shape: N0=%lld m=%lld N1=%lld ldx=%lld ldw=%lld ldq=%lld j0=%lld j1=%lld",
+                         (long long)N0, (long long)m, (long long)N1, (long long)ldx, (long long)ldw, (long long)ldq,
+                         (long long)j0, (long long)j1);
+    if (N0 > 2000000 || m > ((int64_t)1 << 40)) return gpfq_fail(ctx, GPFQ_ERR_ARG, "shape too large");
+    if ((flags & GPFQ_NO_SYNC) && (flags & GPFQ_ALL_DEVICE) != GPFQ_ALL_DEVICE)
+        return gpfq_fail(ctx, GPFQ_ERR_ARG, "GPFQ_NO_SYNC needs all-device pointers");
+    const int64_t nj = j1 - j0;
+    if (nj == 0) return GPFQ_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    ctx->launches = 0;
+    const bool same = (Xq == nullptr || Xq == X);
+    cudaStream_t s = ctx->stream;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], s));
+
+    Alphabets al;
+    GPFQ_TRY(upload_alphabets(ctx, alphabets, K, n_alph, &al));
+
+    const float *dX = X, *dXq = same ? X : Xq, *dW = W;
+    int64_t dldx = ldx, dldw = ldw, dj0 = j0;
+    if (!(flags & GPFQ_X_DEVICE)) {
+        float *bx = nullptr, *bq = nullptr;
+        GPFQ_TRY(gpfq_ws(ctx, WS_X, (size_t)N0 * m * sizeof(float), (void **)&bx));
+        CUDA_TRY(ctx, cudaMemcpy2DAsync(bx, m * sizeof(float), X, ldx * sizeof(float), m * sizeof(float), N0,
+                                        cudaMemcpyHostToDevice, s));
+        dX = dXq = bx;
+        if (!same) {
+            GPFQ_TRY(gpfq_ws(ctx, WS_XQ, (size_t)N0 * m * sizeof(float), (void **)&bq));
+            CUDA_TRY(ctx, cudaMemcpy2DAsync(bq, m * sizeof(float), Xq, ldx * sizeof(float), m * sizeof(float), N0,
+                                            cudaMemcpyHostToDevice, s));
+            dXq = bq;
+        }
+        dldx = m;
+    }
+    if (!(flags & GPFQ_W_DEVICE)) {
+        float *bw = nullptr;
+        GPFQ_TRY(gpfq_ws(ctx, WS_W, (size_t)N0 * nj * sizeof(float), (void **)&bw));
+        CUDA_TRY(ctx, cudaMemcpy2DAsync(bw, nj * sizeof(float), W + j0, ldw * sizeof(float), nj * sizeof(float), N0,
+                                        cudaMemcpyHostToDevice, s));
+        dW = bw;
+        dldw = nj;
+        dj0 = 0;
+    }
+    double *dQ = Q_out;
+    int64_t dldq = ldq, col0 = j0;
+    if (!(flags & GPFQ_Q_DEVICE)) {
+        GPFQ_TRY(gpfq_ws(ctx, WS_Q, (size_t)n_alph * N0 * nj * sizeof(double), (void **)&dQ));
+        dldq = nj;
+        col0 = 0;
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[5], s));
+
+    const int method = choose_dense_method(ctx, flags, N0, m, nj, same, n_alph);
+    if (method == GPFQ_METHOD_GRAM)
+        GPFQ_TRY(dense_gram_path(ctx, dX, dXq, dldx, N0, m, dW, dldw, dj0, nj, al.d_levels, al.d_koff, n_alph, dQ, dldq,
+                                 col0, stats));
+    else
+        GPFQ_TRY(dense_stream_path(ctx, dX, dXq, dldx, N0, m, dW, dldw, dj0, nj, al.d_levels, al.h_koff.data(), n_alph,
+                                   dQ, dldq, col0, stats));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[6], s));
+    if (!(flags & GPFQ_Q_DEVICE)) {
+        for (int a = 0; a < n_alph; ++a)
+            CUDA_TRY(ctx, cudaMemcpy2DAsync(Q_out + (int64_t)a * N0 * ldq + j0, ldq * sizeof(double),
+                                            dQ + (int64_t)a * N0 * nj, nj * sizeof(double), nj * sizeof(double), N0,
+                                            cudaMemcpyDeviceToHost, s));
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], s));
+    if (stats) {
+        stats->kernel_launches = ctx->launches;
+        stats->weights = N0 * nj * n_alph;
+    }
+    if (flags & GPFQ_NO_SYNC) return GPFQ_OK;
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    if (stats) {
+        stats->ms_total = ev_ms(ctx->ev[0], ctx->ev[1]);
+        stats->ms_h2d = ev_ms(ctx->ev[0], ctx->ev[5]);
+        stats->ms_d2h = ev_ms(ctx->ev[6], ctx->ev[1]);
+        if (method == GPFQ_METHOD_GRAM) {
+            stats->ms_gram = ev_ms(ctx->ev[2], ctx->ev[3]);
+            stats->ms_sweep = ev_ms(ctx->ev[3], ctx->ev[4]);
+        } else {
+            stats->ms_stream = ev_ms(ctx->ev[2], ctx->ev[3]);
+        }
+    }
+    return GPFQ_OK;
+}
+
+// Diagnostics: the Gram stage alone (tests check it against an fp64 NumPy Gram).
+// G1_out/G2_out: (N0, N0) fp64, lower triangle + diagonal valid; G1_out may be NULL.
+extern "C" int gpfq_gram_matrices(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx, int64_t N0, int64_t m,
+                                  double *G1_out, double *G2_out, uint32_t flags) {
+    if (!ctx) return GPFQ_ERR_ARG;
+    ctx->err.clear();
+    if (!X || !G2_out || N0 < 1 || m < 1 || ldx < m) return gpfq_fail(ctx, GPFQ_ERR_ARG, "bad arguments");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const bool same = (Xq == nullptr || Xq == X);
+    cudaStream_t s = ctx->stream;
+    const float *dX = X, *dXq = same ? X : Xq;
+    int64_t dld = ldx;
+    if (!(flags & GPFQ_X_DEVICE)) {
+        float *bx = nullptr, *bq = nullptr;
+        GPFQ_TRY(gpfq_ws(ctx, WS_X, (size_t)N0 * m * sizeof(float), (void **)&bx));
+        CUDA_TRY(ctx, cudaMemcpy2DAsync(bx, m * sizeof(float), X, ldx * sizeof(float), m * sizeof(float), N0,
+                                        cudaMemcpyHostToDevice, s));
+        dX = dXq = bx;
+        if (!same) {
+            GPFQ_TRY(gpfq_ws(ctx, WS_XQ, (size_t)N0 * m * sizeof(float), (void **)&bq));
+            CUDA_TRY(ctx, cudaMemcpy2DAsync(bq, m * sizeof(float), Xq, ldx * sizeof(float), m * sizeof(float), N0,
+                                            cudaMemcpyHostToDevice, s));
+            dXq = bq;
+        }
+        dld = m;
+    }
+    double *g1 = nullptr, *g2 = nullptr;
+    GPFQ_TRY(gpfq_ws(ctx, WS_G2, (size_t)N0 * N0 * sizeof(double), (void **)&g2));
+    g1 = g2;
+    if (!same) GPFQ_TRY(gpfq_ws(ctx, WS_G1, (size_t)N0 * N0 * sizeof(double), (void **)&g1));
+    GPFQ_TRY(dense_gram_only(ctx, dX, dXq, dld, N0, m, g1, g2));
+    const cudaMemcpyKind kind = (flags & GPFQ_Q_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    CUDA_TRY(ctx, cudaMemcpyAsync(G2_out, g2, (size_t)N0 * N0 * sizeof(double), kind, s));
+    if (G1_out) CUDA_TRY(ctx, cudaMemcpyAsync(G1_out, g1, (size_t)N0 * N0 * sizeof(double), kind, s));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    return GPFQ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Conv
+// ---------------------------------------------------------------------------------------------
+static int conv_finish(gpfq_ctx *ctx, int kk, const double *partial, int n_ch, int n_chunks, bool same,
+                       const float *W, int64_t C, int64_t F, int64_t c0, const Alphabets &al, int n_alph,
+                       double *Q_out, uint32_t flags) {
+    cudaStream_t s = ctx->stream;
+    double *gram = nullptr;
+    GPFQ_TRY(gpfq_ws(ctx, WS_CG, (size_t)n_ch * 2 * kk * kk * sizeof(double), (void **)&gram));
+    GPFQ_TRY(conv_finalize_stage(ctx, partial, n_ch, n_chunks, kk, same, gram));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], s));
+    const float *dW = W;
+    const size_t wcount = (size_t)kk * C * F;
+    if (!(flags & GPFQ_W_DEVICE)) {
+        float *bw = nullptr;
+        GPFQ_TRY(gpfq_ws(ctx, WS_W, wcount * sizeof(float), (void **)&bw));
+        CUDA_TRY(ctx, cudaMemcpyAsync(bw, W, wcount * sizeof(float), cudaMemcpyHostToDevice, s));
+        dW = bw;
+    }
+    double *dQ = Q_out;
+    if (!(flags & GPFQ_Q_DEVICE)) GPFQ_TRY(gpfq_ws(ctx, WS_Q, (size_t)n_alph * wcount * sizeof(double), (void **)&dQ));
+    GPFQ_TRY(conv_sweep_stage(ctx, kk, gram, dW, dQ, C, F, c0, n_ch, al.d_levels, al.d_koff, n_alph));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], s));
+    if (!(flags & GPFQ_Q_DEVICE)) {
+        for (int a = 0; a < n_alph; ++a) {
+            const size_t off = (size_t)a * wcount + (size_t)c0 * F;
+            CUDA_TRY(ctx, cudaMemcpy2DAsync(Q_out + off, C * F * sizeof(double), dQ + off, C * F * sizeof(double),
+                                            (size_t)n_ch * F * sizeof(double), kk, cudaMemcpyDeviceToHost, s));
+        }
+    }
+    return GPFQ_OK;
+}
+
+static void conv_stats(gpfq_ctx *ctx, gpfq_stats *st, int kk, int64_t n, int64_t n_ch, int64_t F, bool same, int n_alph) {
+    if (!st) return;
+    st->kernel_launches = ctx->launches;
+    st->weights = (int64_t)kk * n_ch * F * n_alph;
+    st->method = GPFQ_METHOD_GRAM >> 4;
+    st->bytes_algorithmic = (same ? 1 : 2) * 4LL * kk * n * n_ch;
+    st->flops_algorithmic = (same ? 0 : 2LL * kk * kk * n * n_ch) + (int64_t)kk * (kk + 1) * n * n_ch;
+}
+
+extern "C" int gpfq_conv_channels(gpfq_ctx *ctx, const float *const *Xp, const float *const *Xqp, int64_t n,
+                                  int32_t kk, const float *W, int64_t C, int64_t F, int64_t c0, int64_t n_ch,
+                                  const double *alphabets, const int32_t *K, int32_t n_alph, double *Q_out,
+                                  uint32_t flags, gpfq_stats *stats) {
+    if (!ctx) return GPFQ_ERR_ARG;
+    ctx->err.clear();
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (!Xp || !W || !Q_out) return gpfq_fail(ctx, GPFQ_ERR_ARG, "NULL Xp, W or Q_out");
+    if (n < 1 || kk < 1 || C < 1 || F < 1 || c0 < 0 || n_ch < 0 || c0 + n_ch > C || n_ch > 65535)
+        return gpfq_fail(ctx, GPFQ_ERR_ARG, "bad shape: n=%lld kk=%d C=%lld F=%lld c0=%lld n_ch=%lld", (long long)n, kk,
+                         (long long)C, (long long)F, (long long)c0, (long long)n_ch);
+    if ((flags & GPFQ_NO_SYNC) && (flags & GPFQ_ALL_DEVICE) != GPFQ_ALL_DEVICE)
+        return gpfq_fail(ctx, GPFQ_ERR_ARG, "GPFQ_NO_SYNC needs all-device pointers");
+    if (n_ch == 0) return GPFQ_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    ctx->launches = 0;
+    bool same = (Xqp == nullptr);
+    if (!same) {
+        same = true;
+        for (int64_t i = 0; i < n_ch; ++i) same = same && (Xqp[i] == Xp[i] || Xqp[i] == nullptr);
+    }
+    for (int64_t i = 0; i < n_ch; ++i)
+        if (!Xp[i] || (!same && !Xqp[i])) return gpfq_fail(ctx, GPFQ_ERR_ARG, "NULL patch pointer for channel %lld", (long long)i);
+
+    if (!conv_supported_kk(kk)) {
+        // generic kernel sizes: each channel is a (kk, F) Dense problem over n_patches samples
+        int64_t launches = 0;
+        for (int64_t i = 0; i < n_ch; ++i) {
+            const int64_t c = c0 + i;
+            // per-alphabet outputs are kk*C*F apart, which is exactly N0*ldq for N0=kk, ldq=C*F
+            GPFQ_TRY(gpfq_dense_layer(ctx, Xp[i], same ? Xp[i] : Xqp[i], n, kk, n, W + c * F, C * F, F, 0, F, alphabets, K,
+                                      n_alph, Q_out + c * F, C * F, (flags & ~GPFQ_NO_SYNC) | GPFQ_METHOD_GRAM, stats));
+            launches += stats ? stats->kernel_launches : 0;
+        }
+        if (stats) { stats->kernel_launches = (int)launches; stats->weights = (int64_t)kk * n_ch * F * n_alph; }
+        return GPFQ_OK;
+    }
+
+    cudaStream_t s = ctx->stream;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], s));
+    Alphabets al;
+    GPFQ_TRY(upload_alphabets(ctx, alphabets, K, n_alph, &al));
+
+    int64_t chunk_cols = 0;
+    const int n_chunks = conv_pick_chunks(ctx, n, (int)n_ch, &chunk_cols);
+    double *partial = nullptr;
+    GPFQ_TRY(gpfq_ws(ctx, WS_CPART, (size_t)n_ch * n_chunks * 2 * kk * kk * sizeof(double), (void **)&partial));
+    const float **d_ptrs = nullptr;
+    GPFQ_TRY(gpfq_ws(ctx, WS_PTRS, (size_t)2 * n_ch * sizeof(float *), (void **)&d_ptrs));
+    std::vector<const float *> h_ptrs(2 * n_ch);
+    const size_t ch_bytes = (size_t)kk * n * sizeof(float);
+
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], s));
+    if (flags & GPFQ_X_DEVICE) {
+        for (int64_t i = 0; i < n_ch; ++i) {
+            h_ptrs[i] = Xp[i];
+            h_ptrs[n_ch + i] = same ? Xp[i] : Xqp[i];
+        }
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_ptrs, h_ptrs.data(), h_ptrs.size() * sizeof(float *), cudaMemcpyHostToDevice, s));
+        ConvPtrs p{d_ptrs, d_ptrs + n_ch};
+        GPFQ_TRY(conv_gram_stage(ctx, kk, p, same, n, (int)n_ch, n_chunks, chunk_cols, partial));
+    } else {
+        // host patches: double-buffered channel batches, copies on the copy stream overlap the Gram kernel
+        const size_t per_ch = ch_bytes * (same ? 1 : 2);
+        const size_t budget = (size_t)6 << 30;
+        int64_t bch = (int64_t)std::max<size_t>(1, budget / per_ch);
+        bch = std::min<int64_t>(bch, n_ch);
+        if (bch * 2 > n_ch && n_ch >= 2) bch = (n_ch + 1) / 2;  // at least two batches so copy and compute overlap
+        float *buf[2] = {nullptr, nullptr};
+        GPFQ_TRY(gpfq_ws(ctx, WS_PATCH_A, (size_t)bch * per_ch, (void **)&buf[0]));
+        GPFQ_TRY(gpfq_ws(ctx, WS_PATCH_B, (size_t)bch * per_ch, (void **)&buf[1]));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_copy[2], s));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy[2], 0));
+        int bi = 0;
+        for (int64_t b0 = 0; b0 < n_ch; b0 += bch, ++bi) {
+            const int64_t nb = std::min<int64_t>(bch, n_ch - b0);
+            float *dst = buf[bi & 1];
+            // the compute that last read this buffer must be done before we overwrite it
+            if (bi >= 2) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy[bi & 1], 0));
+            for (int64_t i = 0; i < nb; ++i) {
+                float *dx = dst + (size_t)i * (per_ch / sizeof(float));
+                CUDA_TRY(ctx, cudaMemcpyAsync(dx, Xp[b0 + i], ch_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+                h_ptrs[b0 + i] = dx;
+                h_ptrs[n_ch + b0 + i] = dx;
+                if (!same) {
+                    float *dq = dx + (size_t)kk * n;
+                    CUDA_TRY(ctx, cudaMemcpyAsync(dq, Xqp[b0 + i], ch_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+                    h_ptrs[n_ch + b0 + i] = dq;
+                }
+            }
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_copy[3], ctx->copy_stream));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->ev_copy[3], 0));
+            // pointer tables for this batch (pageable source: the copy is staged before the call returns)
+            CUDA_TRY(ctx, cudaMemcpyAsync(d_ptrs + b0, h_ptrs.data() + b0, nb * sizeof(float *), cudaMemcpyHostToDevice, s));
+            CUDA_TRY(ctx, cudaMemcpyAsync(d_ptrs + n_ch + b0, h_ptrs.data() + n_ch + b0, nb * sizeof(float *),
+                                          cudaMemcpyHostToDevice, s));
+            ConvPtrs p{d_ptrs + b0, d_ptrs + n_ch + b0};
+            GPFQ_TRY(conv_gram_stage(ctx, kk, p, same, n, (int)nb, n_chunks, chunk_cols,
+                                     partial + (size_t)b0 * n_chunks * 2 * kk * kk));
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_copy[bi & 1], s));
+        }
+    }
+    GPFQ_TRY(conv_finish(ctx, kk, partial, (int)n_ch, n_chunks, same, W, C, F, c0, al, n_alph, Q_out, flags));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], s));
+    conv_stats(ctx, stats, kk, n, n_ch, F, same, n_alph);
+    if (flags & GPFQ_NO_SYNC) return GPFQ_OK;
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    if (stats) {
+        stats->ms_total = ev_ms(ctx->ev[0], ctx->ev[1]);
+        stats->ms_gram = ev_ms(ctx->ev[2], ctx->ev[3]);
+        stats->ms_sweep = ev_ms(ctx->ev[3], ctx->ev[4]);
+        stats->ms_d2h = ev_ms(ctx->ev[4], ctx->ev[1]);
+    }
+    return GPFQ_OK;
+}
+
+extern "C" int gpfq_conv_layer_nhwc(gpfq_ctx *ctx, const float *act, const float *actq, int64_t n_img, int64_t H,
+                                    int64_t Wd, int64_t C, int32_t kh, int32_t kw, int32_t sh, int32_t sw, int32_t rh,
+                                    int32_t rw, int32_t padding_same, const float *W, int64_t F, int64_t c0,
+                                    int64_t n_ch, const double *alphabets, const int32_t *K, int32_t n_alph,
+                                    double *Q_out, uint32_t flags, gpfq_stats *stats) {
+    if (!ctx) return GPFQ_ERR_ARG;
+    ctx->err.clear();
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (!act || !W || !Q_out) return gpfq_fail(ctx, GPFQ_ERR_ARG, "NULL act, W or Q_out");
+    if (n_img < 1 || H < 1 || Wd < 1 || C < 1 || F < 1 || kh < 1 || kw < 1 || sh < 1 || sw < 1 || rh < 1 || rw < 1 ||
+        c0 < 0 || n_ch < 0 || c0 + n_ch > C || H > 65535 || Wd > 65535)
+        return gpfq_fail(ctx, GPFQ_ERR_ARG, "bad conv geometry");
+    const int kk = kh * kw;
+    if (!conv_supported_kk(kk)) return gpfq_fail(ctx, GPFQ_ERR_UNSUPPORTED, "kernel %dx%d: use gpfq_conv_channels", kh, kw);
+    if (n_ch == 0) return GPFQ_OK;
+    // TensorFlow extract_patches geometry (quantized_network.py:158-172)
+    const int keh = (kh - 1) * rh + 1, kew = (kw - 1) * rw + 1;
+    int Ho, Wo, pt = 0, pl = 0;
+    if (padding_same) {
+        Ho = (int)((H + sh - 1) / sh);
+        Wo = (int)((Wd + sw - 1) / sw);
+        const int64_t ph = std::max<int64_t>((int64_t)(Ho - 1) * sh + keh - H, 0);
+        const int64_t pw = std::max<int64_t>((int64_t)(Wo - 1) * sw + kew - Wd, 0);
+        pt = (int)(ph / 2);
+        pl = (int)(pw / 2);
+    } else {
+        if (H < keh || Wd < kew) return gpfq_fail(ctx, GPFQ_ERR_ARG, "VALID padding: input smaller than the kernel");
+        Ho = (int)((H - keh) / sh + 1);
+        Wo = (int)((Wd - kew) / sw + 1);
+    }
+    const int64_t n = n_img * Ho * Wo;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    ctx->launches = 0;
+    cudaStream_t s = ctx->stream;
+    const bool same = (actq == nullptr || actq == act);
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], s));
+    Alphabets al;
+    GPFQ_TRY(upload_alphabets(ctx, alphabets, K, n_alph, &al));
+    const float *dA = act, *dAq = same ? act : actq;
+    const size_t abytes = (size_t)n_img * H * Wd * C * sizeof(float);
+    if (!(flags & GPFQ_X_DEVICE)) {
+        float *ba = nullptr, *bq = nullptr;
+        GPFQ_TRY(gpfq_ws(ctx, WS_ACT_A, abytes, (void **)&ba));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ba, act, abytes, cudaMemcpyHostToDevice, s));
+        dA = dAq = ba;
+        if (!same) {
+            GPFQ_TRY(gpfq_ws(ctx, WS_ACT_B, abytes, (void **)&bq));
+            CUDA_TRY(ctx, cudaMemcpyAsync(bq, actq, abytes, cudaMemcpyHostToDevice, s));
+            dAq = bq;
+        }
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[5], s));
+    int64_t chunk_cols = 0;
+    const int n_chunks = conv_pick_chunks(ctx, n, (int)std::min<int64_t>(n_ch, 64), &chunk_cols);
+    double *partial = nullptr;
+    GPFQ_TRY(gpfq_ws(ctx, WS_CPART, (size_t)n_ch * n_chunks * 2 * kk * kk * sizeof(double), (void **)&partial));
+    const size_t ch_elems = (size_t)kk * n;
+    const size_t per_ch = ch_elems * sizeof(float);
+    const size_t budget = (size_t)8 << 30;
+    int64_t bch = (int64_t)std::max<size_t>(1, budget / (per_ch * (same ? 1 : 2)));
+    bch = std::min<int64_t>(bch, n_ch);
+    float *pa = nullptr, *pq = nullptr;
+    GPFQ_TRY(gpfq_ws(ctx, WS_PATCH_A, (size_t)bch * per_ch, (void **)&pa));
+    if (!same) GPFQ_TRY(gpfq_ws(ctx, WS_PATCH_B, (size_t)bch * per_ch, (void **)&pq));
+    const float **d_ptrs = nullptr;
+    GPFQ_TRY(gpfq_ws(ctx, WS_PTRS, (size_t)2 * bch * sizeof(float *), (void **)&d_ptrs));
+    std::vector<const float *> h_ptrs(2 * bch);
+    for (int64_t i = 0; i < bch; ++i) {
+        h_ptrs[i] = pa + (size_t)i * ch_elems;
+        h_ptrs[bch + i] = same ? h_ptrs[i] : pq + (size_t)i * ch_elems;
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_ptrs, h_ptrs.data(), h_ptrs.size() * sizeof(float *), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], s));
+    for (int64_t b0 = 0; b0 < n_ch; b0 += bch) {
+        const int64_t nb = std::min<int64_t>(bch, n_ch - b0);
+        GPFQ_TRY(im2col_stage(ctx, dA, n_img, (int)H, (int)Wd, C, c0 + b0, (int)nb, kh, kw, sh, sw, rh, rw, pt, pl, Ho, Wo,
+                              pa, (int64_t)ch_elems));
+        if (!same)
+            GPFQ_TRY(im2col_stage(ctx, dAq, n_img, (int)H, (int)Wd, C, c0 + b0, (int)nb, kh, kw, sh, sw, rh, rw, pt, pl, Ho,
+                                  Wo, pq, (int64_t)ch_elems));
+        ConvPtrs p{d_ptrs, d_ptrs + bch};
+        GPFQ_TRY(conv_gram_stage(ctx, kk, p, same, n, (int)nb, n_chunks, chunk_cols,
+                                 partial + (size_t)b0 * n_chunks * 2 * kk * kk));
+    }
+    GPFQ_TRY(conv_finish(ctx, kk, partial, (int)n_ch, n_chunks, same, W, C, F, c0, al, n_alph, Q_out, flags));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], s));
+    conv_stats(ctx, stats, kk, n, n_ch, F, same, n_alph);
+    if (flags & GPFQ_NO_SYNC) {
+        if ((flags & GPFQ_ALL_DEVICE) != GPFQ_ALL_DEVICE) CUDA_TRY(ctx, cudaStreamSynchronize(s));
+        return GPFQ_OK;
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    if (stats) {
+        stats->ms_total = ev_ms(ctx->ev[0], ctx->ev[1]);
+        stats->ms_h2d = ev_ms(ctx->ev[0], ctx->ev[5]);
+        stats->ms_gram = ev_ms(ctx->ev[2], ctx->ev[3]);
+        stats->ms_sweep = ev_ms(ctx->ev[3], ctx->ev[4]);
+        stats->ms_d2h = ev_ms(ctx->ev[4], ctx->ev[1]);
+    }
+    return GPFQ_OK;
+}
+
+static int round_elements(gpfq_ctx *ctx, const void *W, int is_f64, int64_t n, const double *alphabet, int32_t K,
+                          double *Q_out, uint32_t flags) {
+    if (!ctx) return GPFQ_ERR_ARG;
+    ctx->err.clear();
+    if (!W || !Q_out || n < 0) return gpfq_fail(ctx, GPFQ_ERR_ARG, "bad arguments");
+    if (n == 0) return GPFQ_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    ctx->launches = 0;
+    cudaStream_t s = ctx->stream;
+    Alphabets al;
+    GPFQ_TRY(upload_alphabets(ctx, alphabet, &K, 1, &al));
+    const size_t esz = is_f64 ? sizeof(double) : sizeof(float);
+    const void *dW = W;
+    if (!(flags & GPFQ_W_DEVICE)) {
+        void *bw = nullptr;
+        GPFQ_TRY(gpfq_ws(ctx, WS_W, (size_t)n * esz, &bw));
+        CUDA_TRY(ctx, cudaMemcpyAsync(bw, W, (size_t)n * esz, cudaMemcpyHostToDevice, s));
+        dW = bw;
+    }
+    double *dQ = Q_out;
+    if (!(flags & GPFQ_Q_DEVICE)) GPFQ_TRY(gpfq_ws(ctx, WS_Q, (size_t)n * sizeof(double), (void **)&dQ));
+    GPFQ_TRY(msq_stage(ctx, dW, is_f64, n, al.d_levels, K, dQ));
+    if (!(flags & GPFQ_Q_DEVICE))
+        CUDA_TRY(ctx, cudaMemcpyAsync(Q_out, dQ, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (!(flags & GPFQ_NO_SYNC) || !(flags & GPFQ_Q_DEVICE)) CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    return GPFQ_OK;
+}
+
+extern "C" int gpfq_msq(gpfq_ctx *ctx, const float *W, int64_t n, const double *alphabet, int32_t K, double *Q_out,
+                        uint32_t flags) {
+    return round_elements(ctx, W, 0, n, alphabet, K, Q_out, flags);
+}
+
+extern "C" int gpfq_bit_round(gpfq_ctx *ctx, const double *t, int64_t n, const double *alphabet, int32_t K,
+                              double *out, uint32_t flags) {
+    return round_elements(ctx, t, 1, n, alphabet, K, out, flags);
+}

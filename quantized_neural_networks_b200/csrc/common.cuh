@@ -1,0 +1,116 @@
+// common.cuh -- context, workspace pool, error plumbing and the scalar quantizer shared by all
+// GPFQ kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/gpfq.h"
+
+#define GPFQ_DEAD_NORM 1e-16   // quantized_network.py:83
+#define GPFQ_PERP_DOT 1e-10    // quantized_network.py:86
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct ConvPtrs {
+    const float *const *Xp;   // device array of n_channels device pointers
+    const float *const *Xqp;
+};
+
+struct AlphEntry {
+    std::vector<char> blob;  // levels (fp64) followed by the prefix offsets (int32)
+    size_t off = 0;          // byte offset inside the WS_ALPH device buffer
+};
+
+struct gpfq_ctx {
+    int device = 0;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaStream_t stream = nullptr;  // the one kernels launch on
+    cudaEvent_t ev[8] = {};
+    cudaEvent_t ev_copy[4] = {};
+    std::string err = "";
+    int launches = 0;
+    // grow-only named workspaces
+    DevBuf ws[24];
+    DevBuf pinned[4];
+    // alphabets already resident on the device (steady-state calls re-use them: no copy, no sync)
+    std::vector<AlphEntry> alph_cache;
+    size_t alph_used = 0;
+};
+
+enum WsSlot {
+    WS_X = 0, WS_XQ, WS_W, WS_Q, WS_WT, WS_QT, WS_G1, WS_G2, WS_PART, WS_DT, WS_NRM, WS_ALPH,
+    WS_U, WS_PTRS, WS_CG, WS_CPART, WS_PATCH_A, WS_PATCH_B, WS_ACT_A, WS_ACT_B, WS_QIDX, WS_MISC
+};
+
+int gpfq_fail(gpfq_ctx *ctx, int code, const char *fmt, ...);
+int gpfq_ws(gpfq_ctx *ctx, int slot, size_t bytes, void **out);         // device workspace
+int gpfq_pinned(gpfq_ctx *ctx, int slot, size_t bytes, void **out);     // pinned host staging
+
+#define CUDA_TRY(ctx, expr)                                                                    \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            return gpfq_fail((ctx), _e == cudaErrorMemoryAllocation ? GPFQ_ERR_OOM : GPFQ_ERR_CUDA, \
+                             "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+#define GPFQ_TRY(expr)                \
+    do {                              \
+        int _rc = (expr);             \
+        if (_rc != GPFQ_OK) return _rc; \
+    } while (0)
+
+#define KERNEL_CHECK(ctx)                                                                     \
+    do {                                                                                      \
+        (ctx)->launches++;                                                                    \
+        cudaError_t _e = cudaGetLastError();                                                  \
+        if (_e != cudaSuccess)                                                                \
+            return gpfq_fail((ctx), GPFQ_ERR_CUDA, "kernel launch failed: %s (%s:%d)",        \
+                             cudaGetErrorString(_e), __FILE__, __LINE__);                     \
+    } while (0)
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------------------------
+// Scalar quantizer: alphabet[argmin_k |alphabet[k] - v|], first minimal index on ties
+// (quantized_network.py:57).  Same fp64 subtraction/abs/compare as NumPy, so ties break alike.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double gpfq_bit_round(double v, const double *__restrict__ alph, int K) {
+    double best = alph[0];
+    double bd = fabs(__dsub_rn(best, v));
+#pragma unroll 4
+    for (int k = 1; k < K; ++k) {
+        const double a = alph[k];
+        const double d = fabs(__dsub_rn(a, v));
+        if (d < bd) { bd = d; best = a; }
+    }
+    return best;
+}
+
+// One greedy decision in Gram form:
+//   nrm  = (double)(float)sqrt(G2[t,t])         (snrm2 result, quantized_network.py:83)
+//   d    = <Xq_t, u_{t-1}>                       (:86)
+//   num  = <Xq_t, u_{t-1} + w_t X_t>             (:89)
+__device__ __forceinline__ double gpfq_decide(double nrm, double d, double num, double w,
+                                              const double *__restrict__ alph, int K) {
+    if (nrm < GPFQ_DEAD_NORM) return 0.0;
+    if (fabs(d) < GPFQ_PERP_DOT) return gpfq_bit_round(w, alph, K);
+    return gpfq_bit_round(num / (nrm * nrm), alph, K);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}

@@ -1,0 +1,208 @@
+// dense_gram.cu -- Dense layer, Gram form: K1 Gram stage + K2 blocked triangular sweep.
+//
+// Replaces the N0-step loop of _quantize_neuron_parallel (quantized_network.py:117-119) for all
+// neurons of a layer.  With G1[t,s] = <Xq_t, X_s>, G2[t,s] = <Xq_t, Xq_s> (fp64 accumulation of exact
+// fp32 products) the residual dot of step t is
+//     d_t = <Xq_t, u_{t-1}> = sum_{s<t} ( w_s G1[t,s] - q_s G2[t,s] )
+// so q_t = Q( (d_t + w_t G1[t,t]) / fl32(sqrt(G2[t,t]))^2 ) with the two guards of :83-87 intact.
+// The sweep walks blocks of 32 directions: contributions of earlier blocks are one NT contraction
+// per block (gemm_nt.cuh, two segments), the 32 in-block steps run warp-per-neuron with the running
+// d held one-per-lane and exchanged by shuffles.
+#include "gemm_nt.cuh"
+
+static constexpr int SWEEP_B = 32;
+
+// Wt[j - j0][t] = (double) W[t*ldw + j]   (neuron-major copy of the shard, fp64)
+__global__ void transpose_w_kernel(const float *__restrict__ W, int64_t ldw, int64_t N0, int64_t j0,
+                                   int64_t nj, double *__restrict__ Wt) {
+    __shared__ float tile[32][33];
+    const int64_t tb = (int64_t)blockIdx.x * 32, jb = (int64_t)blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int64_t t = tb + r, j = jb + threadIdx.x;
+        tile[r][threadIdx.x] = (t < N0 && j < nj) ? W[t * ldw + j0 + j] : 0.f;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int64_t j = jb + r, t = tb + threadIdx.x;
+        if (j < nj && t < N0) Wt[j * N0 + t] = (double)tile[threadIdx.x][r];
+    }
+}
+
+// Q[t*ldq + j0 + j] = Qt[j][t]
+__global__ void transpose_q_kernel(const double *__restrict__ Qt, int64_t N0, int64_t nj,
+                                   double *__restrict__ Q, int64_t ldq, int64_t col0) {
+    __shared__ double tile[32][33];
+    const int64_t tb = (int64_t)blockIdx.x * 32, jb = (int64_t)blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int64_t j = jb + r, t = tb + threadIdx.x;
+        tile[r][threadIdx.x] = (j < nj && t < N0) ? Qt[j * N0 + t] : 0.0;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int64_t t = tb + r, j = jb + threadIdx.x;
+        if (t < N0 && j < nj) Q[t * ldq + col0 + j] = tile[threadIdx.x][r];
+    }
+}
+
+// In-block steps of the sweep.  One warp per neuron, lane = direction within the block.
+//   G1, G2 : (N0, N0) fp64, lower triangle + diagonal valid
+//   Wt     : (nj, N0) fp64;  Dt : (n_alph, nj, 32) prior-block part of d (ignored for block 0)
+//   Qt     : (n_alph, nj, N0) fp64 output
+__global__ void __launch_bounds__(256)
+sweep_inblock_kernel(const double *__restrict__ G1, const double *__restrict__ G2, int64_t ldg,
+                     int64_t N0, int blk, const double *__restrict__ Wt, const double *__restrict__ Dt,
+                     double *__restrict__ Qt, int64_t nj, const double *__restrict__ alphabets,
+                     const int *__restrict__ Koff) {
+    __shared__ double g1[SWEEP_B][SWEEP_B + 1], g2[SWEEP_B][SWEEP_B + 1];
+    __shared__ double nrm[SWEEP_B];
+    __shared__ double alph[GPFQ_MAX_K];
+    const int64_t t0 = (int64_t)blk * SWEEP_B;
+    const int nb = (int)((N0 - t0) < SWEEP_B ? (N0 - t0) : SWEEP_B);
+    const int a = blockIdx.y;
+    const int K = Koff[a + 1] - Koff[a];
+    for (int e = threadIdx.x; e < SWEEP_B * SWEEP_B; e += blockDim.x) {
+        const int r = e / SWEEP_B, c = e % SWEEP_B;
+        const bool ok = r < nb && c <= r;
+        g1[r][c] = ok ? G1[(t0 + r) * ldg + t0 + c] : 0.0;
+        g2[r][c] = ok ? G2[(t0 + r) * ldg + t0 + c] : 0.0;
+    }
+    for (int e = threadIdx.x; e < K; e += blockDim.x) alph[e] = alphabets[Koff[a] + e];
+    __syncthreads();
+    if (threadIdx.x < SWEEP_B)
+        nrm[threadIdx.x] = threadIdx.x < nb ? (double)(float)sqrt(g2[threadIdx.x][threadIdx.x]) : 0.0;
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (j >= nj) return;
+    const int64_t t = t0 + lane;
+    const double w = (lane < nb) ? Wt[j * N0 + t] : 0.0;
+    double d = (blk > 0 && lane < nb) ? Dt[((int64_t)a * nj + j) * SWEEP_B + lane] : 0.0;
+    double myq = 0.0;
+    for (int tt = 0; tt < nb; ++tt) {
+        const double dtt = __shfl_sync(0xffffffffu, d, tt);
+        const double wtt = __shfl_sync(0xffffffffu, w, tt);
+        const double num = fma(wtt, g1[tt][tt], dtt);
+        const double q = gpfq_decide(nrm[tt], dtt, num, wtt, alph, K);
+        if (lane == tt) myq = q;
+        if (lane > tt) d += g1[lane][tt] * wtt - g2[lane][tt] * q;
+    }
+    if (lane < nb) Qt[((int64_t)a * nj + j) * N0 + t] = myq;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static int pick_splits(gpfq_ctx *ctx, int64_t N0, int64_t m, int BM, int BN, int BK) {
+    const int64_t tm = ceil_div64(N0, BM), tn = ceil_div64(N0, BN);
+    int64_t tiles = 0;  // tiles touching the lower triangle
+    for (int64_t i = 0; i < tm; ++i)
+        for (int64_t jn = 0; jn < tn; ++jn)
+            if (jn * BN <= i * BM + BM - 1) ++tiles;
+    const int64_t target = 2LL * ctx->sm_count * 2;  // two CTAs per SM, two waves
+    int64_t s = ceil_div64(target, tiles > 0 ? tiles : 1);
+    const int64_t max_by_k = m / (8 * BK) > 0 ? m / (8 * BK) : 1;  // at least 8 k-tiles per split
+    if (s > max_by_k) s = max_by_k;
+    if (s > 32) s = 32;
+    while (s > 1 && (size_t)s * N0 * N0 * sizeof(double) > ((size_t)2 << 30)) --s;
+    return (int)(s < 1 ? 1 : s);
+}
+
+// G = A B^T over the sample axis, lower triangle (+ diagonal tiles).  A, B: (N0, m) fp32 device.
+static int gram_stage(gpfq_ctx *ctx, const float *A, const float *B, int64_t ld, int64_t N0, int64_t m,
+                      double *G) {
+    constexpr int BM = 128, BN = 64, BK = 32;
+    const int nsplit = pick_splits(ctx, N0, m, BM, BN, BK);
+    GemmArgs g = {};
+    g.seg[0] = {A, B, ld, ld, m, 1.0};
+    g.nseg = 1;
+    g.M = g.N = N0;
+    g.ldc = N0;
+    g.nsplit = nsplit;
+    g.lower_only = 1;
+    if (nsplit == 1) {
+        g.C = G;
+        g.split_stride = 0;
+        GPFQ_TRY((launch_gemm_nt<float, BM, BN, BK>(ctx, g, 1)));
+    } else {
+        double *part = nullptr;
+        GPFQ_TRY(gpfq_ws(ctx, WS_PART, (size_t)nsplit * N0 * N0 * sizeof(double), (void **)&part));
+        g.C = part;
+        g.split_stride = N0 * N0;
+        GPFQ_TRY((launch_gemm_nt<float, BM, BN, BK>(ctx, g, 1)));
+        const int64_t n = N0 * N0;
+        int blocks = (int)(ceil_div64(n, 256) < 4096 ? ceil_div64(n, 256) : 4096);
+        reduce_splits_kernel<<<blocks, 256, 0, ctx->stream>>>(part, nsplit, N0 * N0, G, n);
+        KERNEL_CHECK(ctx);
+    }
+    return GPFQ_OK;
+}
+
+int dense_gram_only(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx, int64_t N0, int64_t m, double *G1,
+                    double *G2) {
+    GPFQ_TRY(gram_stage(ctx, Xq, Xq, ldx, N0, m, G2));
+    if (G1 != G2) GPFQ_TRY(gram_stage(ctx, Xq, X, ldx, N0, m, G1));
+    return GPFQ_OK;
+}
+
+// Dense layer by Gram + sweep.  All pointers are device pointers.
+//   Qd: (n_alph, N0, ldq) fp64 device output, columns col0..col0+nj-1 written.
+int dense_gram_path(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx, int64_t N0, int64_t m,
+                    const float *W, int64_t ldw, int64_t j0, int64_t nj, const double *d_alph,
+                    const int *d_koff, int n_alph, double *Qd, int64_t ldq, int64_t col0,
+                    gpfq_stats *st) {
+    const bool same = (Xq == X);
+    double *G1 = nullptr, *G2 = nullptr, *Wt = nullptr, *Qt = nullptr, *Dt = nullptr;
+    GPFQ_TRY(gpfq_ws(ctx, WS_G2, (size_t)N0 * N0 * sizeof(double), (void **)&G2));
+    if (same) G1 = G2;
+    else GPFQ_TRY(gpfq_ws(ctx, WS_G1, (size_t)N0 * N0 * sizeof(double), (void **)&G1));
+    GPFQ_TRY(gpfq_ws(ctx, WS_WT, (size_t)nj * N0 * sizeof(double), (void **)&Wt));
+    GPFQ_TRY(gpfq_ws(ctx, WS_QT, (size_t)n_alph * nj * N0 * sizeof(double), (void **)&Qt));
+    GPFQ_TRY(gpfq_ws(ctx, WS_DT, (size_t)n_alph * nj * SWEEP_B * sizeof(double), (void **)&Dt));
+
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    GPFQ_TRY(gram_stage(ctx, Xq, Xq, ldx, N0, m, G2));
+    if (!same) GPFQ_TRY(gram_stage(ctx, Xq, X, ldx, N0, m, G1));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+
+    {
+        dim3 grid((unsigned)ceil_div64(N0, 32), (unsigned)ceil_div64(nj, 32));
+        transpose_w_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(W, ldw, N0, j0, nj, Wt);
+        KERNEL_CHECK(ctx);
+    }
+    const int nblk = (int)ceil_div64(N0, SWEEP_B);
+    for (int b = 0; b < nblk; ++b) {
+        const int64_t p = (int64_t)b * SWEEP_B;
+        const int64_t nb = (N0 - p) < SWEEP_B ? (N0 - p) : SWEEP_B;
+        if (b > 0) {
+            GemmArgs g = {};
+            g.seg[0] = {Wt, G1 + p * N0, N0, N0, p, 1.0};
+            g.seg[1] = {Qt, G2 + p * N0, N0, N0, p, -1.0};
+            g.nseg = 2;
+            g.M = nj;
+            g.N = nb;
+            g.C = Dt;
+            g.ldc = SWEEP_B;
+            g.nsplit = 1;
+            g.batch_strideA1 = nj * N0;
+            g.batch_strideC = nj * SWEEP_B;
+            GPFQ_TRY((launch_gemm_nt<double, 128, 32, 16>(ctx, g, n_alph)));
+        }
+        dim3 grid((unsigned)ceil_div64(nj, 8), (unsigned)n_alph);
+        sweep_inblock_kernel<<<grid, 256, 0, ctx->stream>>>(G1, G2, N0, N0, b, Wt, Dt, Qt, nj, d_alph, d_koff);
+        KERNEL_CHECK(ctx);
+    }
+    for (int a = 0; a < n_alph; ++a) {
+        dim3 grid((unsigned)ceil_div64(N0, 32), (unsigned)ceil_div64(nj, 32));
+        transpose_q_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(Qt + (int64_t)a * nj * N0, N0, nj,
+                                                                  Qd + (int64_t)a * N0 * ldq, ldq, col0);
+        KERNEL_CHECK(ctx);
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
+    if (st) {
+        st->method = GPFQ_METHOD_GRAM >> 4;
+        st->flops_algorithmic = (same ? 1 : 2) * m * N0 * (N0 + 1);  // lower triangles, 2 flops per MAC
+        st->bytes_algorithmic = (same ? 1 : 2) * 4 * N0 * m + (same ? 1 : 2) * 8 * N0 * N0;
+    }
+    return GPFQ_OK;
+}

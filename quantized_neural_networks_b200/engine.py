@@ -1,0 +1,293 @@
+"""Python face of the C ABI: one `GpfqEngine` per GPU.  Accepts NumPy arrays (host pointers; copies
+happen inside the library call) or CUDA torch tensors (device pointers; torch is only the buffer)."""
+from __future__ import annotations
+
+import ctypes
+from ctypes import POINTER, byref, c_double, c_int32, c_void_p
+
+import numpy as np
+
+from . import _lib
+
+try:  # torch is optional plumbing (device buffers / streams)
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+_METHODS = {"auto": _lib.METHOD_AUTO, "stream": _lib.METHOD_STREAM, "gram": _lib.METHOD_GRAM}
+
+
+def _is_torch(x):
+    return torch is not None and isinstance(x, torch.Tensor)
+
+
+def _alph_args(alphabets):
+    """One alphabet (1-D) or a list of alphabets -> (levels*, K*, n, list)."""
+    if isinstance(alphabets, np.ndarray) and alphabets.ndim == 1:
+        alphabets = [alphabets]
+    als = [np.ascontiguousarray(a, dtype=np.float64).reshape(-1) for a in alphabets]
+    flat = np.concatenate(als) if als else np.zeros(0)
+    K = np.array([len(a) for a in als], dtype=np.int32)
+    return flat, K, len(als), als
+
+
+class GpfqEngine:
+    """Owns a `gpfq_ctx` (include/gpfq.h).  Fails loudly when the library or an sm_100 GPU is absent."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib.lib()
+        self._ctx = c_void_p()
+        self.device = int(device)
+        rc = self._lib.gpfq_create(self.device, byref(self._ctx))
+        if rc != 0:
+            self._ctx = c_void_p()
+            raise _lib.GpfqError(rc, f"gpfq_create(device={device}) failed -- libgpfq needs a B200-class (sm_100) GPU; "
+                                     "there is no CPU fallback")
+        self.last_stats = {}
+
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self._lib.gpfq_destroy(self._ctx)
+            self._ctx = c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- helpers --------------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            msg = self._lib.gpfq_last_error(self._ctx)
+            raise _lib.GpfqError(rc, msg.decode() if msg else "")
+
+    def trim(self):
+        self._check(self._lib.gpfq_trim(self._ctx))
+
+    def use_torch_stream(self, enable=True):
+        """Launch on torch's current stream (so torch.cuda.Event brackets see the kernels)."""
+        s = torch.cuda.current_stream(self.device).cuda_stream if enable else None
+        self._check(self._lib.gpfq_set_stream(self._ctx, c_void_p(s)))
+
+    @staticmethod
+    def _f32(x, name):
+        if _is_torch(x):
+            if x.dtype != torch.float32 or not x.is_cuda:
+                raise TypeError(f"{name}: torch tensors must be float32 CUDA tensors")
+            return x
+        return np.asarray(x, dtype=np.float32)
+
+    @staticmethod
+    def _rowmajor2d(x, name):
+        """(ptr, ld) of a 2-D array whose rows are contiguous."""
+        if _is_torch(x):
+            if x.dim() != 2 or x.stride(1) != 1:
+                raise ValueError(f"{name}: need a 2-D tensor with contiguous rows")
+            return x.data_ptr(), (x.stride(0) if x.shape[0] > 1 else x.shape[1])
+        if x.ndim != 2:
+            raise ValueError(f"{name}: need a 2-D array")
+        if x.strides[1] != x.itemsize or (x.shape[0] > 1 and x.strides[0] % x.itemsize):
+            raise ValueError(f"{name}: rows must be contiguous")
+        return x.ctypes.data, (x.strides[0] // x.itemsize if x.shape[0] > 1 else x.shape[1])
+
+    # -- Dense ----------------------------------------------------------------------------------
+    def dense_layer(self, X, Xq, W, alphabets, j0=0, j1=None, method="auto", out=None, sync=True):
+        """Quantize neurons j0..j1-1 of a Dense layer.  X, Xq: (N0, m) fp32 feature-major (Xq may be
+        None or X itself for the first layer); W: (N0, N1) fp32.  Returns Q fp64 (N0, N1) -- or
+        (n_alphabets, N0, N1) when a list of alphabets is given -- with only the shard's columns written."""
+        flat, K, n_alph, als = _alph_args(alphabets)
+        single = isinstance(alphabets, np.ndarray) and alphabets.ndim == 1
+        X = self._f32(X, "X")
+        same = Xq is None or Xq is X
+        Xq = X if same else self._f32(Xq, "Xq")
+        W = self._f32(W, "W")
+        dev = _is_torch(X)
+        if dev != _is_torch(W) or dev != _is_torch(Xq):
+            raise TypeError("X, Xq and W must all be NumPy arrays or all be CUDA tensors")
+        if not dev:
+            X = np.ascontiguousarray(X)
+            Xq = X if same else np.ascontiguousarray(Xq)
+            if W.ndim != 2 or W.strides[1] != W.itemsize:
+                W = np.ascontiguousarray(W)
+        if tuple(Xq.shape) != tuple(X.shape):
+            raise ValueError("X and Xq must have the same shape")
+        N0, m = int(X.shape[0]), int(X.shape[1])
+        if W.shape[0] != N0:
+            raise ValueError(f"W has {W.shape[0]} rows, X has {N0} directions")
+        N1 = int(W.shape[1])
+        j1 = N1 if j1 is None else int(j1)
+        px, ldx = self._rowmajor2d(X, "X")
+        pq, ldq_x = (px, ldx) if same else self._rowmajor2d(Xq, "Xq")
+        if ldq_x != ldx:
+            raise ValueError("X and Xq must share a row stride")
+        pw, ldw = self._rowmajor2d(W, "W")
+        flags = _METHODS[method]
+        if dev:
+            flags |= _lib.ALL_DEVICE
+            if out is None:
+                out = torch.zeros((n_alph, N0, N1), dtype=torch.float64, device=X.device)
+            pout = out.data_ptr()
+            if not sync:
+                flags |= _lib.NO_SYNC
+        else:
+            if out is None:
+                out = np.zeros((n_alph, N0, N1), dtype=np.float64)
+            pout = out.ctypes.data
+        st = _lib.GpfqStats()
+        rc = self._lib.gpfq_dense_layer(self._ctx, c_void_p(px), c_void_p(pq), ldx, N0, m, c_void_p(pw), ldw, N1,
+                                        int(j0), j1, flat.ctypes.data_as(POINTER(c_double)),
+                                        K.ctypes.data_as(POINTER(c_int32)), n_alph, c_void_p(pout), N1, flags,
+                                        byref(st))
+        self._check(rc)
+        self.last_stats = st.as_dict()
+        return out[0] if single else out
+
+    def gram_matrices(self, X, Xq=None):
+        """Diagnostics: (G1, G2) fp64 (N0, N0), lower triangle + diagonal valid."""
+        X = np.ascontiguousarray(X, dtype=np.float32)
+        same = Xq is None or Xq is X
+        Xq = X if same else np.ascontiguousarray(Xq, dtype=np.float32)
+        N0, m = X.shape
+        G2 = np.zeros((N0, N0))
+        G1 = G2 if same else np.zeros((N0, N0))
+        rc = self._lib.gpfq_gram_matrices(self._ctx, c_void_p(X.ctypes.data), c_void_p(Xq.ctypes.data), m, N0, m,
+                                          c_void_p(None if same else G1.ctypes.data), c_void_p(G2.ctypes.data), 0)
+        self._check(rc)
+        return G1, G2
+
+    # -- Conv -----------------------------------------------------------------------------------
+    def conv_channels(self, Xp, Xqp, W, alphabets, c0=0, n_channels=None, out=None, sync=True):
+        """Quantize channels c0..c0+n_channels-1 of a (kh, kw, C, F) kernel from per-channel patch
+        matrices.  Xp/Xqp: sequences (len n_channels) of (kh*kw, n_patches) fp32 arrays/tensors, or one
+        (n_channels, kh*kw, n_patches) array; Xqp None => first conv layer (X == Xq)."""
+        flat, K, n_alph, als = _alph_args(alphabets)
+        single = isinstance(alphabets, np.ndarray) and alphabets.ndim == 1
+        W = self._f32(W, "W")
+        kh, kw, C, F = (int(v) for v in W.shape)
+        kk = kh * kw
+        n_channels = (C - c0) if n_channels is None else int(n_channels)
+        xs = [self._f32(Xp[i], "Xp") for i in range(n_channels)]
+        same = Xqp is None
+        qs = xs if same else [self._f32(Xqp[i], "Xqp") for i in range(n_channels)]
+        dev = _is_torch(W)
+        if any(_is_torch(x) != dev for x in xs + qs):
+            raise TypeError("patches and W must all be NumPy arrays or all be CUDA tensors")
+        if not dev:
+            xs = [np.ascontiguousarray(x) for x in xs]
+            qs = xs if same else [np.ascontiguousarray(q) for q in qs]
+            W = np.ascontiguousarray(W)
+        else:
+            if not W.is_contiguous() or any(not x.is_contiguous() for x in xs + qs):
+                raise ValueError("device tensors must be contiguous")
+        n = int(xs[0].shape[1]) if n_channels else 1
+        for x in xs + qs:
+            if tuple(x.shape) != (kk, n):
+                raise ValueError(f"patch matrix has shape {tuple(x.shape)}, expected {(kk, n)}")
+        ptr = (lambda t: t.data_ptr()) if dev else (lambda t: t.ctypes.data)
+        PX = (c_void_p * max(n_channels, 1))(*[ptr(x) for x in xs])
+        PQ = None if same else (c_void_p * max(n_channels, 1))(*[ptr(q) for q in qs])
+        flags = 0
+        if dev:
+            flags |= _lib.ALL_DEVICE
+            if out is None:
+                out = torch.zeros((n_alph, kh, kw, C, F), dtype=torch.float64, device=W.device)
+            pout = out.data_ptr()
+            if not sync:
+                flags |= _lib.NO_SYNC
+        else:
+            if out is None:
+                out = np.zeros((n_alph, kh, kw, C, F), dtype=np.float64)
+            pout = out.ctypes.data
+        st = _lib.GpfqStats()
+        rc = self._lib.gpfq_conv_channels(self._ctx, PX, PQ, n, kk, c_void_p(ptr(W)), C, F, int(c0), n_channels,
+                                          flat.ctypes.data_as(POINTER(c_double)), K.ctypes.data_as(POINTER(c_int32)),
+                                          n_alph, c_void_p(pout), flags, byref(st))
+        self._check(rc)
+        self.last_stats = st.as_dict()
+        return out[0] if single else out
+
+    def conv_layer_nhwc(self, act, actq, W, alphabets, strides=(1, 1), padding="SAME", rate=(1, 1), c0=0,
+                        n_channels=None, out=None, sync=True):
+        """Quantize a Conv2D kernel straight from the NHWC activations (on-device patch extraction)."""
+        flat, K, n_alph, als = _alph_args(alphabets)
+        single = isinstance(alphabets, np.ndarray) and alphabets.ndim == 1
+        W = self._f32(W, "W")
+        act = self._f32(act, "act")
+        same = actq is None or actq is act
+        actq = act if same else self._f32(actq, "actq")
+        dev = _is_torch(W)
+        if _is_torch(act) != dev or _is_torch(actq) != dev:
+            raise TypeError("act, actq and W must all be NumPy arrays or all be CUDA tensors")
+        if not dev:
+            act = np.ascontiguousarray(act)
+            actq = act if same else np.ascontiguousarray(actq)
+            W = np.ascontiguousarray(W)
+        elif not (act.is_contiguous() and actq.is_contiguous() and W.is_contiguous()):
+            raise ValueError("device tensors must be contiguous")
+        kh, kw, C, F = (int(v) for v in W.shape)
+        n_img, H, Wd, Ca = (int(v) for v in act.shape)
+        if Ca != C or tuple(actq.shape) != tuple(act.shape):
+            raise ValueError("activation / kernel channel mismatch")
+        n_channels = (C - c0) if n_channels is None else int(n_channels)
+        rate = tuple(rate) if rate else (1, 1)
+        ptr = (lambda t: t.data_ptr()) if dev else (lambda t: t.ctypes.data)
+        flags = 0
+        if dev:
+            flags |= _lib.ALL_DEVICE
+            if out is None:
+                out = torch.zeros((n_alph, kh, kw, C, F), dtype=torch.float64, device=W.device)
+            pout = out.data_ptr()
+            if not sync:
+                flags |= _lib.NO_SYNC
+        else:
+            if out is None:
+                out = np.zeros((n_alph, kh, kw, C, F), dtype=np.float64)
+            pout = out.ctypes.data
+        st = _lib.GpfqStats()
+        rc = self._lib.gpfq_conv_layer_nhwc(self._ctx, c_void_p(ptr(act)), c_void_p(ptr(actq)), n_img, H, Wd, C, kh, kw,
+                                            int(strides[0]), int(strides[1]), int(rate[0]), int(rate[1]),
+                                            1 if str(padding).upper() == "SAME" else 0, c_void_p(ptr(W)), F, int(c0),
+                                            n_channels, flat.ctypes.data_as(POINTER(c_double)),
+                                            K.ctypes.data_as(POINTER(c_int32)), n_alph, c_void_p(pout), flags, byref(st))
+        self._check(rc)
+        self.last_stats = st.as_dict()
+        return out[0] if single else out
+
+    def msq(self, W, alphabet):
+        """Plain nearest-level rounding of every weight (the MSQ baseline of the reference's drivers)."""
+        W = np.ascontiguousarray(W, dtype=np.float32)
+        A = np.ascontiguousarray(alphabet, dtype=np.float64)
+        out = np.zeros(W.shape, dtype=np.float64)
+        rc = self._lib.gpfq_msq(self._ctx, c_void_p(W.ctypes.data), W.size, A.ctypes.data_as(POINTER(c_double)), len(A),
+                                c_void_p(out.ctypes.data), 0)
+        self._check(rc)
+        return out
+
+
+    def _bit_round(self, t, alphabet):
+        t = np.ascontiguousarray(t, dtype=np.float64)
+        A = np.ascontiguousarray(alphabet, dtype=np.float64)
+        out = np.zeros(t.shape, dtype=np.float64)
+        rc = self._lib.gpfq_bit_round(self._ctx, c_void_p(t.ctypes.data), t.size, A.ctypes.data_as(POINTER(c_double)),
+                                      len(A), c_void_p(out.ctypes.data), 0)
+        self._check(rc)
+        return out
+
+    bit_round = _bit_round
+
+
+_engines = {}
+
+
+def get_engine(device: int = 0) -> GpfqEngine:
+    """Process-wide engine per device (one context per GPU per process)."""
+    if device not in _engines:
+        _engines[device] = GpfqEngine(device)
+    return _engines[device]
