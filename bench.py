@@ -1,0 +1,475 @@
+#!/usr/bin/env python
+"""bench.py -- GPFQ hot path on B200: quantized weights/s of a full-network pass (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's NumPy path on the host cores
+
+Workload (config.workload): BASELINE.json configs[1], the CIFAR10 CNN of train_cifar10_cnn.py -- six 3x3 'same'
+Conv2D layers handed over as per-channel patch matrices (9 x n_patches, m_img = 5008 images) and two Dense layers
+(2048->128, 128->10, m = 5008), 4-bit alphabet (K = 16), synthetic activations, random-init weights.
+One "step" = one pass of the hot path over all eight layers.
+
+  value   whole-job weights/s with every input resident in HBM when the timed region starts (CUDA events on the
+          launching stream, max over ranks).  Inputs (25.7 GB) are far larger than L2, so no flush is needed.
+  e2e     the same pass through the C ABI with HOST (pinned) buffers: H2D of all patch matrices / activations and
+          D2H of every Q inside the timed region.
+  roofline  the dominant kernel (conv_gram_kernel, HBM-bound): algorithmic bytes / CUDA-event time of that stage.
+  cpu_baseline  the oracle's NumPy restatement of the reference walk (kind "port": the reference is Python and does
+          not travel to the GPU box), one process per host core exactly like the reference's ProcessPoolExecutor, on a
+          bounded sample of every layer, extrapolated linearly in the number of neurons/filters.
+Multi-GPU: conv channels and Dense neurons shard over ranks (no data-path collective); total work is fixed => "strong".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_IMG = 5008
+BITS, CSCALAR = 4, 4
+# (name, kind, C or N0, F or N1, H)   -- SURVEY.md App. B, config 2
+CIFAR_LAYERS = [
+    ("conv0", "conv", 3, 32, 32), ("conv2", "conv", 32, 32, 32), ("conv6", "conv", 32, 64, 16),
+    ("conv8", "conv", 64, 64, 16), ("conv12", "conv", 64, 128, 8), ("conv14", "conv", 128, 128, 8),
+    ("dense19", "dense", 2048, 128, 0), ("dense22", "dense", 128, 10, 0),
+]
+MNIST_LAYERS = [("dense1", "dense", 784, 500, 0), ("dense3", "dense", 500, 300, 0), ("dense5", "dense", 300, 10, 0)]
+
+
+def shard_range(n, rank, world):
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def layer_weights(layer):
+    name, kind, a, b, H = layer
+    return 9 * a * b if kind == "conv" else a * b
+
+
+def make_alphabet(W_abs_median, bits=BITS, c=CSCALAR):
+    return c * float(W_abs_median) * np.linspace(-1, 1, int(round(2 ** bits)))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# synthetic data (device side, torch is only the buffer/generator)
+# ----------------------------------------------------------------------------------------------------------------
+def build_device_inputs(layers, n_img, rank, world, dev):
+    """Per layer: dict with device tensors.  conv: Xp/Xqp lists of (9, n) patch matrices for this rank's channels."""
+    import torch
+    out = []
+    for li, (name, kind, a, b, H) in enumerate(layers):
+        g = torch.Generator(device=dev).manual_seed(1000 + li)
+        if kind == "conv":
+            C, F = a, b
+            W = (torch.rand((3, 3, C, F), device=dev, generator=g) * 2 - 1) * float(np.sqrt(6.0 / (9 * C)))
+            A = make_alphabet(torch.median(W.abs().flatten()))
+            lo, hi = shard_range(C, rank, world)
+            n = n_img * H * H
+            first = li == 0
+            Xp, Xqp = [], []
+            cb = max(1, min(hi - lo, int(1.5e9 // (36 * n))))
+            for c0 in range(lo, hi, cb):
+                c1 = min(hi, c0 + cb)
+                gc = torch.Generator(device=dev).manual_seed(5000 + 100 * li + c0)
+                shape = (c1 - c0, n_img, H, H)
+                if first:   # image-like: uniform[0,1) with half the pixels zero; X == Xq
+                    act = torch.rand(shape, device=dev, generator=gc) * (torch.rand(shape, device=dev, generator=gc) < 0.5)
+                    acts = (act,)
+                else:       # hidden: X = relu(Z), Xq = relu(Z + 0.05 N)
+                    Z = torch.randn(shape, device=dev, generator=gc)
+                    acts = (torch.relu(Z), torch.relu(Z + 0.05 * torch.randn(shape, device=dev, generator=gc)))
+                    del Z
+                mats = []
+                for t in acts:
+                    p = torch.nn.functional.unfold(t.reshape(-1, 1, H, H), 3, padding=1)      # (cb*n_img, 9, H*H)
+                    p = p.reshape(c1 - c0, n_img, 9, H * H).permute(0, 2, 1, 3).reshape(c1 - c0, 9, n).contiguous()
+                    mats.append(p)
+                Xp += list(mats[0])
+                Xqp += list(mats[0] if first else mats[1])
+                del acts, p
+            out.append(dict(name=name, kind=kind, W=W, A=A, Xp=Xp, Xqp=None if first else Xqp, c0=lo, n_ch=hi - lo,
+                            n=n, C=C, F=F, first=first))
+        else:
+            N0, N1 = a, b
+            m = n_img if n_img else 25000
+            W = (torch.rand((N0, N1), device=dev, generator=g) * 2 - 1) * float(np.sqrt(6.0 / N0))
+            A = make_alphabet(torch.median(W.abs().flatten()))
+            first = (li == 0)
+            if first:
+                X = torch.rand((N0, m), device=dev, generator=g) * (torch.rand((N0, m), device=dev, generator=g) < 0.5)
+                Xq = None
+            else:
+                Z = torch.randn((N0, m), device=dev, generator=g)
+                X = torch.relu(Z)
+                Xq = torch.relu(Z + 0.05 * torch.randn((N0, m), device=dev, generator=g))
+                del Z
+            lo, hi = shard_range(N1, rank, world)
+            out.append(dict(name=name, kind=kind, W=W, A=A, X=X, Xq=Xq, j0=lo, j1=hi, N0=N0, N1=N1, m=m, first=first))
+        torch.cuda.empty_cache()
+    return out
+
+
+def run_pass_device(eng, data, outs, sync=False):
+    for d, o in zip(data, outs):
+        if d["kind"] == "conv":
+            eng.conv_channels(d["Xp"], d["Xqp"], d["W"], d["A"], c0=d["c0"], n_channels=d["n_ch"], out=o, sync=sync)
+        else:
+            eng.dense_layer(d["X"], d["Xq"], d["W"], d["A"], j0=d["j0"], j1=d["j1"], out=o, sync=sync)
+
+
+def to_host_pinned(data):
+    """Pinned host copies of every input (what the reference's host code would hand over)."""
+    import torch
+
+    def pin(t):
+        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        h.copy_(t)
+        return h.numpy()
+
+    host, nbytes = [], 0
+    for d in data:
+        if d["kind"] == "conv":
+            Xp = [pin(x) for x in d["Xp"]]
+            Xqp = None if d["Xqp"] is None else [pin(x) for x in d["Xqp"]]
+            nbytes += sum(x.nbytes for x in Xp) + (0 if Xqp is None else sum(x.nbytes for x in Xqp))
+            h = dict(d, Xp=Xp, Xqp=Xqp, W=d["W"].cpu().numpy())
+        else:
+            X = pin(d["X"])
+            Xq = None if d["Xq"] is None else pin(d["Xq"])
+            nbytes += X.nbytes + (0 if Xq is None else Xq.nbytes)
+            h = dict(d, X=X, Xq=Xq, W=d["W"].cpu().numpy())
+        nbytes += h["W"].nbytes
+        host.append(h)
+    return host, nbytes
+
+
+def run_pass_host(eng, host):
+    d2h = 0
+    for d in host:
+        if d["kind"] == "conv":
+            Q = eng.conv_channels(d["Xp"], d["Xqp"], d["W"], d["A"], c0=d["c0"], n_channels=d["n_ch"])
+            d2h += 9 * d["n_ch"] * d["F"] * 8
+        else:
+            Q = eng.dense_layer(d["X"], d["Xq"], d["W"], d["A"], j0=d["j0"], j1=d["j1"])
+            d2h += d["N0"] * (d["j1"] - d["j0"]) * 8
+    return d2h
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle's NumPy walk in a fork pool, one process per core (the reference's own fan-out)
+# ----------------------------------------------------------------------------------------------------------------
+_CPU = {}
+
+
+def _cpu_neuron(args):
+    key, j = args
+    from oracle import gpfq_oracle as O
+    d = _CPU[key]
+    return O.quantize_neuron(d["W"][:, j], d["X"], d["Xq"], d["A"])
+
+
+def cpu_sample_pass(host_layers, cores, budget_per_layer=2.5):
+    """Times a bounded sample of every layer with `cores` worker processes; returns (extrapolated full-net seconds,
+    description).  Neurons / filters are independent and equal-cost, so the extrapolation is linear in their count."""
+    import concurrent.futures as cf
+    import multiprocessing as mp
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    try:
+        from threadpoolctl import threadpool_limits
+        limiter = threadpool_limits(limits=1)
+    except Exception:
+        limiter = None
+    _CPU.clear()
+    jobs = []
+    for li, d in enumerate(host_layers):
+        if d["kind"] == "conv":
+            X = d["Xp"][0]
+            Xq = X if d["Xqp"] is None else d["Xqp"][0]
+            Wc = np.ascontiguousarray(d["W"][:, :, d["c0"], :].reshape(9, d["F"]))
+            units_total = d["n_ch"] * d["F"]
+            take = min(d["F"], cores)
+            weights_per_unit = 9
+        else:
+            X, Xq = d["X"], (d["X"] if d["Xq"] is None else d["Xq"])
+            Wc = d["W"]
+            units_total = d["j1"] - d["j0"]
+            take = min(units_total, 2 * cores if d["N0"] >= 1024 else 4 * cores)
+            weights_per_unit = d["N0"]
+        _CPU[li] = dict(W=Wc, X=X, Xq=Xq, A=np.asarray(d["A"], dtype=np.float64))
+        jobs.append((li, d["name"], take, units_total, weights_per_unit))
+    total_s, desc, sampled_w = 0.0, [], 0
+    ctx = mp.get_context("fork")
+    with cf.ProcessPoolExecutor(max_workers=cores, mp_context=ctx) as ex:
+        list(ex.map(_cpu_neuron, [(jobs[-1][0], 0)] * cores))  # start the workers before timing
+        for li, name, take, units_total, wpu in jobs:
+            t0 = time.perf_counter()
+            list(ex.map(_cpu_neuron, [(li, j) for j in range(take)]))
+            dt = time.perf_counter() - t0
+            total_s += dt * units_total / take
+            sampled_w += take * wpu
+            desc.append(f"{name}:{take}/{units_total}")
+    if limiter is not None:
+        limiter.restore_original_limits()
+    return total_s, sampled_w, "units timed per layer " + " ".join(desc)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gpfq", choices=["gpfq", "reference"])
+    ap.add_argument("--workload", default="cifar10_cnn", choices=["cifar10_cnn", "mnist_mlp"])
+    ap.add_argument("--n-img", type=int, default=0, help="override the image/sample count (debug only)")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    layers = CIFAR_LAYERS if args.workload == "cifar10_cnn" else MNIST_LAYERS
+    n_img = args.n_img or (N_IMG if args.workload == "cifar10_cnn" else 25000)
+    total_weights = sum(layer_weights(l) for l in layers)
+    cores = len(os.sched_getaffinity(0))
+    config = {"workload": f"{args.workload}: " + ("CIFAR10 CNN 6x Conv2D 3x3 (per-channel patch matrices 9 x n_patches) + Dense 2048->128->10"
+                                                    if args.workload == "cifar10_cnn" else "MNIST MLP 784-500-300-10"),
+              "samples": n_img, "alphabet": f"bits={BITS} (K=16), alphabet_scalar={CSCALAR}" if args.workload == "cifar10_cnn"
+              else "ternary", "weights_per_step": total_weights, "sharding": f"conv channels / dense neurons over {world} rank(s)",
+              "l2": "inputs (>= 25 GB per pass) exceed L2; no flush needed"}
+
+    import torch
+    if args.impl == "reference":
+        # The reference's own CPU implementation of the path: Python/NumPy, does not travel -> the oracle port, run
+        # exactly as BASELINE.md section 3 prescribes.  Rank 0 alone works.
+        if rank != 0:
+            return
+        dev = torch.device("cuda", local_rank) if torch.cuda.is_available() else torch.device("cpu")
+        data = build_inputs_for_cpu(layers, n_img)
+        vals = []
+        for it in range(args.warmup + args.steps):
+            sec, sampled_w, desc = cpu_sample_pass(data, cores, 2.0)
+            if it >= args.warmup:
+                vals.append(total_weights / sec)
+            if it == 0 and args.warmup + args.steps > 2 and sec > 0:
+                pass
+        v = float(np.mean(vals))
+        line = {"impl": "reference", "metric": "quantized weights/s, full-network GPFQ pass", "value": v, "unit": "weights/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_weights / v * 1e3,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config,
+                "cpu_baseline": {"value": v, "unit": "weights/s", "cores": cores, "kind": "port",
+                                 "sample": desc + "; extrapolated linearly in neurons/filters; HDF5 I/O excluded"},
+                "e2e": {"value": v, "unit": "weights/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback for the GPFQ hot path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from quantized_neural_networks_b200 import get_engine
+    eng = get_engine(local_rank)
+
+    data = build_device_inputs(layers, n_img, rank, world, dev)
+    outs = []
+    for d in data:
+        if d["kind"] == "conv":
+            outs.append(torch.zeros((1, 3, 3, d["C"], d["F"]), dtype=torch.float64, device=dev))
+        else:
+            outs.append(torch.zeros((1, d["N0"], d["N1"]), dtype=torch.float64, device=dev))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        run_pass_device(eng, data, outs)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            run_pass_device(eng, data, outs)
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = total_weights / (ms_per_step * 1e-3)
+
+    # per-call stage times of the timed region (most recent calls first)
+    ncall = min(len(layers) * args.steps, 120)
+    per_layer = {}
+    launches_per_step = 0
+    for back in range(ncall):
+        st = eng.query_stats(back)
+        name = layers[(len(layers) - 1 - back) % len(layers)][0]
+        per_layer.setdefault(name, []).append(st)
+    conv_bytes = conv_ms = 0.0
+    layer_report = {}
+    for name, sts in per_layer.items():
+        kind = dict((l[0], l[1]) for l in layers)[name]
+        launches_per_step += sts[0]["kernel_launches"]
+        msl = float(np.mean([s["ms_total"] for s in sts]))
+        layer_report[name] = {"ms": round(msl, 4), "weights_per_s": round(sts[0]["weights"] / (msl * 1e-3)) if msl > 0 else None,
+                              "method": {1: "stream", 2: "gram"}.get(sts[0]["method"])}
+        if kind == "conv":
+            conv_bytes += sum(s["bytes_algorithmic"] for s in sts)
+            conv_ms += sum(s["ms_gram"] for s in sts)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = conv_bytes / (conv_ms * 1e-3) / 1e9 if conv_ms > 0 else None
+    roofline = {"kernel": "conv_gram_kernel (per-channel patch Grams, fp64 accumulation)", "bound": "hbm",
+                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": (achieved / hbm_peak) if achieved else None,
+                "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)",
+                "algorithmic_bytes": "72 B per patch column per channel (36 when X == Xq)"}
+
+    # ---- e2e: host (pinned) buffers through the C ABI, copies inside the timed region ---------------------------
+    e2e = None
+    if not args.no_e2e:
+        host, h2d_bytes = to_host_pinned(data)
+        run_pass_host(eng, host)  # warm-up (allocates the staging workspaces)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            d2h_bytes = run_pass_host(eng, host)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": total_weights * args.e2e_steps / dt, "unit": "weights/s", "h2d_bytes_per_step": int(h2d_bytes),
+               "d2h_bytes_per_step": int(d2h_bytes), "steps": args.e2e_steps, "ms_per_step": dt / args.e2e_steps * 1e3,
+               "timing": "host wall clock around synchronous C-ABI calls (copies + kernels), max over ranks"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        host_cpu = host if e2e is not None else to_host_pinned(data)[0]
+        sec, sampled_w, desc = cpu_sample_pass(host_cpu, cores)
+        cpu = {"value": total_weights / sec, "unit": "weights/s", "cores": cores, "kind": "port",
+               "sample": desc + "; extrapolated linearly in neurons/filters; HDF5 I/O excluded",
+               "extrapolated_full_pass_s": sec}
+
+    if rank == 0:
+        line = {"metric": "quantized weights/s, full-network GPFQ pass", "value": value, "unit": "weights/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
+                "roofline": roofline, "cpu_baseline": cpu, "layers": layer_report}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def build_inputs_for_cpu(layers, n_img):
+    """Host-only synthetic inputs for the reference arm: one channel of patches per conv layer is enough for the sample."""
+    rng = np.random.default_rng(0)
+    out = []
+    for li, (name, kind, a, b, H) in enumerate(layers):
+        if kind == "conv":
+            C, F = a, b
+            W = (rng.uniform(-1, 1, (3, 3, C, F)) * np.sqrt(6.0 / (9 * C))).astype(np.float32)
+            A = make_alphabet(np.median(np.abs(W)))
+            n = n_img * H * H
+            first = li == 0
+            shape = (n_img, H, H)
+            if first:
+                act = (rng.random(shape, dtype=np.float32) * (rng.random(shape, dtype=np.float32) < 0.5)).astype(np.float32)
+                acts = [act]
+            else:
+                Z = rng.standard_normal(shape, dtype=np.float32)
+                acts = [np.maximum(Z, 0), np.maximum(Z + 0.05 * rng.standard_normal(shape, dtype=np.float32), 0)]
+            mats = []
+            for t in acts:
+                p = np.zeros((n_img, H + 2, H + 2), np.float32)
+                p[:, 1:-1, 1:-1] = t
+                cols = np.empty((9, n), np.float32)
+                for r in range(3):
+                    for c in range(3):
+                        cols[r * 3 + c] = p[:, r:r + H, c:c + H].reshape(-1)
+                mats.append(cols)
+            out.append(dict(name=name, kind=kind, W=W, A=A, Xp=[mats[0]], Xqp=None if first else [mats[1]], c0=0, n_ch=C,
+                            n=n, C=C, F=F))
+        else:
+            N0, N1 = a, b
+            m = n_img
+            W = (rng.uniform(-1, 1, (N0, N1)) * np.sqrt(6.0 / N0)).astype(np.float32)
+            A = make_alphabet(np.median(np.abs(W)))
+            Z = rng.standard_normal((N0, m), dtype=np.float32)
+            X = np.maximum(Z, 0)
+            Xq = np.maximum(Z + 0.05 * rng.standard_normal((N0, m), dtype=np.float32), 0)
+            out.append(dict(name=name, kind=kind, W=W, A=A, X=X, Xq=Xq, j0=0, j1=N1, N0=N0, N1=N1, m=m))
+    return out
+
+
+if __name__ == "__main__":
+    main()

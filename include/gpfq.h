@@ -75,6 +75,9 @@ int gpfq_version(void);
 /* Launch on the caller's stream (a cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream);
  * NULL restores the library's own stream. */
 int gpfq_set_stream(gpfq_ctx *ctx, void *cuda_stream);
+/* Stage times of an earlier call: calls_back = 0 is the most recent API call, 1 the one before, ...
+ * (a ring of 128).  For GPFQ_NO_SYNC calls, synchronise the stream first; unfinished events read 0. */
+int gpfq_query_stats(gpfq_ctx *ctx, int32_t calls_back, gpfq_stats *out);
 /* Release cached device/pinned workspaces (they are otherwise kept between calls). */
 int gpfq_trim(gpfq_ctx *ctx);
 

@@ -100,7 +100,10 @@ extern "C" int gpfq_create(int device, gpfq_ctx **out) {
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
     bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
-    for (int i = 0; ok && i < 8; ++i) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
+    ctx->ring.resize(GPFQ_RING);
+    for (auto &r : ctx->ring)
+        for (int i = 0; ok && i < 8; ++i) ok = cudaEventCreate(&r.e[i]) == cudaSuccess;
+    ctx->cur = &ctx->ring[0];
     for (int i = 0; ok && i < 4; ++i) ok = cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) {
         delete ctx;
@@ -134,7 +137,8 @@ extern "C" int gpfq_trim(gpfq_ctx *ctx) {
 extern "C" void gpfq_destroy(gpfq_ctx *ctx) {
     if (!ctx) return;
     gpfq_trim(ctx);
-    for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
+    for (auto &r : ctx->ring)
+        for (auto &e : r.e) if (e) cudaEventDestroy(e);
     for (auto &e : ctx->ev_copy) if (e) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -145,7 +149,14 @@ extern "C" const char *gpfq_last_error(const gpfq_ctx *ctx) { return ctx ? ctx->
 
 extern "C" int gpfq_set_stream(gpfq_ctx *ctx, void *cuda_stream) {
     if (!ctx) return GPFQ_ERR_ARG;
-    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    cudaStream_t next = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    if (next != ctx->stream) {
+        // workspaces are shared between calls: work queued on the old stream must finish before the new
+        // stream may reuse them
+        cudaSetDevice(ctx->device);
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) cudaGetLastError();
+        ctx->stream = next;
+    }
     return GPFQ_OK;
 }
 
@@ -198,10 +209,56 @@ static int upload_alphabets(gpfq_ctx *ctx, const double *alphabets, const int32_
     return GPFQ_OK;
 }
 
-static float ev_ms(cudaEvent_t a, cudaEvent_t b) {
+cudaError_t gpfq_record(gpfq_ctx *ctx, int which, cudaStream_t s) {
+    ctx->cur->rec[which] = true;
+    return cudaEventRecord(ctx->cur->e[which], s);
+}
+
+static void begin_call(gpfq_ctx *ctx, int kind) {
+    ctx->cur = &ctx->ring[ctx->calls % GPFQ_RING];
+    ctx->calls++;
+    for (bool &r : ctx->cur->rec) r = false;
+    ctx->cur->kind = kind;
+    ctx->cur->st = gpfq_stats{};
+    ctx->launches = 0;
+}
+
+static float ev_ms(const CallRecord &r, int a, int b) {
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) { cudaGetLastError(); return 0.f; }
+    if (!r.rec[a] || !r.rec[b]) return 0.f;
+    if (cudaEventElapsedTime(&ms, r.e[a], r.e[b]) != cudaSuccess) { cudaGetLastError(); return 0.f; }
     return ms;
+}
+
+// events: 0 call start, 5 inputs resident, 2 main stage start, 3 main stage end, 4 sweep end, 6 before D2H, 1 call end
+static void fill_times(CallRecord &r) {
+    gpfq_stats &st = r.st;
+    st.ms_total = ev_ms(r, 0, 1);
+    st.ms_h2d = ev_ms(r, 0, 5);
+    if (r.kind == 1) {
+        st.ms_stream = ev_ms(r, 2, 3);
+        st.ms_d2h = ev_ms(r, 6, 1);
+    } else {
+        st.ms_gram = ev_ms(r, 2, 3);
+        st.ms_sweep = ev_ms(r, 3, 4);
+        st.ms_d2h = r.kind == 0 ? ev_ms(r, 6, 1) : ev_ms(r, 4, 1);
+    }
+}
+
+static void end_call(gpfq_ctx *ctx, gpfq_stats *stats, bool synced) {
+    CallRecord &r = *ctx->cur;
+    if (stats) r.st = *stats;  // static fields filled by the stage code
+    r.st.kernel_launches = ctx->launches;
+    if (synced) fill_times(r);
+    if (stats) *stats = r.st;
+}
+
+extern "C" int gpfq_query_stats(gpfq_ctx *ctx, int32_t calls_back, gpfq_stats *out) {
+    if (!ctx || !out || calls_back < 0 || calls_back >= GPFQ_RING || calls_back >= ctx->calls) return GPFQ_ERR_ARG;
+    CallRecord &r = ctx->ring[(ctx->calls - 1 - calls_back) % GPFQ_RING];
+    fill_times(r);
+    *out = r.st;
+    return GPFQ_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -242,10 +299,11 @@ extern "C" int gpfq_dense_layer(gpfq_ctx *ctx, const float *X, const float *Xq, 
     const int64_t nj = j1 - j0;
     if (nj == 0) return GPFQ_OK;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    ctx->launches = 0;
     const bool same = (Xq == nullptr || Xq == X);
     cudaStream_t s = ctx->stream;
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], s));
+    const int method = choose_dense_method(ctx, flags, N0, m, nj, same, n_alph);
+    begin_call(ctx, method == GPFQ_METHOD_GRAM ? 0 : 1);
+    CUDA_TRY(ctx, gpfq_record(ctx, 0, s));
 
     Alphabets al;
     GPFQ_TRY(upload_alphabets(ctx, alphabets, K, n_alph, &al));
@@ -282,40 +340,26 @@ extern "C" int gpfq_dense_layer(gpfq_ctx *ctx, const float *X, const float *Xq, 
         dldq = nj;
         col0 = 0;
     }
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[5], s));
+    CUDA_TRY(ctx, gpfq_record(ctx, 5, s));
 
-    const int method = choose_dense_method(ctx, flags, N0, m, nj, same, n_alph);
     if (method == GPFQ_METHOD_GRAM)
         GPFQ_TRY(dense_gram_path(ctx, dX, dXq, dldx, N0, m, dW, dldw, dj0, nj, al.d_levels, al.d_koff, n_alph, dQ, dldq,
                                  col0, stats));
     else
         GPFQ_TRY(dense_stream_path(ctx, dX, dXq, dldx, N0, m, dW, dldw, dj0, nj, al.d_levels, al.h_koff.data(), n_alph,
                                    dQ, dldq, col0, stats));
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[6], s));
+    CUDA_TRY(ctx, gpfq_record(ctx, 6, s));
     if (!(flags & GPFQ_Q_DEVICE)) {
         for (int a = 0; a < n_alph; ++a)
             CUDA_TRY(ctx, cudaMemcpy2DAsync(Q_out + (int64_t)a * N0 * ldq + j0, ldq * sizeof(double),
                                             dQ + (int64_t)a * N0 * nj, nj * sizeof(double), nj * sizeof(double), N0,
                                             cudaMemcpyDeviceToHost, s));
     }
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], s));
-    if (stats) {
-        stats->kernel_launches = ctx->launches;
-        stats->weights = N0 * nj * n_alph;
-    }
-    if (flags & GPFQ_NO_SYNC) return GPFQ_OK;
-    CUDA_TRY(ctx, cudaStreamSynchronize(s));
-    if (stats) {
-        stats->ms_total = ev_ms(ctx->ev[0], ctx->ev[1]);
-        stats->ms_h2d = ev_ms(ctx->ev[0], ctx->ev[5]);
-        stats->ms_d2h = ev_ms(ctx->ev[6], ctx->ev[1]);
-        if (method == GPFQ_METHOD_GRAM) {
-            stats->ms_gram = ev_ms(ctx->ev[2], ctx->ev[3]);
-            stats->ms_sweep = ev_ms(ctx->ev[3], ctx->ev[4]);
-        } else {
-            stats->ms_stream = ev_ms(ctx->ev[2], ctx->ev[3]);
-        }
-    }
+    CUDA_TRY(ctx, gpfq_record(ctx, 1, s));
+    if (stats) stats->weights = N0 * nj * n_alph;
+    const bool synced = !(flags & GPFQ_NO_SYNC);
+    if (synced) CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    end_call(ctx, stats, synced);
     return GPFQ_OK;
 }
 
@@ -367,7 +411,6 @@ static int conv_finish(gpfq_ctx *ctx, int kk, const double *partial, int n_ch, i
     double *gram = nullptr;
     GPFQ_TRY(gpfq_ws(ctx, WS_CG, (size_t)n_ch * 2 * kk * kk * sizeof(double), (void **)&gram));
     GPFQ_TRY(conv_finalize_stage(ctx, partial, n_ch, n_chunks, kk, same, gram));
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], s));
     const float *dW = W;
     const size_t wcount = (size_t)kk * C * F;
     if (!(flags & GPFQ_W_DEVICE)) {
@@ -379,7 +422,7 @@ static int conv_finish(gpfq_ctx *ctx, int kk, const double *partial, int n_ch, i
     double *dQ = Q_out;
     if (!(flags & GPFQ_Q_DEVICE)) GPFQ_TRY(gpfq_ws(ctx, WS_Q, (size_t)n_alph * wcount * sizeof(double), (void **)&dQ));
     GPFQ_TRY(conv_sweep_stage(ctx, kk, gram, dW, dQ, C, F, c0, n_ch, al.d_levels, al.d_koff, n_alph));
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], s));
+    CUDA_TRY(ctx, gpfq_record(ctx, 4, s));
     if (!(flags & GPFQ_Q_DEVICE)) {
         for (int a = 0; a < n_alph; ++a) {
             const size_t off = (size_t)a * wcount + (size_t)c0 * F;
@@ -392,7 +435,6 @@ static int conv_finish(gpfq_ctx *ctx, int kk, const double *partial, int n_ch, i
 
 static void conv_stats(gpfq_ctx *ctx, gpfq_stats *st, int kk, int64_t n, int64_t n_ch, int64_t F, bool same, int n_alph) {
     if (!st) return;
-    st->kernel_launches = ctx->launches;
     st->weights = (int64_t)kk * n_ch * F * n_alph;
     st->method = GPFQ_METHOD_GRAM >> 4;
     st->bytes_algorithmic = (same ? 1 : 2) * 4LL * kk * n * n_ch;
@@ -414,7 +456,6 @@ extern "C" int gpfq_conv_channels(gpfq_ctx *ctx, const float *const *Xp, const f
         return gpfq_fail(ctx, GPFQ_ERR_ARG, "GPFQ_NO_SYNC needs all-device pointers");
     if (n_ch == 0) return GPFQ_OK;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    ctx->launches = 0;
     bool same = (Xqp == nullptr);
     if (!same) {
         same = true;
@@ -438,7 +479,8 @@ extern "C" int gpfq_conv_channels(gpfq_ctx *ctx, const float *const *Xp, const f
     }
 
     cudaStream_t s = ctx->stream;
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], s));
+    begin_call(ctx, 2);
+    CUDA_TRY(ctx, gpfq_record(ctx, 0, s));
     Alphabets al;
     GPFQ_TRY(upload_alphabets(ctx, alphabets, K, n_alph, &al));
 
@@ -451,7 +493,7 @@ extern "C" int gpfq_conv_channels(gpfq_ctx *ctx, const float *const *Xp, const f
     std::vector<const float *> h_ptrs(2 * n_ch);
     const size_t ch_bytes = (size_t)kk * n * sizeof(float);
 
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], s));
+    CUDA_TRY(ctx, gpfq_record(ctx, 2, s));
     if (flags & GPFQ_X_DEVICE) {
         for (int64_t i = 0; i < n_ch; ++i) {
             h_ptrs[i] = Xp[i];
@@ -501,17 +543,14 @@ extern "C" int gpfq_conv_channels(gpfq_ctx *ctx, const float *const *Xp, const f
             CUDA_TRY(ctx, cudaEventRecord(ctx->ev_copy[bi & 1], s));
         }
     }
+    CUDA_TRY(ctx, gpfq_record(ctx, 3, s));
     GPFQ_TRY(conv_finish(ctx, kk, partial, (int)n_ch, n_chunks, same, W, C, F, c0, al, n_alph, Q_out, flags));
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], s));
-    conv_stats(ctx, stats, kk, n, n_ch, F, same, n_alph);
-    if (flags & GPFQ_NO_SYNC) return GPFQ_OK;
-    CUDA_TRY(ctx, cudaStreamSynchronize(s));
-    if (stats) {
-        stats->ms_total = ev_ms(ctx->ev[0], ctx->ev[1]);
-        stats->ms_gram = ev_ms(ctx->ev[2], ctx->ev[3]);
-        stats->ms_sweep = ev_ms(ctx->ev[3], ctx->ev[4]);
-        stats->ms_d2h = ev_ms(ctx->ev[4], ctx->ev[1]);
-    }
+    CUDA_TRY(ctx, gpfq_record(ctx, 1, s));
+    gpfq_stats local = {};
+    conv_stats(ctx, stats ? stats : &local, kk, n, n_ch, F, same, n_alph);
+    const bool synced = !(flags & GPFQ_NO_SYNC);
+    if (synced) CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    end_call(ctx, stats ? stats : &local, synced);
     return GPFQ_OK;
 }
 
@@ -547,10 +586,10 @@ extern "C" int gpfq_conv_layer_nhwc(gpfq_ctx *ctx, const float *act, const float
     }
     const int64_t n = n_img * Ho * Wo;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    ctx->launches = 0;
     cudaStream_t s = ctx->stream;
     const bool same = (actq == nullptr || actq == act);
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], s));
+    begin_call(ctx, 2);
+    CUDA_TRY(ctx, gpfq_record(ctx, 0, s));
     Alphabets al;
     GPFQ_TRY(upload_alphabets(ctx, alphabets, K, n_alph, &al));
     const float *dA = act, *dAq = same ? act : actq;
@@ -566,7 +605,7 @@ extern "C" int gpfq_conv_layer_nhwc(gpfq_ctx *ctx, const float *act, const float
             dAq = bq;
         }
     }
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[5], s));
+    CUDA_TRY(ctx, gpfq_record(ctx, 5, s));
     int64_t chunk_cols = 0;
     const int n_chunks = conv_pick_chunks(ctx, n, (int)std::min<int64_t>(n_ch, 64), &chunk_cols);
     double *partial = nullptr;
@@ -587,7 +626,7 @@ extern "C" int gpfq_conv_layer_nhwc(gpfq_ctx *ctx, const float *act, const float
         h_ptrs[bch + i] = same ? h_ptrs[i] : pq + (size_t)i * ch_elems;
     }
     CUDA_TRY(ctx, cudaMemcpyAsync(d_ptrs, h_ptrs.data(), h_ptrs.size() * sizeof(float *), cudaMemcpyHostToDevice, s));
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], s));
+    CUDA_TRY(ctx, gpfq_record(ctx, 2, s));
     for (int64_t b0 = 0; b0 < n_ch; b0 += bch) {
         const int64_t nb = std::min<int64_t>(bch, n_ch - b0);
         GPFQ_TRY(im2col_stage(ctx, dA, n_img, (int)H, (int)Wd, C, c0 + b0, (int)nb, kh, kw, sh, sw, rh, rw, pt, pl, Ho, Wo,
@@ -599,21 +638,14 @@ extern "C" int gpfq_conv_layer_nhwc(gpfq_ctx *ctx, const float *act, const float
         GPFQ_TRY(conv_gram_stage(ctx, kk, p, same, n, (int)nb, n_chunks, chunk_cols,
                                  partial + (size_t)b0 * n_chunks * 2 * kk * kk));
     }
+    CUDA_TRY(ctx, gpfq_record(ctx, 3, s));
     GPFQ_TRY(conv_finish(ctx, kk, partial, (int)n_ch, n_chunks, same, W, C, F, c0, al, n_alph, Q_out, flags));
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], s));
-    conv_stats(ctx, stats, kk, n, n_ch, F, same, n_alph);
-    if (flags & GPFQ_NO_SYNC) {
-        if ((flags & GPFQ_ALL_DEVICE) != GPFQ_ALL_DEVICE) CUDA_TRY(ctx, cudaStreamSynchronize(s));
-        return GPFQ_OK;
-    }
-    CUDA_TRY(ctx, cudaStreamSynchronize(s));
-    if (stats) {
-        stats->ms_total = ev_ms(ctx->ev[0], ctx->ev[1]);
-        stats->ms_h2d = ev_ms(ctx->ev[0], ctx->ev[5]);
-        stats->ms_gram = ev_ms(ctx->ev[2], ctx->ev[3]);
-        stats->ms_sweep = ev_ms(ctx->ev[3], ctx->ev[4]);
-        stats->ms_d2h = ev_ms(ctx->ev[4], ctx->ev[1]);
-    }
+    CUDA_TRY(ctx, gpfq_record(ctx, 1, s));
+    gpfq_stats local = {};
+    conv_stats(ctx, stats ? stats : &local, kk, n, n_ch, F, same, n_alph);
+    const bool synced = !(flags & GPFQ_NO_SYNC);
+    if (synced) CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    end_call(ctx, stats ? stats : &local, synced);
     return GPFQ_OK;
 }
 
@@ -624,7 +656,7 @@ static int round_elements(gpfq_ctx *ctx, const void *W, int is_f64, int64_t n, c
     if (!W || !Q_out || n < 0) return gpfq_fail(ctx, GPFQ_ERR_ARG, "bad arguments");
     if (n == 0) return GPFQ_OK;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    ctx->launches = 0;
+    begin_call(ctx, 2);
     cudaStream_t s = ctx->stream;
     Alphabets al;
     GPFQ_TRY(upload_alphabets(ctx, alphabet, &K, 1, &al));

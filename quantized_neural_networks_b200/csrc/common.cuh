@@ -29,6 +29,16 @@ struct AlphEntry {
     size_t off = 0;          // byte offset inside the WS_ALPH device buffer
 };
 
+// One set of timing events + the static part of the report per API call; a ring of them lets callers
+// enqueue many GPFQ_NO_SYNC calls and read every call's stage times afterwards (gpfq_query_stats).
+struct CallRecord {
+    cudaEvent_t e[8] = {};
+    bool rec[8] = {};
+    int kind = 0;  // 0 dense Gram+sweep, 1 dense stream, 2 conv
+    gpfq_stats st = {};
+};
+static constexpr int GPFQ_RING = 128;
+
 struct gpfq_ctx {
     int device = 0;
     int sm_count = 148;
@@ -36,7 +46,9 @@ struct gpfq_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t copy_stream = nullptr;
     cudaStream_t stream = nullptr;  // the one kernels launch on
-    cudaEvent_t ev[8] = {};
+    std::vector<CallRecord> ring;
+    int64_t calls = 0;          // API calls begun so far
+    CallRecord *cur = nullptr;  // record of the call in progress
     cudaEvent_t ev_copy[4] = {};
     std::string err = "";
     int launches = 0;
@@ -54,6 +66,7 @@ enum WsSlot {
 };
 
 int gpfq_fail(gpfq_ctx *ctx, int code, const char *fmt, ...);
+cudaError_t gpfq_record(gpfq_ctx *ctx, int which, cudaStream_t s);  // record timing event `which` of the current call
 int gpfq_ws(gpfq_ctx *ctx, int slot, size_t bytes, void **out);         // device workspace
 int gpfq_pinned(gpfq_ctx *ctx, int slot, size_t bytes, void **out);     // pinned host staging
 

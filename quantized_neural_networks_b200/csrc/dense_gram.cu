@@ -160,10 +160,10 @@ int dense_gram_path(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx,
     GPFQ_TRY(gpfq_ws(ctx, WS_QT, (size_t)n_alph * nj * N0 * sizeof(double), (void **)&Qt));
     GPFQ_TRY(gpfq_ws(ctx, WS_DT, (size_t)n_alph * nj * SWEEP_B * sizeof(double), (void **)&Dt));
 
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    CUDA_TRY(ctx, gpfq_record(ctx, 2, ctx->stream));
     GPFQ_TRY(gram_stage(ctx, Xq, Xq, ldx, N0, m, G2));
     if (!same) GPFQ_TRY(gram_stage(ctx, Xq, X, ldx, N0, m, G1));
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+    CUDA_TRY(ctx, gpfq_record(ctx, 3, ctx->stream));
 
     {
         dim3 grid((unsigned)ceil_div64(N0, 32), (unsigned)ceil_div64(nj, 32));
@@ -198,7 +198,7 @@ int dense_gram_path(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx,
                                                                   Qd + (int64_t)a * N0 * ldq, ldq, col0);
         KERNEL_CHECK(ctx);
     }
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
+    CUDA_TRY(ctx, gpfq_record(ctx, 4, ctx->stream));
     if (st) {
         st->method = GPFQ_METHOD_GRAM >> 4;
         st->flops_algorithmic = (same ? 1 : 2) * m * N0 * (N0 + 1);  // lower triangles, 2 flops per MAC

@@ -142,7 +142,7 @@ int dense_stream_path(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ld
                       gpfq_stats *st) {
     double *nrm = nullptr;
     GPFQ_TRY(gpfq_ws(ctx, WS_NRM, (size_t)N0 * sizeof(double), (void **)&nrm));
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    CUDA_TRY(ctx, gpfq_record(ctx, 2, ctx->stream));
     row_norms_kernel<<<(unsigned)N0, 256, 0, ctx->stream>>>(Xq, ldx, m, nrm);
     KERNEL_CHECK(ctx);
     // neurons per CTA: share each streamed row among J neurons once the GPU is full
@@ -158,7 +158,7 @@ int dense_stream_path(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ld
         else if (J == 2) GPFQ_TRY(launch_stream<2>(ctx, X, Xq, ldx, N0, m, W, ldw, j0, nj, nrm, al, K, Qa, ldq, col0));
         else GPFQ_TRY(launch_stream<1>(ctx, X, Xq, ldx, N0, m, W, ldw, j0, nj, nrm, al, K, Qa, ldq, col0));
     }
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+    CUDA_TRY(ctx, gpfq_record(ctx, 3, ctx->stream));
     if (st) {
         st->method = GPFQ_METHOD_STREAM >> 4;
         st->flops_algorithmic = 6 * m * N0 * nj * n_alph;

@@ -71,10 +71,18 @@ class GpfqEngine:
     def trim(self):
         self._check(self._lib.gpfq_trim(self._ctx))
 
-    def use_torch_stream(self, enable=True):
-        """Launch on torch's current stream (so torch.cuda.Event brackets see the kernels)."""
-        s = torch.cuda.current_stream(self.device).cuda_stream if enable else None
+    def _bind_stream(self, dev):
+        """Device-tensor calls launch on torch's CURRENT stream: the tensors were produced there, so this is what
+        orders our kernels after their producers (and lets torch.cuda.Event brackets time them).  Host-array
+        calls use the library's own stream."""
+        s = torch.cuda.current_stream(self.device).cuda_stream if dev else None
         self._check(self._lib.gpfq_set_stream(self._ctx, c_void_p(s)))
+
+    def query_stats(self, calls_back=0):
+        """Stage times of an earlier (possibly GPFQ_NO_SYNC) call; synchronise first."""
+        st = _lib.GpfqStats()
+        self._check(self._lib.gpfq_query_stats(self._ctx, int(calls_back), byref(st)))
+        return st.as_dict()
 
     @staticmethod
     def _f32(x, name):
@@ -128,6 +136,7 @@ class GpfqEngine:
         if ldq_x != ldx:
             raise ValueError("X and Xq must share a row stride")
         pw, ldw = self._rowmajor2d(W, "W")
+        self._bind_stream(dev)
         flags = _METHODS[method]
         if dev:
             flags |= _lib.ALL_DEVICE
@@ -157,6 +166,7 @@ class GpfqEngine:
         N0, m = X.shape
         G2 = np.zeros((N0, N0))
         G1 = G2 if same else np.zeros((N0, N0))
+        self._bind_stream(False)
         rc = self._lib.gpfq_gram_matrices(self._ctx, c_void_p(X.ctypes.data), c_void_p(Xq.ctypes.data), m, N0, m,
                                           c_void_p(None if same else G1.ctypes.data), c_void_p(G2.ctypes.data), 0)
         self._check(rc)
@@ -193,6 +203,7 @@ class GpfqEngine:
         ptr = (lambda t: t.data_ptr()) if dev else (lambda t: t.ctypes.data)
         PX = (c_void_p * max(n_channels, 1))(*[ptr(x) for x in xs])
         PQ = None if same else (c_void_p * max(n_channels, 1))(*[ptr(q) for q in qs])
+        self._bind_stream(dev)
         flags = 0
         if dev:
             flags |= _lib.ALL_DEVICE
@@ -238,6 +249,7 @@ class GpfqEngine:
         n_channels = (C - c0) if n_channels is None else int(n_channels)
         rate = tuple(rate) if rate else (1, 1)
         ptr = (lambda t: t.data_ptr()) if dev else (lambda t: t.ctypes.data)
+        self._bind_stream(dev)
         flags = 0
         if dev:
             flags |= _lib.ALL_DEVICE
@@ -265,6 +277,7 @@ class GpfqEngine:
         W = np.ascontiguousarray(W, dtype=np.float32)
         A = np.ascontiguousarray(alphabet, dtype=np.float64)
         out = np.zeros(W.shape, dtype=np.float64)
+        self._bind_stream(False)
         rc = self._lib.gpfq_msq(self._ctx, c_void_p(W.ctypes.data), W.size, A.ctypes.data_as(POINTER(c_double)), len(A),
                                 c_void_p(out.ctypes.data), 0)
         self._check(rc)
@@ -275,6 +288,7 @@ class GpfqEngine:
         t = np.ascontiguousarray(t, dtype=np.float64)
         A = np.ascontiguousarray(alphabet, dtype=np.float64)
         out = np.zeros(t.shape, dtype=np.float64)
+        self._bind_stream(False)
         rc = self._lib.gpfq_bit_round(self._ctx, c_void_p(t.ctypes.data), t.size, A.ctypes.data_as(POINTER(c_double)),
                                       len(A), c_void_p(out.ctypes.data), 0)
         self._check(rc)

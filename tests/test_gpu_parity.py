@@ -257,3 +257,35 @@ def test_full_size_properties_mnist_layer(engine):
     Qref = c_oracle.quantize_layer(Wsub, X, X, A)
     assert np.array_equal(Qs[:, sub], Qref)
     assert O.agreement(Qg[:, sub], Qref) >= AGREE
+
+
+def test_conv_many_patches_both_paths(engine):
+    """n_patches beyond one grid sweep of the patch-extraction kernel (> 2048*256 columns): both conv entry
+    points against the Gram-form oracle fed with fp64 Grams of torch-unfolded patches."""
+    import torch
+    rng = np.random.default_rng(21)
+    n_img, H, C, F = 640, 32, 2, 8
+    act = np.maximum(rng.standard_normal((n_img, H, H, C)), 0).astype(np.float32)
+    actq = np.maximum(act + 0.05 * rng.standard_normal(act.shape), 0).astype(np.float32)
+    W = (rng.uniform(-1, 1, (3, 3, C, F)) * 0.3).astype(np.float32)
+    A = O.layer_alphabet(W, 4, O.unit_alphabet(4))
+    n = n_img * H * H
+
+    def unfold(a):
+        t = torch.from_numpy(a).cuda().permute(3, 0, 1, 2).reshape(C * n_img, 1, H, H)
+        p = torch.nn.functional.unfold(t, 3, padding=1)
+        return p.reshape(C, n_img, 9, H * H).permute(0, 2, 1, 3).reshape(C, 9, n).contiguous()
+
+    Xp, Xqp = unfold(act), unfold(actq)
+    Qref = np.zeros(W.shape)
+    for c in range(C):
+        xd, qd = Xp[c].double(), Xqp[c].double()
+        G1, G2 = (qd @ xd.T).cpu().numpy(), (qd @ qd.T).cpu().numpy()
+        Qref[:, :, c, :] = O.gram_quantize_layer(W[:, :, c, :].reshape(9, F), None, None, A, grams=(G1, G2)).reshape(3, 3, F)
+    Wd = torch.from_numpy(W).cuda()
+    Qp = engine.conv_channels(list(Xp), list(Xqp), Wd, A).cpu().numpy()
+    Qn = engine.conv_layer_nhwc(act, actq, W, A)
+    assert O.agreement(Qp, Qref) == 1.0, O.agreement(Qp, Qref)
+    assert O.agreement(Qn, Qref) == 1.0, O.agreement(Qn, Qref)
+    Qn_dev = engine.conv_layer_nhwc(torch.from_numpy(act).cuda(), torch.from_numpy(actq).cuda(), Wd, A).cpu().numpy()
+    assert np.array_equal(Qn_dev, Qn)
