@@ -73,7 +73,8 @@ void gpfq_destroy(gpfq_ctx *ctx);
 const char *gpfq_last_error(const gpfq_ctx *ctx); /* never NULL; valid until the next call */
 int gpfq_version(void);
 /* Launch on the caller's stream (a cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream);
- * NULL restores the library's own stream. */
+ * NULL restores the library's own stream; for the default stream pass cudaStreamLegacy ((void*)0x1)
+ * or cudaStreamPerThread ((void*)0x2), not 0. */
 int gpfq_set_stream(gpfq_ctx *ctx, void *cuda_stream);
 /* Stage times of an earlier call: calls_back = 0 is the most recent API call, 1 the one before, ...
  * (a ring of 128).  For GPFQ_NO_SYNC calls, synchronise the stream first; unfinished events read 0. */

@@ -75,7 +75,11 @@ class GpfqEngine:
         """Device-tensor calls launch on torch's CURRENT stream: the tensors were produced there, so this is what
         orders our kernels after their producers (and lets torch.cuda.Event brackets time them).  Host-array
         calls use the library's own stream."""
-        s = torch.cuda.current_stream(self.device).cuda_stream if dev else None
+        s = None
+        if dev:
+            # torch's default stream has handle 0, which the C ABI reads as "the library's own stream":
+            # name the legacy default stream explicitly (cudaStreamLegacy == 0x1)
+            s = torch.cuda.current_stream(self.device).cuda_stream or 1
         self._check(self._lib.gpfq_set_stream(self._ctx, c_void_p(s)))
 
     def query_stats(self, calls_back=0):

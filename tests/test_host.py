@@ -1,0 +1,148 @@
+"""CPU: host-side logic of the drop-in layer (no compute calls into libgpfq) -- the TF-free Keras stand-in, activation
+collection, patch extraction, sharding and the world_size-2 (gloo) gather of Q shards."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import gpfq_oracle as O  # noqa: E402  (tests may use the oracle; the product never does)
+from quantized_neural_networks_b200 import hostnet  # noqa: E402
+from quantized_neural_networks_b200.quantized_network import (  # noqa: E402
+    LayerData, QuantizedCNN, QuantizedNeuralNetwork, shard_range)
+
+
+@pytest.mark.parametrize("padding,strides,rate", [("SAME", (1, 1), (1, 1)), ("VALID", (1, 1), (1, 1)),
+                                                  ("SAME", (2, 2), (1, 1)), ("VALID", (1, 2), (1, 1)),
+                                                  ("SAME", (1, 1), (2, 2))])
+def test_extract_patches_matches_oracle_im2col(padding, strides, rate):
+    rng = np.random.default_rng(3)
+    act = rng.standard_normal((3, 7, 6, 2)).astype(np.float32)
+    for c in range(2):
+        ch = act[..., c:c + 1]
+        p = hostnet.extract_patches(ch, [1, 3, 3, 1], [1, *strides, 1], [1, *rate, 1], padding)
+        mine = p.reshape(-1, p.shape[-1]).T
+        ref = O.channel_patches(act, c, (3, 3), strides, padding, rate)
+        assert np.array_equal(mine, ref)
+
+
+@pytest.mark.parametrize("n,world", [(10, 1), (10, 3), (128, 8), (3, 8), (37, 4)])
+def test_shard_range_partitions(n, world):
+    seen = []
+    for r in range(world):
+        lo, hi = shard_range(n, r, world)
+        assert 0 <= lo <= hi <= n
+        seen += list(range(lo, hi))
+    assert seen == list(range(n))
+    sizes = [shard_range(n, r, world)[1] - shard_range(n, r, world)[0] for r in range(world)]
+    assert max(sizes) - min(sizes) <= 1
+
+
+def test_constructor_surface_matches_reference():
+    """quantized_network.py:332-400 / :594-650: attributes the drivers read, alphabet, cloned twin with equal weights."""
+    net = hostnet.mnist_mlp(seed=1, widths=(12, 8), n_in=16, n_out=4)
+    x = np.random.default_rng(0).random((6, 4, 4)).astype(np.float32)
+    seq = hostnet.ArraySequence(x, np.zeros(6), 3)
+    q = QuantizedNeuralNetwork(net, 3, seq, bits=2, alphabet_scalar=3, ignore_layers=[5])
+    assert np.array_equal(q.alphabet, np.linspace(-1, 1, 4))
+    assert q.alphabet_scalar == 3 and q.bits == 2 and q.ignore_layers == [5]
+    assert q.trained_net is net and q.quantized_net is not net
+    for a, b in zip(net.get_weights(), q.quantized_net.get_weights()):
+        assert np.array_equal(a, b)
+    assert set(q.layer_dims) == {1, 3, 5} and q.layer_dims[1] == (16, 12)
+    c = QuantizedCNN(hostnet.cifar10_cnn(seed=2, size=8, widths=(2, 3, 4), dense=5, n_out=3), 2,
+                     hostnet.ArraySequence(np.zeros((4, 8, 8, 3), np.float32), np.zeros(4), 2))
+    assert np.array_equal(c.alphabet, np.array([-1.0, 0.0, 1.0]))
+    assert c.patch_mini_batch_size == 5000 and c.is_quantize_conv2d is True
+
+
+def test_layer_data_collection_dense_and_conv():
+    """_get_layer_data_generator (:408-502): wX/qX of the layer's inbound activations, feature-major when transposed."""
+    net = hostnet.mnist_mlp(seed=1, widths=(12, 8), n_in=16, n_out=4)
+    x = np.random.default_rng(0).random((6, 4, 4)).astype(np.float32)
+    q = QuantizedNeuralNetwork(net, 3, hostnet.ArraySequence(x, np.zeros(6), 3))
+    d = q._get_layer_data_generator(1, transpose=True)
+    assert d.wX.shape == (16, 6) and d.same
+    assert np.array_equal(d.wX, x.reshape(6, 16).T)
+    # perturb the quantized twin's first Dense layer: layer 3's inputs now differ between the two nets
+    W = q.quantized_net.layers[1].get_weights()
+    q.quantized_net.layers[1].set_weights([np.round(W[0] * 4) / 4, W[1]])
+    d3 = q._get_layer_data_generator(3, transpose=True)
+    assert d3.wX.shape == (12, 6) and not d3.same
+    assert np.array_equal(d3.wX.T, net.run(x, 0, 2))
+    assert np.array_equal(d3.qX.T, q.quantized_net.run(x, 0, 2))
+
+    cnn = hostnet.cifar10_cnn(seed=2, size=8, widths=(2, 3, 4), dense=5, n_out=3)
+    xi = np.random.default_rng(1).random((4, 8, 8, 3)).astype(np.float32)
+    c = QuantizedCNN(cnn, 2, hostnet.ArraySequence(xi, np.zeros(4), 2))
+    dc = c._get_layer_data_generator(2)
+    assert dc.wX.shape == (4, 8, 8, 2)
+    assert np.array_equal(dc.wX, cnn.run(xi, 0, 1))
+    patches = c._build_patch_array(1, (3, 3), (1, 1), "SAME", (1, 1), dc, 3)
+    assert np.array_equal(patches["wX_channel1"], O.channel_patches(dc.wX, 1, (3, 3), (1, 1), "SAME"))
+
+
+def test_layer_alphabet_matches_reference_dtype_ladder():
+    """rad = alphabet_scalar * median(|W|) stays float32 for a Python scalar (NEP 50), :544-545."""
+    rng = np.random.default_rng(5)
+    W = rng.standard_normal((9, 7)).astype(np.float32)
+    net = hostnet.mnist_mlp(seed=1, widths=(12, 8), n_in=16, n_out=4)
+    q = QuantizedNeuralNetwork(net, 3, hostnet.ArraySequence(np.zeros((2, 4, 4), np.float32), np.zeros(2), 2),
+                               bits=3, alphabet_scalar=4)
+    assert np.array_equal(q._layer_alphabet(W), O.layer_alphabet(W, 4, O.unit_alphabet(3)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gather_worker(rank, world, port, axis, shape, ret):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        full = np.arange(np.prod(shape), dtype=np.float64).reshape(shape) + 1.0
+        net = hostnet.mnist_mlp(seed=1, widths=(6,), n_in=4, n_out=3)
+        q = QuantizedNeuralNetwork(net, 1, hostnet.ArraySequence(np.zeros((1, 2, 2), np.float32), np.zeros(1), 1),
+                                   shard=(rank, world))
+        n = shape[axis]
+        lo, hi = shard_range(n, rank, world)
+        mine = np.zeros(shape)
+        sl = [slice(None)] * len(shape)
+        sl[axis] = slice(lo, hi)
+        mine[tuple(sl)] = full[tuple(sl)]        # what this rank's C-ABI call would have written
+        out = q._gather_columns(mine, lo, hi, axis)
+        ret[rank] = bool(np.array_equal(out, full))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("axis,shape", [(1, (5, 7)), (2, (3, 3, 5, 4)), (1, (4, 1))])
+def test_world2_gloo_gather_reassembles_q(axis, shape):
+    """N > 1: every rank quantizes its shard of neurons / channels, Q blocks are all-gathered; no other collective."""
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r, world, port, axis, shape, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert dict(ret) == {0: True, 1: True}
+
+
+def test_layerdata_same_detection():
+    a = np.ones((3, 4), np.float32)
+    assert LayerData(a, a).same and LayerData(a, a.copy()).same and not LayerData(a, a * 2).same
