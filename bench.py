@@ -376,7 +376,7 @@ def main():
         launches_per_step += sts[0]["kernel_launches"]
         msl = float(np.mean([s["ms_total"] for s in sts]))
         layer_report[name] = {"ms": round(msl, 4), "weights_per_s": round(sts[0]["weights"] / (msl * 1e-3)) if msl > 0 else None,
-                              "method": {1: "stream", 2: "gram"}.get(sts[0]["method"])}
+                              "method": {1: "stream", 2: "gram", 3: "stream_fast"}.get(sts[0]["method"])}
         if kind == "conv":
             conv_bytes += sum(s["bytes_algorithmic"] for s in sts)
             conv_ms += sum(s["ms_gram"] for s in sts)

@@ -44,8 +44,9 @@ enum {
 #define GPFQ_Q_DEVICE (1u << 2)   /* Q_out is a device pointer */
 #define GPFQ_ALL_DEVICE (GPFQ_X_DEVICE | GPFQ_W_DEVICE | GPFQ_Q_DEVICE)
 #define GPFQ_METHOD_AUTO (0u << 4)    /* pick streaming vs Gram+sweep by the measured cost table */
-#define GPFQ_METHOD_STREAM (1u << 4)  /* literal residual walk, u kept on chip */
+#define GPFQ_METHOD_STREAM (1u << 4)  /* literal residual walk (the reference's dtype ladder: fp32-rounded w*X), u on chip */
 #define GPFQ_METHOD_GRAM (2u << 4)    /* Gram stage + blocked triangular sweep */
+#define GPFQ_METHOD_STREAM_FAST (3u << 4) /* residual walk on exact fp32 x fp32 products (the Gram form's numerics) */
 #define GPFQ_METHOD_MASK (3u << 4)
 #define GPFQ_NO_SYNC (1u << 8)        /* all-device calls only: return after enqueueing */
 
@@ -54,7 +55,7 @@ enum {
 /* per-call report (optional, may be NULL).  Times are CUDA-event milliseconds on the library's
  * stream; they are 0 when GPFQ_NO_SYNC is set. */
 typedef struct gpfq_stats {
-    int32_t method;          /* GPFQ_METHOD_STREAM or GPFQ_METHOD_GRAM actually used (>>4) */
+    int32_t method;          /* GPFQ_METHOD_STREAM, _GRAM or _STREAM_FAST actually used (>>4) */
     int32_t kernel_launches; /* kernels launched by this call */
     float ms_total;          /* whole call, including copies for host pointers */
     float ms_h2d, ms_d2h;    /* copies (host-pointer calls) */

@@ -14,7 +14,7 @@ CSRC = os.path.join(_HERE, "csrc")
 # flags (include/gpfq.h)
 X_DEVICE, W_DEVICE, Q_DEVICE = 1, 2, 4
 ALL_DEVICE = 7
-METHOD_AUTO, METHOD_STREAM, METHOD_GRAM = 0 << 4, 1 << 4, 2 << 4
+METHOD_AUTO, METHOD_STREAM, METHOD_GRAM, METHOD_STREAM_FAST = 0 << 4, 1 << 4, 2 << 4, 3 << 4
 NO_SYNC = 1 << 8
 MAX_K = 64
 

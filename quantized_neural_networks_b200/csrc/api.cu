@@ -1,5 +1,7 @@
 // api.cu -- C ABI of libgpfq (include/gpfq.h): context, workspaces, host<->device staging, method choice.
+#include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -12,8 +14,8 @@ int dense_stream_path(gpfq_ctx *, const float *, const float *, int64_t, int64_t
                       int64_t, int64_t, const double *, const int *, int, double *, int64_t, int64_t, gpfq_stats *);
 int dense_gram_only(gpfq_ctx *, const float *, const float *, int64_t, int64_t, int64_t, double *, double *);
 int conv_supported_kk(int kk);
-int conv_pick_chunks(gpfq_ctx *, int64_t, int, int64_t *);
-int conv_gram_stage(gpfq_ctx *, int, ConvPtrs, bool, int64_t, int, int, int64_t, double *);
+int conv_pick_chunks(gpfq_ctx *, int64_t, int, int64_t *, int, bool);
+int conv_gram_stage(gpfq_ctx *, int, ConvPtrs, bool, int64_t, int, int, int64_t, double *, bool);
 int conv_finalize_stage(gpfq_ctx *, const double *, int, int, int, bool, double *);
 int conv_sweep_stage(gpfq_ctx *, int, const double *, const float *, double *, int64_t, int64_t, int64_t, int,
                      const double *, const int *, int);
@@ -110,6 +112,8 @@ extern "C" int gpfq_create(int device, gpfq_ctx **out) {
         return GPFQ_ERR_CUDA;
     }
     ctx->stream = ctx->own_stream;
+    if (const char *v = getenv("GPFQ_CONV_KERNEL"))  // A/B switch for profiling: tma (default) | ldg | generic
+        ctx->conv_variant = !strcmp(v, "ldg") ? 1 : (!strcmp(v, "generic") ? 2 : 0);
     *out = ctx;
     return GPFQ_OK;
 }
@@ -266,19 +270,23 @@ extern "C" int gpfq_query_stats(gpfq_ctx *ctx, int32_t calls_back, gpfq_stats *o
 // ---------------------------------------------------------------------------------------------
 static int choose_dense_method(gpfq_ctx *ctx, uint32_t flags, int64_t N0, int64_t m, int64_t nj, bool same, int n_alph) {
     const uint32_t want = flags & GPFQ_METHOD_MASK;
-    if (want == GPFQ_METHOD_STREAM) return GPFQ_METHOD_STREAM;
-    if (want == GPFQ_METHOD_GRAM) return GPFQ_METHOD_GRAM;
-    // Cost table (DESIGN.md "method choice"; constants fitted to B200 measurements, profiles/):
-    //   streaming: ~3 fp64 MACs per (sample, direction, neuron), walked once per alphabet
-    //   Gram+sweep: (1 or 1/2) m N0^2 MACs once + N0^2 nj MACs and 2 launches per 32 directions per alphabet
-    const double stream_rate = 2.0e12, gram_rate = 9.0e12, sweep_rate = 4.0e12, launch_s = 6e-6;
-    const bool u_fits = (size_t)m * sizeof(double) + 8192 <= ctx->smem_optin;
-    double t_stream = 3.0 * (double)m * N0 * nj * n_alph / stream_rate * (u_fits ? 1.0 : 6.0);
-    double t_gram = (same ? 0.5 : 1.0) * (double)m * N0 * N0 / gram_rate +
-                    n_alph * ((double)N0 * N0 * nj / sweep_rate) + 2.0 * (N0 / 32.0) * launch_s;
+    if (want != GPFQ_METHOD_AUTO) return (int)want;
+    // Cost table (DESIGN.md "method choice"), in fp64-pipe slots at the measured 18.5 T slots/s:
+    //   streaming : 3 slots per (sample, direction, neuron), per alphabet; a step cannot be shorter than ~0.5 us
+    //               (row ingest + block reduction); long sample axes (residual not register-resident) cost ~4x
+    //   Gram+sweep: m N0^2 / 2 slots per Gram (lower triangle) once + N0^2 nj per alphabet + 2 launches per 32 directions
+    const double slots_per_s = 18.5e12 * 0.6;
+    const bool u_in_regs = m <= 512 * 16;
+    const double ctas = (double)((nj + 0) / 1);
+    const double waves = ceil(ctas / (double)ctx->sm_count);
+    double t_stream = n_alph * (3.0 * (double)m * N0 * nj / slots_per_s * (u_in_regs ? 1.0 : 4.0));
+    const double t_steps = n_alph * waves * (double)N0 * 0.5e-6;
+    if (t_stream < t_steps) t_stream = t_steps;
+    double t_gram = (same ? 0.5 : 1.0) * (double)m * N0 * N0 / slots_per_s +
+                    n_alph * ((double)N0 * N0 * nj / slots_per_s) + 2.0 * (N0 / 32.0) * 6e-6;
     const double gram_bytes = (same ? 1.0 : 2.0) * 8.0 * N0 * N0;
-    if (gram_bytes > 48e9) return GPFQ_METHOD_STREAM;
-    return t_gram < t_stream ? GPFQ_METHOD_GRAM : GPFQ_METHOD_STREAM;
+    if (gram_bytes > 48e9) return GPFQ_METHOD_STREAM_FAST;
+    return t_gram < t_stream ? GPFQ_METHOD_GRAM : GPFQ_METHOD_STREAM_FAST;
 }
 
 extern "C" int gpfq_dense_layer(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx, int64_t N0, int64_t m,
@@ -345,9 +353,12 @@ extern "C" int gpfq_dense_layer(gpfq_ctx *ctx, const float *X, const float *Xq, 
     if (method == GPFQ_METHOD_GRAM)
         GPFQ_TRY(dense_gram_path(ctx, dX, dXq, dldx, N0, m, dW, dldw, dj0, nj, al.d_levels, al.d_koff, n_alph, dQ, dldq,
                                  col0, stats));
-    else
+    else {
+        ctx->stream_literal = (method == GPFQ_METHOD_STREAM);
         GPFQ_TRY(dense_stream_path(ctx, dX, dXq, dldx, N0, m, dW, dldw, dj0, nj, al.d_levels, al.h_koff.data(), n_alph,
                                    dQ, dldq, col0, stats));
+        if (stats) stats->method = method >> 4;
+    }
     CUDA_TRY(ctx, gpfq_record(ctx, 6, s));
     if (!(flags & GPFQ_Q_DEVICE)) {
         for (int a = 0; a < n_alph; ++a)
@@ -484,8 +495,12 @@ extern "C" int gpfq_conv_channels(gpfq_ctx *ctx, const float *const *Xp, const f
     Alphabets al;
     GPFQ_TRY(upload_alphabets(ctx, alphabets, K, n_alph, &al));
 
+    bool vec_ok = n % 4 == 0;  // float4 / bulk-copy paths: every row of every patch matrix 16-byte aligned
+    if (flags & GPFQ_X_DEVICE)
+        for (int64_t i = 0; i < n_ch; ++i)
+            vec_ok = vec_ok && ((uintptr_t)Xp[i] % 16 == 0) && (same || (uintptr_t)Xqp[i] % 16 == 0);
     int64_t chunk_cols = 0;
-    const int n_chunks = conv_pick_chunks(ctx, n, (int)n_ch, &chunk_cols);
+    const int n_chunks = conv_pick_chunks(ctx, n, (int)n_ch, &chunk_cols, kk, vec_ok);
     double *partial = nullptr;
     GPFQ_TRY(gpfq_ws(ctx, WS_CPART, (size_t)n_ch * n_chunks * 2 * kk * kk * sizeof(double), (void **)&partial));
     const float **d_ptrs = nullptr;
@@ -501,7 +516,7 @@ extern "C" int gpfq_conv_channels(gpfq_ctx *ctx, const float *const *Xp, const f
         }
         CUDA_TRY(ctx, cudaMemcpyAsync(d_ptrs, h_ptrs.data(), h_ptrs.size() * sizeof(float *), cudaMemcpyHostToDevice, s));
         ConvPtrs p{d_ptrs, d_ptrs + n_ch};
-        GPFQ_TRY(conv_gram_stage(ctx, kk, p, same, n, (int)n_ch, n_chunks, chunk_cols, partial));
+        GPFQ_TRY(conv_gram_stage(ctx, kk, p, same, n, (int)n_ch, n_chunks, chunk_cols, partial, vec_ok));
     } else {
         // host patches: double-buffered channel batches, copies on the copy stream overlap the Gram kernel
         const size_t per_ch = ch_bytes * (same ? 1 : 2);
@@ -539,7 +554,7 @@ extern "C" int gpfq_conv_channels(gpfq_ctx *ctx, const float *const *Xp, const f
                                           cudaMemcpyHostToDevice, s));
             ConvPtrs p{d_ptrs + b0, d_ptrs + n_ch + b0};
             GPFQ_TRY(conv_gram_stage(ctx, kk, p, same, n, (int)nb, n_chunks, chunk_cols,
-                                     partial + (size_t)b0 * n_chunks * 2 * kk * kk));
+                                     partial + (size_t)b0 * n_chunks * 2 * kk * kk, vec_ok));
             CUDA_TRY(ctx, cudaEventRecord(ctx->ev_copy[bi & 1], s));
         }
     }
@@ -607,7 +622,7 @@ extern "C" int gpfq_conv_layer_nhwc(gpfq_ctx *ctx, const float *act, const float
     }
     CUDA_TRY(ctx, gpfq_record(ctx, 5, s));
     int64_t chunk_cols = 0;
-    const int n_chunks = conv_pick_chunks(ctx, n, (int)std::min<int64_t>(n_ch, 64), &chunk_cols);
+    const int n_chunks = conv_pick_chunks(ctx, n, (int)std::min<int64_t>(n_ch, 64), &chunk_cols, kk, n % 4 == 0);
     double *partial = nullptr;
     GPFQ_TRY(gpfq_ws(ctx, WS_CPART, (size_t)n_ch * n_chunks * 2 * kk * kk * sizeof(double), (void **)&partial));
     const size_t ch_elems = (size_t)kk * n;
@@ -636,7 +651,7 @@ extern "C" int gpfq_conv_layer_nhwc(gpfq_ctx *ctx, const float *act, const float
                                   Wo, pq, (int64_t)ch_elems));
         ConvPtrs p{d_ptrs, d_ptrs + bch};
         GPFQ_TRY(conv_gram_stage(ctx, kk, p, same, n, (int)nb, n_chunks, chunk_cols,
-                                 partial + (size_t)b0 * n_chunks * 2 * kk * kk));
+                                 partial + (size_t)b0 * n_chunks * 2 * kk * kk, n % 4 == 0));
     }
     CUDA_TRY(ctx, gpfq_record(ctx, 3, s));
     GPFQ_TRY(conv_finish(ctx, kk, partial, (int)n_ch, n_chunks, same, W, C, F, c0, al, n_alph, Q_out, flags));

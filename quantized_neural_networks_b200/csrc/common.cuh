@@ -52,6 +52,8 @@ struct gpfq_ctx {
     cudaEvent_t ev_copy[4] = {};
     std::string err = "";
     int launches = 0;
+    int conv_variant = 0;         // 3x3 patch-Gram kernel: 0 TMA-staged (default), 1 direct LDG, 2 generic
+    bool stream_literal = false;  // streaming walk: reproduce the reference's fp32-rounded w*X products (set per call)
     // grow-only named workspaces
     DevBuf ws[24];
     DevBuf pinned[4];

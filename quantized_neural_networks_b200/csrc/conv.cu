@@ -121,6 +121,271 @@ conv_gram_kernel(ConvPtrs ptrs, int64_t n, int64_t chunk_cols, double *__restric
     }
 }
 
+// ---- stage 1, 3x3 fast path ---------------------------------------------------------------------
+// KK = 9 on the fp64 tensor pipe.  Lane l = (g, k) = (l >> 2, l & 3) owns patch row g of four columns per
+// step (a float4 per row per 16 columns, so every request is a run of full 32-byte sectors).  The 8 x 8
+// corners of G1 = Xq X^T and G2 = Xq Xq^T are one DMMA.8x8x4 each per 4 columns (the A fragment of Xq
+// rows 0..7 is also the B fragment of G2); the ninth row / column (26 entries) are five DFMAs per lane.
+// Per column: 168 fp64-pipe slots for 126 useful products and 32 F2F (XU pipe), ~100 registers, no
+// shared-memory staging -- occupancy (16 warps/SM, 8 LDG.128 in flight per lane) covers the HBM latency.
+// Needs n % 4 == 0 and 16-byte aligned patch matrices; everything else takes the generic kernel above.
+__device__ __forceinline__ float4 ldg_stream4(const float *p) { return __ldcs(reinterpret_cast<const float4 *>(p)); }
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+struct Gram9Acc {
+    double g1[2], g2[2];  // C fragments: G[g][2k], G[g][2k+1]
+    double a1, a2, a3, a4, a5;  // G1[g][8], G1[8][g], G2[8][g], G1[8][8], G2[8][8] (partial over this lane's columns)
+};
+
+template <bool SAME>
+__device__ __forceinline__ void gram9_step(Gram9Acc &acc, float q, float x, float q8, float x8) {
+    const double qd = (double)q, q8d = (double)q8;
+    dmma884(acc.g2[0], acc.g2[1], qd, qd);
+    acc.a3 = fma(q8d, qd, acc.a3);
+    acc.a5 = fma(q8d, q8d, acc.a5);
+    if (!SAME) {
+        const double xd = (double)x, x8d = (double)x8;
+        dmma884(acc.g1[0], acc.g1[1], qd, xd);
+        acc.a1 = fma(qd, x8d, acc.a1);
+        acc.a2 = fma(q8d, xd, acc.a2);
+        acc.a4 = fma(q8d, x8d, acc.a4);
+    }
+}
+
+// Fragments -> one 2*81-entry partial [G1 | G2] in shared memory (lower triangle of G2 valid).
+template <bool SAME>
+__device__ __forceinline__ void gram9_store(Gram9Acc &acc, double *r, int g, int k) {
+    constexpr int KK = 9;
+    // the ninth row / column: sum this lane group's four column phases (fixed butterfly order)
+    double *edge[5] = {&acc.a1, &acc.a2, &acc.a3, &acc.a4, &acc.a5};
+#pragma unroll
+    for (int e = 0; e < 5; ++e) {
+        double v = *edge[e];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        *edge[e] = v;
+    }
+    if (!SAME) {
+        r[g * KK + 2 * k] = acc.g1[0];
+        r[g * KK + 2 * k + 1] = acc.g1[1];
+    }
+    r[KK * KK + g * KK + 2 * k] = acc.g2[0];
+    r[KK * KK + g * KK + 2 * k + 1] = acc.g2[1];
+    if (k == 0) {
+        if (!SAME) {
+            r[g * KK + 8] = acc.a1;
+            r[8 * KK + g] = acc.a2;
+        }
+        r[KK * KK + 8 * KK + g] = acc.a3;
+        r[KK * KK + g * KK + 8] = 0.0;  // above the diagonal, never read
+        if (g == 0) {
+            if (!SAME) r[8 * KK + 8] = acc.a4;
+            r[KK * KK + 8 * KK + 8] = acc.a5;
+        }
+    }
+}
+
+template <bool SAME>
+__global__ void __launch_bounds__(CONV_BLOCK, 2)
+conv_gram9_dmma_kernel(ConvPtrs ptrs, int64_t n, int64_t chunk_cols, double *__restrict__ partial) {
+    constexpr int KK = 9, NW = CONV_BLOCK / 32, SZ = 2 * KK * KK;
+    __shared__ double red[NW][SZ];
+    const int ch = blockIdx.y, chunk = blockIdx.x;
+    const float *X = ptrs.Xp[ch];
+    const float *Xq = SAME ? X : ptrs.Xqp[ch];
+    const int64_t c_beg = (int64_t)chunk * chunk_cols;
+    const int64_t c_end = (c_beg + chunk_cols < n) ? c_beg + chunk_cols : n;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, k = lane & 3;
+    const float *qrow = Xq + (int64_t)g * n, *q8row = Xq + (int64_t)8 * n;
+    const float *xrow = X + (int64_t)g * n, *x8row = X + (int64_t)8 * n;
+
+    Gram9Acc acc = {};
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 q[2], x[2], q8[2], x8[2];
+    auto load = [&](int64_t base, float4 *lq, float4 *lx, float4 *lq8, float4 *lx8) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int64_t c = base + 16 * u + 4 * k;
+            const bool ok = c < c_end;  // n % 4 == 0: a float4 is wholly inside or wholly outside
+            lq[u] = ok ? ldg_stream4(qrow + c) : z4;
+            lq8[u] = ok ? ldg_stream4(q8row + c) : z4;
+            if (!SAME) {
+                lx[u] = ok ? ldg_stream4(xrow + c) : z4;
+                lx8[u] = ok ? ldg_stream4(x8row + c) : z4;
+            }
+        }
+    };
+    auto compute = [&](const float4 *lq, const float4 *lx, const float4 *lq8, const float4 *lx8) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            gram9_step<SAME>(acc, lq[u].x, lx[u].x, lq8[u].x, lx8[u].x);
+            gram9_step<SAME>(acc, lq[u].y, lx[u].y, lq8[u].y, lx8[u].y);
+            gram9_step<SAME>(acc, lq[u].z, lx[u].z, lq8[u].z, lx8[u].z);
+            gram9_step<SAME>(acc, lq[u].w, lx[u].w, lq8[u].w, lx8[u].w);
+        }
+    };
+    // two register buffers in ping-pong: the loads of the next 32 columns are in flight while the current 32 are
+    // multiplied (out-of-range loads return zeros, which add nothing)
+    float4 p[2], px[2], p8[2], px8[2];
+    constexpr int64_t S = NW * 32;
+    int64_t base = c_beg + (int64_t)warp * 32;
+    load(base, q, x, q8, x8);
+    for (; base < c_end; base += 2 * S) {
+        load(base + S, p, px, p8, px8);
+        compute(q, x, q8, x8);
+        load(base + 2 * S, q, x, q8, x8);
+        compute(p, px, p8, px8);
+    }
+    gram9_store<SAME>(acc, red[warp], g, k);
+    __syncthreads();
+    double *out = partial + ((size_t)ch * gridDim.x + chunk) * SZ;
+    for (int e = threadIdx.x; e < SZ; e += CONV_BLOCK) {
+        if (SAME && e < KK * KK) continue;
+        double tot = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) tot += red[w][e];  // warps in index order
+        out[e] = tot;
+    }
+}
+
+// ---- stage 1, 3x3 fast path with TMA staging ------------------------------------------------------
+// Same arithmetic and lane mapping as conv_gram9_dmma_kernel, but the patch rows reach the SM as bulk
+// async copies (cp.async.bulk = UBLKCP, completion on an mbarrier) into a ring of shared-memory stages,
+// issued by a dedicated producer warp: the bytes in flight (4 of 5 stages of 18 rows x 512 columns,
+// ~150 KB per SM) no longer live in registers, so 16 consumer warps keep the fp64 pipe fed while the
+// whole HBM latency is covered.  Each consumer warp owns a fixed 32-column slice of every stage, so the
+// summation order is fixed.  Row pitch is COLS + 16 floats: lane groups g and g+1 then start 16 banks
+// apart and the LDS.128 fragments are conflict free.
+namespace tma9 {
+constexpr int CWARPS = 16;                 // consumer warps
+constexpr int COLS = CWARPS * 32;          // columns per stage
+constexpr int PITCH = COLS + 16;           // floats
+constexpr int STAGES = 5;
+constexpr int THREADS = (CWARPS + 1) * 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nWAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+}  // namespace tma9
+
+template <bool SAME>
+__global__ void __launch_bounds__(tma9::THREADS, 1)
+conv_gram9_tma_kernel(ConvPtrs ptrs, int64_t n, int64_t chunk_cols, double *__restrict__ partial) {
+    using namespace tma9;
+    constexpr int KK = 9, SZ = 2 * KK * KK, ROWS = SAME ? KK : 2 * KK;
+    constexpr int STAGE_FLOATS = ROWS * PITCH;
+    extern __shared__ __align__(128) unsigned char tma9_smem[];
+    float *stages = reinterpret_cast<float *>(tma9_smem);                                     // STAGES x ROWS x PITCH
+    double *red = reinterpret_cast<double *>(tma9_smem + (size_t)STAGES * STAGE_FLOATS * 4);  // CWARPS x SZ
+    uint64_t *full = reinterpret_cast<uint64_t *>(red + CWARPS * SZ);
+    uint64_t *empty = full + STAGES;
+
+    const int ch = blockIdx.y, chunk = blockIdx.x;
+    const float *X = ptrs.Xp[ch];
+    const float *Xq = SAME ? X : ptrs.Xqp[ch];
+    const int64_t c_beg = (int64_t)chunk * chunk_cols;
+    const int64_t c_end = (c_beg + chunk_cols < n) ? c_beg + chunk_cols : n;
+    const int n_iter = (int)((c_end - c_beg + COLS - 1) / COLS);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], CWARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == CWARPS) {
+        // ---- producer: one lane streams the rows of every stage
+        if (lane == 0) {
+            for (int it = 0; it < n_iter; ++it) {
+                const int s = it % STAGES;
+                if (it >= STAGES) mbar_wait(&empty[s], ((it / STAGES) - 1) & 1);
+                const int64_t c0 = c_beg + (int64_t)it * COLS;
+                const int64_t cols = (c_end - c0 < COLS) ? c_end - c0 : COLS;
+                const uint32_t bytes = (uint32_t)cols * 4u;
+                mbar_expect_tx(&full[s], bytes * ROWS);
+                float *dst = stages + (size_t)s * STAGE_FLOATS;
+#pragma unroll 1
+                for (int r = 0; r < KK; ++r) {
+                    bulk_g2s(dst + r * PITCH, Xq + (int64_t)r * n + c0, bytes, &full[s]);
+                    if (!SAME) bulk_g2s(dst + (KK + r) * PITCH, X + (int64_t)r * n + c0, bytes, &full[s]);
+                }
+            }
+        }
+        return;
+    }
+
+    // ---- consumers
+    const int g = lane >> 2, k = lane & 3;
+    Gram9Acc acc = {};
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int it = 0; it < n_iter; ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&full[s], (it / STAGES) & 1);
+        const float *st = stages + (size_t)s * STAGE_FLOATS;
+        const int64_t valid = c_end - (c_beg + (int64_t)it * COLS);  // columns present in this stage (multiple of 4)
+        float4 q[2], x[2], q8[2], x8[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int c = warp * 32 + 16 * u + 4 * k;
+            const bool ok = c < valid;
+            q[u] = ok ? *reinterpret_cast<const float4 *>(st + g * PITCH + c) : z4;
+            q8[u] = ok ? *reinterpret_cast<const float4 *>(st + 8 * PITCH + c) : z4;
+            if (!SAME) {
+                x[u] = ok ? *reinterpret_cast<const float4 *>(st + (KK + g) * PITCH + c) : z4;
+                x8[u] = ok ? *reinterpret_cast<const float4 *>(st + (KK + 8) * PITCH + c) : z4;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);  // the slice is in registers: hand the stage back
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            gram9_step<SAME>(acc, q[u].x, x[u].x, q8[u].x, x8[u].x);
+            gram9_step<SAME>(acc, q[u].y, x[u].y, q8[u].y, x8[u].y);
+            gram9_step<SAME>(acc, q[u].z, x[u].z, q8[u].z, x8[u].z);
+            gram9_step<SAME>(acc, q[u].w, x[u].w, q8[u].w, x8[u].w);
+        }
+    }
+    gram9_store<SAME>(acc, red + warp * SZ, g, k);
+    // consumer-only barrier (the producer warp has left)
+    asm volatile("bar.sync 1, %0;\n" ::"r"(CWARPS * 32));
+    double *out = partial + ((size_t)ch * gridDim.x + chunk) * SZ;
+    for (int e = threadIdx.x; e < SZ; e += CWARPS * 32) {
+        if (SAME && e < KK * KK) continue;
+        double tot = 0.0;
+#pragma unroll
+        for (int w = 0; w < CWARPS; ++w) tot += red[w * SZ + e];  // warps in index order
+        out[e] = tot;
+    }
+}
+
 // ---- stage 2 ---------------------------------------------------------------------------------
 // gram: (n_channels, 2*kk*kk): [G1 | G2], lower triangle + diagonal of each valid.
 __global__ void conv_finalize_kernel(const double *__restrict__ partial, int n_chunks, int kk, int same,
@@ -210,8 +475,28 @@ __global__ void msq_kernel(const T *__restrict__ W, int64_t n, const double *__r
 // ---------------------------------------------------------------------------------------------
 template <int KK>
 static int launch_conv_gram(gpfq_ctx *ctx, ConvPtrs ptrs, bool same, int64_t n, int n_ch, int n_chunks,
-                            int64_t chunk_cols, double *partial) {
+                            int64_t chunk_cols, double *partial, bool vec_ok) {
     dim3 grid((unsigned)n_chunks, (unsigned)n_ch);
+    if (KK == 9 && vec_ok && ctx->conv_variant == 0) {
+        using namespace tma9;
+        constexpr size_t tail = (size_t)CWARPS * 2 * 81 * sizeof(double) + 2 * STAGES * sizeof(uint64_t);
+        const size_t smem = (size_t)STAGES * (same ? 9 : 18) * PITCH * sizeof(float) + tail;
+        if (same) {
+            CUDA_TRY(ctx, cudaFuncSetAttribute(conv_gram9_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            conv_gram9_tma_kernel<true><<<grid, THREADS, smem, ctx->stream>>>(ptrs, n, chunk_cols, partial);
+        } else {
+            CUDA_TRY(ctx, cudaFuncSetAttribute(conv_gram9_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            conv_gram9_tma_kernel<false><<<grid, THREADS, smem, ctx->stream>>>(ptrs, n, chunk_cols, partial);
+        }
+        KERNEL_CHECK(ctx);
+        return GPFQ_OK;
+    }
+    if (KK == 9 && vec_ok && ctx->conv_variant == 1) {
+        if (same) conv_gram9_dmma_kernel<true><<<grid, CONV_BLOCK, 0, ctx->stream>>>(ptrs, n, chunk_cols, partial);
+        else conv_gram9_dmma_kernel<false><<<grid, CONV_BLOCK, 0, ctx->stream>>>(ptrs, n, chunk_cols, partial);
+        KERNEL_CHECK(ctx);
+        return GPFQ_OK;
+    }
     constexpr int NG = (KK >= 9) ? 2 : 1;
     if (same) conv_gram_kernel<KK, true, 1><<<grid, CONV_BLOCK, 0, ctx->stream>>>(ptrs, n, chunk_cols, partial);
     else conv_gram_kernel<KK, false, NG><<<grid, CONV_BLOCK, 0, ctx->stream>>>(ptrs, n, chunk_cols, partial);
@@ -221,27 +506,34 @@ static int launch_conv_gram(gpfq_ctx *ctx, ConvPtrs ptrs, bool same, int64_t n, 
 
 int conv_supported_kk(int kk) { return kk == 1 || kk == 2 || kk == 3 || kk == 4 || kk == 6 || kk == 9; }
 
-int conv_pick_chunks(gpfq_ctx *ctx, int64_t n, int n_ch, int64_t *chunk_cols) {
-    int64_t want = ceil_div64(4LL * ctx->sm_count, n_ch);
-    const int64_t max_chunks = ceil_div64(n, 4096) > 0 ? ceil_div64(n, 4096) : 1;
+// Column chunks per channel: grid = n_chunks x n_ch CTAs.  TMA kernel (kk == 9, vectorisable): one CTA per SM, whole
+// waves of sm_count CTAs, chunks a multiple of the 512-column stage; the other kernels: two CTAs per SM.
+int conv_pick_chunks(gpfq_ctx *ctx, int64_t n, int n_ch, int64_t *chunk_cols, int kk, bool vec_ok) {
+    const bool tma = (kk == 9 && vec_ok && ctx->conv_variant == 0);
+    const int64_t per_wave = tma ? ctx->sm_count : 2LL * ctx->sm_count;
+    const int64_t min_cols = tma ? 32768 : 4096, align = tma ? tma9::COLS : 128;
+    int64_t waves = ((int64_t)n * n_ch) / (per_wave * min_cols);
+    waves = waves < 1 ? 1 : (waves > 4 ? 4 : waves);
+    int64_t want = (waves * per_wave) / n_ch;
+    const int64_t max_chunks = ceil_div64(n, min_cols) > 0 ? ceil_div64(n, min_cols) : 1;
     if (want > max_chunks) want = max_chunks;
     if (want < 1) want = 1;
     int64_t cols = ceil_div64(n, want);
-    cols = ceil_div64(cols, 128) * 128;
+    cols = ceil_div64(cols, align) * align;
     *chunk_cols = cols;
     return (int)ceil_div64(n, cols);
 }
 
 // Gram partials of n_ch channels whose patch pointers (device) are in d_ptrs.
 int conv_gram_stage(gpfq_ctx *ctx, int kk, ConvPtrs d_ptrs, bool same, int64_t n, int n_ch, int n_chunks,
-                    int64_t chunk_cols, double *partial) {
+                    int64_t chunk_cols, double *partial, bool vec_ok) {
     switch (kk) {
-        case 1: return launch_conv_gram<1>(ctx, d_ptrs, same, n, n_ch, n_chunks, chunk_cols, partial);
-        case 2: return launch_conv_gram<2>(ctx, d_ptrs, same, n, n_ch, n_chunks, chunk_cols, partial);
-        case 3: return launch_conv_gram<3>(ctx, d_ptrs, same, n, n_ch, n_chunks, chunk_cols, partial);
-        case 4: return launch_conv_gram<4>(ctx, d_ptrs, same, n, n_ch, n_chunks, chunk_cols, partial);
-        case 6: return launch_conv_gram<6>(ctx, d_ptrs, same, n, n_ch, n_chunks, chunk_cols, partial);
-        case 9: return launch_conv_gram<9>(ctx, d_ptrs, same, n, n_ch, n_chunks, chunk_cols, partial);
+        case 1: return launch_conv_gram<1>(ctx, d_ptrs, same, n, n_ch, n_chunks, chunk_cols, partial, vec_ok);
+        case 2: return launch_conv_gram<2>(ctx, d_ptrs, same, n, n_ch, n_chunks, chunk_cols, partial, vec_ok);
+        case 3: return launch_conv_gram<3>(ctx, d_ptrs, same, n, n_ch, n_chunks, chunk_cols, partial, vec_ok);
+        case 4: return launch_conv_gram<4>(ctx, d_ptrs, same, n, n_ch, n_chunks, chunk_cols, partial, vec_ok);
+        case 6: return launch_conv_gram<6>(ctx, d_ptrs, same, n, n_ch, n_chunks, chunk_cols, partial, vec_ok);
+        case 9: return launch_conv_gram<9>(ctx, d_ptrs, same, n, n_ch, n_chunks, chunk_cols, partial, vec_ok);
     }
     return gpfq_fail(ctx, GPFQ_ERR_UNSUPPORTED, "conv kernel size kk=%d has no specialised kernel", kk);
 }

@@ -14,7 +14,8 @@ try:  # torch is optional plumbing (device buffers / streams)
 except Exception:  # pragma: no cover
     torch = None
 
-_METHODS = {"auto": _lib.METHOD_AUTO, "stream": _lib.METHOD_STREAM, "gram": _lib.METHOD_GRAM}
+_METHODS = {"auto": _lib.METHOD_AUTO, "stream": _lib.METHOD_STREAM, "gram": _lib.METHOD_GRAM,
+            "stream_fast": _lib.METHOD_STREAM_FAST}
 
 
 def _is_torch(x):

@@ -27,7 +27,7 @@ def check(Q, Qref, W=None, X=None, Xq=None, exact=False):
 
 
 # ---- golden vectors (outputs of the unmodified reference) ------------------------------------------
-@pytest.mark.parametrize("method", ["stream", "gram", "auto"])
+@pytest.mark.parametrize("method", ["stream", "stream_fast", "gram", "auto"])
 def test_kat_reference_fixture(engine, method):
     z = golden("kat_settings_fixture")
     X0 = np.ascontiguousarray(z["data"].T)
@@ -38,7 +38,7 @@ def test_kat_reference_fixture(engine, method):
         assert np.array_equal(Q1, z[f"{tag}_Q1"]), (tag, Q1)
 
 
-@pytest.mark.parametrize("method", ["stream", "gram"])
+@pytest.mark.parametrize("method", ["stream", "stream_fast", "gram"])
 @pytest.mark.parametrize("name,xq,tags", [("dense_first_ternary", None, ["c1", "c2", "c3", "c6"]),
                                           ("dense_hidden_grid", "Xq", ["k3", "k4", "k8", "k16"]),
                                           ("dense_int_pixels", None, [""]), ("dense_wide_short", "Xq", [""])])
@@ -131,7 +131,7 @@ SHAPES = [  # (N0, N1, m, bits, c, first-layer?)
 ]
 
 
-@pytest.mark.parametrize("method", ["stream", "gram"])
+@pytest.mark.parametrize("method", ["stream", "stream_fast", "gram"])
 @pytest.mark.parametrize("N0,N1,m,bits,c,first", SHAPES)
 def test_dense_vs_oracle(engine, method, N0, N1, m, bits, c, first):
     rng = np.random.default_rng(N0 * 7 + N1 * 3 + m)
@@ -146,7 +146,7 @@ def test_dense_vs_oracle(engine, method, N0, N1, m, bits, c, first):
     Qref = c_oracle.quantize_layer(W, X, Xq, A)
     Q = engine.dense_layer(X, None if first else Xq, W, A, method=method)
     check(Q, Qref, W, X, Xq, exact=(method == "stream"))
-    assert engine.last_stats["method"] == (1 if method == "stream" else 2)
+    assert engine.last_stats["method"] == {"stream": 1, "gram": 2, "stream_fast": 3}[method]
     assert engine.last_stats["kernel_launches"] > 0
 
 
@@ -156,7 +156,7 @@ def test_dense_neuron_shards_are_bit_identical(engine):
     X, Xq = hidden_pair(rng, 256, 1500)
     W = glorot(rng, 256, 37)
     A = O.layer_alphabet(W, 3, O.unit_alphabet(np.log2(3)))
-    for method in ("stream", "gram"):
+    for method in ("stream", "stream_fast", "gram"):
         full = engine.dense_layer(X, Xq, W, A, method=method)
         for world in (2, 4, 8):
             acc = np.zeros_like(full)
@@ -289,3 +289,66 @@ def test_conv_many_patches_both_paths(engine):
     assert O.agreement(Qn, Qref) == 1.0, O.agreement(Qn, Qref)
     Qn_dev = engine.conv_layer_nhwc(torch.from_numpy(act).cuda(), torch.from_numpy(actq).cuda(), Wd, A).cpu().numpy()
     assert np.array_equal(Qn_dev, Qn)
+
+
+def test_long_sample_axis_streaming(engine):
+    """m beyond the register-resident limit (512 x 16 samples): the shared-memory residual kernel."""
+    rng = np.random.default_rng(5)
+    N0, N1, m = 40, 6, 9000
+    X, Xq = hidden_pair(rng, N0, m)
+    W = glorot(rng, N0, N1)
+    A = O.layer_alphabet(W, 3, O.unit_alphabet(3))
+    Qref = c_oracle.quantize_layer(W, X, Xq, A)
+    for method in ("stream", "stream_fast"):
+        assert np.array_equal(engine.dense_layer(X, Xq, W, A, method=method), Qref)
+
+
+@pytest.mark.parametrize("J_neurons", [3, 40, 700, 2500])
+def test_streaming_neuron_tiles(engine, J_neurons):
+    """Every (samples-per-thread, neurons-per-CTA) tile of the register-resident walk: wide layers put up to 8
+    neurons in one CTA; the tiling must not change a single bit (neurons are independent)."""
+    rng = np.random.default_rng(J_neurons)
+    N0 = 24
+    for m in (700, 1504, 2600, 3900, 5008, 8000):
+        X, Xq = hidden_pair(rng, N0, m)
+        W = glorot(rng, N0, J_neurons)
+        A = O.layer_alphabet(W, 2, O.unit_alphabet(np.log2(3)))
+        Qref = c_oracle.quantize_layer(W, X, Xq, A)
+        assert np.array_equal(engine.dense_layer(X, Xq, W, A, method="stream"), Qref), m
+        assert O.agreement(engine.dense_layer(X, Xq, W, A, method="stream_fast"), Qref) >= AGREE, m
+
+
+def test_conv_gram_kernel_variants_agree():
+    """The three 3x3 patch-Gram kernels (TMA-staged, direct LDG, generic) produce the same quantized kernel, on
+    ragged column counts (tail stages, several chunks) and on the unaligned fallback (n % 4 != 0)."""
+    import os
+    import torch
+    from quantized_neural_networks_b200 import GpfqEngine
+    rng = np.random.default_rng(77)
+    C, F = 3, 5
+    W = (rng.uniform(-1, 1, (3, 3, C, F)) * 0.3).astype(np.float32)
+    A = O.layer_alphabet(W, 4, O.unit_alphabet(4))
+    for n in (4, 516, 70000, 300004, 70001):
+        Xp = np.maximum(rng.standard_normal((C, 9, n)), 0).astype(np.float32)
+        Xqp = np.maximum(Xp + 0.05 * rng.standard_normal(Xp.shape), 0).astype(np.float32)
+        Qref = np.zeros(W.shape)
+        for c in range(C):
+            G1 = Xqp[c].astype(np.float64) @ Xp[c].astype(np.float64).T
+            G2 = Xqp[c].astype(np.float64) @ Xqp[c].astype(np.float64).T
+            Qref[:, :, c, :] = O.gram_quantize_layer(W[:, :, c, :].reshape(9, F), None, None, A, grams=(G1, G2)).reshape(3, 3, F)
+        outs = {}
+        for variant in ("tma", "ldg", "generic"):
+            os.environ["GPFQ_CONV_KERNEL"] = variant
+            try:
+                with GpfqEngine(0) as eng:
+                    outs[variant] = eng.conv_channels(list(Xp), list(Xqp), W, A)
+                    same = eng.conv_channels(list(Xqp), None, W, A)
+                    dev = eng.conv_channels([torch.from_numpy(x).cuda() for x in Xp], [torch.from_numpy(x).cuda() for x in Xqp],
+                                            torch.from_numpy(W).cuda(), A).cpu().numpy()
+                    assert np.array_equal(dev, outs[variant]), (variant, n)
+                    outs[variant + "_same"] = same
+            finally:
+                os.environ.pop("GPFQ_CONV_KERNEL", None)
+        assert O.agreement(outs["tma"], Qref) == 1.0, n
+        assert np.array_equal(outs["tma"], outs["ldg"]) and np.array_equal(outs["tma"], outs["generic"]), n
+        assert np.array_equal(outs["tma_same"], outs["ldg_same"]) and np.array_equal(outs["tma_same"], outs["generic_same"]), n

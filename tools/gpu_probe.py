@@ -19,7 +19,7 @@ def alphabet(W, bits, c):
     return c * med * np.linspace(-1, 1, int(round(2 ** bits)))
 
 
-def dense(eng, N0, N1, m, bits, c, same, methods=("stream", "gram"), reps=2):
+def dense(eng, N0, N1, m, bits, c, same, methods=("stream", "stream_fast", "gram"), reps=2):
     g = torch.Generator(device="cuda").manual_seed(0)
     Z = torch.randn((N0, m), device="cuda", generator=g)
     X = torch.relu(Z)
@@ -42,9 +42,9 @@ def dense(eng, N0, N1, m, bits, c, same, methods=("stream", "gram"), reps=2):
                   f"  sweep {st['ms_sweep']:8.3f}  stream {st['ms_stream']:8.3f}  launches {st['kernel_launches']:5d}"
                   f"  {w / st['ms_total'] * 1e3:.3e} w/s  flops_alg {st['flops_algorithmic']:.3e}"
                   f" -> {st['flops_algorithmic'] / max(st['ms_gram'] if meth == 'gram' else st['ms_stream'], 1e-6) / 1e9:.1f} TF/s")
-    if len(res) == 2:
-        a, b = res["stream"], res["gram"]
-        print(f"    stream vs gram agreement: {float((a == b).double().mean()):.6f}")
+    names = list(res)
+    for other in names[1:]:
+        print(f"    {names[0]} vs {other} agreement: {float((res[names[0]] == res[other]).double().mean()):.6f}")
     del X, Xq, Z, W
     torch.cuda.empty_cache()
 
@@ -88,6 +88,21 @@ if __name__ == "__main__":
                          shell=True, capture_output=True, text=True).stdout)
     eng = get_engine(0)
     t0 = time.time()
+    if len(sys.argv) > 1 and sys.argv[1] == "dense":
+        # python tools/gpu_probe.py dense N0 N1 m bits c same method[,method...] [reps]
+        N0, N1, m = (int(v) for v in sys.argv[2:5])
+        bits, c, same = float(sys.argv[5]), float(sys.argv[6]), sys.argv[7] in ("1", "true", "same")
+        dense(eng, N0, N1, m, bits, c, same, methods=tuple(sys.argv[8].split(",")), reps=int(sys.argv[9]) if len(sys.argv) > 9 else 2)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "sweep":   # BASELINE configs 1-4 Dense shapes
+        shapes = [(784, 500, 25000, True), (500, 300, 25000, False), (300, 10, 25000, False), (2048, 128, 5008, False),
+                  (128, 10, 5008, False), (4096, 4096, 1504, False), (4096, 1000, 1504, False), (25088, 4096, 1504, False),
+                  (1024, 1024, 5000, False), (1024, 1024, 25000, False), (1024, 1024, 100000, False),
+                  (4096, 4096, 5000, False), (4096, 4096, 25000, False), (4096, 4096, 100000, False)]
+        for N0, N1, m, same in shapes:
+            meths = ("stream_fast", "gram") if N0 * N0 * 16 < 40e9 and not (N0 > 8192) else ("stream_fast",)
+            dense(eng, N0, N1, m, np.log2(3), 2, same, methods=meths, reps=1)
+        sys.exit(0)
     dense(eng, 784, 500, 25000, np.log2(3), 2, True)
     dense(eng, 500, 300, 25000, np.log2(3), 2, False)
     dense(eng, 300, 10, 25000, np.log2(3), 2, False)
