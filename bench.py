@@ -11,8 +11,10 @@ One "step" = one pass of the hot path over all eight layers.
 
   value   whole-job weights/s with every input resident in HBM when the timed region starts (CUDA events on the
           launching stream, max over ranks).  Inputs (25.7 GB) are far larger than L2, so no flush is needed.
-  e2e     the same pass through the C ABI with HOST (pinned) buffers: H2D of all patch matrices / activations and
-          D2H of every Q inside the timed region.
+  e2e     the same pass through the reference-facing C ABI with HOST (pinned) buffers, copies inside the timed region.
+          Conv layers go through gpfq_conv_layer_nhwc (the coarser override point of INTEGRATION.md: the layer's
+          (n_img, H, W, C) activations are handed over, patches are extracted on the device -- 9x fewer PCIe bytes
+          than per-channel patch matrices), Dense layers through gpfq_dense_layer; every Q comes back to the host.
   roofline  the dominant kernel (conv_gram_kernel, HBM-bound): algorithmic bytes / CUDA-event time of that stage.
   cpu_baseline  the oracle's NumPy restatement of the reference walk (kind "port": the reference is Python and does
           not travel to the GPU box), one process per host core exactly like the reference's ProcessPoolExecutor, on a
@@ -64,7 +66,9 @@ def make_alphabet(W_abs_median, bits=BITS, c=CSCALAR):
 # synthetic data (device side, torch is only the buffer/generator)
 # ----------------------------------------------------------------------------------------------------------------
 def build_device_inputs(layers, n_img, rank, world, dev):
-    """Per layer: dict with device tensors.  conv: Xp/Xqp lists of (9, n) patch matrices for this rank's channels."""
+    """Per layer: dict with device tensors.  conv: NHWC activations act/actq (what the reference's host code collects,
+    quantized_network.py:468) and, derived from them, Xp/Xqp = per-channel (9, n) patch matrices of this rank's channels
+    (what _build_patch_array hands to the workers, :789-797)."""
     import torch
     out = []
     for li, (name, kind, a, b, H) in enumerate(layers):
@@ -76,29 +80,31 @@ def build_device_inputs(layers, n_img, rank, world, dev):
             lo, hi = shard_range(C, rank, world)
             n = n_img * H * H
             first = li == 0
+            shape = (n_img, H, H, C)
+            if first:   # image-like: uniform[0,1) with half the pixels zero; X == Xq
+                act = torch.rand(shape, device=dev, generator=g) * (torch.rand(shape, device=dev, generator=g) < 0.5)
+                actq = None
+            else:       # hidden: X = relu(Z), Xq = relu(Z + 0.05 N)
+                Z = torch.randn(shape, device=dev, generator=g)
+                act = torch.relu(Z)
+                actq = torch.relu(Z + 0.05 * torch.randn(shape, device=dev, generator=g))
+                del Z
             Xp, Xqp = [], []
             cb = max(1, min(hi - lo, int(1.5e9 // (36 * n))))
             for c0 in range(lo, hi, cb):
                 c1 = min(hi, c0 + cb)
-                gc = torch.Generator(device=dev).manual_seed(5000 + 100 * li + c0)
-                shape = (c1 - c0, n_img, H, H)
-                if first:   # image-like: uniform[0,1) with half the pixels zero; X == Xq
-                    act = torch.rand(shape, device=dev, generator=gc) * (torch.rand(shape, device=dev, generator=gc) < 0.5)
-                    acts = (act,)
-                else:       # hidden: X = relu(Z), Xq = relu(Z + 0.05 N)
-                    Z = torch.randn(shape, device=dev, generator=gc)
-                    acts = (torch.relu(Z), torch.relu(Z + 0.05 * torch.randn(shape, device=dev, generator=gc)))
-                    del Z
                 mats = []
-                for t in acts:
-                    p = torch.nn.functional.unfold(t.reshape(-1, 1, H, H), 3, padding=1)      # (cb*n_img, 9, H*H)
+                for t in ((act,) if first else (act, actq)):
+                    tc = t[..., c0:c1].permute(3, 0, 1, 2).reshape(-1, 1, H, H)
+                    p = torch.nn.functional.unfold(tc, 3, padding=1)                          # (cb*n_img, 9, H*H)
                     p = p.reshape(c1 - c0, n_img, 9, H * H).permute(0, 2, 1, 3).reshape(c1 - c0, 9, n).contiguous()
                     mats.append(p)
+                    del tc
                 Xp += list(mats[0])
                 Xqp += list(mats[0] if first else mats[1])
-                del acts, p
+                del p, mats
             out.append(dict(name=name, kind=kind, W=W, A=A, Xp=Xp, Xqp=None if first else Xqp, c0=lo, n_ch=hi - lo,
-                            n=n, C=C, F=F, first=first))
+                            n=n, C=C, F=F, first=first, act=act, actq=actq))
         else:
             N0, N1 = a, b
             m = n_img if n_img else 25000
@@ -128,7 +134,8 @@ def run_pass_device(eng, data, outs, sync=False):
 
 
 def to_host_pinned(data):
-    """Pinned host copies of every input (what the reference's host code would hand over)."""
+    """Pinned host copies of what the reference's host code holds: NHWC activations per conv layer, (N0, m) matrices per
+    Dense layer, the kernels."""
     import torch
 
     def pin(t):
@@ -139,10 +146,10 @@ def to_host_pinned(data):
     host, nbytes = [], 0
     for d in data:
         if d["kind"] == "conv":
-            Xp = [pin(x) for x in d["Xp"]]
-            Xqp = None if d["Xqp"] is None else [pin(x) for x in d["Xqp"]]
-            nbytes += sum(x.nbytes for x in Xp) + (0 if Xqp is None else sum(x.nbytes for x in Xqp))
-            h = dict(d, Xp=Xp, Xqp=Xqp, W=d["W"].cpu().numpy())
+            act = pin(d["act"])
+            actq = None if d["actq"] is None else pin(d["actq"])
+            nbytes += act.nbytes + (0 if actq is None else actq.nbytes)
+            h = dict(d, act=act, actq=actq, W=d["W"].cpu().numpy(), Xp=None, Xqp=None)
         else:
             X = pin(d["X"])
             Xq = None if d["Xq"] is None else pin(d["Xq"])
@@ -153,16 +160,30 @@ def to_host_pinned(data):
     return host, nbytes
 
 
-def run_pass_host(eng, host):
+def run_pass_host(eng, host, keep=None):
     d2h = 0
     for d in host:
         if d["kind"] == "conv":
-            Q = eng.conv_channels(d["Xp"], d["Xqp"], d["W"], d["A"], c0=d["c0"], n_channels=d["n_ch"])
+            Q = eng.conv_layer_nhwc(d["act"], d["actq"], d["W"], d["A"], c0=d["c0"], n_channels=d["n_ch"])
             d2h += 9 * d["n_ch"] * d["F"] * 8
         else:
             Q = eng.dense_layer(d["X"], d["Xq"], d["W"], d["A"], j0=d["j0"], j1=d["j1"])
             d2h += d["N0"] * (d["j1"] - d["j0"]) * 8
+        if keep is not None:
+            keep.append(Q)
     return d2h
+
+
+def host_channel_patches(act, c):
+    """(9, n) patch matrix of channel c of an NHWC host array, 3x3 'same' stride 1 -- what _build_patch_array yields."""
+    n_img, H = act.shape[0], act.shape[1]
+    p = np.zeros((n_img, H + 2, H + 2), np.float32)
+    p[:, 1:-1, 1:-1] = act[..., c]
+    cols = np.empty((9, n_img * H * H), np.float32)
+    for r in range(3):
+        for cc in range(3):
+            cols[r * 3 + cc] = p[:, r:r + H, cc:cc + H].reshape(-1)
+    return cols
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -236,8 +257,12 @@ def cpu_sample_pass(host_layers, cores, budget_per_layer=2.5):
     jobs = []
     for li, d in enumerate(host_layers):
         if d["kind"] == "conv":
-            X = d["Xp"][0]
-            Xq = X if d["Xqp"] is None else d["Xqp"][0]
+            if d.get("Xp"):
+                X = d["Xp"][0]
+                Xq = X if d["Xqp"] is None else d["Xqp"][0]
+            else:
+                X = host_channel_patches(d["act"], d["c0"])
+                Xq = X if d["actq"] is None else host_channel_patches(d["actq"], d["c0"])
             Wc = np.ascontiguousarray(d["W"][:, :, d["c0"], :].reshape(9, d["F"]))
             units_total = d["n_ch"] * d["F"]
             take = min(d["F"], cores)
@@ -396,8 +421,16 @@ def main():
     e2e = None
     if not args.no_e2e:
         host, h2d_bytes = to_host_pinned(data)
-        run_pass_host(eng, host)  # warm-up (allocates the staging workspaces)
+        kept = []
+        run_pass_host(eng, host, kept)  # warm-up (allocates the staging workspaces)
         barrier()
+        for d, o, Qh in zip(data, outs, kept):   # both entry points must produce the same bits
+            Qd = o[0].cpu().numpy()
+            if d["kind"] == "conv":
+                assert np.array_equal(Qd[:, :, d["c0"]:d["c0"] + d["n_ch"]], Qh[:, :, d["c0"]:d["c0"] + d["n_ch"]]), d["name"]
+            else:
+                assert np.array_equal(Qd[:, d["j0"]:d["j1"]], Qh[:, d["j0"]:d["j1"]]), d["name"]
+        del kept
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
             d2h_bytes = run_pass_host(eng, host)
@@ -409,7 +442,8 @@ def main():
             dt = float(t.item())
         e2e = {"value": total_weights * args.e2e_steps / dt, "unit": "weights/s", "h2d_bytes_per_step": int(h2d_bytes),
                "d2h_bytes_per_step": int(d2h_bytes), "steps": args.e2e_steps, "ms_per_step": dt / args.e2e_steps * 1e3,
-               "timing": "host wall clock around synchronous C-ABI calls (copies + kernels), max over ranks"}
+               "timing": "host wall clock around synchronous C-ABI calls (copies + kernels), max over ranks",
+               "api": "gpfq_conv_layer_nhwc (host NHWC activations) + gpfq_dense_layer (host matrices)"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -4,24 +4,27 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <cmath>
 
 #include "common.cuh"
 
 // kernels / stages implemented in the other translation units
 int dense_gram_path(gpfq_ctx *, const float *, const float *, int64_t, int64_t, int64_t, const float *, int64_t,
-                    int64_t, int64_t, const double *, const int *, int, double *, int64_t, int64_t, gpfq_stats *);
+                    int64_t, int64_t, const double *, const int *, const int *, int, double *, int64_t, int64_t,
+                    gpfq_stats *);
 int dense_stream_path(gpfq_ctx *, const float *, const float *, int64_t, int64_t, int64_t, const float *, int64_t,
-                      int64_t, int64_t, const double *, const int *, int, double *, int64_t, int64_t, gpfq_stats *);
+                      int64_t, int64_t, const double *, const int *, const int *, int, double *, int64_t, int64_t,
+                      gpfq_stats *);
 int dense_gram_only(gpfq_ctx *, const float *, const float *, int64_t, int64_t, int64_t, double *, double *);
 int conv_supported_kk(int kk);
 int conv_pick_chunks(gpfq_ctx *, int64_t, int, int64_t *, int, bool);
-int conv_gram_stage(gpfq_ctx *, int, ConvPtrs, bool, int64_t, int, int, int64_t, double *, bool);
+int conv_gram_stage(gpfq_ctx *, int, ConvPtrs, bool, int64_t, int, int, int64_t, double *, bool, int);
 int conv_finalize_stage(gpfq_ctx *, const double *, int, int, int, bool, double *);
 int conv_sweep_stage(gpfq_ctx *, int, const double *, const float *, double *, int64_t, int64_t, int64_t, int,
-                     const double *, const int *, int);
+                     const double *, const int *, const int *, int);
 int im2col_stage(gpfq_ctx *, const float *, int64_t, int, int, int64_t, int64_t, int, int, int, int, int, int, int,
                  int, int, int, int, float *, int64_t);
-int msq_stage(gpfq_ctx *, const void *, int, int64_t, const double *, int, double *);
+int msq_stage(gpfq_ctx *, const void *, int, int64_t, const double *, int, int, double *);
 
 // ---------------------------------------------------------------------------------------------
 int gpfq_fail(gpfq_ctx *ctx, int code, const char *fmt, ...) {
@@ -114,6 +117,8 @@ extern "C" int gpfq_create(int device, gpfq_ctx **out) {
     ctx->stream = ctx->own_stream;
     if (const char *v = getenv("GPFQ_CONV_KERNEL"))  // A/B switch for profiling: tma (default) | ldg | generic
         ctx->conv_variant = !strcmp(v, "ldg") ? 1 : (!strcmp(v, "generic") ? 2 : 0);
+    if (const char *v = getenv("GPFQ_SWEEP_KERNEL"))  // A/B switch: tile (default) | blocks
+        ctx->sweep_variant = !strcmp(v, "blocks") ? 1 : 0;
     *out = ctx;
     return GPFQ_OK;
 }
@@ -170,8 +175,18 @@ extern "C" int gpfq_set_stream(gpfq_ctx *ctx, void *cuda_stream) {
 struct Alphabets {
     const double *d_levels = nullptr;
     const int *d_koff = nullptr;
-    std::vector<int> h_koff;
+    const int *d_flags = nullptr;  // per alphabet: 1 = ascending and equispaced (fast rounding window)
+    std::vector<int> h_koff, h_flags;
 };
+
+static int alphabet_is_equispaced(const double *a, int K) {
+    if (K < 2) return 0;
+    const double step = (a[K - 1] - a[0]) / (K - 1);
+    if (!(step > 0.0) || !std::isfinite(step)) return 0;
+    for (int k = 0; k < K; ++k)
+        if (!(fabs(a[k] - (a[0] + k * step)) <= 0.01 * step)) return 0;
+    return 1;
+}
 
 static int upload_alphabets(gpfq_ctx *ctx, const double *alphabets, const int32_t *K, int n_alph, Alphabets *out) {
     if (!alphabets || !K || n_alph < 1 || n_alph > 1024) return gpfq_fail(ctx, GPFQ_ERR_ARG, "bad alphabet arguments");
@@ -183,10 +198,14 @@ static int upload_alphabets(gpfq_ctx *ctx, const double *alphabets, const int32_
     }
     const size_t nlev = out->h_koff[n_alph];
     const size_t lev_bytes = nlev * sizeof(double);
-    const size_t bytes = (lev_bytes + (n_alph + 1) * sizeof(int) + 15) & ~(size_t)15;
+    out->h_flags.assign(n_alph, 0);
+    for (int a = 0; a < n_alph; ++a) out->h_flags[a] = alphabet_is_equispaced(alphabets + out->h_koff[a], K[a]);
+    const size_t koff_bytes = (n_alph + 1) * sizeof(int);
+    const size_t bytes = (lev_bytes + koff_bytes + n_alph * sizeof(int) + 15) & ~(size_t)15;
     std::vector<char> blob(bytes, 0);
     memcpy(blob.data(), alphabets, lev_bytes);
-    memcpy(blob.data() + lev_bytes, out->h_koff.data(), (n_alph + 1) * sizeof(int));
+    memcpy(blob.data() + lev_bytes, out->h_koff.data(), koff_bytes);
+    memcpy(blob.data() + lev_bytes + koff_bytes, out->h_flags.data(), n_alph * sizeof(int));
     const size_t cap = (size_t)1 << 20;
     char *d = nullptr;
     GPFQ_TRY(gpfq_ws(ctx, WS_ALPH, cap, (void **)&d));
@@ -210,6 +229,7 @@ static int upload_alphabets(gpfq_ctx *ctx, const double *alphabets, const int32_
     }
     out->d_levels = reinterpret_cast<const double *>(d + hit->off);
     out->d_koff = reinterpret_cast<const int *>(d + hit->off + lev_bytes);
+    out->d_flags = reinterpret_cast<const int *>(d + hit->off + lev_bytes + koff_bytes);
     return GPFQ_OK;
 }
 
@@ -351,12 +371,12 @@ extern "C" int gpfq_dense_layer(gpfq_ctx *ctx, const float *X, const float *Xq, 
     CUDA_TRY(ctx, gpfq_record(ctx, 5, s));
 
     if (method == GPFQ_METHOD_GRAM)
-        GPFQ_TRY(dense_gram_path(ctx, dX, dXq, dldx, N0, m, dW, dldw, dj0, nj, al.d_levels, al.d_koff, n_alph, dQ, dldq,
-                                 col0, stats));
+        GPFQ_TRY(dense_gram_path(ctx, dX, dXq, dldx, N0, m, dW, dldw, dj0, nj, al.d_levels, al.d_koff, al.d_flags, n_alph, dQ,
+                                 dldq, col0, stats));
     else {
         ctx->stream_literal = (method == GPFQ_METHOD_STREAM);
-        GPFQ_TRY(dense_stream_path(ctx, dX, dXq, dldx, N0, m, dW, dldw, dj0, nj, al.d_levels, al.h_koff.data(), n_alph,
-                                   dQ, dldq, col0, stats));
+        GPFQ_TRY(dense_stream_path(ctx, dX, dXq, dldx, N0, m, dW, dldw, dj0, nj, al.d_levels, al.h_koff.data(),
+                                   al.h_flags.data(), n_alph, dQ, dldq, col0, stats));
         if (stats) stats->method = method >> 4;
     }
     CUDA_TRY(ctx, gpfq_record(ctx, 6, s));
@@ -432,7 +452,7 @@ static int conv_finish(gpfq_ctx *ctx, int kk, const double *partial, int n_ch, i
     }
     double *dQ = Q_out;
     if (!(flags & GPFQ_Q_DEVICE)) GPFQ_TRY(gpfq_ws(ctx, WS_Q, (size_t)n_alph * wcount * sizeof(double), (void **)&dQ));
-    GPFQ_TRY(conv_sweep_stage(ctx, kk, gram, dW, dQ, C, F, c0, n_ch, al.d_levels, al.d_koff, n_alph));
+    GPFQ_TRY(conv_sweep_stage(ctx, kk, gram, dW, dQ, C, F, c0, n_ch, al.d_levels, al.d_koff, al.d_flags, n_alph));
     CUDA_TRY(ctx, gpfq_record(ctx, 4, s));
     if (!(flags & GPFQ_Q_DEVICE)) {
         for (int a = 0; a < n_alph; ++a) {
@@ -516,7 +536,7 @@ extern "C" int gpfq_conv_channels(gpfq_ctx *ctx, const float *const *Xp, const f
         }
         CUDA_TRY(ctx, cudaMemcpyAsync(d_ptrs, h_ptrs.data(), h_ptrs.size() * sizeof(float *), cudaMemcpyHostToDevice, s));
         ConvPtrs p{d_ptrs, d_ptrs + n_ch};
-        GPFQ_TRY(conv_gram_stage(ctx, kk, p, same, n, (int)n_ch, n_chunks, chunk_cols, partial, vec_ok));
+        GPFQ_TRY(conv_gram_stage(ctx, kk, p, same, n, (int)n_ch, n_chunks, chunk_cols, partial, vec_ok, n_chunks));
     } else {
         // host patches: double-buffered channel batches, copies on the copy stream overlap the Gram kernel
         const size_t per_ch = ch_bytes * (same ? 1 : 2);
@@ -554,7 +574,7 @@ extern "C" int gpfq_conv_channels(gpfq_ctx *ctx, const float *const *Xp, const f
                                           cudaMemcpyHostToDevice, s));
             ConvPtrs p{d_ptrs + b0, d_ptrs + n_ch + b0};
             GPFQ_TRY(conv_gram_stage(ctx, kk, p, same, n, (int)nb, n_chunks, chunk_cols,
-                                     partial + (size_t)b0 * n_chunks * 2 * kk * kk, vec_ok));
+                                     partial + (size_t)b0 * n_chunks * 2 * kk * kk, vec_ok, n_chunks));
             CUDA_TRY(ctx, cudaEventRecord(ctx->ev_copy[bi & 1], s));
         }
     }
@@ -608,24 +628,41 @@ extern "C" int gpfq_conv_layer_nhwc(gpfq_ctx *ctx, const float *act, const float
     Alphabets al;
     GPFQ_TRY(upload_alphabets(ctx, alphabets, K, n_alph, &al));
     const float *dA = act, *dAq = same ? act : actq;
-    const size_t abytes = (size_t)n_img * H * Wd * C * sizeof(float);
-    if (!(flags & GPFQ_X_DEVICE)) {
+    const size_t img_elems = (size_t)H * Wd * C;
+    const size_t abytes = (size_t)n_img * img_elems * sizeof(float);
+    const bool host_act = !(flags & GPFQ_X_DEVICE);
+    // Host activations: the images go over in chunks on the copy stream while the compute stream turns the chunks
+    // that have landed into patches and partial Grams (the Gram is a sum over patches, so image chunks are just
+    // more partial slots, summed in index order by the finalize kernel).
+    int64_t ipc = n_img;  // images per chunk
+    if (host_act) {
+        const size_t target = (size_t)96 << 20;
+        ipc = (int64_t)std::max<size_t>(1, target / (img_elems * sizeof(float)));
+        ipc = std::max<int64_t>(ipc, ceil_div64(n_img, 32));  // at most 32 chunks
+        ipc = std::min<int64_t>(ceil_div64(ipc, 4) * 4, n_img);
+    }
+    const int n_ic = (int)ceil_div64(n_img, ipc);
+    if (host_act) {
         float *ba = nullptr, *bq = nullptr;
         GPFQ_TRY(gpfq_ws(ctx, WS_ACT_A, abytes, (void **)&ba));
-        CUDA_TRY(ctx, cudaMemcpyAsync(ba, act, abytes, cudaMemcpyHostToDevice, s));
         dA = dAq = ba;
         if (!same) {
             GPFQ_TRY(gpfq_ws(ctx, WS_ACT_B, abytes, (void **)&bq));
-            CUDA_TRY(ctx, cudaMemcpyAsync(bq, actq, abytes, cudaMemcpyHostToDevice, s));
             dAq = bq;
         }
     }
     CUDA_TRY(ctx, gpfq_record(ctx, 5, s));
+    const int64_t hw_out = (int64_t)Ho * Wo;
+    const int64_t n_c = ipc * hw_out;  // patch columns of a full image chunk
+    bool vec_ok = n_c % 4 == 0 && ((n_img - (int64_t)(n_ic - 1) * ipc) * hw_out) % 4 == 0;
     int64_t chunk_cols = 0;
-    const int n_chunks = conv_pick_chunks(ctx, n, (int)std::min<int64_t>(n_ch, 64), &chunk_cols, kk, n % 4 == 0);
+    const int n_chunks = conv_pick_chunks(ctx, n_c, (int)std::min<int64_t>(n_ch, 64), &chunk_cols, kk, vec_ok);
+    const int slots = n_ic * n_chunks;
     double *partial = nullptr;
-    GPFQ_TRY(gpfq_ws(ctx, WS_CPART, (size_t)n_ch * n_chunks * 2 * kk * kk * sizeof(double), (void **)&partial));
-    const size_t ch_elems = (size_t)kk * n;
+    const size_t part_bytes = (size_t)n_ch * slots * 2 * kk * kk * sizeof(double);
+    GPFQ_TRY(gpfq_ws(ctx, WS_CPART, part_bytes, (void **)&partial));
+    if (n_ic > 1) CUDA_TRY(ctx, cudaMemsetAsync(partial, 0, part_bytes, s));  // a short last chunk leaves slots unused
+    const size_t ch_elems = (size_t)kk * n_c;
     const size_t per_ch = ch_elems * sizeof(float);
     const size_t budget = (size_t)8 << 30;
     int64_t bch = (int64_t)std::max<size_t>(1, budget / (per_ch * (same ? 1 : 2)));
@@ -634,27 +671,48 @@ extern "C" int gpfq_conv_layer_nhwc(gpfq_ctx *ctx, const float *act, const float
     GPFQ_TRY(gpfq_ws(ctx, WS_PATCH_A, (size_t)bch * per_ch, (void **)&pa));
     if (!same) GPFQ_TRY(gpfq_ws(ctx, WS_PATCH_B, (size_t)bch * per_ch, (void **)&pq));
     const float **d_ptrs = nullptr;
-    GPFQ_TRY(gpfq_ws(ctx, WS_PTRS, (size_t)2 * bch * sizeof(float *), (void **)&d_ptrs));
-    std::vector<const float *> h_ptrs(2 * bch);
-    for (int64_t i = 0; i < bch; ++i) {
-        h_ptrs[i] = pa + (size_t)i * ch_elems;
-        h_ptrs[bch + i] = same ? h_ptrs[i] : pq + (size_t)i * ch_elems;
-    }
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_ptrs, h_ptrs.data(), h_ptrs.size() * sizeof(float *), cudaMemcpyHostToDevice, s));
+    GPFQ_TRY(gpfq_ws(ctx, WS_PTRS, (size_t)2 * bch * n_ic * sizeof(float *), (void **)&d_ptrs));
     CUDA_TRY(ctx, gpfq_record(ctx, 2, s));
-    for (int64_t b0 = 0; b0 < n_ch; b0 += bch) {
-        const int64_t nb = std::min<int64_t>(bch, n_ch - b0);
-        GPFQ_TRY(im2col_stage(ctx, dA, n_img, (int)H, (int)Wd, C, c0 + b0, (int)nb, kh, kw, sh, sw, rh, rw, pt, pl, Ho, Wo,
-                              pa, (int64_t)ch_elems));
-        if (!same)
-            GPFQ_TRY(im2col_stage(ctx, dAq, n_img, (int)H, (int)Wd, C, c0 + b0, (int)nb, kh, kw, sh, sw, rh, rw, pt, pl, Ho,
-                                  Wo, pq, (int64_t)ch_elems));
-        ConvPtrs p{d_ptrs, d_ptrs + bch};
-        GPFQ_TRY(conv_gram_stage(ctx, kk, p, same, n, (int)nb, n_chunks, chunk_cols,
-                                 partial + (size_t)b0 * n_chunks * 2 * kk * kk, n % 4 == 0));
+    if (host_act) {  // the copy stream may not overwrite the staging buffers before earlier work on s is done
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_copy[2], s));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy[2], 0));
+    }
+    std::vector<const float *> h_ptrs((size_t)2 * bch * n_ic);
+    for (int ic = 0; ic < n_ic; ++ic) {
+        const int64_t img0 = (int64_t)ic * ipc;
+        const int64_t imgs = std::min<int64_t>(ipc, n_img - img0);
+        const int64_t n_this = imgs * hw_out;
+        if (host_act) {
+            const size_t off = (size_t)img0 * img_elems, bytes = (size_t)imgs * img_elems * sizeof(float);
+            CUDA_TRY(ctx, cudaMemcpyAsync(const_cast<float *>(dA) + off, act + off, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+            if (!same)
+                CUDA_TRY(ctx, cudaMemcpyAsync(const_cast<float *>(dAq) + off, actq + off, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_copy[ic & 1], ctx->copy_stream));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->ev_copy[ic & 1], 0));
+        }
+        // patch pointers of this chunk: channel i at pa + i * kk * n_this (rows stay 16-byte aligned when vec_ok)
+        const float **hp = h_ptrs.data() + (size_t)2 * bch * ic;
+        for (int64_t i = 0; i < bch; ++i) {
+            hp[i] = pa + (size_t)i * kk * n_this;
+            hp[bch + i] = same ? hp[i] : pq + (size_t)i * kk * n_this;
+        }
+        const float **dp = d_ptrs + (size_t)2 * bch * ic;
+        CUDA_TRY(ctx, cudaMemcpyAsync(dp, hp, (size_t)2 * bch * sizeof(float *), cudaMemcpyHostToDevice, s));
+        const int chunks_this = (int)ceil_div64(n_this, chunk_cols);
+        for (int64_t b0 = 0; b0 < n_ch; b0 += bch) {
+            const int64_t nb = std::min<int64_t>(bch, n_ch - b0);
+            GPFQ_TRY(im2col_stage(ctx, dA + (size_t)img0 * img_elems, imgs, (int)H, (int)Wd, C, c0 + b0, (int)nb, kh, kw, sh, sw,
+                                  rh, rw, pt, pl, Ho, Wo, pa, (int64_t)kk * n_this));
+            if (!same)
+                GPFQ_TRY(im2col_stage(ctx, dAq + (size_t)img0 * img_elems, imgs, (int)H, (int)Wd, C, c0 + b0, (int)nb, kh, kw,
+                                      sh, sw, rh, rw, pt, pl, Ho, Wo, pq, (int64_t)kk * n_this));
+            ConvPtrs p{dp, dp + bch};
+            GPFQ_TRY(conv_gram_stage(ctx, kk, p, same, n_this, (int)nb, chunks_this, chunk_cols,
+                                     partial + ((size_t)b0 * slots + (size_t)ic * n_chunks) * 2 * kk * kk, vec_ok, slots));
+        }
     }
     CUDA_TRY(ctx, gpfq_record(ctx, 3, s));
-    GPFQ_TRY(conv_finish(ctx, kk, partial, (int)n_ch, n_chunks, same, W, C, F, c0, al, n_alph, Q_out, flags));
+    GPFQ_TRY(conv_finish(ctx, kk, partial, (int)n_ch, slots, same, W, C, F, c0, al, n_alph, Q_out, flags));
     CUDA_TRY(ctx, gpfq_record(ctx, 1, s));
     gpfq_stats local = {};
     conv_stats(ctx, stats ? stats : &local, kk, n, n_ch, F, same, n_alph);
@@ -685,7 +743,7 @@ static int round_elements(gpfq_ctx *ctx, const void *W, int is_f64, int64_t n, c
     }
     double *dQ = Q_out;
     if (!(flags & GPFQ_Q_DEVICE)) GPFQ_TRY(gpfq_ws(ctx, WS_Q, (size_t)n * sizeof(double), (void **)&dQ));
-    GPFQ_TRY(msq_stage(ctx, dW, is_f64, n, al.d_levels, K, dQ));
+    GPFQ_TRY(msq_stage(ctx, dW, is_f64, n, al.d_levels, K, al.h_flags[0], dQ));
     if (!(flags & GPFQ_Q_DEVICE))
         CUDA_TRY(ctx, cudaMemcpyAsync(Q_out, dQ, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (!(flags & GPFQ_NO_SYNC) || !(flags & GPFQ_Q_DEVICE)) CUDA_TRY(ctx, cudaStreamSynchronize(s));

@@ -25,7 +25,7 @@ struct ConvPtrs {
 };
 
 struct AlphEntry {
-    std::vector<char> blob;  // levels (fp64) followed by the prefix offsets (int32)
+    std::vector<char> blob;  // levels (fp64), the prefix offsets (int32), one equispaced flag per alphabet (int32)
     size_t off = 0;          // byte offset inside the WS_ALPH device buffer
 };
 
@@ -53,6 +53,7 @@ struct gpfq_ctx {
     std::string err = "";
     int launches = 0;
     int conv_variant = 0;         // 3x3 patch-Gram kernel: 0 TMA-staged (default), 1 direct LDG, 2 generic
+    int sweep_variant = 0;        // triangular sweep: 0 persistent neuron-tile kernel (default), 1 one launch pair per block
     bool stream_literal = false;  // streaming walk: reproduce the reference's fp32-rounded w*X products (set per call)
     // grow-only named workspaces
     DevBuf ws[24];
@@ -113,15 +114,40 @@ __device__ __forceinline__ double gpfq_bit_round(double v, const double *__restr
     return best;
 }
 
+// The same quantizer when the levels are ascending and equispaced (`rad * linspace(-1, 1, K)`, :396/:545 -- the host
+// checks this per alphabet): |a_k - v| is unimodal in k, so the first minimal index of the full scan lies in a window
+// of four levels around the grid guess.  The window is scanned with the very same subtraction / abs / strict-less
+// comparisons in ascending order, so ties still go to the lower index.  inv_step <= 0: literal scan.
+__device__ __forceinline__ double gpfq_bit_round_eq(double v, const double *__restrict__ alph, int K, double inv_step) {
+    const double gpos = (v - alph[0]) * inv_step;
+    if (!(inv_step > 0.0) || !(fabs(gpos) < 1e9)) return gpfq_bit_round(v, alph, K);  // also NaN / inf arguments
+    int k0 = (int)floor(gpos) - 1;
+    k0 = k0 < 0 ? 0 : (k0 > K - 1 ? K - 1 : k0);
+    const int k1 = k0 + 3 < K - 1 ? k0 + 3 : K - 1;
+    double best = alph[k0];
+    double bd = fabs(__dsub_rn(best, v));
+    for (int k = k0 + 1; k <= k1; ++k) {
+        const double a = alph[k];
+        const double d = fabs(__dsub_rn(a, v));
+        if (d < bd) { bd = d; best = a; }
+    }
+    return best;
+}
+
+// inv_step of an alphabet staged in shared memory (flag from the host: 1 = ascending and equispaced)
+__device__ __forceinline__ double gpfq_inv_step(const double *alph, int K, int equispaced) {
+    return (equispaced && K >= 2) ? (double)(K - 1) / (alph[K - 1] - alph[0]) : 0.0;
+}
+
 // One greedy decision in Gram form:
 //   nrm  = (double)(float)sqrt(G2[t,t])         (snrm2 result, quantized_network.py:83)
 //   d    = <Xq_t, u_{t-1}>                       (:86)
 //   num  = <Xq_t, u_{t-1} + w_t X_t>             (:89)
 __device__ __forceinline__ double gpfq_decide(double nrm, double d, double num, double w,
-                                              const double *__restrict__ alph, int K) {
+                                              const double *__restrict__ alph, int K, double inv_step = 0.0) {
     if (nrm < GPFQ_DEAD_NORM) return 0.0;
-    if (fabs(d) < GPFQ_PERP_DOT) return gpfq_bit_round(w, alph, K);
-    return gpfq_bit_round(num / (nrm * nrm), alph, K);
+    if (fabs(d) < GPFQ_PERP_DOT) return gpfq_bit_round_eq(w, alph, K, inv_step);
+    return gpfq_bit_round_eq(num / (nrm * nrm), alph, K, inv_step);
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

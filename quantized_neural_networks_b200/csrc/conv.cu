@@ -92,14 +92,14 @@ __device__ __forceinline__ void conv_gram_body(const float *__restrict__ X, cons
 // partial: (n_channels, n_chunks, 2*KK*KK)
 template <int KK, bool SAME, int NG>
 __global__ void __launch_bounds__(CONV_BLOCK, 1)
-conv_gram_kernel(ConvPtrs ptrs, int64_t n, int64_t chunk_cols, double *__restrict__ partial) {
+conv_gram_kernel(ConvPtrs ptrs, int64_t n, int64_t chunk_cols, double *__restrict__ partial, int slots) {
     __shared__ double red[(CONV_BLOCK / 32) * 2 * KK * KK];
     const int ch = blockIdx.y, chunk = blockIdx.x;
     const float *X = ptrs.Xp[ch];
     const float *Xq = SAME ? X : ptrs.Xqp[ch];
     const int64_t c_beg = (int64_t)chunk * chunk_cols;
     const int64_t c_end = (c_beg + chunk_cols < n) ? c_beg + chunk_cols : n;
-    double *out = partial + ((size_t)ch * gridDim.x + chunk) * (2 * KK * KK);
+    double *out = partial + ((size_t)ch * slots + chunk) * (2 * KK * KK);
     constexpr int GT = CONV_BLOCK / NG;
     const int g = threadIdx.x / GT, tg = threadIdx.x % GT;
     if (NG == 1) {
@@ -192,7 +192,7 @@ __device__ __forceinline__ void gram9_store(Gram9Acc &acc, double *r, int g, int
 
 template <bool SAME>
 __global__ void __launch_bounds__(CONV_BLOCK, 2)
-conv_gram9_dmma_kernel(ConvPtrs ptrs, int64_t n, int64_t chunk_cols, double *__restrict__ partial) {
+conv_gram9_dmma_kernel(ConvPtrs ptrs, int64_t n, int64_t chunk_cols, double *__restrict__ partial, int slots) {
     constexpr int KK = 9, NW = CONV_BLOCK / 32, SZ = 2 * KK * KK;
     __shared__ double red[NW][SZ];
     const int ch = blockIdx.y, chunk = blockIdx.x;
@@ -244,7 +244,7 @@ conv_gram9_dmma_kernel(ConvPtrs ptrs, int64_t n, int64_t chunk_cols, double *__r
     }
     gram9_store<SAME>(acc, red[warp], g, k);
     __syncthreads();
-    double *out = partial + ((size_t)ch * gridDim.x + chunk) * SZ;
+    double *out = partial + ((size_t)ch * slots + chunk) * SZ;
     for (int e = threadIdx.x; e < SZ; e += CONV_BLOCK) {
         if (SAME && e < KK * KK) continue;
         double tot = 0.0;
@@ -294,7 +294,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 
 template <bool SAME>
 __global__ void __launch_bounds__(tma9::THREADS, 1)
-conv_gram9_tma_kernel(ConvPtrs ptrs, int64_t n, int64_t chunk_cols, double *__restrict__ partial) {
+conv_gram9_tma_kernel(ConvPtrs ptrs, int64_t n, int64_t chunk_cols, double *__restrict__ partial, int slots) {
     using namespace tma9;
     constexpr int KK = 9, SZ = 2 * KK * KK, ROWS = SAME ? KK : 2 * KK;
     constexpr int STAGE_FLOATS = ROWS * PITCH;
@@ -376,7 +376,7 @@ conv_gram9_tma_kernel(ConvPtrs ptrs, int64_t n, int64_t chunk_cols, double *__re
     gram9_store<SAME>(acc, red + warp * SZ, g, k);
     // consumer-only barrier (the producer warp has left)
     asm volatile("bar.sync 1, %0;\n" ::"r"(CWARPS * 32));
-    double *out = partial + ((size_t)ch * gridDim.x + chunk) * SZ;
+    double *out = partial + ((size_t)ch * slots + chunk) * SZ;
     for (int e = threadIdx.x; e < SZ; e += CWARPS * 32) {
         if (SAME && e < KK * KK) continue;
         double tot = 0.0;
@@ -408,7 +408,7 @@ template <int KK>
 __global__ void __launch_bounds__(128)
 conv_sweep_kernel(const double *__restrict__ gram, const float *__restrict__ W, double *__restrict__ Q,
                   int64_t CF, int64_t F, int64_t c0, const double *__restrict__ alphabets,
-                  const int *__restrict__ Koff, int64_t q_alph_stride) {
+                  const int *__restrict__ Koff, const int *__restrict__ Flags, int64_t q_alph_stride) {
     __shared__ double g1[KK * KK], g2[KK * KK], nrm[KK], alph[GPFQ_MAX_K];
     const int ch = blockIdx.y, a = blockIdx.z;
     const int K = Koff[a + 1] - Koff[a];
@@ -420,6 +420,7 @@ conv_sweep_kernel(const double *__restrict__ gram, const float *__restrict__ W, 
     __syncthreads();
     if (threadIdx.x < KK) nrm[threadIdx.x] = (double)(float)sqrt(g2[threadIdx.x * KK + threadIdx.x]);
     __syncthreads();
+    const double inv_step = gpfq_inv_step(alph, K, Flags[a]);
     const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= F) return;
     const int64_t base = (c0 + ch) * F + f;
@@ -433,7 +434,7 @@ conv_sweep_kernel(const double *__restrict__ gram, const float *__restrict__ W, 
         for (int s = 0; s < KK; ++s)
             if (s < t) d += w[s] * g1[t * KK + s] - q[s] * g2[t * KK + s];
         const double num = fma(w[t], g1[t * KK + t], d);
-        q[t] = gpfq_decide(nrm[t], d, num, w[t], alph, K);
+        q[t] = gpfq_decide(nrm[t], d, num, w[t], alph, K, inv_step);
         Q[(int64_t)a * q_alph_stride + (int64_t)t * CF + base] = q[t];
     }
 }
@@ -461,13 +462,14 @@ __global__ void im2col_kernel(const float *__restrict__ act, int64_t n_img, int 
 
 // ---- MSQ -------------------------------------------------------------------------------------
 template <typename T>
-__global__ void msq_kernel(const T *__restrict__ W, int64_t n, const double *__restrict__ alphabet, int K,
+__global__ void msq_kernel(const T *__restrict__ W, int64_t n, const double *__restrict__ alphabet, int K, int equispaced,
                            double *__restrict__ Q) {
     __shared__ double alph[GPFQ_MAX_K];
     for (int e = threadIdx.x; e < K; e += blockDim.x) alph[e] = alphabet[e];
     __syncthreads();
+    const double inv_step = gpfq_inv_step(alph, K, equispaced);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        Q[i] = gpfq_bit_round((double)W[i], alph, K);
+        Q[i] = gpfq_bit_round_eq((double)W[i], alph, K, inv_step);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -475,7 +477,7 @@ __global__ void msq_kernel(const T *__restrict__ W, int64_t n, const double *__r
 // ---------------------------------------------------------------------------------------------
 template <int KK>
 static int launch_conv_gram(gpfq_ctx *ctx, ConvPtrs ptrs, bool same, int64_t n, int n_ch, int n_chunks,
-                            int64_t chunk_cols, double *partial, bool vec_ok) {
+                            int64_t chunk_cols, double *partial, bool vec_ok, int slots) {
     dim3 grid((unsigned)n_chunks, (unsigned)n_ch);
     if (KK == 9 && vec_ok && ctx->conv_variant == 0) {
         using namespace tma9;
@@ -483,23 +485,23 @@ static int launch_conv_gram(gpfq_ctx *ctx, ConvPtrs ptrs, bool same, int64_t n, 
         const size_t smem = (size_t)STAGES * (same ? 9 : 18) * PITCH * sizeof(float) + tail;
         if (same) {
             CUDA_TRY(ctx, cudaFuncSetAttribute(conv_gram9_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            conv_gram9_tma_kernel<true><<<grid, THREADS, smem, ctx->stream>>>(ptrs, n, chunk_cols, partial);
+            conv_gram9_tma_kernel<true><<<grid, THREADS, smem, ctx->stream>>>(ptrs, n, chunk_cols, partial, slots);
         } else {
             CUDA_TRY(ctx, cudaFuncSetAttribute(conv_gram9_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            conv_gram9_tma_kernel<false><<<grid, THREADS, smem, ctx->stream>>>(ptrs, n, chunk_cols, partial);
+            conv_gram9_tma_kernel<false><<<grid, THREADS, smem, ctx->stream>>>(ptrs, n, chunk_cols, partial, slots);
         }
         KERNEL_CHECK(ctx);
         return GPFQ_OK;
     }
     if (KK == 9 && vec_ok && ctx->conv_variant == 1) {
-        if (same) conv_gram9_dmma_kernel<true><<<grid, CONV_BLOCK, 0, ctx->stream>>>(ptrs, n, chunk_cols, partial);
-        else conv_gram9_dmma_kernel<false><<<grid, CONV_BLOCK, 0, ctx->stream>>>(ptrs, n, chunk_cols, partial);
+        if (same) conv_gram9_dmma_kernel<true><<<grid, CONV_BLOCK, 0, ctx->stream>>>(ptrs, n, chunk_cols, partial, slots);
+        else conv_gram9_dmma_kernel<false><<<grid, CONV_BLOCK, 0, ctx->stream>>>(ptrs, n, chunk_cols, partial, slots);
         KERNEL_CHECK(ctx);
         return GPFQ_OK;
     }
     constexpr int NG = (KK >= 9) ? 2 : 1;
-    if (same) conv_gram_kernel<KK, true, 1><<<grid, CONV_BLOCK, 0, ctx->stream>>>(ptrs, n, chunk_cols, partial);
-    else conv_gram_kernel<KK, false, NG><<<grid, CONV_BLOCK, 0, ctx->stream>>>(ptrs, n, chunk_cols, partial);
+    if (same) conv_gram_kernel<KK, true, 1><<<grid, CONV_BLOCK, 0, ctx->stream>>>(ptrs, n, chunk_cols, partial, slots);
+    else conv_gram_kernel<KK, false, NG><<<grid, CONV_BLOCK, 0, ctx->stream>>>(ptrs, n, chunk_cols, partial, slots);
     KERNEL_CHECK(ctx);
     return GPFQ_OK;
 }
@@ -525,15 +527,17 @@ int conv_pick_chunks(gpfq_ctx *ctx, int64_t n, int n_ch, int64_t *chunk_cols, in
 }
 
 // Gram partials of n_ch channels whose patch pointers (device) are in d_ptrs.
+// `slots` = partial slots per channel (>= n_chunks; image-chunked callers interleave several launches), this launch
+// fills slots [0, n_chunks) relative to `partial`.
 int conv_gram_stage(gpfq_ctx *ctx, int kk, ConvPtrs d_ptrs, bool same, int64_t n, int n_ch, int n_chunks,
-                    int64_t chunk_cols, double *partial, bool vec_ok) {
+                    int64_t chunk_cols, double *partial, bool vec_ok, int slots) {
     switch (kk) {
-        case 1: return launch_conv_gram<1>(ctx, d_ptrs, same, n, n_ch, n_chunks, chunk_cols, partial, vec_ok);
-        case 2: return launch_conv_gram<2>(ctx, d_ptrs, same, n, n_ch, n_chunks, chunk_cols, partial, vec_ok);
-        case 3: return launch_conv_gram<3>(ctx, d_ptrs, same, n, n_ch, n_chunks, chunk_cols, partial, vec_ok);
-        case 4: return launch_conv_gram<4>(ctx, d_ptrs, same, n, n_ch, n_chunks, chunk_cols, partial, vec_ok);
-        case 6: return launch_conv_gram<6>(ctx, d_ptrs, same, n, n_ch, n_chunks, chunk_cols, partial, vec_ok);
-        case 9: return launch_conv_gram<9>(ctx, d_ptrs, same, n, n_ch, n_chunks, chunk_cols, partial, vec_ok);
+        case 1: return launch_conv_gram<1>(ctx, d_ptrs, same, n, n_ch, n_chunks, chunk_cols, partial, vec_ok, slots);
+        case 2: return launch_conv_gram<2>(ctx, d_ptrs, same, n, n_ch, n_chunks, chunk_cols, partial, vec_ok, slots);
+        case 3: return launch_conv_gram<3>(ctx, d_ptrs, same, n, n_ch, n_chunks, chunk_cols, partial, vec_ok, slots);
+        case 4: return launch_conv_gram<4>(ctx, d_ptrs, same, n, n_ch, n_chunks, chunk_cols, partial, vec_ok, slots);
+        case 6: return launch_conv_gram<6>(ctx, d_ptrs, same, n, n_ch, n_chunks, chunk_cols, partial, vec_ok, slots);
+        case 9: return launch_conv_gram<9>(ctx, d_ptrs, same, n, n_ch, n_chunks, chunk_cols, partial, vec_ok, slots);
     }
     return gpfq_fail(ctx, GPFQ_ERR_UNSUPPORTED, "conv kernel size kk=%d has no specialised kernel", kk);
 }
@@ -546,11 +550,12 @@ int conv_finalize_stage(gpfq_ctx *ctx, const double *partial, int n_ch, int n_ch
 }
 
 int conv_sweep_stage(gpfq_ctx *ctx, int kk, const double *gram, const float *W, double *Q, int64_t C,
-                     int64_t F, int64_t c0, int n_ch, const double *d_alph, const int *d_koff, int n_alph) {
+                     int64_t F, int64_t c0, int n_ch, const double *d_alph, const int *d_koff, const int *d_flags,
+                     int n_alph) {
     dim3 grid((unsigned)ceil_div64(F, 128), (unsigned)n_ch, (unsigned)n_alph);
     const int64_t CF = C * F, qs = (int64_t)kk * CF;
 #define SWEEP_CASE(KKV) \
-    case KKV: conv_sweep_kernel<KKV><<<grid, 128, 0, ctx->stream>>>(gram, W, Q, CF, F, c0, d_alph, d_koff, qs); break;
+    case KKV: conv_sweep_kernel<KKV><<<grid, 128, 0, ctx->stream>>>(gram, W, Q, CF, F, c0, d_alph, d_koff, d_flags, qs); break;
     switch (kk) {
         SWEEP_CASE(1) SWEEP_CASE(2) SWEEP_CASE(3) SWEEP_CASE(4) SWEEP_CASE(6) SWEEP_CASE(9)
         default: return gpfq_fail(ctx, GPFQ_ERR_UNSUPPORTED, "conv kernel size kk=%d has no specialised kernel", kk);
@@ -572,11 +577,11 @@ int im2col_stage(gpfq_ctx *ctx, const float *act, int64_t n_img, int H, int Wd, 
     return GPFQ_OK;
 }
 
-int msq_stage(gpfq_ctx *ctx, const void *W, int is_f64, int64_t n, const double *d_alph, int K, double *Q) {
+int msq_stage(gpfq_ctx *ctx, const void *W, int is_f64, int64_t n, const double *d_alph, int K, int equispaced, double *Q) {
     int bx = (int)(ceil_div64(n, 256) < 1184 ? ceil_div64(n, 256) : 1184);
     if (bx < 1) bx = 1;
-    if (is_f64) msq_kernel<double><<<bx, 256, 0, ctx->stream>>>((const double *)W, n, d_alph, K, Q);
-    else msq_kernel<float><<<bx, 256, 0, ctx->stream>>>((const float *)W, n, d_alph, K, Q);
+    if (is_f64) msq_kernel<double><<<bx, 256, 0, ctx->stream>>>((const double *)W, n, d_alph, K, equispaced, Q);
+    else msq_kernel<float><<<bx, 256, 0, ctx->stream>>>((const float *)W, n, d_alph, K, equispaced, Q);
     KERNEL_CHECK(ctx);
     return GPFQ_OK;
 }

@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(256)
 sweep_inblock_kernel(const double *__restrict__ G1, const double *__restrict__ G2, int64_t ldg,
                      int64_t N0, int blk, const double *__restrict__ Wt, const double *__restrict__ Dt,
                      double *__restrict__ Qt, int64_t nj, const double *__restrict__ alphabets,
-                     const int *__restrict__ Koff) {
+                     const int *__restrict__ Koff, const int *__restrict__ Flags) {
     __shared__ double g1[SWEEP_B][SWEEP_B + 1], g2[SWEEP_B][SWEEP_B + 1];
     __shared__ double nrm[SWEEP_B];
     __shared__ double alph[GPFQ_MAX_K];
@@ -71,6 +71,7 @@ sweep_inblock_kernel(const double *__restrict__ G1, const double *__restrict__ G
     if (threadIdx.x < SWEEP_B)
         nrm[threadIdx.x] = threadIdx.x < nb ? (double)(float)sqrt(g2[threadIdx.x][threadIdx.x]) : 0.0;
     __syncthreads();
+    const double inv_step = gpfq_inv_step(alph, K, Flags[a]);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
@@ -83,11 +84,197 @@ sweep_inblock_kernel(const double *__restrict__ G1, const double *__restrict__ G
         const double dtt = __shfl_sync(0xffffffffu, d, tt);
         const double wtt = __shfl_sync(0xffffffffu, w, tt);
         const double num = fma(wtt, g1[tt][tt], dtt);
-        const double q = gpfq_decide(nrm[tt], dtt, num, wtt, alph, K);
+        const double q = gpfq_decide(nrm[tt], dtt, num, wtt, alph, K, inv_step);
         if (lane == tt) myq = q;
         if (lane > tt) d += g1[lane][tt] * wtt - g2[lane][tt] * q;
     }
     if (lane < nb) Qt[((int64_t)a * nj + j) * N0 + t] = myq;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Persistent sweep: one CTA owns NT neurons and walks ALL direction blocks for them -- one launch per
+// layer, no inter-CTA dependency (neurons are independent).  Per block of 32 directions:
+//   panel   D[32 x NT] = G1[blk, :p] Wt[tile, :p]^T - G2[blk, :p] Qt[tile, :p]^T   on the fp64 tensor pipe
+//           (DMMA.8x8x4; warp w owns direction rows 8w..8w+7), K streamed through a cp.async ring;
+//           the Gram rows are shared by every CTA (L2), the W / Q panels are the CTA's own;
+//   inblock thread-per-neuron: d[32] and w[32] in registers, Gram diagonal block broadcast from shared
+//           memory, 32 fully unrolled greedy steps (decision + rank-1 update of the remaining d);
+//   Q block -> shared memory -> Qt (neuron-major), read back by the later panels of this same CTA.
+// ---------------------------------------------------------------------------------------------
+template <int NT, bool ALIGNED>
+__global__ void __launch_bounds__(256)
+sweep_tile_kernel(const double *__restrict__ G1, const double *__restrict__ G2, int64_t ldg, int64_t N0,
+                  const double *__restrict__ Wt, double *__restrict__ Qt, int64_t nj,
+                  const double *__restrict__ alphabets, const int *__restrict__ Koff,
+                  const int *__restrict__ Flags) {
+    constexpr int B = SWEEP_B, KC = 32, LD = KC + 4, STAGES = 4, THREADS = 256, NA = NT / 8;
+    constexpr int GCH = B * (KC / 2) / THREADS;                          // 16-byte chunks of the Gram tile per thread (2)
+    constexpr int WCH = (NT * (KC / 2) + THREADS - 1) / THREADS;         // ... of the W / Q tile per thread (2, 1, 1)
+    extern __shared__ __align__(16) unsigned char sweep_smem[];
+    double *gst = reinterpret_cast<double *>(sweep_smem);   // STAGES x B x LD   (Gram rows of the block)
+    double *wst = gst + STAGES * B * LD;                    // STAGES x NT x LD  (W or Q panel of the tile)
+    double *g1d = wst + STAGES * NT * LD;                   // B x (B+1) diagonal blocks
+    double *g2d = g1d + B * (B + 1);
+    double *dsm = g2d + B * (B + 1);                        // 2 x B x (NT+1): one partial per K-half warp group
+    double *wblk = dsm + 2 * B * (NT + 1);                  // NT x (B+1)
+    double *qblk = wblk + NT * (B + 1);                     // NT x (B+1)
+    double *nrm = qblk + NT * (B + 1);                      // B
+    double *alph = nrm + B;                                 // GPFQ_MAX_K
+
+    const int a = blockIdx.y;
+    const int K = Koff[a + 1] - Koff[a];
+    const int64_t jt = (int64_t)blockIdx.x * NT;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, grp = lane >> 2, tig = lane & 3;
+    const int strip = warp & 3, khalf = warp >> 2;  // direction rows 8*strip.., k-steps [16*khalf, 16*khalf + 16)
+    double *Qa = Qt + (int64_t)a * nj * N0;
+    for (int e = tid; e < K; e += THREADS) alph[e] = alphabets[Koff[a] + e];
+    __syncthreads();
+    const double inv_step = gpfq_inv_step(alph, K, Flags[a]);
+
+    // this thread's 16-byte chunks of every W / Q tile (fixed for the whole walk)
+    int w_off[WCH];
+    const double *w_src[WCH], *q_src[WCH];
+    int w_bytes[WCH];
+#pragma unroll
+    for (int i = 0; i < WCH; ++i) {
+        const int idx = tid + i * THREADS, r = idx / (KC / 2), c = idx % (KC / 2);
+        const bool in_tile = idx < NT * (KC / 2);
+        const bool ok = in_tile && (jt + r < nj);
+        w_off[i] = in_tile ? r * LD + c * 2 : -1;
+        w_src[i] = Wt + (ok ? (jt + r) * N0 + c * 2 : 0);
+        q_src[i] = Qa + (ok ? (jt + r) * N0 + c * 2 : 0);
+        w_bytes[i] = ok ? 16 : 0;
+    }
+
+    const int nblk = (int)((N0 + B - 1) / B);
+    for (int b = 0; b < nblk; ++b) {
+        const int64_t t0 = (int64_t)b * B;
+        const int nb = (int)((N0 - t0) < B ? (N0 - t0) : B);
+        // ---- panel: contributions of all earlier blocks
+        int g_off[GCH], g_bytes[GCH];
+        const double *g1_src[GCH], *g2_src[GCH];
+#pragma unroll
+        for (int i = 0; i < GCH; ++i) {
+            const int idx = tid + i * THREADS, r = idx / (KC / 2), c = idx % (KC / 2);
+            const bool ok = t0 + r < N0;
+            g_off[i] = r * LD + c * 2;
+            g1_src[i] = G1 + (ok ? (t0 + r) * ldg + c * 2 : 0);
+            g2_src[i] = G2 + (ok ? (t0 + r) * ldg + c * 2 : 0);
+            g_bytes[i] = ok ? 16 : 0;
+        }
+        double acc[NA][2];
+#pragma unroll
+        for (int i = 0; i < NA; ++i) acc[i][0] = acc[i][1] = 0.0;
+        const int total = 2 * b;  // chunks: b of (G1, W), then b of (G2, Q)
+        auto issue = [&](int it) {
+            if (it < total) {
+                const int seg = it >= b;
+                const int64_t k0 = (int64_t)(seg ? it - b : it) * KC;
+                const int st = it % STAGES;
+                if (ALIGNED) {
+#pragma unroll
+                    for (int i = 0; i < GCH; ++i)
+                        cp_async16(gst + st * B * LD + g_off[i], (seg ? g2_src[i] : g1_src[i]) + k0, g_bytes[i]);
+#pragma unroll
+                    for (int i = 0; i < WCH; ++i)
+                        if (w_off[i] >= 0)
+                            cp_async16(wst + st * NT * LD + w_off[i], (seg ? q_src[i] : w_src[i]) + k0, w_bytes[i]);
+                } else {
+                    load_tile<double, B, KC, THREADS, false>(gst + st * B * LD, seg ? G2 : G1, ldg, t0, N0, k0, t0);
+                    load_tile<double, NT, KC, THREADS, false>(wst + st * NT * LD, seg ? Qa : Wt, N0, jt, nj, k0, t0);
+                }
+            }
+            cp_async_commit();
+        };
+        issue(0);
+        issue(1);
+        issue(2);
+        for (int it = 0; it < total; ++it) {
+            cp_async_wait<2>();
+            __syncthreads();  // chunk `it` landed for everyone; chunk it-1 fully consumed
+            issue(it + 3);
+            const int st = it % STAGES;
+            const double *as = gst + st * B * LD + (strip * 8 + grp) * LD + tig + khalf * (KC / 2);
+            const double *bs = wst + st * NT * LD + grp * LD + tig + khalf * (KC / 2);
+            const bool neg = it >= b;
+#pragma unroll
+            for (int kk = 0; kk < KC / 2; kk += 4) {
+                const double av = neg ? -as[kk] : as[kk];
+#pragma unroll
+                for (int i = 0; i < NA; ++i) dmma_m8n8k4(acc[i][0], acc[i][1], av, bs[i * 8 * LD + kk]);
+            }
+        }
+        cp_async_wait<0>();
+        // ---- stage the block's operands
+#pragma unroll
+        for (int i = 0; i < NA; ++i) {
+            double *dp = dsm + khalf * B * (NT + 1) + (strip * 8 + grp) * (NT + 1) + i * 8 + tig * 2;
+            dp[0] = acc[i][0];
+            dp[1] = acc[i][1];
+        }
+        for (int e = tid; e < B * B; e += THREADS) {
+            const int r = e / B, c = e % B;
+            const bool ok = r < nb && c <= r;
+            g1d[r * (B + 1) + c] = ok ? G1[(t0 + r) * ldg + t0 + c] : 0.0;
+            g2d[r * (B + 1) + c] = ok ? G2[(t0 + r) * ldg + t0 + c] : 0.0;
+        }
+        for (int e = tid; e < NT * B; e += THREADS) {
+            const int j = e / B, t = e % B;
+            wblk[j * (B + 1) + t] = (jt + j < nj && t < nb) ? Wt[(jt + j) * N0 + t0 + t] : 0.0;
+        }
+        __syncthreads();
+        if (tid < B) nrm[tid] = tid < nb ? (double)(float)sqrt(g2d[tid * (B + 1) + tid]) : 0.0;
+        __syncthreads();
+        // ---- in-block steps: thread j walks the 32 directions of neuron jt + j
+        if (tid < NT) {
+            double d[B], wv[B];
+#pragma unroll
+            for (int t = 0; t < B; ++t) {
+                d[t] = dsm[t * (NT + 1) + tid] + dsm[B * (NT + 1) + t * (NT + 1) + tid];  // K-halves in fixed order
+                wv[t] = wblk[tid * (B + 1) + t];
+            }
+#pragma unroll
+            for (int tt = 0; tt < B; ++tt) {
+                if (tt < nb) {
+                    const double num = fma(wv[tt], g1d[tt * (B + 1) + tt], d[tt]);
+                    const double q = gpfq_decide(nrm[tt], d[tt], num, wv[tt], alph, K, inv_step);
+                    qblk[tid * (B + 1) + tt] = q;
+#pragma unroll
+                    for (int t = tt + 1; t < B; ++t)
+                        d[t] += g1d[t * (B + 1) + tt] * wv[tt] - g2d[t * (B + 1) + tt] * q;
+                }
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < NT * B; e += THREADS) {
+            const int j = e / B, t = e % B;
+            if (jt + j < nj && t < nb) Qa[(jt + j) * N0 + t0 + t] = qblk[j * (B + 1) + t];
+        }
+        __syncthreads();  // Q block visible to this CTA's later panel loads
+    }
+}
+
+template <int NT>
+static int launch_sweep_tile(gpfq_ctx *ctx, const double *G1, const double *G2, int64_t N0, const double *Wt,
+                             double *Qt, int64_t nj, const double *d_alph, const int *d_koff, const int *d_flags,
+                             int n_alph) {
+    constexpr int B = SWEEP_B, LD = 36, STAGES = 4;
+    const size_t smem = sizeof(double) * ((size_t)STAGES * B * LD + (size_t)STAGES * NT * LD + 2 * B * (B + 1) +
+                                          2 * B * (NT + 1) + 2 * NT * (B + 1) + B + GPFQ_MAX_K);
+    dim3 grid((unsigned)ceil_div64(nj, NT), (unsigned)n_alph);
+    const bool aligned = (N0 % 2 == 0) && ((uintptr_t)G1 % 16 == 0) && ((uintptr_t)G2 % 16 == 0) &&
+                         ((uintptr_t)Wt % 16 == 0) && ((uintptr_t)Qt % 16 == 0) && ((nj * N0) % 2 == 0);
+    if (aligned) {
+        auto k = sweep_tile_kernel<NT, true>;
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, 256, smem, ctx->stream>>>(G1, G2, N0, N0, Wt, Qt, nj, d_alph, d_koff, d_flags);
+    } else {
+        auto k = sweep_tile_kernel<NT, false>;
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, 256, smem, ctx->stream>>>(G1, G2, N0, N0, Wt, Qt, nj, d_alph, d_koff, d_flags);
+    }
+    KERNEL_CHECK(ctx);
+    return GPFQ_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -149,7 +336,7 @@ int dense_gram_only(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx,
 //   Qd: (n_alph, N0, ldq) fp64 device output, columns col0..col0+nj-1 written.
 int dense_gram_path(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx, int64_t N0, int64_t m,
                     const float *W, int64_t ldw, int64_t j0, int64_t nj, const double *d_alph,
-                    const int *d_koff, int n_alph, double *Qd, int64_t ldq, int64_t col0,
+                    const int *d_koff, const int *d_flags, int n_alph, double *Qd, int64_t ldq, int64_t col0,
                     gpfq_stats *st) {
     const bool same = (Xq == X);
     double *G1 = nullptr, *G2 = nullptr, *Wt = nullptr, *Qt = nullptr, *Dt = nullptr;
@@ -170,27 +357,39 @@ int dense_gram_path(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx,
         transpose_w_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(W, ldw, N0, j0, nj, Wt);
         KERNEL_CHECK(ctx);
     }
-    const int nblk = (int)ceil_div64(N0, SWEEP_B);
-    for (int b = 0; b < nblk; ++b) {
-        const int64_t p = (int64_t)b * SWEEP_B;
-        const int64_t nb = (N0 - p) < SWEEP_B ? (N0 - p) : SWEEP_B;
-        if (b > 0) {
-            GemmArgs g = {};
-            g.seg[0] = {Wt, G1 + p * N0, N0, N0, p, 1.0};
-            g.seg[1] = {Qt, G2 + p * N0, N0, N0, p, -1.0};
-            g.nseg = 2;
-            g.M = nj;
-            g.N = nb;
-            g.C = Dt;
-            g.ldc = SWEEP_B;
-            g.nsplit = 1;
-            g.batch_strideA1 = nj * N0;
-            g.batch_strideC = nj * SWEEP_B;
-            GPFQ_TRY((launch_gemm_nt<double, 128, 32, 16>(ctx, g, n_alph)));
+    if (ctx->sweep_variant == 0) {
+        // neurons per CTA: the widest tile that still gives every SM a CTA
+        const int64_t ctas32 = ceil_div64(nj, 32) * n_alph, ctas16 = ceil_div64(nj, 16) * n_alph;
+        if (ctas32 >= ctx->sm_count)
+            GPFQ_TRY(launch_sweep_tile<32>(ctx, G1, G2, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph));
+        else if (ctas16 >= ctx->sm_count)
+            GPFQ_TRY(launch_sweep_tile<16>(ctx, G1, G2, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph));
+        else
+            GPFQ_TRY(launch_sweep_tile<8>(ctx, G1, G2, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph));
+    } else {
+        // multi-launch reference: one NT contraction + one in-block kernel per 32 directions
+        const int nblk = (int)ceil_div64(N0, SWEEP_B);
+        for (int b = 0; b < nblk; ++b) {
+            const int64_t p = (int64_t)b * SWEEP_B;
+            const int64_t nb = (N0 - p) < SWEEP_B ? (N0 - p) : SWEEP_B;
+            if (b > 0) {
+                GemmArgs g = {};
+                g.seg[0] = {Wt, G1 + p * N0, N0, N0, p, 1.0};
+                g.seg[1] = {Qt, G2 + p * N0, N0, N0, p, -1.0};
+                g.nseg = 2;
+                g.M = nj;
+                g.N = nb;
+                g.C = Dt;
+                g.ldc = SWEEP_B;
+                g.nsplit = 1;
+                g.batch_strideA1 = nj * N0;
+                g.batch_strideC = nj * SWEEP_B;
+                GPFQ_TRY((launch_gemm_nt<double, 128, 32, 16>(ctx, g, n_alph)));
+            }
+            dim3 grid((unsigned)ceil_div64(nj, 8), (unsigned)n_alph);
+            sweep_inblock_kernel<<<grid, 256, 0, ctx->stream>>>(G1, G2, N0, N0, b, Wt, Dt, Qt, nj, d_alph, d_koff, d_flags);
+            KERNEL_CHECK(ctx);
         }
-        dim3 grid((unsigned)ceil_div64(nj, 8), (unsigned)n_alph);
-        sweep_inblock_kernel<<<grid, 256, 0, ctx->stream>>>(G1, G2, N0, N0, b, Wt, Dt, Qt, nj, d_alph, d_koff);
-        KERNEL_CHECK(ctx);
     }
     for (int a = 0; a < n_alph; ++a) {
         dim3 grid((unsigned)ceil_div64(N0, 32), (unsigned)ceil_div64(nj, 32));
