@@ -25,6 +25,9 @@ int conv_sweep_stage(gpfq_ctx *, int, const double *, const float *, double *, i
 int im2col_stage(gpfq_ctx *, const float *, int64_t, int, int, int64_t, int64_t, int, int, int, int, int, int, int,
                  int, int, int, int, float *, int64_t);
 int msq_stage(gpfq_ctx *, const void *, int, int64_t, const double *, int, int, double *);
+int nhwc9_plan(int, int, int, int, int, int, int, int, int *, int *);
+int conv_gram9_nhwc_stage(gpfq_ctx *, const float *, const float *, bool, int64_t, int64_t, int, int, int64_t, int64_t, int,
+                          int, int, int, int, int, int, int, double *, int);
 
 // ---------------------------------------------------------------------------------------------
 int gpfq_fail(gpfq_ctx *ctx, int code, const char *fmt, ...) {
@@ -652,6 +655,48 @@ extern "C" int gpfq_conv_layer_nhwc(gpfq_ctx *ctx, const float *act, const float
         }
     }
     CUDA_TRY(ctx, gpfq_record(ctx, 5, s));
+    int planeP = 0, bandR = 0;
+    if (ctx->conv_variant == 0 && nhwc9_plan(kh, kw, sh, sw, rh, rw, Ho, Wo, &planeP, &bandR)) {
+        // ---- fused path: Grams straight from the activations, no patch matrices
+        const int64_t groups = ceil_div64(n_ch, 8);
+        int64_t per_ic = ceil_div64(4LL * 2 * ctx->sm_count, groups * n_ic);  // ~4 waves of two CTAs per SM overall
+        per_ic = std::max<int64_t>(1, std::min<int64_t>(per_ic, ipc));
+        const int slots = (int)(n_ic * per_ic);
+        double *partial = nullptr;
+        const size_t part_bytes = (size_t)groups * 8 * slots * 2 * kk * kk * sizeof(double);
+        GPFQ_TRY(gpfq_ws(ctx, WS_CPART, part_bytes, (void **)&partial));
+        CUDA_TRY(ctx, cudaMemsetAsync(partial, 0, part_bytes, s));  // short chunks leave slots unused
+        CUDA_TRY(ctx, gpfq_record(ctx, 2, s));
+        if (host_act) {
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_copy[2], s));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy[2], 0));
+        }
+        for (int ic = 0; ic < n_ic; ++ic) {
+            const int64_t img0 = (int64_t)ic * ipc;
+            const int64_t imgs = std::min<int64_t>(ipc, n_img - img0);
+            if (host_act) {
+                const size_t off = (size_t)img0 * img_elems, bytes = (size_t)imgs * img_elems * sizeof(float);
+                CUDA_TRY(ctx, cudaMemcpyAsync(const_cast<float *>(dA) + off, act + off, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+                if (!same)
+                    CUDA_TRY(ctx, cudaMemcpyAsync(const_cast<float *>(dAq) + off, actq + off, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+                CUDA_TRY(ctx, cudaEventRecord(ctx->ev_copy[ic & 1], ctx->copy_stream));
+                CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->ev_copy[ic & 1], 0));
+            }
+            GPFQ_TRY(conv_gram9_nhwc_stage(ctx, dA, dAq, same, img0, imgs, (int)H, (int)Wd, C, c0, (int)n_ch, Ho, Wo, pt, pl,
+                                           planeP, bandR, (int)per_ic, partial + (size_t)ic * per_ic * 2 * kk * kk, slots));
+        }
+        CUDA_TRY(ctx, gpfq_record(ctx, 3, s));
+        GPFQ_TRY(conv_finish(ctx, kk, partial, (int)n_ch, slots, same, W, C, F, c0, al, n_alph, Q_out, flags));
+        CUDA_TRY(ctx, gpfq_record(ctx, 1, s));
+        gpfq_stats local = {};
+        gpfq_stats *st = stats ? stats : &local;
+        conv_stats(ctx, st, kk, n, n_ch, F, same, n_alph);
+        st->bytes_algorithmic = (same ? 1 : 2) * 4LL * n_img * H * Wd * n_ch;  // the activations, once
+        const bool synced = !(flags & GPFQ_NO_SYNC);
+        if (synced) CUDA_TRY(ctx, cudaStreamSynchronize(s));
+        end_call(ctx, st, synced);
+        return GPFQ_OK;
+    }
     const int64_t hw_out = (int64_t)Ho * Wo;
     const int64_t n_c = ipc * hw_out;  // patch columns of a full image chunk
     bool vec_ok = n_c % 4 == 0 && ((n_img - (int64_t)(n_ic - 1) * ipc) * hw_out) % 4 == 0;

@@ -150,6 +150,23 @@ __device__ __forceinline__ double gpfq_decide(double nrm, double d, double num, 
     return gpfq_bit_round_eq(num / (nrm * nrm), alph, K, inv_step);
 }
 
+// The same decision for the sweep's in-block walk, out of line (32 unrolled call sites share one copy) and with the
+// division by nrm^2 done as a Markstein correction of num * RN(1/nrm^2): q0 = RN(num r), e = RN(num - q0 den) (exact,
+// fma), v = RN(q0 + e r) is the correctly rounded quotient, i.e. bit-identical to num / den, while the reciprocal
+// is computed once per direction instead of once per neuron and step.
+static __device__ __noinline__ double gpfq_decide_rcp(double nrm, double rinv, double d, double num, double w,
+                                               const double *__restrict__ alph, int K, double inv_step) {
+    if (nrm < GPFQ_DEAD_NORM) return 0.0;
+    double v = w;
+    if (!(fabs(d) < GPFQ_PERP_DOT)) {
+        const double den = nrm * nrm;
+        const double q0 = num * rinv;
+        const double e = fma(-q0, den, num);
+        v = fma(e, rinv, q0);
+    }
+    return gpfq_bit_round_eq(v, alph, K, inv_step);
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

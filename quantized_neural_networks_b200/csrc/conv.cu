@@ -386,6 +386,132 @@ conv_gram9_tma_kernel(ConvPtrs ptrs, int64_t n, int64_t chunk_cols, double *__re
     }
 }
 
+// ---- stage 1, 3x3 / stride 1 straight from the NHWC activations --------------------------------------
+// The patch matrix of a 3x3 stride-1 convolution is nine shifted views of the (zero-padded) channel image, so
+// it never has to exist: a CTA stages a band of rows of CG = 8 channels of one image in shared memory as
+// per-channel planes (pitch P, halo included), and warp w runs the DMMA/DFMA Gram of conv_gram9_* for channel
+// w with its operands read from the plane at (row + r_g, col + c_g).  Lane (g, k) takes output columns
+// col4 + k of four "cells" of four columns per step, so the 32 lanes of an LDS touch a 3 x 6 window per
+// cell: neighbouring lanes hit the same word (broadcast) and a pitch with P mod 32 in [8, 12] keeps the three
+// rows on disjoint banks.  HBM traffic drops from 72 to 8 bytes per patch column and channel; the kernel is
+// bound by the fp64 pipe (168 slots per column).  Geometry outside 3x3 / stride 1 / rate 1 / Wo % 4 == 0 goes
+// through im2col_kernel + the patch kernels.
+namespace nhwc9 {
+constexpr int CG = 8;              // channels per CTA = consumer warps
+constexpr int THREADS = CG * 32;
+constexpr int MAX_PLANE = 1664;    // floats per plane: 2 matrices x 8 channels x 6.5 KB = 104 KB -> two CTAs per SM
+}  // namespace nhwc9
+
+struct Nhwc9Geom {
+    int H, W, Ho, Wo, pt, pl;      // input size, output size, top / left padding (SAME: 1, VALID: 0)
+    int P, BR;                     // plane pitch (floats), output rows per band
+    int64_t C;                     // channels of the activation tensor
+    int64_t c_first;               // first channel handled by blockIdx.y == 0
+    int n_ch;                      // channels handled by this launch
+    int64_t img0, n_img;           // image range of this launch
+    int imgs_per_cta;
+};
+
+template <bool SAME>
+__global__ void __launch_bounds__(nhwc9::THREADS, 2)
+conv_gram9_nhwc_kernel(const float *__restrict__ act, const float *__restrict__ actq, Nhwc9Geom gm,
+                       double *__restrict__ partial, int slots) {
+    using namespace nhwc9;
+    constexpr int KK = 9, SZ = 2 * KK * KK;
+    extern __shared__ __align__(16) float nhwc9_smem[];
+    const int plane = (gm.BR + 2) * gm.P;
+    float *planes_q = nhwc9_smem;                    // CG planes of Xq
+    float *planes_x = SAME ? planes_q : planes_q + CG * plane;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, k = lane & 3;
+    const int r_g = g / 3, c_g = g % 3;
+    const int64_t ch0 = gm.c_first + (int64_t)blockIdx.y * CG;          // first channel of this CTA
+    const int nch_cta = (gm.n_ch - (int)blockIdx.y * CG) < CG ? (gm.n_ch - (int)blockIdx.y * CG) : CG;
+    const int64_t ia = gm.img0 + (int64_t)blockIdx.x * gm.imgs_per_cta;
+    const int64_t ib = (ia + gm.imgs_per_cta < gm.img0 + gm.n_img) ? ia + gm.imgs_per_cta : gm.img0 + gm.n_img;
+    const int Wp = gm.Wo + 2, cells_per_row = gm.Wo >> 2;
+    const bool vec4 = (gm.C % 4 == 0) && (ch0 % 4 == 0) && (nch_cta == CG);
+
+    Gram9Acc acc = {};
+    for (int64_t img = ia; img < ib; ++img) {
+        const float *ai = act + img * (int64_t)gm.H * gm.W * gm.C;
+        const float *aq = SAME ? ai : actq + img * (int64_t)gm.H * gm.W * gm.C;
+        for (int i0 = 0; i0 < gm.Ho; i0 += gm.BR) {
+            const int br = (gm.Ho - i0) < gm.BR ? (gm.Ho - i0) : gm.BR;
+            __syncthreads();  // the previous band has been consumed
+            // ---- stage rows [i0 - pt, i0 - pt + br + 2) x cols [-pl, Wo + 2 - pl) of CG channels, zero outside the image
+            const int npix = (br + 2) * Wp;
+            if (vec4) {
+                for (int e = tid; e < npix * 2; e += THREADS) {
+                    const int quad = e & 1, pix = e >> 1;
+                    const int rr = pix / Wp, cc = pix - rr * Wp;
+                    const int iy = i0 - gm.pt + rr, ix = cc - gm.pl;
+                    float4 vq = make_float4(0.f, 0.f, 0.f, 0.f), vx = vq;
+                    if (iy >= 0 && iy < gm.H && ix >= 0 && ix < gm.W) {
+                        const int64_t off = ((int64_t)iy * gm.W + ix) * gm.C + ch0 + quad * 4;
+                        vq = __ldg(reinterpret_cast<const float4 *>(aq + off));
+                        if (!SAME) vx = __ldg(reinterpret_cast<const float4 *>(ai + off));
+                    }
+                    float *dq = planes_q + (quad * 4) * plane + rr * gm.P + cc;
+                    dq[0] = vq.x; dq[plane] = vq.y; dq[2 * plane] = vq.z; dq[3 * plane] = vq.w;
+                    if (!SAME) {
+                        float *dx = planes_x + (quad * 4) * plane + rr * gm.P + cc;
+                        dx[0] = vx.x; dx[plane] = vx.y; dx[2 * plane] = vx.z; dx[3 * plane] = vx.w;
+                    }
+                }
+            } else {
+                for (int e = tid; e < npix * CG; e += THREADS) {
+                    const int ch = e % CG, pix = e / CG;
+                    const int rr = pix / Wp, cc = pix - rr * Wp;
+                    const int iy = i0 - gm.pt + rr, ix = cc - gm.pl;
+                    float vq = 0.f, vx = 0.f;
+                    if (ch < nch_cta && iy >= 0 && iy < gm.H && ix >= 0 && ix < gm.W) {
+                        const int64_t off = ((int64_t)iy * gm.W + ix) * gm.C + ch0 + ch;
+                        vq = __ldg(aq + off);
+                        if (!SAME) vx = __ldg(ai + off);
+                    }
+                    planes_q[ch * plane + rr * gm.P + cc] = vq;
+                    if (!SAME) planes_x[ch * plane + rr * gm.P + cc] = vx;
+                }
+            }
+            __syncthreads();
+            if (warp >= nch_cta) continue;
+            // ---- this warp's channel: four cells (16 output columns) per step
+            const float *pq = planes_q + warp * plane, *px = planes_x + warp * plane;
+            const int ncell = br * cells_per_row;
+            int row = 0, cell = 0;  // (row, cell-in-row) of the step's first cell
+            for (int f0 = 0; f0 < ncell; f0 += 4) {
+                float q[4], x[4], q8[4], x8[4];
+                int rw = row, cl = cell;
+#pragma unroll
+                for (int sgrp = 0; sgrp < 4; ++sgrp) {
+                    const bool ok = f0 + sgrp < ncell;
+                    const int base = rw * gm.P + cl * 4 + k;
+                    q[sgrp] = ok ? pq[base + r_g * gm.P + c_g] : 0.f;
+                    q8[sgrp] = ok ? pq[base + 2 * gm.P + 2] : 0.f;
+                    if (!SAME) {
+                        x[sgrp] = ok ? px[base + r_g * gm.P + c_g] : 0.f;
+                        x8[sgrp] = ok ? px[base + 2 * gm.P + 2] : 0.f;
+                    }
+                    if (++cl == cells_per_row) { cl = 0; ++rw; }
+                }
+                row = rw; cell = cl;
+#pragma unroll
+                for (int sgrp = 0; sgrp < 4; ++sgrp) gram9_step<SAME>(acc, q[sgrp], x[sgrp], q8[sgrp], x8[sgrp]);
+            }
+        }
+    }
+    __syncthreads();
+    double *red = reinterpret_cast<double *>(nhwc9_smem);  // the planes are dead: reuse them for the fragments
+    if (warp < nch_cta) gram9_store<SAME>(acc, red + warp * SZ, g, k);
+    __syncthreads();
+    for (int e = tid; e < nch_cta * SZ; e += THREADS) {
+        const int ch = e / SZ, idx = e % SZ;
+        if (SAME && idx < KK * KK) continue;
+        partial[(((size_t)blockIdx.y * CG + ch) * slots + blockIdx.x) * SZ + idx] = red[ch * SZ + idx];
+    }
+}
+
 // ---- stage 2 ---------------------------------------------------------------------------------
 // gram: (n_channels, 2*kk*kk): [G1 | G2], lower triangle + diagonal of each valid.
 __global__ void conv_finalize_kernel(const double *__restrict__ partial, int n_chunks, int kk, int same,
@@ -573,6 +699,45 @@ int im2col_stage(gpfq_ctx *ctx, const float *act, int64_t n_img, int H, int Wd, 
     dim3 grid((unsigned)bx, (unsigned)n_ch, (unsigned)(kh * kw));
     im2col_kernel<<<grid, 256, 0, ctx->stream>>>(act, n_img, H, Wd, C, c_first, kh, kw, sh, sw, rh, rw, pt, pl,
                                                  Ho, Wo, out, ch_stride);
+    KERNEL_CHECK(ctx);
+    return GPFQ_OK;
+}
+
+// Fused NHWC path: is this geometry eligible, and with which plane pitch / band height?
+int nhwc9_plan(int kh, int kw, int sh, int sw, int rh, int rw, int Ho, int Wo, int *P_out, int *BR_out) {
+    if (kh != 3 || kw != 3 || sh != 1 || sw != 1 || rh != 1 || rw != 1 || Wo % 4 != 0 || Wo < 4) return 0;
+    int P = Wo + 2;
+    while (P % 32 < 8 || P % 32 > 12) ++P;  // three plane rows on disjoint banks for the 3 x 6 window reads
+    int BR = nhwc9::MAX_PLANE / P - 2;
+    if (BR > Ho) BR = Ho;
+    if (BR < 4 && BR < Ho) return 0;         // very wide images: the halo would dominate
+    *P_out = P;
+    *BR_out = BR;
+    return 1;
+}
+
+// Partial Grams of channels [c_first, c_first + n_ch) over images [img0, img0 + n_img): fills slots
+// [0, n_slots) (relative to `partial`) of every channel; `slots` = total slots per channel.
+int conv_gram9_nhwc_stage(gpfq_ctx *ctx, const float *act, const float *actq, bool same, int64_t img0, int64_t n_img,
+                          int H, int Wd, int64_t C, int64_t c_first, int n_ch, int Ho, int Wo, int pt, int pl, int P,
+                          int BR, int n_slots, double *partial, int slots) {
+    using namespace nhwc9;
+    Nhwc9Geom gm;
+    gm.H = H; gm.W = Wd; gm.Ho = Ho; gm.Wo = Wo; gm.pt = pt; gm.pl = pl; gm.P = P; gm.BR = BR;
+    gm.C = C; gm.c_first = c_first; gm.n_ch = n_ch; gm.img0 = img0; gm.n_img = n_img;
+    gm.imgs_per_cta = (int)ceil_div64(n_img, n_slots);
+    const size_t plane_bytes = (size_t)(BR + 2) * P * sizeof(float) * CG;
+    size_t smem = plane_bytes * (same ? 1 : 2);
+    const size_t red_bytes = (size_t)CG * 2 * 81 * sizeof(double);
+    if (smem < red_bytes) smem = red_bytes;
+    dim3 grid((unsigned)ceil_div64(n_img, gm.imgs_per_cta), (unsigned)ceil_div64(n_ch, CG));
+    if (same) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(conv_gram9_nhwc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conv_gram9_nhwc_kernel<true><<<grid, THREADS, smem, ctx->stream>>>(act, act, gm, partial, slots);
+    } else {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(conv_gram9_nhwc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conv_gram9_nhwc_kernel<false><<<grid, THREADS, smem, ctx->stream>>>(act, actq, gm, partial, slots);
+    }
     KERNEL_CHECK(ctx);
     return GPFQ_OK;
 }

@@ -11,6 +11,7 @@
 #include "gemm_nt.cuh"
 
 static constexpr int SWEEP_B = 32;
+static constexpr int64_t SWEEP_OUTER = 512;  // directions per range of the two-level sweep
 
 // Wt[j - j0][t] = (double) W[t*ldw + j]   (neuron-major copy of the shard, fp64)
 __global__ void transpose_w_kernel(const float *__restrict__ W, int64_t ldw, int64_t N0, int64_t j0,
@@ -106,7 +107,10 @@ __global__ void __launch_bounds__(256)
 sweep_tile_kernel(const double *__restrict__ G1, const double *__restrict__ G2, int64_t ldg, int64_t N0,
                   const double *__restrict__ Wt, double *__restrict__ Qt, int64_t nj,
                   const double *__restrict__ alphabets, const int *__restrict__ Koff,
-                  const int *__restrict__ Flags) {
+                  const int *__restrict__ Flags, int64_t t_begin, int64_t t_end, const double *__restrict__ Dt,
+                  int64_t ldd) {
+    // Directions [t_begin, t_end) (t_begin a multiple of 32).  Dt (nullable): (n_alph, nj, ldd) contributions of the
+    // directions before t_begin, from one large NT contraction on the host side (two-level blocking).
     constexpr int B = SWEEP_B, KC = 32, LD = KC + 4, STAGES = 4, THREADS = 256, NA = NT / 8;
     constexpr int GCH = B * (KC / 2) / THREADS;                          // 16-byte chunks of the Gram tile per thread (2)
     constexpr int WCH = (NT * (KC / 2) + THREADS - 1) / THREADS;         // ... of the W / Q tile per thread (2, 1, 1)
@@ -119,7 +123,8 @@ sweep_tile_kernel(const double *__restrict__ G1, const double *__restrict__ G2, 
     double *wblk = dsm + 2 * B * (NT + 1);                  // NT x (B+1)
     double *qblk = wblk + NT * (B + 1);                     // NT x (B+1)
     double *nrm = qblk + NT * (B + 1);                      // B
-    double *alph = nrm + B;                                 // GPFQ_MAX_K
+    double *rinv = nrm + B;                                 // B: RN(1 / nrm^2)
+    double *alph = rinv + B;                                // GPFQ_MAX_K
 
     const int a = blockIdx.y;
     const int K = Koff[a + 1] - Koff[a];
@@ -146,11 +151,12 @@ sweep_tile_kernel(const double *__restrict__ G1, const double *__restrict__ G2, 
         w_bytes[i] = ok ? 16 : 0;
     }
 
-    const int nblk = (int)((N0 + B - 1) / B);
+    const int nblk = (int)((t_end - t_begin + B - 1) / B);
+    const double *Da = Dt ? Dt + (int64_t)a * nj * ldd : nullptr;
     for (int b = 0; b < nblk; ++b) {
-        const int64_t t0 = (int64_t)b * B;
-        const int nb = (int)((N0 - t0) < B ? (N0 - t0) : B);
-        // ---- panel: contributions of all earlier blocks
+        const int64_t t0 = t_begin + (int64_t)b * B;
+        const int nb = (int)((t_end - t0) < B ? (t_end - t0) : B);
+        // ---- panel: contributions of the earlier blocks of this range
         int g_off[GCH], g_bytes[GCH];
         const double *g1_src[GCH], *g2_src[GCH];
 #pragma unroll
@@ -169,7 +175,7 @@ sweep_tile_kernel(const double *__restrict__ G1, const double *__restrict__ G2, 
         auto issue = [&](int it) {
             if (it < total) {
                 const int seg = it >= b;
-                const int64_t k0 = (int64_t)(seg ? it - b : it) * KC;
+                const int64_t k0 = t_begin + (int64_t)(seg ? it - b : it) * KC;
                 const int st = it % STAGES;
                 if (ALIGNED) {
 #pragma unroll
@@ -220,24 +226,31 @@ sweep_tile_kernel(const double *__restrict__ G1, const double *__restrict__ G2, 
         }
         for (int e = tid; e < NT * B; e += THREADS) {
             const int j = e / B, t = e % B;
-            wblk[j * (B + 1) + t] = (jt + j < nj && t < nb) ? Wt[(jt + j) * N0 + t0 + t] : 0.0;
+            const bool ok = jt + j < nj && t < nb;
+            wblk[j * (B + 1) + t] = ok ? Wt[(jt + j) * N0 + t0 + t] : 0.0;
+            qblk[j * (B + 1) + t] = (ok && Da) ? Da[(jt + j) * ldd + (t0 - t_begin) + t] : 0.0;  // prior ranges
         }
         __syncthreads();
-        if (tid < B) nrm[tid] = tid < nb ? (double)(float)sqrt(g2d[tid * (B + 1) + tid]) : 0.0;
+        if (tid < B) {
+            const double nv = tid < nb ? (double)(float)sqrt(g2d[tid * (B + 1) + tid]) : 0.0;
+            nrm[tid] = nv;
+            rinv[tid] = nv < GPFQ_DEAD_NORM ? 0.0 : 1.0 / (nv * nv);
+        }
         __syncthreads();
         // ---- in-block steps: thread j walks the 32 directions of neuron jt + j
         if (tid < NT) {
             double d[B], wv[B];
 #pragma unroll
             for (int t = 0; t < B; ++t) {
-                d[t] = dsm[t * (NT + 1) + tid] + dsm[B * (NT + 1) + t * (NT + 1) + tid];  // K-halves in fixed order
+                // prior ranges + the two K-halves of this range's panel, in fixed order
+                d[t] = qblk[tid * (B + 1) + t] + (dsm[t * (NT + 1) + tid] + dsm[B * (NT + 1) + t * (NT + 1) + tid]);
                 wv[t] = wblk[tid * (B + 1) + t];
             }
 #pragma unroll
             for (int tt = 0; tt < B; ++tt) {
                 if (tt < nb) {
                     const double num = fma(wv[tt], g1d[tt * (B + 1) + tt], d[tt]);
-                    const double q = gpfq_decide(nrm[tt], d[tt], num, wv[tt], alph, K, inv_step);
+                    const double q = gpfq_decide_rcp(nrm[tt], rinv[tt], d[tt], num, wv[tt], alph, K, inv_step);
                     qblk[tid * (B + 1) + tt] = q;
 #pragma unroll
                     for (int t = tt + 1; t < B; ++t)
@@ -257,21 +270,21 @@ sweep_tile_kernel(const double *__restrict__ G1, const double *__restrict__ G2, 
 template <int NT>
 static int launch_sweep_tile(gpfq_ctx *ctx, const double *G1, const double *G2, int64_t N0, const double *Wt,
                              double *Qt, int64_t nj, const double *d_alph, const int *d_koff, const int *d_flags,
-                             int n_alph) {
+                             int n_alph, int64_t t_begin, int64_t t_end, const double *Dt, int64_t ldd) {
     constexpr int B = SWEEP_B, LD = 36, STAGES = 4;
     const size_t smem = sizeof(double) * ((size_t)STAGES * B * LD + (size_t)STAGES * NT * LD + 2 * B * (B + 1) +
-                                          2 * B * (NT + 1) + 2 * NT * (B + 1) + B + GPFQ_MAX_K);
+                                          2 * B * (NT + 1) + 2 * NT * (B + 1) + 2 * B + GPFQ_MAX_K);
     dim3 grid((unsigned)ceil_div64(nj, NT), (unsigned)n_alph);
     const bool aligned = (N0 % 2 == 0) && ((uintptr_t)G1 % 16 == 0) && ((uintptr_t)G2 % 16 == 0) &&
                          ((uintptr_t)Wt % 16 == 0) && ((uintptr_t)Qt % 16 == 0) && ((nj * N0) % 2 == 0);
     if (aligned) {
         auto k = sweep_tile_kernel<NT, true>;
         CUDA_TRY(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, 256, smem, ctx->stream>>>(G1, G2, N0, N0, Wt, Qt, nj, d_alph, d_koff, d_flags);
+        k<<<grid, 256, smem, ctx->stream>>>(G1, G2, N0, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, t_begin, t_end, Dt, ldd);
     } else {
         auto k = sweep_tile_kernel<NT, false>;
         CUDA_TRY(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, 256, smem, ctx->stream>>>(G1, G2, N0, N0, Wt, Qt, nj, d_alph, d_koff, d_flags);
+        k<<<grid, 256, smem, ctx->stream>>>(G1, G2, N0, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, t_begin, t_end, Dt, ldd);
     }
     KERNEL_CHECK(ctx);
     return GPFQ_OK;
@@ -345,7 +358,8 @@ int dense_gram_path(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx,
     else GPFQ_TRY(gpfq_ws(ctx, WS_G1, (size_t)N0 * N0 * sizeof(double), (void **)&G1));
     GPFQ_TRY(gpfq_ws(ctx, WS_WT, (size_t)nj * N0 * sizeof(double), (void **)&Wt));
     GPFQ_TRY(gpfq_ws(ctx, WS_QT, (size_t)n_alph * nj * N0 * sizeof(double), (void **)&Qt));
-    GPFQ_TRY(gpfq_ws(ctx, WS_DT, (size_t)n_alph * nj * SWEEP_B * sizeof(double), (void **)&Dt));
+    if (ctx->sweep_variant != 0)
+        GPFQ_TRY(gpfq_ws(ctx, WS_DT, (size_t)n_alph * nj * SWEEP_B * sizeof(double), (void **)&Dt));
 
     CUDA_TRY(ctx, gpfq_record(ctx, 2, ctx->stream));
     GPFQ_TRY(gram_stage(ctx, Xq, Xq, ldx, N0, m, G2));
@@ -358,14 +372,37 @@ int dense_gram_path(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx,
         KERNEL_CHECK(ctx);
     }
     if (ctx->sweep_variant == 0) {
-        // neurons per CTA: the widest tile that still gives every SM a CTA
+        // Two-level blocking: directions in ranges of SWEEP_OUTER; what the earlier ranges contribute to a range is ONE
+        // large NT contraction (all SMs, split over neurons x directions), the persistent neuron-tile kernel then walks
+        // the range.  Neurons per CTA: the widest tile that still gives every SM a CTA.
         const int64_t ctas32 = ceil_div64(nj, 32) * n_alph, ctas16 = ceil_div64(nj, 16) * n_alph;
-        if (ctas32 >= ctx->sm_count)
-            GPFQ_TRY(launch_sweep_tile<32>(ctx, G1, G2, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph));
-        else if (ctas16 >= ctx->sm_count)
-            GPFQ_TRY(launch_sweep_tile<16>(ctx, G1, G2, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph));
-        else
-            GPFQ_TRY(launch_sweep_tile<8>(ctx, G1, G2, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph));
+        const int NT = ctas32 >= ctx->sm_count ? 32 : (ctas16 >= ctx->sm_count ? 16 : 8);
+        double *Do = nullptr;
+        if (N0 > SWEEP_OUTER) GPFQ_TRY(gpfq_ws(ctx, WS_DT, (size_t)n_alph * nj * SWEEP_OUTER * sizeof(double), (void **)&Do));
+        for (int64_t tb = 0; tb < N0; tb += SWEEP_OUTER) {
+            const int64_t te = tb + SWEEP_OUTER < N0 ? tb + SWEEP_OUTER : N0;
+            if (tb > 0) {
+                GemmArgs g = {};
+                g.seg[0] = {Wt, G1 + tb * N0, N0, N0, tb, 1.0};
+                g.seg[1] = {Qt, G2 + tb * N0, N0, N0, tb, -1.0};
+                g.nseg = 2;
+                g.M = nj;
+                g.N = te - tb;
+                g.C = Do;
+                g.ldc = SWEEP_OUTER;
+                g.nsplit = 1;
+                g.batch_strideA1 = nj * N0;
+                g.batch_strideC = nj * SWEEP_OUTER;
+                GPFQ_TRY((launch_gemm_nt<double, 128, 64, 16>(ctx, g, n_alph)));
+            }
+            const double *Dp = tb > 0 ? Do : nullptr;
+            if (NT == 32)
+                GPFQ_TRY(launch_sweep_tile<32>(ctx, G1, G2, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph, tb, te, Dp, SWEEP_OUTER));
+            else if (NT == 16)
+                GPFQ_TRY(launch_sweep_tile<16>(ctx, G1, G2, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph, tb, te, Dp, SWEEP_OUTER));
+            else
+                GPFQ_TRY(launch_sweep_tile<8>(ctx, G1, G2, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph, tb, te, Dp, SWEEP_OUTER));
+        }
     } else {
         // multi-launch reference: one NT contraction + one in-block kernel per 32 directions
         const int nblk = (int)ceil_div64(N0, SWEEP_B);

@@ -352,3 +352,36 @@ def test_conv_gram_kernel_variants_agree():
         assert O.agreement(outs["tma"], Qref) == 1.0, n
         assert np.array_equal(outs["tma"], outs["ldg"]) and np.array_equal(outs["tma"], outs["generic"]), n
         assert np.array_equal(outs["tma_same"], outs["ldg_same"]) and np.array_equal(outs["tma_same"], outs["generic_same"]), n
+
+
+@pytest.mark.parametrize("n_img,H,Wd,C,F,pad", [(5, 7, 12, 5, 4, "SAME"), (9, 10, 8, 8, 3, "VALID"), (3, 32, 32, 16, 6, "SAME"),
+                                                (70, 6, 6, 3, 2, "VALID"), (2, 40, 44, 12, 2, "SAME")])
+def test_conv_nhwc_fused_matches_patch_path(n_img, H, Wd, C, F, pad):
+    """The fused NHWC kernel (planes in shared memory, no patch matrices) against the im2col + patch-Gram path and the
+    oracle: ragged channel groups (scalar loader), full groups (LDG.128 loader), SAME / VALID, several bands."""
+    import os
+    import torch
+    from quantized_neural_networks_b200 import GpfqEngine
+    rng = np.random.default_rng(n_img * 31 + C)
+    act = np.maximum(rng.standard_normal((n_img, H, Wd, C)), 0).astype(np.float32)
+    actq = np.maximum(act + 0.05 * rng.standard_normal(act.shape), 0).astype(np.float32)
+    W = (rng.uniform(-1, 1, (3, 3, C, F)) * 0.3).astype(np.float32)
+    A = O.layer_alphabet(W, 3, O.unit_alphabet(3))
+    patches = lambda ch: (O.channel_patches(act, ch, (3, 3), (1, 1), pad), O.channel_patches(actq, ch, (3, 3), (1, 1), pad))
+    Qref = c_oracle.quantize_conv_layer(W, patches, A)
+    outs = {}
+    for variant in ("tma", "ldg"):
+        os.environ["GPFQ_CONV_KERNEL"] = variant
+        try:
+            with GpfqEngine(0) as eng:
+                outs[variant] = eng.conv_layer_nhwc(act, actq, W, A, padding=pad)
+                outs[variant + "_same"] = eng.conv_layer_nhwc(actq, None, W, A, padding=pad)
+                dev = eng.conv_layer_nhwc(torch.from_numpy(act).cuda(), torch.from_numpy(actq).cuda(), torch.from_numpy(W).cuda(),
+                                          A, padding=pad).cpu().numpy()
+                assert np.array_equal(dev, outs[variant])
+                part = eng.conv_layer_nhwc(act, actq, W, A, padding=pad, c0=1, n_channels=C - 2)
+                assert np.array_equal(part[:, :, 1:C - 1], outs[variant][:, :, 1:C - 1]) and np.all(part[:, :, 0] == 0)
+        finally:
+            os.environ.pop("GPFQ_CONV_KERNEL", None)
+    assert O.agreement(outs["tma"], Qref) == 1.0
+    assert np.array_equal(outs["tma"], outs["ldg"]) and np.array_equal(outs["tma_same"], outs["ldg_same"])
