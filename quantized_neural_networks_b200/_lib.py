@@ -27,6 +27,7 @@ class GpfqStats(ctypes.Structure):
         ("ms_total", c_float), ("ms_h2d", c_float), ("ms_d2h", c_float),
         ("ms_gram", c_float), ("ms_sweep", c_float), ("ms_stream", c_float),
         ("weights", c_int64), ("bytes_algorithmic", c_int64), ("flops_algorithmic", c_int64),
+        ("gram_kernel", c_int32), ("reserved", c_int32),
     ]
 
     def as_dict(self):
@@ -46,6 +47,7 @@ EXPORTS = {
     "gpfq_destroy": (None, [c_void_p]),
     "gpfq_last_error": (c_char_p, [c_void_p]),
     "gpfq_set_stream": (c_int, [c_void_p, c_void_p]),
+    "gpfq_set_option": (c_int, [c_void_p, c_char_p, c_int64]),
     "gpfq_trim": (c_int, [c_void_p]),
     "gpfq_query_stats": (c_int, [c_void_p, c_int32, POINTER(GpfqStats)]),
     "gpfq_dense_layer": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64,

@@ -16,6 +16,7 @@ int dense_stream_path(gpfq_ctx *, const float *, const float *, int64_t, int64_t
                       int64_t, int64_t, const double *, const int *, const int *, int, double *, int64_t, int64_t,
                       gpfq_stats *);
 int dense_gram_only(gpfq_ctx *, const float *, const float *, int64_t, int64_t, int64_t, double *, double *);
+bool dense_gram_uses_i8(gpfq_ctx *, int64_t, int64_t, bool);
 int conv_supported_kk(int kk);
 int conv_pick_chunks(gpfq_ctx *, int64_t, int, int64_t *, int, bool);
 int conv_gram_stage(gpfq_ctx *, int, ConvPtrs, bool, int64_t, int, int, int64_t, double *, bool, int);
@@ -122,6 +123,8 @@ extern "C" int gpfq_create(int device, gpfq_ctx **out) {
         ctx->conv_variant = !strcmp(v, "ldg") ? 1 : (!strcmp(v, "generic") ? 2 : 0);
     if (const char *v = getenv("GPFQ_SWEEP_KERNEL"))  // A/B switch: tile (default) | blocks
         ctx->sweep_variant = !strcmp(v, "blocks") ? 1 : 0;
+    if (const char *v = getenv("GPFQ_GRAM_KERNEL"))   // A/B switch: auto (default) | dmma | i8
+        ctx->gram_variant = !strcmp(v, "dmma") ? 1 : (!strcmp(v, "i8") ? 2 : 0);
     *out = ctx;
     return GPFQ_OK;
 }
@@ -143,6 +146,7 @@ extern "C" int gpfq_trim(gpfq_ctx *ctx) {
     }
     ctx->alph_cache.clear();
     ctx->alph_used = 0;
+    ctx->i8_oom_bytes = 0;
     return GPFQ_OK;
 }
 
@@ -158,6 +162,27 @@ extern "C" void gpfq_destroy(gpfq_ctx *ctx) {
 }
 
 extern "C" const char *gpfq_last_error(const gpfq_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int gpfq_set_option(gpfq_ctx *ctx, const char *key, int64_t value) {
+    if (!ctx || !key) return GPFQ_ERR_ARG;
+    ctx->err.clear();
+    if (!strcmp(key, "gram_kernel")) {          // 0 auto, 1 fp64 DMMA, 2 int8 slices on tcgen05
+        if (value < 0 || value > 2) return gpfq_fail(ctx, GPFQ_ERR_ARG, "gram_kernel must be 0, 1 or 2");
+        ctx->gram_variant = (int)value;
+    } else if (!strcmp(key, "i8_pairs_d")) {    // 0 default; else keep slice pairs with k + l <= value
+        if (value != 0 && (value < 2 || value > 10)) return gpfq_fail(ctx, GPFQ_ERR_ARG, "i8_pairs_d must be 0 or 2..10");
+        ctx->i8_pairs_d = (int)value;
+    } else if (!strcmp(key, "conv_kernel")) {   // 0 TMA-staged / fused NHWC, 1 direct LDG, 2 generic
+        if (value < 0 || value > 2) return gpfq_fail(ctx, GPFQ_ERR_ARG, "conv_kernel must be 0, 1 or 2");
+        ctx->conv_variant = (int)value;
+    } else if (!strcmp(key, "sweep_kernel")) {  // 0 persistent neuron-tile kernel, 1 one launch pair per block
+        if (value < 0 || value > 1) return gpfq_fail(ctx, GPFQ_ERR_ARG, "sweep_kernel must be 0 or 1");
+        ctx->sweep_variant = (int)value;
+    } else {
+        return gpfq_fail(ctx, GPFQ_ERR_ARG, "unknown option '%s'", key);
+    }
+    return GPFQ_OK;
+}
 
 extern "C" int gpfq_set_stream(gpfq_ctx *ctx, void *cuda_stream) {
     if (!ctx) return GPFQ_ERR_ARG;
@@ -305,8 +330,14 @@ static int choose_dense_method(gpfq_ctx *ctx, uint32_t flags, int64_t N0, int64_
     double t_stream = n_alph * (3.0 * (double)m * N0 * nj / slots_per_s * (u_in_regs ? 1.0 : 4.0));
     const double t_steps = n_alph * waves * (double)N0 * 0.5e-6;
     if (t_stream < t_steps) t_stream = t_steps;
-    double t_gram = (same ? 0.5 : 1.0) * (double)m * N0 * N0 / slots_per_s +
-                    n_alph * ((double)N0 * N0 * nj / slots_per_s) + 2.0 * (N0 / 32.0) * 6e-6;
+    double t_gram_stage = (same ? 0.5 : 1.0) * (double)m * N0 * N0 / slots_per_s;
+    if (dense_gram_uses_i8(ctx, N0, m, same)) {
+        // int8 slices on tcgen05: 15 slice pairs, lower-triangular 128 x 256 tiles, ~2e15 int8 op/s sustained (the
+        // single-CTA tile is bound by the L2 -> shared-memory operand stream), plus the slicing pass and launches
+        const double tile_area = (double)N0 * N0 * 0.5 + 192.0 * N0;
+        t_gram_stage = (same ? 1.0 : 2.0) * (15.0 * 2.0 * tile_area * (double)m / 2.0e15 + 24.0 * N0 * (double)m / 5e12) + 4e-5;
+    }
+    double t_gram = t_gram_stage + n_alph * ((double)N0 * N0 * nj / slots_per_s) + 2.0 * (N0 / 32.0) * 6e-6;
     const double gram_bytes = (same ? 1.0 : 2.0) * 8.0 * N0 * N0;
     if (gram_bytes > 48e9) return GPFQ_METHOD_STREAM_FAST;
     return t_gram < t_stream ? GPFQ_METHOD_GRAM : GPFQ_METHOD_STREAM_FAST;

@@ -8,6 +8,8 @@
 // The sweep walks blocks of 32 directions: contributions of earlier blocks are one NT contraction
 // per block (gemm_nt.cuh, two segments), the 32 in-block steps run warp-per-neuron with the running
 // d held one-per-lane and exchanged by shuffles.
+#include <algorithm>
+
 #include "gemm_nt.cuh"
 
 static constexpr int SWEEP_B = 32;
@@ -93,17 +95,42 @@ sweep_inblock_kernel(const double *__restrict__ G1, const double *__restrict__ G
 }
 
 // ---------------------------------------------------------------------------------------------
-// Persistent sweep: one CTA owns NT neurons and walks ALL direction blocks for them -- one launch per
-// layer, no inter-CTA dependency (neurons are independent).  Per block of 32 directions:
+// Persistent sweep: one CTA owns NT neurons and walks ALL direction blocks of a range for them -- one launch per
+// range, no inter-CTA dependency (neurons are independent).  Per block of 32 directions:
 //   panel   D[32 x NT] = G1[blk, :p] Wt[tile, :p]^T - G2[blk, :p] Qt[tile, :p]^T   on the fp64 tensor pipe
-//           (DMMA.8x8x4; warp w owns direction rows 8w..8w+7), K streamed through a cp.async ring;
-//           the Gram rows are shared by every CTA (L2), the W / Q panels are the CTA's own;
-//   inblock thread-per-neuron: d[32] and w[32] in registers, Gram diagonal block broadcast from shared
-//           memory, 32 fully unrolled greedy steps (decision + rank-1 update of the remaining d);
+//           (DMMA.8x8x4; warp w owns direction rows 8(w&3).., K half w>>2), K streamed through a cp.async ring;
+//           the Gram rows are shared by every CTA (L2), the W / Q panels are the CTA's own.  The last K chunk is the
+//           strictly-lower part of the block's own G1 diagonal tile: everything the weights contribute to the
+//           residual dots is known before the walk starts, only the q-terms are sequential;
+//   walk    thread-per-neuron: d[32] in registers, 32 fully unrolled greedy steps -- decision (reciprocal + Markstein
+//           correction, equispaced rounding window), then one DFMA per remaining direction (d -= q G2[t][tt], the
+//           Gram column broadcast from shared memory).  Measured dependent latencies on B200 (tools/fp64_latency.cu):
+//           DFMA 8.3, LDS.64 35, F2I+I2F 36 cycles, so a step is ~250 cycles; the other seven warps wait, which is
+//           why two CTAs share an SM (launch bounds, <= 106 KB shared memory): one walks while the other contracts;
 //   Q block -> shared memory -> Qt (neuron-major), read back by the later panels of this same CTA.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double gpfq_decide_rcp_inl(double nrm, double rinv, double d, double num, double w,
+                                                      const double *__restrict__ alph, int K, double inv_step) {
+    if (nrm < GPFQ_DEAD_NORM) return 0.0;
+    double v = w;
+    if (!(fabs(d) < GPFQ_PERP_DOT)) {
+        const double den = nrm * nrm;
+        const double q0 = num * rinv;
+        const double e = fma(-q0, den, num);
+        v = fma(e, rinv, q0);
+    }
+    return gpfq_bit_round_eq(v, alph, K, inv_step);
+}
+
+template <int NT>
+struct SweepCfg {
+    static constexpr int B = SWEEP_B, KC = 32, LD = KC + 4, STAGES = 3, THREADS = 256;
+    static constexpr size_t SMEM = sizeof(double) * ((size_t)STAGES * B * LD + (size_t)STAGES * NT * LD + 2 * B * (B + 1) +
+                                                     2 * B * (NT + 1) + 2 * NT * (B + 1) + 3 * B + GPFQ_MAX_K);
+};
+
 template <int NT, bool ALIGNED>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 sweep_tile_kernel(const double *__restrict__ G1, const double *__restrict__ G2, int64_t ldg, int64_t N0,
                   const double *__restrict__ Wt, double *__restrict__ Qt, int64_t nj,
                   const double *__restrict__ alphabets, const int *__restrict__ Koff,
@@ -111,9 +138,12 @@ sweep_tile_kernel(const double *__restrict__ G1, const double *__restrict__ G2, 
                   int64_t ldd) {
     // Directions [t_begin, t_end) (t_begin a multiple of 32).  Dt (nullable): (n_alph, nj, ldd) contributions of the
     // directions before t_begin, from one large NT contraction on the host side (two-level blocking).
-    constexpr int B = SWEEP_B, KC = 32, LD = KC + 4, STAGES = 4, THREADS = 256, NA = NT / 8;
+    using Cfg = SweepCfg<NT>;
+    constexpr int B = Cfg::B, KC = Cfg::KC, LD = Cfg::LD, STAGES = Cfg::STAGES, THREADS = Cfg::THREADS, NA = NT / 8;
     constexpr int GCH = B * (KC / 2) / THREADS;                          // 16-byte chunks of the Gram tile per thread (2)
     constexpr int WCH = (NT * (KC / 2) + THREADS - 1) / THREADS;         // ... of the W / Q tile per thread (2, 1, 1)
+    constexpr int DPT = B * B / THREADS;                                 // diagonal-tile entries per thread (4)
+    constexpr int WPT = (NT * B + THREADS - 1) / THREADS;                // W-block entries per thread (4, 2, 1)
     extern __shared__ __align__(16) unsigned char sweep_smem[];
     double *gst = reinterpret_cast<double *>(sweep_smem);   // STAGES x B x LD   (Gram rows of the block)
     double *wst = gst + STAGES * B * LD;                    // STAGES x NT x LD  (W or Q panel of the tile)
@@ -124,7 +154,8 @@ sweep_tile_kernel(const double *__restrict__ G1, const double *__restrict__ G2, 
     double *qblk = wblk + NT * (B + 1);                     // NT x (B+1)
     double *nrm = qblk + NT * (B + 1);                      // B
     double *rinv = nrm + B;                                 // B: RN(1 / nrm^2)
-    double *alph = rinv + B;                                // GPFQ_MAX_K
+    double *g1dd = rinv + B;                                // B: G1[t][t]
+    double *alph = g1dd + B;                                // GPFQ_MAX_K
 
     const int a = blockIdx.y;
     const int K = Koff[a + 1] - Koff[a];
@@ -156,6 +187,22 @@ sweep_tile_kernel(const double *__restrict__ G1, const double *__restrict__ G2, 
     for (int b = 0; b < nblk; ++b) {
         const int64_t t0 = t_begin + (int64_t)b * B;
         const int nb = (int)((t_end - t0) < B ? (t_end - t0) : B);
+        // ---- the block's own operands: requested now, parked in registers while the panel runs
+        double pg1[DPT], pg2[DPT], pw[WPT], pd[WPT];
+#pragma unroll
+        for (int i = 0; i < DPT; ++i) {
+            const int e = tid + i * THREADS, r = e / B, c = e % B;
+            const bool ok = r < nb && c <= r;
+            pg1[i] = ok ? __ldg(G1 + (t0 + r) * ldg + t0 + c) : 0.0;
+            pg2[i] = ok ? __ldg(G2 + (t0 + r) * ldg + t0 + c) : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < WPT; ++i) {
+            const int e = tid + i * THREADS, j = e / B, t = e % B;
+            const bool ok = e < NT * B && jt + j < nj && t < nb;
+            pw[i] = ok ? __ldg(Wt + (jt + j) * N0 + t0 + t) : 0.0;
+            pd[i] = (ok && Da) ? __ldg(Da + (jt + j) * ldd + (t0 - t_begin) + t) : 0.0;  // prior ranges
+        }
         // ---- panel: contributions of the earlier blocks of this range
         int g_off[GCH], g_bytes[GCH];
         const double *g1_src[GCH], *g2_src[GCH];
@@ -192,69 +239,74 @@ sweep_tile_kernel(const double *__restrict__ G1, const double *__restrict__ G2, 
             }
             cp_async_commit();
         };
-        issue(0);
-        issue(1);
-        issue(2);
-        for (int it = 0; it < total; ++it) {
-            cp_async_wait<2>();
-            __syncthreads();  // chunk `it` landed for everyone; chunk it-1 fully consumed
-            issue(it + 3);
-            const int st = it % STAGES;
-            const double *as = gst + st * B * LD + (strip * 8 + grp) * LD + tig + khalf * (KC / 2);
-            const double *bs = wst + st * NT * LD + grp * LD + tig + khalf * (KC / 2);
-            const bool neg = it >= b;
+        auto contract = [&](const double *gs, const double *ws, bool neg) {
+            const double *as = gs + (strip * 8 + grp) * LD + tig + khalf * (KC / 2);
+            const double *bs = ws + grp * LD + tig + khalf * (KC / 2);
 #pragma unroll
             for (int kk = 0; kk < KC / 2; kk += 4) {
                 const double av = neg ? -as[kk] : as[kk];
 #pragma unroll
                 for (int i = 0; i < NA; ++i) dmma_m8n8k4(acc[i][0], acc[i][1], av, bs[i * 8 * LD + kk]);
             }
+        };
+        issue(0);
+        issue(1);
+        for (int it = 0; it < total; ++it) {
+            cp_async_wait<1>();
+            __syncthreads();  // chunk `it` landed for everyone; chunk it-1 fully consumed
+            issue(it + 2);
+            const int st = it % STAGES;
+            contract(gst + st * B * LD, wst + st * NT * LD, it >= b);
         }
         cp_async_wait<0>();
+        __syncthreads();      // every warp is done with the ring: stage 0 takes the block's own (masked) tile
         // ---- stage the block's operands
+#pragma unroll
+        for (int i = 0; i < DPT; ++i) {
+            const int e = tid + i * THREADS, r = e / B, c = e % B;
+            g1d[r * (B + 1) + c] = pg1[i];
+            g2d[r * (B + 1) + c] = pg2[i];
+            gst[r * LD + c] = c < r ? pg1[i] : 0.0;   // strictly lower: what w_s (s < t, same block) adds to d_t
+        }
+#pragma unroll
+        for (int i = 0; i < WPT; ++i) {
+            const int e = tid + i * THREADS, j = e / B, t = e % B;
+            if (e < NT * B) {
+                wblk[j * (B + 1) + t] = pw[i];
+                qblk[j * (B + 1) + t] = pd[i];
+                wst[j * LD + t] = pw[i];
+            }
+        }
+        __syncthreads();
+        contract(gst, wst, false);
 #pragma unroll
         for (int i = 0; i < NA; ++i) {
             double *dp = dsm + khalf * B * (NT + 1) + (strip * 8 + grp) * (NT + 1) + i * 8 + tig * 2;
             dp[0] = acc[i][0];
             dp[1] = acc[i][1];
         }
-        for (int e = tid; e < B * B; e += THREADS) {
-            const int r = e / B, c = e % B;
-            const bool ok = r < nb && c <= r;
-            g1d[r * (B + 1) + c] = ok ? G1[(t0 + r) * ldg + t0 + c] : 0.0;
-            g2d[r * (B + 1) + c] = ok ? G2[(t0 + r) * ldg + t0 + c] : 0.0;
-        }
-        for (int e = tid; e < NT * B; e += THREADS) {
-            const int j = e / B, t = e % B;
-            const bool ok = jt + j < nj && t < nb;
-            wblk[j * (B + 1) + t] = ok ? Wt[(jt + j) * N0 + t0 + t] : 0.0;
-            qblk[j * (B + 1) + t] = (ok && Da) ? Da[(jt + j) * ldd + (t0 - t_begin) + t] : 0.0;  // prior ranges
-        }
-        __syncthreads();
         if (tid < B) {
             const double nv = tid < nb ? (double)(float)sqrt(g2d[tid * (B + 1) + tid]) : 0.0;
             nrm[tid] = nv;
             rinv[tid] = nv < GPFQ_DEAD_NORM ? 0.0 : 1.0 / (nv * nv);
+            g1dd[tid] = g1d[tid * (B + 1) + tid];
         }
         __syncthreads();
-        // ---- in-block steps: thread j walks the 32 directions of neuron jt + j
+        // ---- the walk: thread j takes neuron jt + j through the block's 32 directions
         if (tid < NT) {
-            double d[B], wv[B];
+            double d[B];
 #pragma unroll
-            for (int t = 0; t < B; ++t) {
-                // prior ranges + the two K-halves of this range's panel, in fixed order
+            for (int t = 0; t < B; ++t)  // prior ranges + the two K-halves of this range's panel, in fixed order
                 d[t] = qblk[tid * (B + 1) + t] + (dsm[t * (NT + 1) + tid] + dsm[B * (NT + 1) + t * (NT + 1) + tid]);
-                wv[t] = wblk[tid * (B + 1) + t];
-            }
 #pragma unroll
             for (int tt = 0; tt < B; ++tt) {
                 if (tt < nb) {
-                    const double num = fma(wv[tt], g1d[tt * (B + 1) + tt], d[tt]);
-                    const double q = gpfq_decide_rcp(nrm[tt], rinv[tt], d[tt], num, wv[tt], alph, K, inv_step);
+                    const double wv = wblk[tid * (B + 1) + tt];
+                    const double num = fma(wv, g1dd[tt], d[tt]);
+                    const double q = gpfq_decide_rcp_inl(nrm[tt], rinv[tt], d[tt], num, wv, alph, K, inv_step);
                     qblk[tid * (B + 1) + tt] = q;
 #pragma unroll
-                    for (int t = tt + 1; t < B; ++t)
-                        d[t] += g1d[t * (B + 1) + tt] * wv[tt] - g2d[t * (B + 1) + tt] * q;
+                    for (int t = tt + 1; t < B; ++t) d[t] = fma(-g2d[t * (B + 1) + tt], q, d[t]);
                 }
             }
         }
@@ -271,9 +323,7 @@ template <int NT>
 static int launch_sweep_tile(gpfq_ctx *ctx, const double *G1, const double *G2, int64_t N0, const double *Wt,
                              double *Qt, int64_t nj, const double *d_alph, const int *d_koff, const int *d_flags,
                              int n_alph, int64_t t_begin, int64_t t_end, const double *Dt, int64_t ldd) {
-    constexpr int B = SWEEP_B, LD = 36, STAGES = 4;
-    const size_t smem = sizeof(double) * ((size_t)STAGES * B * LD + (size_t)STAGES * NT * LD + 2 * B * (B + 1) +
-                                          2 * B * (NT + 1) + 2 * NT * (B + 1) + 2 * B + GPFQ_MAX_K);
+    const size_t smem = SweepCfg<NT>::SMEM;
     dim3 grid((unsigned)ceil_div64(nj, NT), (unsigned)n_alph);
     const bool aligned = (N0 % 2 == 0) && ((uintptr_t)G1 % 16 == 0) && ((uintptr_t)G2 % 16 == 0) &&
                          ((uintptr_t)Wt % 16 == 0) && ((uintptr_t)Qt % 16 == 0) && ((nj * N0) % 2 == 0);
@@ -338,10 +388,32 @@ static int gram_stage(gpfq_ctx *ctx, const float *A, const float *B, int64_t ld,
     return GPFQ_OK;
 }
 
+// Which kernel computes the Dense Grams: the int8-slice tcgen05 kernel (gram_i8.cu) when the layer is large enough
+// to feed it and its slice workspace fits, else the fp64 DMMA contraction above.  ctx->gram_variant forces one.
+size_t gram_i8_workspace_bytes(gpfq_ctx *, int64_t, int64_t, bool);
+int gram_i8_stage(gpfq_ctx *, const float *, const float *, int64_t, int64_t, int64_t, double *, double *);
+
+bool dense_gram_uses_i8(gpfq_ctx *ctx, int64_t N0, int64_t m, bool same) {
+    if (ctx->gram_variant == 1) return false;
+    if (N0 > 65000 || m >= ((int64_t)1 << 31) - 256) return false;
+    if (ctx->gram_variant != 2 && (N0 < 256 || m < 1024)) return false;
+    // an earlier call of this size or smaller ran out of device memory for the slices: do not try again
+    return ctx->i8_oom_bytes == 0 || gram_i8_workspace_bytes(ctx, N0, m, same) < ctx->i8_oom_bytes;
+}
+
 int dense_gram_only(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx, int64_t N0, int64_t m, double *G1,
                     double *G2) {
+    const bool same = G1 == G2;
+    if (dense_gram_uses_i8(ctx, N0, m, same)) {
+        ctx->last_gram_kernel = 2;
+        const int rc = gram_i8_stage(ctx, same ? Xq : X, Xq, ldx, N0, m, G1, G2);
+        if (rc != GPFQ_ERR_OOM) return rc;
+        ctx->i8_oom_bytes = gram_i8_workspace_bytes(ctx, N0, m, same);  // workspaces are allocated before any launch
+        ctx->err.clear();
+    }
+    ctx->last_gram_kernel = 1;
     GPFQ_TRY(gram_stage(ctx, Xq, Xq, ldx, N0, m, G2));
-    if (G1 != G2) GPFQ_TRY(gram_stage(ctx, Xq, X, ldx, N0, m, G1));
+    if (!same) GPFQ_TRY(gram_stage(ctx, Xq, X, ldx, N0, m, G1));
     return GPFQ_OK;
 }
 
@@ -362,8 +434,7 @@ int dense_gram_path(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx,
         GPFQ_TRY(gpfq_ws(ctx, WS_DT, (size_t)n_alph * nj * SWEEP_B * sizeof(double), (void **)&Dt));
 
     CUDA_TRY(ctx, gpfq_record(ctx, 2, ctx->stream));
-    GPFQ_TRY(gram_stage(ctx, Xq, Xq, ldx, N0, m, G2));
-    if (!same) GPFQ_TRY(gram_stage(ctx, Xq, X, ldx, N0, m, G1));
+    GPFQ_TRY(dense_gram_only(ctx, X, Xq, ldx, N0, m, G1, G2));
     CUDA_TRY(ctx, gpfq_record(ctx, 3, ctx->stream));
 
     {
@@ -372,15 +443,27 @@ int dense_gram_path(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx,
         KERNEL_CHECK(ctx);
     }
     if (ctx->sweep_variant == 0) {
-        // Two-level blocking: directions in ranges of SWEEP_OUTER; what the earlier ranges contribute to a range is ONE
-        // large NT contraction (all SMs, split over neurons x directions), the persistent neuron-tile kernel then walks
-        // the range.  Neurons per CTA: the widest tile that still gives every SM a CTA.
-        const int64_t ctas32 = ceil_div64(nj, 32) * n_alph, ctas16 = ceil_div64(nj, 16) * n_alph;
-        const int NT = ctas32 >= ctx->sm_count ? 32 : (ctas16 >= ctx->sm_count ? 16 : 8);
-        double *Do = nullptr;
-        if (N0 > SWEEP_OUTER) GPFQ_TRY(gpfq_ws(ctx, WS_DT, (size_t)n_alph * nj * SWEEP_OUTER * sizeof(double), (void **)&Do));
-        for (int64_t tb = 0; tb < N0; tb += SWEEP_OUTER) {
-            const int64_t te = tb + SWEEP_OUTER < N0 ? tb + SWEEP_OUTER : N0;
+        // Two-level blocking: directions in ranges of R; what the earlier ranges contribute to a range is ONE large NT
+        // contraction (all SMs, split over neurons x directions, and over K when that is too few tiles), the
+        // persistent neuron-tile kernel then walks the range.  Neurons per CTA: the narrowest tile that still fits
+        // every CTA on the chip at once (two per SM, so that one CTA's serial walk overlaps another's contraction).
+        const int64_t slots = 2LL * ctx->sm_count;
+        const int NT = ceil_div64(nj, 8) * n_alph <= slots ? 8 : (ceil_div64(nj, 16) * n_alph <= slots ? 16 : 32);
+        // R: a multiple of the contraction's 64-column tile that fills whole rounds of CTA slots
+        const int64_t tiles_m = ceil_div64(nj, 128) * n_alph;
+        int64_t R = SWEEP_OUTER;
+        if (tiles_m * 4 > ctx->sm_count) {
+            double best = 0.0;
+            for (int64_t n = 5; n <= 12; ++n) {
+                const int64_t tiles = tiles_m * n;
+                const double eff = (double)tiles / (double)(ceil_div64(tiles, slots) * slots) - 0.004 * (double)llabs(n - 8);
+                if (eff > best) { best = eff; R = 64 * n; }
+            }
+        }
+        double *Do = nullptr, *Dpart = nullptr;
+        if (N0 > R) GPFQ_TRY(gpfq_ws(ctx, WS_DT, (size_t)n_alph * nj * R * sizeof(double), (void **)&Do));
+        for (int64_t tb = 0; tb < N0; tb += R) {
+            const int64_t te = tb + R < N0 ? tb + R : N0;
             if (tb > 0) {
                 GemmArgs g = {};
                 g.seg[0] = {Wt, G1 + tb * N0, N0, N0, tb, 1.0};
@@ -389,19 +472,35 @@ int dense_gram_path(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx,
                 g.M = nj;
                 g.N = te - tb;
                 g.C = Do;
-                g.ldc = SWEEP_OUTER;
+                g.ldc = R;
                 g.nsplit = 1;
                 g.batch_strideA1 = nj * N0;
-                g.batch_strideC = nj * SWEEP_OUTER;
-                GPFQ_TRY((launch_gemm_nt<double, 128, 64, 16>(ctx, g, n_alph)));
+                g.batch_strideC = nj * R;
+                // few neurons: split K (the earlier directions) so that every SM gets a CTA; fixed-order reduction
+                const int64_t tiles = tiles_m * ceil_div64(te - tb, 64);
+                int64_t ns = tiles >= ctx->sm_count ? 1 : ctx->sm_count / tiles;
+                ns = std::min<int64_t>(std::min<int64_t>(ns, 16), std::max<int64_t>(1, tb / 128));
+                if (ns > 1) {
+                    const size_t one = (size_t)n_alph * nj * R;
+                    GPFQ_TRY(gpfq_ws(ctx, WS_PART, (size_t)ns * one * sizeof(double), (void **)&Dpart));
+                    g.C = Dpart;
+                    g.nsplit = (int)ns;
+                    g.split_stride = (int64_t)one;
+                    GPFQ_TRY((launch_gemm_nt<double, 128, 64, 16>(ctx, g, n_alph)));
+                    int blocks = (int)std::min<int64_t>(ceil_div64((int64_t)one, 256), 4096);
+                    reduce_splits_kernel<<<blocks, 256, 0, ctx->stream>>>(Dpart, (int)ns, (int64_t)one, Do, (int64_t)one);
+                    KERNEL_CHECK(ctx);
+                } else {
+                    GPFQ_TRY((launch_gemm_nt<double, 128, 64, 16>(ctx, g, n_alph)));
+                }
             }
             const double *Dp = tb > 0 ? Do : nullptr;
             if (NT == 32)
-                GPFQ_TRY(launch_sweep_tile<32>(ctx, G1, G2, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph, tb, te, Dp, SWEEP_OUTER));
+                GPFQ_TRY(launch_sweep_tile<32>(ctx, G1, G2, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph, tb, te, Dp, R));
             else if (NT == 16)
-                GPFQ_TRY(launch_sweep_tile<16>(ctx, G1, G2, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph, tb, te, Dp, SWEEP_OUTER));
+                GPFQ_TRY(launch_sweep_tile<16>(ctx, G1, G2, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph, tb, te, Dp, R));
             else
-                GPFQ_TRY(launch_sweep_tile<8>(ctx, G1, G2, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph, tb, te, Dp, SWEEP_OUTER));
+                GPFQ_TRY(launch_sweep_tile<8>(ctx, G1, G2, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph, tb, te, Dp, R));
         }
     } else {
         // multi-launch reference: one NT contraction + one in-block kernel per 32 directions
@@ -437,6 +536,7 @@ int dense_gram_path(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx,
     CUDA_TRY(ctx, gpfq_record(ctx, 4, ctx->stream));
     if (st) {
         st->method = GPFQ_METHOD_GRAM >> 4;
+        st->gram_kernel = ctx->last_gram_kernel;
         st->flops_algorithmic = (same ? 1 : 2) * m * N0 * (N0 + 1);  // lower triangles, 2 flops per MAC
         st->bytes_algorithmic = (same ? 1 : 2) * 4 * N0 * m + (same ? 1 : 2) * 8 * N0 * N0;
     }

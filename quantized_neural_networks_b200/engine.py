@@ -72,6 +72,10 @@ class GpfqEngine:
     def trim(self):
         self._check(self._lib.gpfq_trim(self._ctx))
 
+    def set_option(self, key: str, value: int):
+        """A/B switches of include/gpfq.h (`gram_kernel`, `i8_pairs_d`, `conv_kernel`, `sweep_kernel`)."""
+        self._check(self._lib.gpfq_set_option(self._ctx, key.encode(), int(value)))
+
     def _bind_stream(self, dev):
         """Device-tensor calls launch on torch's CURRENT stream: the tensors were produced there, so this is what
         orders our kernels after their producers (and lets torch.cuda.Event brackets time them).  Host-array

@@ -108,13 +108,17 @@ def test_conv_channel_shards_compose(engine):
 def test_gram_stage_fp64(engine, N0, m):
     rng = np.random.default_rng(N0 + m)
     X, Xq = hidden_pair(rng, N0, m)
-    G1, G2 = engine.gram_matrices(X, Xq)
+    engine.set_option("gram_kernel", 1)   # the fp64 DMMA contraction (the tcgen05 kernel has its own tests below)
+    try:
+        G1, G2 = engine.gram_matrices(X, Xq)
+        _, G2s = engine.gram_matrices(X, None)
+    finally:
+        engine.set_option("gram_kernel", 0)
     R1, R2 = O.gram_matrices(X, Xq)
     tri = np.tril_indices(N0)
     for G, R in ((G1, R1), (G2, R2)):
         err = np.max(np.abs(G[tri] - R[tri]) / np.maximum(np.abs(R[tri]), 1e-300))
         assert err < 1e-12, err
-    _, G2s = engine.gram_matrices(X, None)
     assert np.max(np.abs(G2s[tri] - (X.astype(np.float64) @ X.astype(np.float64).T)[tri])) < 1e-9 * np.max(R2)
 
 
@@ -385,3 +389,94 @@ def test_conv_nhwc_fused_matches_patch_path(n_img, H, Wd, C, F, pad):
             os.environ.pop("GPFQ_CONV_KERNEL", None)
     assert O.agreement(outs["tma"], Qref) == 1.0
     assert np.array_equal(outs["tma"], outs["ldg"]) and np.array_equal(outs["tma_same"], outs["ldg_same"])
+
+
+# ---- Dense Gram stage on tcgen05 (int8 slices, gram_i8.cu) ------------------------------------------------------------
+class _gram_kernel:
+    """Force the Dense Gram kernel for a block: 1 = fp64 DMMA contraction, 2 = int8 slices on tcgen05."""
+
+    def __init__(self, engine, variant, pairs_d=0):
+        self.engine, self.variant, self.pairs_d = engine, variant, pairs_d
+
+    def __enter__(self):
+        self.engine.set_option("gram_kernel", self.variant)
+        self.engine.set_option("i8_pairs_d", self.pairs_d)
+
+    def __exit__(self, *exc):
+        self.engine.set_option("gram_kernel", 0)
+        self.engine.set_option("i8_pairs_d", 0)
+
+
+def _gram_inputs(kind, N0, m):
+    rng = np.random.default_rng(N0 * 7 + m)
+    if kind == "hidden":
+        return hidden_pair(rng, N0, m)
+    if kind == "signed":   # no ReLU: products of both signs, Gram entries with heavy cancellation
+        X = rng.standard_normal((N0, m)).astype(np.float32)
+        return X, (X + 0.05 * rng.standard_normal((N0, m))).astype(np.float32)
+    if kind == "wide":     # tiny entries next to a few large ones: the slicing kernel must keep every slice pair
+        X = (rng.standard_normal((N0, m)) * 1e-4).astype(np.float32)
+        X[:, ::97] = 50.0
+        return X, (X * (1 + 1e-3 * rng.standard_normal((N0, m)))).astype(np.float32)
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("N0,m,kind", [(96, 400, "hidden"), (256, 1024, "hidden"), (300, 3001, "hidden"), (1000, 129, "signed"),
+                                       (520, 2048, "wide"), (2048, 1504, "hidden"), (256, 30000, "hidden"),
+                                       (1500, 5008, "signed")])
+def test_gram_i8_tcgen05_vs_fp64(engine, N0, m, kind):
+    """int8-slice Grams (15+ of 25 slice pairs, exact integer accumulation in TMEM) against fp64 NumPy: the error is
+    measured against |Xq| |X|^T, the scale every product is rounded at, and must stay far inside the 1e-9 parity budget
+    (SURVEY.md App. C).  Covers ragged tiles, K splits (few tiles), several K chunks (m > 26112) and the wide-row switch."""
+    X, Xq = _gram_inputs(kind, N0, m)
+    A, B = X.astype(np.float64), Xq.astype(np.float64)
+    tri = np.tril_indices(N0)
+    with _gram_kernel(engine, 2):
+        G1, G2 = engine.gram_matrices(X, Xq)
+    for G, R, S in ((G2, B @ B.T, np.abs(B) @ np.abs(B).T), (G1, B @ A.T, np.abs(B) @ np.abs(A).T)):
+        err = np.max(np.abs(G[tri] - R[tri]) / np.maximum(S[tri], 1e-300))
+        assert err < 1e-10, (kind, err)
+    with _gram_kernel(engine, 2, pairs_d=10):   # every slice pair: only the 2^-38 slice rounding is left
+        _, G2x = engine.gram_matrices(X, Xq)
+    assert np.max(np.abs(G2x[tri] - (B @ B.T)[tri]) / np.maximum((np.abs(B) @ np.abs(B).T)[tri], 1e-300)) < 2e-11
+
+
+def test_gram_i8_is_exact_on_integer_pixels(engine):
+    """MNIST-style un-normalised pixels (integers 0..255, dead rows; train_mnist_mlp.py:48-53): the slices hold the values
+    exactly and the integer accumulation makes the Gram bit-exact."""
+    rng = np.random.default_rng(5)
+    N0, m = 784, 6000
+    X = (rng.integers(0, 256, (N0, m)) * (rng.random((N0, m)) < 0.4)).astype(np.float32)
+    X[:30] = 0
+    with _gram_kernel(engine, 2):
+        _, G2 = engine.gram_matrices(X, None)
+    R = X.astype(np.float64) @ X.astype(np.float64).T
+    tri = np.tril_indices(N0)
+    assert np.array_equal(G2[tri], R[tri])
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_dense_gram_kernels_match_the_oracle(engine, variant):
+    """Gram + sweep with the Gram stage forced onto the DMMA contraction (1) and onto tcgen05 (2): golden vectors exact,
+    seeded layers against the literal C oracle, and both kernels give the same quantized layer."""
+    with _gram_kernel(engine, variant):
+        for name in ("dense_first_ternary", "dense_hidden_grid", "dense_wide_short"):
+            z = golden(name)
+            Xq = z["Xq"] if "Xq" in z.files else None
+            for qk in [k for k in z.files if k == "Q" or k.startswith("Q_")]:
+                Q = engine.dense_layer(z["X"], Xq, z["W"], z["A" + qk[1:]], method="gram")
+                assert np.array_equal(Q, z[qk]), (name, qk)
+        rng = np.random.default_rng(321)
+        for N0, N1, m, first in ((784, 40, 3000, True), (512, 24, 2500, False), (2048, 12, 1504, False)):
+            if first:
+                X = (rng.uniform(0, 1, (N0, m)) * (rng.uniform(0, 1, (N0, m)) < 0.5)).astype(np.float32)
+                X[:20] = 0
+                Xq = X
+            else:
+                X, Xq = hidden_pair(rng, N0, m)
+            W = glorot(rng, N0, N1)
+            A = O.layer_alphabet(W, 3, O.unit_alphabet(4))
+            Qref = c_oracle.quantize_layer(W, X, Xq, A)
+            Q = engine.dense_layer(X, None if first else Xq, W, A, method="gram")
+            assert engine.last_stats["gram_kernel"] == variant
+            check(Q, Qref, W, X, Xq, exact=True)
