@@ -119,13 +119,18 @@ __device__ __forceinline__ double gpfq_bit_round(double v, const double *__restr
     return best;
 }
 
+// out-of-line copy for the rarely taken branches of the fast paths (keeps their loop bodies small)
+static __device__ __noinline__ double gpfq_bit_round_slow(double v, const double *__restrict__ alph, int K) {
+    return gpfq_bit_round(v, alph, K);
+}
+
 // The same quantizer when the levels are ascending and equispaced (`rad * linspace(-1, 1, K)`, :396/:545 -- the host
 // checks this per alphabet): |a_k - v| is unimodal in k, so the first minimal index of the full scan lies in a window
 // of four levels around the grid guess.  The window is scanned with the very same subtraction / abs / strict-less
 // comparisons in ascending order, so ties still go to the lower index.  inv_step <= 0: literal scan.
 __device__ __forceinline__ double gpfq_bit_round_eq(double v, const double *__restrict__ alph, int K, double inv_step) {
     const double gpos = (v - alph[0]) * inv_step;
-    if (!(inv_step > 0.0) || !(fabs(gpos) < 1e9)) return gpfq_bit_round(v, alph, K);  // also NaN / inf arguments
+    if (!(inv_step > 0.0) || !(fabs(gpos) < 1e9)) return gpfq_bit_round_slow(v, alph, K);  // also NaN / inf arguments
     int k0 = (int)floor(gpos) - 1;
     k0 = k0 < 0 ? 0 : (k0 > K - 1 ? K - 1 : k0);
     const int k1 = k0 + 3 < K - 1 ? k0 + 3 : K - 1;

@@ -127,6 +127,8 @@ struct SweepCfg {
     static constexpr int B = SWEEP_B, KC = 32, LD = KC + 4, STAGES = 3, THREADS = 256;
     static constexpr size_t SMEM = sizeof(double) * ((size_t)STAGES * B * LD + (size_t)STAGES * NT * LD + 2 * B * (B + 1) +
                                                      2 * B * (NT + 1) + 2 * NT * (B + 1) + 3 * B + GPFQ_MAX_K);
+    // (2 B x (B+1) is the G2 diagonal tile plus B rows of zeros: the walk reads 31 entries below the diagonal at every
+    //  step, whatever the step)
 };
 
 template <int NT, bool ALIGNED>
@@ -147,9 +149,8 @@ sweep_tile_kernel(const double *__restrict__ G1, const double *__restrict__ G2, 
     extern __shared__ __align__(16) unsigned char sweep_smem[];
     double *gst = reinterpret_cast<double *>(sweep_smem);   // STAGES x B x LD   (Gram rows of the block)
     double *wst = gst + STAGES * B * LD;                    // STAGES x NT x LD  (W or Q panel of the tile)
-    double *g1d = wst + STAGES * NT * LD;                   // B x (B+1) diagonal blocks
-    double *g2d = g1d + B * (B + 1);
-    double *dsm = g2d + B * (B + 1);                        // 2 x B x (NT+1): one partial per K-half warp group
+    double *g2d = wst + STAGES * NT * LD;                   // 2B x (B+1): G2 diagonal tile, then B rows of zeros
+    double *dsm = g2d + 2 * B * (B + 1);                    // 2 x B x (NT+1): one partial per K-half warp group
     double *wblk = dsm + 2 * B * (NT + 1);                  // NT x (B+1)
     double *qblk = wblk + NT * (B + 1);                     // NT x (B+1)
     double *nrm = qblk + NT * (B + 1);                      // B
@@ -164,6 +165,7 @@ sweep_tile_kernel(const double *__restrict__ G1, const double *__restrict__ G2, 
     const int strip = warp & 3, khalf = warp >> 2;  // direction rows 8*strip.., k-steps [16*khalf, 16*khalf + 16)
     double *Qa = Qt + (int64_t)a * nj * N0;
     for (int e = tid; e < K; e += THREADS) alph[e] = alphabets[Koff[a] + e];
+    for (int e = tid; e < B * (B + 1); e += THREADS) g2d[B * (B + 1) + e] = 0.0;
     __syncthreads();
     const double inv_step = gpfq_inv_step(alph, K, Flags[a]);
 
@@ -264,9 +266,14 @@ sweep_tile_kernel(const double *__restrict__ G1, const double *__restrict__ G2, 
 #pragma unroll
         for (int i = 0; i < DPT; ++i) {
             const int e = tid + i * THREADS, r = e / B, c = e % B;
-            g1d[r * (B + 1) + c] = pg1[i];
             g2d[r * (B + 1) + c] = pg2[i];
             gst[r * LD + c] = c < r ? pg1[i] : 0.0;   // strictly lower: what w_s (s < t, same block) adds to d_t
+            if (c == r) {
+                const double nv = r < nb ? (double)(float)sqrt(pg2[i]) : 0.0;
+                nrm[r] = nv;
+                rinv[r] = nv < GPFQ_DEAD_NORM ? 0.0 : 1.0 / (nv * nv);
+                g1dd[r] = pg1[i];
+            }
         }
 #pragma unroll
         for (int i = 0; i < WPT; ++i) {
@@ -285,12 +292,6 @@ sweep_tile_kernel(const double *__restrict__ G1, const double *__restrict__ G2, 
             dp[0] = acc[i][0];
             dp[1] = acc[i][1];
         }
-        if (tid < B) {
-            const double nv = tid < nb ? (double)(float)sqrt(g2d[tid * (B + 1) + tid]) : 0.0;
-            nrm[tid] = nv;
-            rinv[tid] = nv < GPFQ_DEAD_NORM ? 0.0 : 1.0 / (nv * nv);
-            g1dd[tid] = g1d[tid * (B + 1) + tid];
-        }
         __syncthreads();
         // ---- the walk: thread j takes neuron jt + j through the block's 32 directions
         if (tid < NT) {
@@ -298,16 +299,21 @@ sweep_tile_kernel(const double *__restrict__ G1, const double *__restrict__ G2, 
 #pragma unroll
             for (int t = 0; t < B; ++t)  // prior ranges + the two K-halves of this range's panel, in fixed order
                 d[t] = qblk[tid * (B + 1) + t] + (dsm[t * (NT + 1) + tid] + dsm[B * (NT + 1) + t * (NT + 1) + tid]);
+            // A ROLLED loop (the unrolled walk is 160 KB of straight-line code run by one warp: instruction-fetch bound).
+            // d[] shifts down one slot per step, so the body is the same for every step: d[0] is the current direction
+            // and slot i takes the q-term of direction tt + 1 + i, read from the zero-padded G2 tile.
+            const double *wrow = wblk + tid * (B + 1);
+            double *qrow = qblk + tid * (B + 1);
+#pragma unroll 1
+            for (int tt = 0; tt < nb; ++tt) {
+                const double wv = wrow[tt], d0 = d[0];
+                const double num = fma(wv, g1dd[tt], d0);
+                const double q = gpfq_decide_rcp_inl(nrm[tt], rinv[tt], d0, num, wv, alph, K, inv_step);
+                qrow[tt] = q;
+                const double *gcol = g2d + (tt + 1) * (B + 1) + tt;  // G2[tt + 1 + i][tt] at gcol[i * (B + 1)]
 #pragma unroll
-            for (int tt = 0; tt < B; ++tt) {
-                if (tt < nb) {
-                    const double wv = wblk[tid * (B + 1) + tt];
-                    const double num = fma(wv, g1dd[tt], d[tt]);
-                    const double q = gpfq_decide_rcp_inl(nrm[tt], rinv[tt], d[tt], num, wv, alph, K, inv_step);
-                    qblk[tid * (B + 1) + tt] = q;
-#pragma unroll
-                    for (int t = tt + 1; t < B; ++t) d[t] = fma(-g2d[t * (B + 1) + tt], q, d[t]);
-                }
+                for (int i = 0; i < B - 1; ++i) d[i] = fma(-gcol[i * (B + 1)], q, d[i + 1]);
+                d[B - 1] = 0.0;
             }
         }
         __syncthreads();

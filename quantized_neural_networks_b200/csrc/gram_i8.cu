@@ -42,7 +42,9 @@ constexpr int D_NARROW = S + 1;               // slice pairs with k + l <= D: 15
 constexpr int D_MEDIUM = S + 2;               // 19 of 25 (max / mean <= 128)
 constexpr int D_ALL = 2 * S;                  // every pair
 constexpr int KC_BLOCKS = 204;                // K blocks per chunk: 5 pairs * 204 * 128 * 128^2 < 2^31
-constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+constexpr int EPI_PITCH = 33;                 // words: per-warp 32 x 32 transposing tile of the epilogue
+constexpr size_t EPI_BYTES = (size_t)4 * 32 * EPI_PITCH * 4;
+constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */ + EPI_BYTES;
 constexpr double RATIO_NARROW = 12.0, RATIO_MEDIUM = 128.0;  // 2^e / mean|non-zero x| of the worst row
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -217,6 +219,7 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     uint64_t *acc_full = empty + STAGES;    // [2]
     uint64_t *acc_empty = acc_full + 2;     // [2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+    int *epi_tiles = reinterpret_cast<int *>(smem + (size_t)STAGES * STAGE_BYTES + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gram = (int)(blockIdx.x % args.ngram);
@@ -299,11 +302,13 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             }
         }
     } else {
-        // ---- epilogue: TMEM lanes 32*(warp % 4) .. +31 are this warp's tile rows
+        // ---- epilogue: TMEM lanes 32*(warp % 4) .. +31 are this warp's tile rows.  tcgen05.ld hands a thread one ROW of
+        // 32 accumulators; a 32 x 32 transposing tile in shared memory turns that into one COLUMN per lane, so that every
+        // global access of the read-modify-write is a full 256-byte row segment.
         const int quad = warp & 3;
-        const int64_t row = (int64_t)ti * TM + quad * 32 + lane;
-        const int64_t row_hi = (int64_t)ti * TM + quad * 32 + 31;
-        double *out = args.out[gram] + (int64_t)split * args.split_stride + row * args.N0;
+        const int64_t row_lo = (int64_t)ti * TM + quad * 32, row_hi = row_lo + 31;
+        double *out = args.out[gram] + (int64_t)split * args.split_stride;
+        int *tile = epi_tiles + quad * 32 * EPI_PITCH;
         int p = 0;
         for (int c = 0; c < n_chunks; ++c) {
             for (int d = 2; d <= D; ++d, ++p) {
@@ -316,15 +321,20 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                     if (col0 > row_hi || col0 >= args.N0) break;  // warp-uniform: the rest of the tile is above the diagonal
                     uint32_t v[32];
                     tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * TN + cc * 32), v);
-                    if (row < args.N0) {
-                        double *o = out + col0;
-                        double acc[32];
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) acc[i] = (p > 0 && col0 + i <= row) ? o[i] : 0.0;
+                    for (int i = 0; i < 32; ++i) tile[lane * EPI_PITCH + i] = (int)v[i];
+                    __syncwarp();
+                    const int64_t col = col0 + lane;
+                    double *o = out + row_lo * args.N0 + col;
+                    const int n_rows = (int)min((int64_t)32, args.N0 - row_lo);
+                    double acc[32];
 #pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (col0 + i <= row) o[i] = fma((double)(int)v[i], scale, acc[i]);
-                    }
+                    for (int r = 0; r < 32; ++r)
+                        acc[r] = (p > 0 && r < n_rows && col <= row_lo + r) ? o[(int64_t)r * args.N0] : 0.0;
+#pragma unroll
+                    for (int r = 0; r < 32; ++r)
+                        if (r < n_rows && col <= row_lo + r) o[(int64_t)r * args.N0] = fma((double)tile[r * EPI_PITCH + lane], scale, acc[r]);
+                    __syncwarp();
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
                 __syncwarp();
