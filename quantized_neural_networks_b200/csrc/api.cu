@@ -319,16 +319,18 @@ extern "C" int gpfq_query_stats(gpfq_ctx *ctx, int32_t calls_back, gpfq_stats *o
 static int choose_dense_method(gpfq_ctx *ctx, uint32_t flags, int64_t N0, int64_t m, int64_t nj, bool same, int n_alph) {
     const uint32_t want = flags & GPFQ_METHOD_MASK;
     if (want != GPFQ_METHOD_AUTO) return (int)want;
-    // Cost table (DESIGN.md "method choice"), in fp64-pipe slots at the measured 18.5 T slots/s:
-    //   streaming : 3 slots per (sample, direction, neuron), per alphabet; a step cannot be shorter than ~0.5 us
-    //               (row ingest + block reduction); long sample axes (residual not register-resident) cost ~4x
-    //   Gram+sweep: m N0^2 / 2 slots per Gram (lower triangle) once + N0^2 nj per alphabet + 2 launches per 32 directions
+    // Cost table (DESIGN.md "method choice"), calibrated on B200 (tools/dense_bench.py), fp64-pipe slots at the measured
+    // 18.5 T slots/s:
+    //   streaming : 3 slots per (sample, direction, neuron), per alphabet; a step (row ingest + CTA-wide reduction +
+    //               decision) takes 0.6 us + 0.37 us per 2048 samples; long sample axes (residual not in registers) ~4x
+    //   Gram+sweep: Gram stage (DMMA: m N0^2 / 2 slots per Gram; int8 tcgen05: see below) once, then per alphabet
+    //               N0^2 nj slots of contractions and a serial walk of ~0.6 us per direction and round of CTAs
     const double slots_per_s = 18.5e12 * 0.6;
     const bool u_in_regs = m <= 512 * 16;
-    const double ctas = (double)((nj + 0) / 1);
-    const double waves = ceil(ctas / (double)ctx->sm_count);
+    const double waves = ceil((double)nj / (double)ctx->sm_count);
+    const double epv = ceil((double)m / 2048.0);
     double t_stream = n_alph * (3.0 * (double)m * N0 * nj / slots_per_s * (u_in_regs ? 1.0 : 4.0));
-    const double t_steps = n_alph * waves * (double)N0 * 0.5e-6;
+    const double t_steps = n_alph * waves * (double)N0 * (0.6e-6 + 0.37e-6 * (u_in_regs ? epv : 4.0 * epv));
     if (t_stream < t_steps) t_stream = t_steps;
     double t_gram_stage = (same ? 0.5 : 1.0) * (double)m * N0 * N0 / slots_per_s;
     if (dense_gram_uses_i8(ctx, N0, m, same)) {
@@ -337,7 +339,8 @@ static int choose_dense_method(gpfq_ctx *ctx, uint32_t flags, int64_t N0, int64_
         const double tile_area = (double)N0 * N0 * 0.5 + 192.0 * N0;
         t_gram_stage = (same ? 1.0 : 2.0) * (15.0 * 2.0 * tile_area * (double)m / 2.0e15 + 24.0 * N0 * (double)m / 5e12) + 4e-5;
     }
-    double t_gram = t_gram_stage + n_alph * ((double)N0 * N0 * nj / slots_per_s) + 2.0 * (N0 / 32.0) * 6e-6;
+    const double sweep_rounds = ceil((double)ceil_div64(nj, 32) * n_alph / (2.0 * ctx->sm_count));
+    double t_gram = t_gram_stage + n_alph * ((double)N0 * N0 * nj / slots_per_s) + sweep_rounds * (double)N0 * 0.6e-6;
     const double gram_bytes = (same ? 1.0 : 2.0) * 8.0 * N0 * N0;
     if (gram_bytes > 48e9) return GPFQ_METHOD_STREAM_FAST;
     return t_gram < t_stream ? GPFQ_METHOD_GRAM : GPFQ_METHOD_STREAM_FAST;

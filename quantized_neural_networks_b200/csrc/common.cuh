@@ -125,22 +125,22 @@ static __device__ __noinline__ double gpfq_bit_round_slow(double v, const double
 }
 
 // The same quantizer when the levels are ascending and equispaced (`rad * linspace(-1, 1, K)`, :396/:545 -- the host
-// checks this per alphabet): |a_k - v| is unimodal in k, so the first minimal index of the full scan lies in a window
-// of four levels around the grid guess.  The window is scanned with the very same subtraction / abs / strict-less
-// comparisons in ascending order, so ties still go to the lower index.  inv_step <= 0: literal scan.
+// checks this per alphabet): |a_k - v| is unimodal in k, so the first minimal index of the full scan is the grid guess
+// rint((v - a_0) / step) or one of its two neighbours (the guess is off by at most one, at a tie either side is in the
+// window).  The three candidates are compared with the very same subtraction / abs / strict-less tests in ascending
+// order, so ties still go to the lower index; indices clamped at the ends only repeat a level, which never wins a
+// strict comparison against its own earlier copy.  Branch-free: this sits on the serial critical path of every walk.
+// inv_step <= 0 (not equispaced) or a non-finite / huge argument: literal scan.
 __device__ __forceinline__ double gpfq_bit_round_eq(double v, const double *__restrict__ alph, int K, double inv_step) {
     const double gpos = (v - alph[0]) * inv_step;
     if (!(inv_step > 0.0) || !(fabs(gpos) < 1e9)) return gpfq_bit_round_slow(v, alph, K);  // also NaN / inf arguments
-    int k0 = (int)floor(gpos) - 1;
-    k0 = k0 < 0 ? 0 : (k0 > K - 1 ? K - 1 : k0);
-    const int k1 = k0 + 3 < K - 1 ? k0 + 3 : K - 1;
-    double best = alph[k0];
-    double bd = fabs(__dsub_rn(best, v));
-    for (int k = k0 + 1; k <= k1; ++k) {
-        const double a = alph[k];
-        const double d = fabs(__dsub_rn(a, v));
-        if (d < bd) { bd = d; best = a; }
-    }
+    const int kr = __double2int_rn(gpos), hi = K - 1;
+    const int i1 = min(max(kr, 0), hi), i0 = max(i1 - 1, 0), i2 = min(i1 + 1, hi);
+    const double a0 = alph[i0], a1 = alph[i1], a2 = alph[i2];
+    const double d0 = fabs(__dsub_rn(a0, v)), d1 = fabs(__dsub_rn(a1, v)), d2 = fabs(__dsub_rn(a2, v));
+    double best = a0, bd = d0;
+    if (d1 < bd) { bd = d1; best = a1; }
+    if (d2 < bd) best = a2;
     return best;
 }
 

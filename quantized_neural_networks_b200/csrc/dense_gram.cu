@@ -458,7 +458,7 @@ int dense_gram_path(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx,
         // R: a multiple of the contraction's 64-column tile that fills whole rounds of CTA slots
         const int64_t tiles_m = ceil_div64(nj, 128) * n_alph;
         int64_t R = SWEEP_OUTER;
-        if (tiles_m * 4 > ctx->sm_count) {
+        if (tiles_m * 8 >= ctx->sm_count) {
             double best = 0.0;
             for (int64_t n = 5; n <= 12; ++n) {
                 const int64_t tiles = tiles_m * n;
