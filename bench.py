@@ -15,7 +15,8 @@ One "step" = one pass of the hot path over all eight layers.
           Conv layers go through gpfq_conv_layer_nhwc (the coarser override point of INTEGRATION.md: the layer's
           (n_img, H, W, C) activations are handed over, patches are extracted on the device -- 9x fewer PCIe bytes
           than per-channel patch matrices), Dense layers through gpfq_dense_layer; every Q comes back to the host.
-  roofline  the dominant kernel (conv_gram_kernel, HBM-bound): algorithmic bytes / CUDA-event time of that stage.
+  roofline  the dominant kernel (conv_gram9_tma_kernel, HBM-bound, 74 % of the step): algorithmic bytes / CUDA-event time
+          of that stage.  roofline_tensor_stage: the Dense Gram stage on tcgen05 (int8 slices), against 2 x measured bf16.
   cpu_baseline  the oracle's NumPy restatement of the reference walk (kind "port": the reference is Python and does
           not travel to the GPU box), one process per host core exactly like the reference's ProcessPoolExecutor, on a
           bounded sample of every layer, extrapolated linearly in the number of neurons/filters.
@@ -401,7 +402,8 @@ def main():
         launches_per_step += sts[0]["kernel_launches"]
         msl = float(np.mean([s["ms_total"] for s in sts]))
         layer_report[name] = {"ms": round(msl, 4), "weights_per_s": round(sts[0]["weights"] / (msl * 1e-3)) if msl > 0 else None,
-                              "method": {1: "stream", 2: "gram", 3: "stream_fast"}.get(sts[0]["method"])}
+                              "method": {1: "stream", 2: "gram", 3: "stream_fast"}.get(sts[0]["method"]),
+                              "gram_kernel": {1: "dmma", 2: "i8_tcgen05"}.get(sts[0].get("gram_kernel"))}
         if kind == "conv":
             conv_bytes += sum(s["bytes_algorithmic"] for s in sts)
             conv_ms += sum(s["ms_gram"] for s in sts)
@@ -412,10 +414,33 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = conv_bytes / (conv_ms * 1e-3) / 1e9 if conv_ms > 0 else None
-    roofline = {"kernel": "conv_gram_kernel (per-channel patch Grams, fp64 accumulation)", "bound": "hbm",
+    # DRAM bytes ncu measured for three launches of this kernel (conv8, conv12, conv14; profiles/r1c_conv_gram9_tma.md)
+    # against their algorithmic bytes: 10.352e9 vs 10.339e9 -- every byte is read exactly once
+    roofline = {"kernel": "conv_gram9_tma_kernel (3x3 per-channel patch Grams: UBLKCP/mbarrier ring, DMMA corners + DFMA edge; "
+                          "74 % of the step, profiles/r1g_bench_launches.md)", "bound": "hbm",
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": (achieved / hbm_peak) if achieved else None,
-                "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)",
-                "algorithmic_bytes": "72 B per patch column per channel (36 when X == Xq)"}
+                "traffic": 10.352e9, "traffic_note": "dram read+write of the conv8+conv12+conv14 launches (ncu --set full); "
+                                                     "algorithmic bytes of the same launches: 10.339e9",
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy)" if peaks else "fallback (B200_PROFILING.md)",
+                "algorithmic_bytes": "72 B per patch column per channel (36 when X == Xq); the stage time is CUDA events around "
+                                     "the Gram launches of every conv call of the timed region"}
+    # the one tensor-core stage of the pass: the Dense Gram (dense19, 2048 x 2048 over m = 5008) as int8 slices on tcgen05
+    tensor = None
+    for name, sts in per_layer.items():
+        kind = dict((l[0], l[1]) for l in layers)[name]
+        if kind == "dense" and sts[0].get("gram_kernel") == 2 and sts[0]["ms_gram"] > 0:
+            d = [x for x in data if x["name"] == name][0]
+            N0, m = d["N0"], d["m"]
+            tiles = sum((ti >> 1) + 1 for ti in range(-(-N0 // 128)))
+            ops = 15 * tiles * 128 * 256 * 2 * (-(-m // 128) * 128) * (1 if d["first"] else 2)
+            ms_g = float(np.mean([x["ms_gram"] for x in sts]))
+            peak_i8 = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
+            tensor = {"kernel": "gram_i8_kernel (tcgen05.mma kind::i8 + TMA + TMEM; 15 int8 slice pairs)", "layer": name, "bound": "tensor",
+                      "achieved": ops / (ms_g * 1e-3) / 1e12, "peak": peak_i8, "unit": "TOP/s (int8)",
+                      "frac": ops / (ms_g * 1e-3) / 1e12 / peak_i8,
+                      "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops (int8 issues at twice the bf16 rate; no int8 peak is measured)",
+                      "fp64_equivalent_tflops": (1 if d["first"] else 2) * m * N0 * (N0 + 1) / (ms_g * 1e-3) / 1e12,
+                      "note": "stage time includes the slicing and exponent kernels; a 0.5 ms stage is mostly fill/drain"}
 
     # ---- e2e: host (pinned) buffers through the C ABI, copies inside the timed region ---------------------------
     e2e = None
@@ -458,7 +483,7 @@ def main():
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
-                "roofline": roofline, "cpu_baseline": cpu, "layers": layer_report}
+                "roofline": roofline, "roofline_tensor_stage": tensor, "cpu_baseline": cpu, "layers": layer_report}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
