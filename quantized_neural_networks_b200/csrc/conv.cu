@@ -279,10 +279,10 @@ conv_gram9_dmma_kernel(ConvPtrs ptrs, int64_t n, int64_t chunk_cols, double *__r
 // summation order is fixed.  Row pitch is COLS + 16 floats: lane groups g and g+1 then start 16 banks
 // apart and the LDS.128 fragments are conflict free.
 namespace tma9 {
-constexpr int CWARPS = 16;                 // consumer warps
+constexpr int CWARPS = 24;                 // consumer warps
 constexpr int COLS = CWARPS * 32;          // columns per stage
 constexpr int PITCH = COLS + 16;           // floats
-constexpr int STAGES = 5;
+constexpr int STAGES = 3;
 constexpr int THREADS = (CWARPS + 1) * 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }

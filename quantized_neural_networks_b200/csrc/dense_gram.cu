@@ -124,7 +124,9 @@ __device__ __forceinline__ double gpfq_decide_rcp_inl(double nrm, double rinv, d
 
 template <int NT>
 struct SweepCfg {
-    static constexpr int B = SWEEP_B, KC = 32, LD = KC + 4, STAGES = 3, THREADS = 256;
+    // K chunk per pipeline stage: 64 earlier directions (one barrier per chunk: fewer, fatter steps on the latency-bound
+    // in-range panel) where two CTAs still fit an SM, 32 for the 32-neuron tile
+    static constexpr int B = SWEEP_B, KC = NT == 32 ? 32 : 64, LD = KC + 4, STAGES = 3, THREADS = 256;
     static constexpr size_t SMEM = sizeof(double) * ((size_t)STAGES * B * LD + (size_t)STAGES * NT * LD + 2 * B * (B + 1) +
                                                      2 * B * (NT + 1) + 2 * NT * (B + 1) + 3 * B + GPFQ_MAX_K);
     // (2 B x (B+1) is the G2 diagonal tile plus B rows of zeros: the walk reads 31 entries below the diagonal at every
@@ -220,20 +222,27 @@ sweep_tile_kernel(const double *__restrict__ G1, const double *__restrict__ G2, 
         double acc[NA][2];
 #pragma unroll
         for (int i = 0; i < NA; ++i) acc[i][0] = acc[i][1] = 0.0;
-        const int total = 2 * b;  // chunks: b of (G1, W), then b of (G2, Q)
+        const int nck = (b * B + KC - 1) / KC;  // chunks per segment: the b * 32 earlier directions of this range
+        const int total = 2 * nck;              // nck of (G1, W), then nck of (G2, Q)
         auto issue = [&](int it) {
             if (it < total) {
-                const int seg = it >= b;
-                const int64_t k0 = t_begin + (int64_t)(seg ? it - b : it) * KC;
+                const int seg = it >= nck;
+                const int krel = (seg ? it - nck : it) * KC;   // first direction of the chunk, relative to t_begin
+                const int64_t k0 = t_begin + krel;
+                const int kleft = b * B - krel;                // directions of the chunk that exist (a multiple of 32)
                 const int st = it % STAGES;
                 if (ALIGNED) {
 #pragma unroll
-                    for (int i = 0; i < GCH; ++i)
-                        cp_async16(gst + st * B * LD + g_off[i], (seg ? g2_src[i] : g1_src[i]) + k0, g_bytes[i]);
+                    for (int i = 0; i < GCH; ++i) {
+                        const bool in = ((tid + i * THREADS) % (KC / 2)) * 2 < kleft;
+                        cp_async16(gst + st * B * LD + g_off[i], in ? (seg ? g2_src[i] : g1_src[i]) + k0 : G1, in ? g_bytes[i] : 0);
+                    }
 #pragma unroll
                     for (int i = 0; i < WCH; ++i)
-                        if (w_off[i] >= 0)
-                            cp_async16(wst + st * NT * LD + w_off[i], (seg ? q_src[i] : w_src[i]) + k0, w_bytes[i]);
+                        if (w_off[i] >= 0) {
+                            const bool in = ((tid + i * THREADS) % (KC / 2)) * 2 < kleft;
+                            cp_async16(wst + st * NT * LD + w_off[i], in ? (seg ? q_src[i] : w_src[i]) + k0 : Wt, in ? w_bytes[i] : 0);
+                        }
                 } else {
                     load_tile<double, B, KC, THREADS, false>(gst + st * B * LD, seg ? G2 : G1, ldg, t0, N0, k0, t0);
                     load_tile<double, NT, KC, THREADS, false>(wst + st * NT * LD, seg ? Qa : Wt, N0, jt, nj, k0, t0);
@@ -258,7 +267,7 @@ sweep_tile_kernel(const double *__restrict__ G1, const double *__restrict__ G2, 
             __syncthreads();  // chunk `it` landed for everyone; chunk it-1 fully consumed
             issue(it + 2);
             const int st = it % STAGES;
-            contract(gst + st * B * LD, wst + st * NT * LD, it >= b);
+            contract(gst + st * B * LD, wst + st * NT * LD, it >= nck);
         }
         cp_async_wait<0>();
         __syncthreads();      // every warp is done with the ring: stage 0 takes the block's own (masked) tile
@@ -268,6 +277,7 @@ sweep_tile_kernel(const double *__restrict__ G1, const double *__restrict__ G2, 
             const int e = tid + i * THREADS, r = e / B, c = e % B;
             g2d[r * (B + 1) + c] = pg2[i];
             gst[r * LD + c] = c < r ? pg1[i] : 0.0;   // strictly lower: what w_s (s < t, same block) adds to d_t
+            if (KC > B) gst[r * LD + B + c] = 0.0;    // the block's own chunk is 32 directions wide: zero the rest
             if (c == r) {
                 const double nv = r < nb ? (double)(float)sqrt(pg2[i]) : 0.0;
                 nrm[r] = nv;
@@ -282,6 +292,7 @@ sweep_tile_kernel(const double *__restrict__ G1, const double *__restrict__ G2, 
                 wblk[j * (B + 1) + t] = pw[i];
                 qblk[j * (B + 1) + t] = pd[i];
                 wst[j * LD + t] = pw[i];
+                if (KC > B) wst[j * LD + B + t] = 0.0;
             }
         }
         __syncthreads();
@@ -293,27 +304,46 @@ sweep_tile_kernel(const double *__restrict__ G1, const double *__restrict__ G2, 
             dp[1] = acc[i][1];
         }
         __syncthreads();
-        // ---- the walk: thread j takes neuron jt + j through the block's 32 directions
-        if (tid < NT) {
-            double d[B];
+        // ---- the walk: FOUR lanes per neuron (lane = 4 j + r) take neuron jt + j through the block's 32 directions.
+        // Lane r keeps the residual dots of directions = r (mod 4) in d[0..7]; a step broadcasts the current direction's
+        // dot from its owner lane (one 64-bit shuffle), all four lanes take the same decision, and each applies the
+        // q-term to its own eight directions -- 8 instead of 31 LDS + DFMA per lane and step on the serial path.
+        // The loop over groups of four steps is ROLLED (unrolled it is 160 KB of straight-line code: instruction-fetch
+        // bound); the register file shifts down one slot per group, folded into the group's last update, so the body
+        // is the same for every group; rows 32..63 of the G2 tile are zeros.
+        if (tid < 4 * NT) {
+            const int j = tid >> 2, r = tid & 3;
+            double d[8];
 #pragma unroll
-            for (int t = 0; t < B; ++t)  // prior ranges + the two K-halves of this range's panel, in fixed order
-                d[t] = qblk[tid * (B + 1) + t] + (dsm[t * (NT + 1) + tid] + dsm[B * (NT + 1) + t * (NT + 1) + tid]);
-            // A ROLLED loop (the unrolled walk is 160 KB of straight-line code run by one warp: instruction-fetch bound).
-            // d[] shifts down one slot per step, so the body is the same for every step: d[0] is the current direction
-            // and slot i takes the q-term of direction tt + 1 + i, read from the zero-padded G2 tile.
-            const double *wrow = wblk + tid * (B + 1);
-            double *qrow = qblk + tid * (B + 1);
+            for (int i = 0; i < 8; ++i) {  // prior ranges + the two K-halves of this range's panel, in fixed order
+                const int t = 4 * i + r;
+                d[i] = qblk[j * (B + 1) + t] + (dsm[t * (NT + 1) + j] + dsm[B * (NT + 1) + t * (NT + 1) + j]);
+            }
+            __syncwarp();  // every lane has read its prior-range values before the first q lands in qblk
+            const double *wrow = wblk + j * (B + 1);
+            double *qrow = qblk + j * (B + 1);
+            const int ngrp = (nb + 3) >> 2;
 #pragma unroll 1
-            for (int tt = 0; tt < nb; ++tt) {
-                const double wv = wrow[tt], d0 = d[0];
-                const double num = fma(wv, g1dd[tt], d0);
-                const double q = gpfq_decide_rcp_inl(nrm[tt], rinv[tt], d0, num, wv, alph, K, inv_step);
-                qrow[tt] = q;
-                const double *gcol = g2d + (tt + 1) * (B + 1) + tt;  // G2[tt + 1 + i][tt] at gcol[i * (B + 1)]
+            for (int g4 = 0; g4 < ngrp; ++g4) {
+                const double *gbase = g2d + (4 * g4 + r) * (B + 1) + 4 * g4;  // G2[4 (g4 + i) + r][4 g4 + rr] at gbase[4 i (B+1) + rr]
 #pragma unroll
-                for (int i = 0; i < B - 1; ++i) d[i] = fma(-gcol[i * (B + 1)], q, d[i + 1]);
-                d[B - 1] = 0.0;
+                for (int rr = 0; rr < 4; ++rr) {
+                    const int tt = 4 * g4 + rr;
+                    const double d0 = __shfl_sync(0xffffffffu, d[0], (lane & ~3) + rr);
+                    const double wv = wrow[tt];
+                    const double num = fma(wv, g1dd[tt], d0);
+                    double q = gpfq_decide_rcp_inl(nrm[tt], rinv[tt], d0, num, wv, alph, K, inv_step);
+                    if (tt >= nb) q = 0.0;  // past the end of a partial block: no decision, no update
+                    if (r == rr && tt < nb) qrow[tt] = q;
+                    if (rr < 3) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) d[i] = fma(-gbase[4 * i * (B + 1) + rr], q, d[i]);
+                    } else {  // last step of the group: slot 0 is spent in every lane, shift down while updating
+#pragma unroll
+                        for (int i = 0; i < 7; ++i) d[i] = fma(-gbase[4 * (i + 1) * (B + 1) + rr], q, d[i + 1]);
+                        d[7] = 0.0;
+                    }
+                }
             }
         }
         __syncthreads();
