@@ -424,8 +424,9 @@ conv_gram9_tma_kernel(ConvPtrs ptrs, int64_t n, int64_t chunk_cols, double *__re
 // col4 + k of four "cells" of four columns per step, so the 32 lanes of an LDS touch a 3 x 6 window per
 // cell: neighbouring lanes hit the same word (broadcast) and a pitch with P mod 32 in [8, 12] keeps the three
 // rows on disjoint banks.  HBM traffic drops from 72 to 8 bytes per patch column and channel; the kernel is
-// bound by the fp64 pipe (168 slots per column).  Geometry outside 3x3 / stride 1 / rate 1 / Wo % 4 == 0 goes
-// through im2col_kernel + the patch kernels.
+// bound by the fp64 pipe (168 slots per column).  Output widths that are not a multiple of four take a ragged last
+// cell (its extra lanes contribute zeros).  Geometry outside 3x3 / stride 1 / rate 1 goes through im2col_kernel + the
+// patch kernels.
 namespace nhwc9 {
 constexpr int CG = 8;              // channels per CTA = consumer warps
 constexpr int THREADS = CG * 32;
@@ -459,7 +460,7 @@ conv_gram9_nhwc_kernel(const float *__restrict__ act, const float *__restrict__ 
     const int nch_cta = (gm.n_ch - (int)blockIdx.y * CG) < CG ? (gm.n_ch - (int)blockIdx.y * CG) : CG;
     const int64_t ia = gm.img0 + (int64_t)blockIdx.x * gm.imgs_per_cta;
     const int64_t ib = (ia + gm.imgs_per_cta < gm.img0 + gm.n_img) ? ia + gm.imgs_per_cta : gm.img0 + gm.n_img;
-    const int Wp = gm.Wo + 2, cells_per_row = gm.Wo >> 2;
+    const int cells_per_row = (gm.Wo + 3) >> 2, Wp = cells_per_row * 4 + 2;  // a ragged last cell reads zero-filled columns
     const bool vec4 = (gm.C % 4 == 0) && (ch0 % 4 == 0) && (nch_cta == CG);
 
     Gram9Acc acc = {};
@@ -515,7 +516,7 @@ conv_gram9_nhwc_kernel(const float *__restrict__ act, const float *__restrict__ 
                 int rw = row, cl = cell;
 #pragma unroll
                 for (int sgrp = 0; sgrp < 4; ++sgrp) {
-                    const bool ok = f0 + sgrp < ncell;
+                    const bool ok = f0 + sgrp < ncell && cl * 4 + k < gm.Wo;  // columns past Wo are not patches
                     const int base = rw * gm.P + cl * 4 + k;
                     q[sgrp] = ok ? pq[base + r_g * gm.P + c_g] : 0.f;
                     q8[sgrp] = ok ? pq[base + 2 * gm.P + 2] : 0.f;
@@ -735,8 +736,8 @@ int im2col_stage(gpfq_ctx *ctx, const float *act, int64_t n_img, int H, int Wd, 
 
 // Fused NHWC path: is this geometry eligible, and with which plane pitch / band height?
 int nhwc9_plan(int kh, int kw, int sh, int sw, int rh, int rw, int Ho, int Wo, int *P_out, int *BR_out) {
-    if (kh != 3 || kw != 3 || sh != 1 || sw != 1 || rh != 1 || rw != 1 || Wo % 4 != 0 || Wo < 4) return 0;
-    int P = Wo + 2;
+    if (kh != 3 || kw != 3 || sh != 1 || sw != 1 || rh != 1 || rw != 1) return 0;
+    int P = (Wo + 3) / 4 * 4 + 2;
     while (P % 32 < 8 || P % 32 > 12) ++P;  // three plane rows on disjoint banks for the 3 x 6 window reads
     int BR = nhwc9::MAX_PLANE / P - 2;
     if (BR > Ho) BR = Ho;

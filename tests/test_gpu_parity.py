@@ -359,10 +359,12 @@ def test_conv_gram_kernel_variants_agree():
 
 
 @pytest.mark.parametrize("n_img,H,Wd,C,F,pad", [(5, 7, 12, 5, 4, "SAME"), (9, 10, 8, 8, 3, "VALID"), (3, 32, 32, 16, 6, "SAME"),
-                                                (70, 6, 6, 3, 2, "VALID"), (2, 40, 44, 12, 2, "SAME")])
+                                                (70, 6, 6, 3, 2, "VALID"), (2, 40, 44, 12, 2, "SAME"),
+                                                (4, 14, 14, 8, 3, "SAME"), (3, 9, 7, 4, 2, "SAME"), (6, 5, 5, 9, 2, "VALID")])
 def test_conv_nhwc_fused_matches_patch_path(n_img, H, Wd, C, F, pad):
     """The fused NHWC kernel (planes in shared memory, no patch matrices) against the im2col + patch-Gram path and the
-    oracle: ragged channel groups (scalar loader), full groups (LDG.128 loader), SAME / VALID, several bands."""
+    oracle: ragged channel groups (scalar loader), full groups (LDG.128 loader), SAME / VALID, several bands, output widths that
+    are not a multiple of four (VGG block 5 is 14 x 14)."""
     import os
     import torch
     from quantized_neural_networks_b200 import GpfqEngine

@@ -1,0 +1,134 @@
+"""VGG16-shaped full-network GPFQ pass (BASELINE.json configs[2]: quantize_pretrained_imagenet.py, ternary), device-resident
+synthetic inputs, random-init weights -- per-layer times and roofline fractions.
+
+    python tools/vgg_bench.py [--n-img 1504] [--reps 2] [--gpus-emulated 1]
+
+Conv layers go through gpfq_conv_layer_nhwc (activations (n_img, H, W, C): at 1504 images the per-channel patch matrices of
+block 1 would be 348 GB, the activations are 19 GB), Dense layers through gpfq_dense_layer.  One JSON line per layer + a total.
+Roofline per layer: conv -> the fp64 pipe (168 slots per patch column and channel, 18.55e12 slots/s measured) and the HBM bytes
+actually needed (8 B per column and channel); Dense -> fp64 pipe for the sweep (N0^2 N1 MACs), int8 tensor pipe for the Gram.
+`--shard r/w` runs rank r's share of every layer (channels / neurons) to emulate one rank of a w-GPU job on one GPU.
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+CONV = [(3, 64, 224), (64, 64, 224), (64, 128, 112), (128, 128, 112), (128, 256, 56), (256, 256, 56), (256, 256, 56),
+        (256, 512, 28), (512, 512, 28), (512, 512, 28), (512, 512, 14), (512, 512, 14), (512, 512, 14)]
+DENSE = [(25088, 4096), (4096, 4096), (4096, 1000)]
+FP64_SLOTS = 18.55e12
+
+
+def shard_range(n, rank, world):
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n-img", type=int, default=1504)
+    ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--shard", default="0/1")
+    ap.add_argument("--skip-conv", action="store_true")
+    args = ap.parse_args()
+    rank, world = (int(v) for v in args.shard.split("/"))
+    import torch
+    from quantized_neural_networks_b200 import get_engine
+    eng = get_engine(0)
+    dev = torch.device("cuda", 0)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0)) * 1e9
+    i8_peak = 2.0 * float(peaks.get("bf16_tflops", 1590.0)) * 1e12
+    alph = lambda W: 3 * float(torch.median(W.abs().flatten())) * np.linspace(-1, 1, 3)
+    total_ms, total_w = 0.0, 0
+    if not args.skip_conv:
+        for li, (C, F, H) in enumerate(CONV):
+            g = torch.Generator(device=dev).manual_seed(100 + li)
+            shape = (args.n_img, H, H, C)
+            if li == 0:
+                act = torch.rand(shape, device=dev, generator=g)
+                actq = None
+            else:
+                act = torch.empty(shape, device=dev)
+                actq = torch.empty(shape, device=dev)
+                step = max(1, args.n_img // 8)
+                for i0 in range(0, args.n_img, step):   # chunked: the temporaries of a 19 GB randn would double the footprint
+                    z = torch.randn((min(step, args.n_img - i0), H, H, C), device=dev, generator=g)
+                    act[i0:i0 + step] = torch.relu(z)
+                    actq[i0:i0 + step] = torch.relu(z + 0.05 * torch.randn(z.shape, device=dev, generator=g))
+                    del z
+            W = (torch.rand((3, 3, C, F), device=dev, generator=g) * 2 - 1) * float(np.sqrt(6.0 / (9 * C)))
+            A = alph(W)
+            lo, hi = shard_range(C, rank, world)
+            out = torch.zeros((1, 3, 3, C, F), dtype=torch.float64, device=dev)
+            best = None
+            for _ in range(args.reps):
+                eng.conv_layer_nhwc(act, actq, W, A, c0=lo, n_channels=hi - lo, out=out, sync=True)
+                st = dict(eng.last_stats)
+                if best is None or st["ms_total"] < best["ms_total"]:
+                    best = st
+            colch = args.n_img * H * H * (hi - lo)
+            slots = colch * (84 if li == 0 else 168)
+            bytes_alg = colch * (4 if li == 0 else 8)
+            ms = best["ms_total"]
+            print(json.dumps({"layer": f"conv{li}", "C": C, "F": F, "H": H, "channels": [lo, hi], "weights": 9 * (hi - lo) * F,
+                              "ms": round(ms, 3), "ms_gram": round(best["ms_gram"], 3),
+                              "fp64_pipe_frac": round(slots / FP64_SLOTS / (best["ms_gram"] * 1e-3), 3),
+                              "hbm_frac": round(bytes_alg / hbm / (best["ms_gram"] * 1e-3), 3),
+                              "weights_per_s": round(9 * (hi - lo) * F / (ms * 1e-3))}), flush=True)
+            total_ms += ms
+            total_w += 9 * (hi - lo) * F
+            del act, actq, W, out
+            torch.cuda.empty_cache()
+            eng.trim()
+    m = args.n_img
+    for li, (N0, N1) in enumerate(DENSE):
+        g = torch.Generator(device=dev).manual_seed(200 + li)
+        Z = torch.randn((N0, m), device=dev, generator=g)
+        X = torch.relu(Z)
+        Xq = torch.relu(Z + 0.05 * torch.randn((N0, m), device=dev, generator=g))
+        del Z
+        W = (torch.rand((N0, N1), device=dev, generator=g) * 2 - 1) * float(np.sqrt(6.0 / (N0 + N1)))
+        A = alph(W)
+        lo, hi = shard_range(N1, rank, world)
+        out = torch.zeros((1, N0, N1), dtype=torch.float64, device=dev)
+        best = None
+        for _ in range(args.reps):
+            eng.dense_layer(X, Xq, W, A, j0=lo, j1=hi, out=out, sync=True)
+            st = dict(eng.last_stats)
+            if best is None or st["ms_total"] < best["ms_total"]:
+                best = st
+        ms = best["ms_total"]
+        nj = hi - lo
+        line = {"layer": f"fc{li + 1}", "N0": N0, "N1": N1, "m": m, "neurons": [lo, hi], "weights": N0 * nj, "ms": round(ms, 3),
+                "method": {1: "stream", 2: "gram", 3: "stream_fast"}[best["method"]], "ms_gram": round(best["ms_gram"], 3),
+                "ms_sweep": round(best["ms_sweep"], 3), "ms_stream": round(best["ms_stream"], 3),
+                "weights_per_s": round(N0 * nj / (ms * 1e-3))}
+        if best["method"] == 2:
+            line["sweep_fp64_pipe_frac"] = round(N0 * N0 * nj / FP64_SLOTS / (best["ms_sweep"] * 1e-3), 3)
+            if best["gram_kernel"] == 2:
+                tiles = sum((ti >> 1) + 1 for ti in range(-(-N0 // 128)))
+                ops = 15 * tiles * 128 * 256 * 2 * (-(-m // 128) * 128) * 2
+                line["gram_int8_frac_of_2x_bf16"] = round(ops / i8_peak / (best["ms_gram"] * 1e-3), 3)
+        print(json.dumps(line), flush=True)
+        total_ms += ms
+        total_w += N0 * nj
+        del X, Xq, W, out
+        torch.cuda.empty_cache()
+        eng.trim()
+    print(json.dumps({"total_ms": round(total_ms, 2), "weights": total_w, "weights_per_s": round(total_w / (total_ms * 1e-3)),
+                      "n_img": args.n_img, "shard": args.shard}))
+
+
+if __name__ == "__main__":
+    main()
