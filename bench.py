@@ -403,7 +403,7 @@ def main():
         msl = float(np.mean([s["ms_total"] for s in sts]))
         layer_report[name] = {"ms": round(msl, 4), "weights_per_s": round(sts[0]["weights"] / (msl * 1e-3)) if msl > 0 else None,
                               "method": {1: "stream", 2: "gram", 3: "stream_fast"}.get(sts[0]["method"]),
-                              "gram_kernel": {1: "dmma", 2: "i8_tcgen05"}.get(sts[0].get("gram_kernel"))}
+                              "gram_kernel": {1: "dmma", 2: "i8_tcgen05", 3: "block_diagonal"}.get(sts[0].get("gram_kernel"))}
         if kind == "conv":
             conv_bytes += sum(s["bytes_algorithmic"] for s in sts)
             conv_ms += sum(s["ms_gram"] for s in sts)

@@ -65,7 +65,8 @@ typedef struct gpfq_stats {
     int64_t weights;         /* quantized weights produced (per alphabet x n_alphabets) */
     int64_t bytes_algorithmic; /* algorithmic HBM bytes of the dominant kernel */
     int64_t flops_algorithmic; /* algorithmic fp64 flops of the dominant kernel */
-    int32_t gram_kernel;     /* Dense Gram stage ran as: 0 none, 1 fp64 DMMA (mma.sync), 2 int8 slices on tcgen05 */
+    int32_t gram_kernel;     /* Dense Gram stage ran as: 0 none, 1 fp64 DMMA (mma.sync), 2 int8 slices on tcgen05,
+                                3 block-diagonal tiles only (residual form of the sweep's outer level) */
     int32_t reserved;
 } gpfq_stats;
 
@@ -82,7 +83,8 @@ int gpfq_set_stream(gpfq_ctx *ctx, void *cuda_stream);
 /* Tuning / A-B switches (profiling and tests; the defaults pick by shape):
  *   "gram_kernel"  0 auto, 1 fp64 DMMA contraction, 2 int8 slices on tcgen05 (Dense Gram stage)
  *   "i8_pairs_d"   0 default, else keep int8 slice pairs with k + l <= value (2..10; 10 = every pair)
- *   "conv_kernel"  0 TMA-staged / fused NHWC, 1 direct LDG, 2 generic      "sweep_kernel"  0 persistent tile, 1 per block */
+ *   "conv_kernel"  0 TMA-staged / fused NHWC, 1 direct LDG, 2 generic      "sweep_kernel"  0 persistent tile, 1 per block
+ *   "sweep_outer"  0 auto, 1 Gram rows of all earlier directions, 2 carried residuals (3 m N0 N1 MACs: wins when m << N0) */
 int gpfq_set_option(gpfq_ctx *ctx, const char *key, int64_t value);
 /* Stage times of an earlier call: calls_back = 0 is the most recent API call, 1 the one before, ...
  * (a ring of 128).  For GPFQ_NO_SYNC calls, synchronise the stream first; unfinished events read 0. */

@@ -56,6 +56,7 @@ struct gpfq_ctx {
     int sweep_variant = 0;        // triangular sweep: 0 persistent neuron-tile kernel (default), 1 one launch pair per block
     bool stream_literal = false;  // streaming walk: reproduce the reference's fp32-rounded w*X products (set per call)
     int gram_variant = 0;         // Dense Gram stage: 0 auto, 1 fp64 DMMA (mma.sync), 2 int8 slices on tcgen05 (gram_i8.cu)
+    int lowrank_variant = 0;      // sweep outer level: 0 auto, 1 Gram rows, 2 residual (low-rank) form
     int i8_pairs_d = 0;           // int8 Gram: keep slice pairs with k + l <= this (0: the default of gram_i8.cu)
     int last_gram_kernel = 0;     // what the last Dense Gram stage ran (1 DMMA, 2 int8 tcgen05)
     size_t i8_oom_bytes = 0;      // smallest int8-Gram workspace that failed to allocate (0: none yet)
@@ -70,7 +71,7 @@ struct gpfq_ctx {
 enum WsSlot {
     WS_X = 0, WS_XQ, WS_W, WS_Q, WS_WT, WS_QT, WS_G1, WS_G2, WS_PART, WS_DT, WS_NRM, WS_ALPH,
     WS_U, WS_PTRS, WS_CG, WS_CPART, WS_PATCH_A, WS_PATCH_B, WS_ACT_A, WS_ACT_B, WS_QIDX, WS_MISC,
-    WS_I8_SQ, WS_I8_SX, WS_I8_E, WS_I8_TILES
+    WS_I8_SQ, WS_I8_SX, WS_I8_E, WS_I8_TILES, WS_LR_XD, WS_LR_XT, WS_LR_U
 };
 
 int gpfq_fail(gpfq_ctx *ctx, int code, const char *fmt, ...);

@@ -356,21 +356,21 @@ sweep_tile_kernel(const double *__restrict__ G1, const double *__restrict__ G2, 
 }
 
 template <int NT>
-static int launch_sweep_tile(gpfq_ctx *ctx, const double *G1, const double *G2, int64_t N0, const double *Wt,
+static int launch_sweep_tile(gpfq_ctx *ctx, const double *G1, const double *G2, int64_t ldg, int64_t N0, const double *Wt,
                              double *Qt, int64_t nj, const double *d_alph, const int *d_koff, const int *d_flags,
                              int n_alph, int64_t t_begin, int64_t t_end, const double *Dt, int64_t ldd) {
     const size_t smem = SweepCfg<NT>::SMEM;
     dim3 grid((unsigned)ceil_div64(nj, NT), (unsigned)n_alph);
-    const bool aligned = (N0 % 2 == 0) && ((uintptr_t)G1 % 16 == 0) && ((uintptr_t)G2 % 16 == 0) &&
+    const bool aligned = (N0 % 2 == 0) && (ldg % 2 == 0) && ((uintptr_t)G1 % 16 == 0) && ((uintptr_t)G2 % 16 == 0) &&
                          ((uintptr_t)Wt % 16 == 0) && ((uintptr_t)Qt % 16 == 0) && ((nj * N0) % 2 == 0);
     if (aligned) {
         auto k = sweep_tile_kernel<NT, true>;
         CUDA_TRY(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, 256, smem, ctx->stream>>>(G1, G2, N0, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, t_begin, t_end, Dt, ldd);
+        k<<<grid, 256, smem, ctx->stream>>>(G1, G2, ldg, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, t_begin, t_end, Dt, ldd);
     } else {
         auto k = sweep_tile_kernel<NT, false>;
         CUDA_TRY(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, 256, smem, ctx->stream>>>(G1, G2, N0, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, t_begin, t_end, Dt, ldd);
+        k<<<grid, 256, smem, ctx->stream>>>(G1, G2, ldg, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, t_begin, t_end, Dt, ldd);
     }
     KERNEL_CHECK(ctx);
     return GPFQ_OK;
@@ -453,6 +453,147 @@ int dense_gram_only(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx,
     return GPFQ_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Low-rank form of the outer level (m << N0, e.g. VGG16 fc1: N0 = 25088, m = 1504).
+// What the directions before a range contribute to it is  D[t] = <X~_t, u>  with the residual
+//     u = sum_{s < range} (w_s X_s - q_s X~_s)   (m numbers per neuron)   -- quantized_network.py:119 itself,
+// so instead of contracting Gram rows over ALL earlier directions (2 R tb nj MACs per range, N0^2 nj in total) the
+// residuals U (nj x m, fp64) are carried along:   U += W_range X_range - Q_range X~_range   (2 R m nj MACs),
+// D_range = U X~_range^T (R m nj MACs): 3 m N0 nj in total, and only the block-diagonal R x R Gram tiles are ever
+// computed.  Same exact-product numerics as the Gram form; the range walk (sweep_tile_kernel) is unchanged.
+// ---------------------------------------------------------------------------------------------
+// Xd[t][i] = (double) X[t][i]  and  Xt[i][t] = (double) X[t][i]
+__global__ void widen_transpose_kernel(const float *__restrict__ X, int64_t ldx, int64_t N0, int64_t m,
+                                       double *__restrict__ Xd, double *__restrict__ Xt) {
+    __shared__ float tile[32][33];
+    const int64_t ib = (int64_t)blockIdx.x * 32, tb = (int64_t)blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int64_t t = tb + r, i = ib + threadIdx.x;
+        const float v = (t < N0 && i < m) ? X[t * ldx + i] : 0.f;
+        tile[r][threadIdx.x] = v;
+        if (t < N0 && i < m) Xd[t * m + i] = (double)v;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int64_t i = ib + r, t = tb + threadIdx.x;
+        if (i < m && t < N0) Xt[i * N0 + t] = (double)tile[threadIdx.x][r];
+    }
+}
+
+static bool dense_uses_lowrank(gpfq_ctx *ctx, int64_t N0, int64_t m, int64_t nj) {
+    if (ctx->sweep_variant != 0 || ctx->lowrank_variant == 1) return false;
+    if (ctx->lowrank_variant == 2) return N0 > 64;
+    return 3 * m < N0 && N0 >= 4096 && nj >= 256;
+}
+
+static int64_t pick_range_length(gpfq_ctx *ctx, int64_t nj, int n_alph) {
+    // R: a multiple of the contraction's 64-column tile that fills whole rounds of CTA slots (two CTAs per SM)
+    const int64_t slots = 2LL * ctx->sm_count, tiles_m = ceil_div64(nj, 128) * n_alph;
+    int64_t R = SWEEP_OUTER;
+    if (tiles_m * 8 >= ctx->sm_count) {
+        double best = 0.0;
+        for (int64_t n = 5; n <= 12; ++n) {
+            const int64_t tiles = tiles_m * n;
+            const double eff = (double)tiles / (double)(ceil_div64(tiles, slots) * slots) - 0.004 * (double)llabs(n - 8);
+            if (eff > best) { best = eff; R = 64 * n; }
+        }
+    }
+    return R;
+}
+
+static int dispatch_sweep_tile(gpfq_ctx *ctx, int NT, const double *G1, const double *G2, int64_t ldg, int64_t N0,
+                               const double *Wt, double *Qt, int64_t nj, const double *d_alph, const int *d_koff,
+                               const int *d_flags, int n_alph, int64_t tb, int64_t te, const double *Dp, int64_t R) {
+    if (NT == 32) return launch_sweep_tile<32>(ctx, G1, G2, ldg, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph, tb, te, Dp, R);
+    if (NT == 16) return launch_sweep_tile<16>(ctx, G1, G2, ldg, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph, tb, te, Dp, R);
+    return launch_sweep_tile<8>(ctx, G1, G2, ldg, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph, tb, te, Dp, R);
+}
+
+// Sweep with the low-rank outer level.  Wt (nj, N0) is ready; Qt (n_alph, nj, N0) receives the result.
+static int dense_lowrank_sweep(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx, int64_t N0, int64_t m,
+                               const double *Wt, double *Qt, int64_t nj, const double *d_alph, const int *d_koff,
+                               const int *d_flags, int n_alph, int NT) {
+    const bool same = (Xq == X);
+    cudaStream_t st = ctx->stream;
+    const int64_t R = pick_range_length(ctx, nj, n_alph);
+    double *Xd = nullptr, *Xt = nullptr, *Xqd = nullptr, *Xqt = nullptr, *Ut = nullptr, *Gc1 = nullptr, *Gc2 = nullptr, *Do = nullptr;
+    const size_t xbytes = (size_t)N0 * m * sizeof(double);
+    GPFQ_TRY(gpfq_ws(ctx, WS_LR_XD, xbytes * (same ? 1 : 2), (void **)&Xd));
+    GPFQ_TRY(gpfq_ws(ctx, WS_LR_XT, xbytes * (same ? 1 : 2), (void **)&Xt));
+    Xqd = same ? Xd : Xd + (size_t)N0 * m;
+    Xqt = same ? Xt : Xt + (size_t)N0 * m;
+    GPFQ_TRY(gpfq_ws(ctx, WS_LR_U, (size_t)n_alph * nj * m * sizeof(double), (void **)&Ut));
+    GPFQ_TRY(gpfq_ws(ctx, WS_G2, (size_t)N0 * R * sizeof(double), (void **)&Gc2));
+    if (same) Gc1 = Gc2;
+    else GPFQ_TRY(gpfq_ws(ctx, WS_G1, (size_t)N0 * R * sizeof(double), (void **)&Gc1));
+    GPFQ_TRY(gpfq_ws(ctx, WS_DT, (size_t)n_alph * nj * R * sizeof(double), (void **)&Do));
+
+    CUDA_TRY(ctx, gpfq_record(ctx, 2, st));
+    {
+        dim3 grid((unsigned)ceil_div64(m, 32), (unsigned)ceil_div64(N0, 32));
+        widen_transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(X, ldx, N0, m, Xd, Xt);
+        KERNEL_CHECK(ctx);
+        if (!same) {
+            widen_transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(Xq, ldx, N0, m, Xqd, Xqt);
+            KERNEL_CHECK(ctx);
+        }
+    }
+    // block-diagonal Gram tiles, compact: Gc[t][s - tb(t)], row stride R (exact fp32 x fp32 products, fp64 sums)
+    for (int64_t tb = 0; tb < N0; tb += R) {
+        const int64_t te = tb + R < N0 ? tb + R : N0;
+        for (int which = 0; which < (same ? 1 : 2); ++which) {
+            GemmArgs g = {};
+            g.seg[0] = {Xq + tb * ldx, (which ? X : Xq) + tb * ldx, ldx, ldx, m, 1.0};
+            g.nseg = 1;
+            g.M = g.N = te - tb;
+            g.C = (which ? Gc1 : Gc2) + tb * R;
+            g.ldc = R;
+            g.nsplit = 1;
+            g.lower_only = 1;
+            GPFQ_TRY((launch_gemm_nt<float, 128, 64, 32>(ctx, g, 1)));
+        }
+    }
+    CUDA_TRY(ctx, gpfq_record(ctx, 3, st));
+    CUDA_TRY(ctx, cudaMemsetAsync(Ut, 0, (size_t)n_alph * nj * m * sizeof(double), st));
+    for (int64_t tb = 0, pb = 0; tb < N0; pb = tb, tb += R) {
+        const int64_t te = tb + R < N0 ? tb + R : N0;
+        if (tb > 0) {
+            {   // U += W[pb:tb] X[pb:tb] - Q[pb:tb] X~[pb:tb]
+                GemmArgs g = {};
+                g.seg[0] = {Wt + pb, Xt + pb, N0, N0, tb - pb, 1.0};
+                g.seg[1] = {Qt + pb, Xqt + pb, N0, N0, tb - pb, -1.0};
+                g.nseg = 2;
+                g.M = nj;
+                g.N = m;
+                g.C = Ut;
+                g.ldc = m;
+                g.nsplit = 1;
+                g.accumulate = 1;
+                g.batch_strideA1 = nj * N0;
+                g.batch_strideC = nj * m;
+                GPFQ_TRY((launch_gemm_nt<double, 128, 64, 16>(ctx, g, n_alph)));
+            }
+            {   // D[range] = U X~[range]^T
+                GemmArgs g = {};
+                g.seg[0] = {Ut, Xqd + tb * m, m, m, m, 1.0};
+                g.nseg = 1;
+                g.M = nj;
+                g.N = te - tb;
+                g.C = Do;
+                g.ldc = R;
+                g.nsplit = 1;
+                g.batch_strideA0 = nj * m;
+                g.batch_strideC = nj * R;
+                GPFQ_TRY((launch_gemm_nt<double, 128, 64, 16>(ctx, g, n_alph)));
+            }
+        }
+        // the compact tiles are addressed like the full matrices: column s of row t lives at Gc[t * R + (s - tb)]
+        GPFQ_TRY(dispatch_sweep_tile(ctx, NT, Gc1 - tb, Gc2 - tb, R, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph, tb, te,
+                                     tb > 0 ? Do : nullptr, R));
+    }
+    return GPFQ_OK;
+}
+
 // Dense layer by Gram + sweep.  All pointers are device pointers.
 //   Qd: (n_alph, N0, ldq) fp64 device output, columns col0..col0+nj-1 written.
 int dense_gram_path(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx, int64_t N0, int64_t m,
@@ -461,11 +602,38 @@ int dense_gram_path(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx,
                     gpfq_stats *st) {
     const bool same = (Xq == X);
     double *G1 = nullptr, *G2 = nullptr, *Wt = nullptr, *Qt = nullptr, *Dt = nullptr;
+    const bool lowrank = dense_uses_lowrank(ctx, N0, m, nj);
+    // Neurons per CTA of the range walk: the narrowest tile that still fits every CTA on the chip at once (two per SM, so
+    // that one CTA's serial walk overlaps another's contraction).
+    const int64_t slots = 2LL * ctx->sm_count;
+    const int NT = ceil_div64(nj, 8) * n_alph <= slots ? 8 : (ceil_div64(nj, 16) * n_alph <= slots ? 16 : 32);
+    GPFQ_TRY(gpfq_ws(ctx, WS_WT, (size_t)nj * N0 * sizeof(double), (void **)&Wt));
+    GPFQ_TRY(gpfq_ws(ctx, WS_QT, (size_t)n_alph * nj * N0 * sizeof(double), (void **)&Qt));
+    {
+        dim3 grid((unsigned)ceil_div64(N0, 32), (unsigned)ceil_div64(nj, 32));
+        transpose_w_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(W, ldw, N0, j0, nj, Wt);
+        KERNEL_CHECK(ctx);
+    }
+    if (lowrank) {
+        GPFQ_TRY(dense_lowrank_sweep(ctx, X, Xq, ldx, N0, m, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph, NT));
+        for (int a = 0; a < n_alph; ++a) {
+            dim3 grid((unsigned)ceil_div64(N0, 32), (unsigned)ceil_div64(nj, 32));
+            transpose_q_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(Qt + (int64_t)a * nj * N0, N0, nj,
+                                                                      Qd + (int64_t)a * N0 * ldq, ldq, col0);
+            KERNEL_CHECK(ctx);
+        }
+        CUDA_TRY(ctx, gpfq_record(ctx, 4, ctx->stream));
+        if (st) {
+            st->method = GPFQ_METHOD_GRAM >> 4;
+            st->gram_kernel = 3;
+            st->flops_algorithmic = 6 * m * N0 * nj * n_alph;
+            st->bytes_algorithmic = (same ? 1 : 2) * 4 * N0 * m;
+        }
+        return GPFQ_OK;
+    }
     GPFQ_TRY(gpfq_ws(ctx, WS_G2, (size_t)N0 * N0 * sizeof(double), (void **)&G2));
     if (same) G1 = G2;
     else GPFQ_TRY(gpfq_ws(ctx, WS_G1, (size_t)N0 * N0 * sizeof(double), (void **)&G1));
-    GPFQ_TRY(gpfq_ws(ctx, WS_WT, (size_t)nj * N0 * sizeof(double), (void **)&Wt));
-    GPFQ_TRY(gpfq_ws(ctx, WS_QT, (size_t)n_alph * nj * N0 * sizeof(double), (void **)&Qt));
     if (ctx->sweep_variant != 0)
         GPFQ_TRY(gpfq_ws(ctx, WS_DT, (size_t)n_alph * nj * SWEEP_B * sizeof(double), (void **)&Dt));
 
@@ -473,29 +641,12 @@ int dense_gram_path(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx,
     GPFQ_TRY(dense_gram_only(ctx, X, Xq, ldx, N0, m, G1, G2));
     CUDA_TRY(ctx, gpfq_record(ctx, 3, ctx->stream));
 
-    {
-        dim3 grid((unsigned)ceil_div64(N0, 32), (unsigned)ceil_div64(nj, 32));
-        transpose_w_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(W, ldw, N0, j0, nj, Wt);
-        KERNEL_CHECK(ctx);
-    }
     if (ctx->sweep_variant == 0) {
         // Two-level blocking: directions in ranges of R; what the earlier ranges contribute to a range is ONE large NT
         // contraction (all SMs, split over neurons x directions, and over K when that is too few tiles), the
-        // persistent neuron-tile kernel then walks the range.  Neurons per CTA: the narrowest tile that still fits
-        // every CTA on the chip at once (two per SM, so that one CTA's serial walk overlaps another's contraction).
-        const int64_t slots = 2LL * ctx->sm_count;
-        const int NT = ceil_div64(nj, 8) * n_alph <= slots ? 8 : (ceil_div64(nj, 16) * n_alph <= slots ? 16 : 32);
-        // R: a multiple of the contraction's 64-column tile that fills whole rounds of CTA slots
+        // persistent neuron-tile kernel then walks the range.
         const int64_t tiles_m = ceil_div64(nj, 128) * n_alph;
-        int64_t R = SWEEP_OUTER;
-        if (tiles_m * 8 >= ctx->sm_count) {
-            double best = 0.0;
-            for (int64_t n = 5; n <= 12; ++n) {
-                const int64_t tiles = tiles_m * n;
-                const double eff = (double)tiles / (double)(ceil_div64(tiles, slots) * slots) - 0.004 * (double)llabs(n - 8);
-                if (eff > best) { best = eff; R = 64 * n; }
-            }
-        }
+        const int64_t R = pick_range_length(ctx, nj, n_alph);
         double *Do = nullptr, *Dpart = nullptr;
         if (N0 > R) GPFQ_TRY(gpfq_ws(ctx, WS_DT, (size_t)n_alph * nj * R * sizeof(double), (void **)&Do));
         for (int64_t tb = 0; tb < N0; tb += R) {
@@ -530,13 +681,8 @@ int dense_gram_path(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx,
                     GPFQ_TRY((launch_gemm_nt<double, 128, 64, 16>(ctx, g, n_alph)));
                 }
             }
-            const double *Dp = tb > 0 ? Do : nullptr;
-            if (NT == 32)
-                GPFQ_TRY(launch_sweep_tile<32>(ctx, G1, G2, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph, tb, te, Dp, R));
-            else if (NT == 16)
-                GPFQ_TRY(launch_sweep_tile<16>(ctx, G1, G2, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph, tb, te, Dp, R));
-            else
-                GPFQ_TRY(launch_sweep_tile<8>(ctx, G1, G2, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph, tb, te, Dp, R));
+            GPFQ_TRY(dispatch_sweep_tile(ctx, NT, G1, G2, N0, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph, tb, te,
+                                         tb > 0 ? Do : nullptr, R));
         }
     } else {
         // multi-launch reference: one NT contraction + one in-block kernel per 32 directions

@@ -482,3 +482,37 @@ def test_dense_gram_kernels_match_the_oracle(engine, variant):
             Q = engine.dense_layer(X, None if first else Xq, W, A, method="gram")
             assert engine.last_stats["gram_kernel"] == variant
             check(Q, Qref, W, X, Xq, exact=True)
+
+
+# ---- sweep with carried residuals (low-rank outer level, m << N0: VGG16 fc1 regime) ------------------------------------
+@pytest.mark.parametrize("N0,N1,m,first", [(1000, 8, 96, False), (2304, 40, 200, False), (1500, 300, 64, True), (700, 20, 1500, False)])
+def test_sweep_lowrank_outer_level_matches_the_oracle(engine, N0, N1, m, first):
+    """`sweep_outer = 2`: the earlier ranges enter through the residuals U (nj x m) instead of Gram rows, and only
+    block-diagonal Gram tiles exist.  Same decisions as the literal oracle walk and as the Gram-row form."""
+    rng = np.random.default_rng(N0 + N1 + m)
+    if first:
+        X = (rng.uniform(0, 1, (N0, m)) * (rng.uniform(0, 1, (N0, m)) < 0.5)).astype(np.float32)
+        X[:10] = 0
+        Xq = X
+    else:
+        X, Xq = hidden_pair(rng, N0, m)
+    W = glorot(rng, N0, N1)
+    A = O.layer_alphabet(W, 2, O.unit_alphabet(np.log2(3)))
+    Qref = c_oracle.quantize_layer(W, X, Xq, A)
+    engine.set_option("sweep_outer", 2)
+    try:
+        Q = engine.dense_layer(X, None if first else Xq, W, A, method="gram")
+        assert engine.last_stats["gram_kernel"] == 3
+        A2 = O.layer_alphabet(W, 4, O.unit_alphabet(3))
+        Qm = engine.dense_layer(X, None if first else Xq, W, [A, A2], method="gram", j0=1, j1=N1 - 1)
+    finally:
+        engine.set_option("sweep_outer", 0)
+    check(Q, Qref, W, X, Xq, exact=True)
+    engine.set_option("sweep_outer", 1)
+    try:
+        Qg = engine.dense_layer(X, None if first else Xq, W, A, method="gram")
+    finally:
+        engine.set_option("sweep_outer", 0)
+    assert np.array_equal(Q, Qg)
+    assert np.array_equal(Qm[0][:, 1:N1 - 1], Q[:, 1:N1 - 1])      # batched alphabets + a neuron shard
+    assert np.array_equal(Qm[1][:, 1:N1 - 1], c_oracle.quantize_layer(W, X, Xq, A2)[:, 1:N1 - 1])

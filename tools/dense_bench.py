@@ -61,7 +61,7 @@ def main():
             pairs = 2 if Xq is not None else 1
             gram_flops = pairs * m * N0 * (N0 + 1)
             line = {"shape": [N0, N1, m], "requested": meth, "method": {1: "stream", 2: "gram", 3: "stream_fast"}[best["method"]],
-                    "gram_kernel": {0: None, 1: "dmma", 2: "i8_tcgen05"}[best["gram_kernel"]],
+                    "gram_kernel": {0: None, 1: "dmma", 2: "i8_tcgen05", 3: "block_diagonal_dmma (residual outer level)"}[best["gram_kernel"]],
                     "ms_total": round(best["ms_total"], 4), "ms_gram": round(best["ms_gram"], 4), "ms_sweep": round(best["ms_sweep"], 4),
                     "ms_stream": round(best["ms_stream"], 4), "launches": best["kernel_launches"],
                     "weights_per_s": round(N0 * N1 / (best["ms_total"] * 1e-3)),
