@@ -161,18 +161,35 @@ def to_host_pinned(data):
     return host, nbytes
 
 
-def run_pass_host(eng, host, keep=None):
-    d2h = 0
+def run_pass_host(eng, host, keep=None, rank=0, world=1, dev=None):
+    """One pass from HOST buffers.  world == 1: host pointers straight into the C ABI (the library overlaps its chunked
+    H2D copies with the Gram kernels).  world > 1: every rank needs the whole layer input, so each copies 1/world of the
+    leading axis over its own PCIe link and ONE NCCL all-gather over NVLink completes it (replicate.py), then the
+    device-pointer entry points run on the rank's shard of channels / neurons; Q blocks go back to the host.
+    Returns (d2h bytes, h2d bytes that crossed this rank's host link)."""
+    import torch
+    from quantized_neural_networks_b200.replicate import h2d_bytes_per_rank, replicate_leading_axis
+    d2h = h2d = 0
     for d in host:
-        if d["kind"] == "conv":
-            Q = eng.conv_layer_nhwc(d["act"], d["actq"], d["W"], d["A"], c0=d["c0"], n_channels=d["n_ch"])
-            d2h += 9 * d["n_ch"] * d["F"] * 8
+        conv = d["kind"] == "conv"
+        a, aq = (d["act"], d["actq"]) if conv else (d["X"], d["Xq"])
+        if world == 1:
+            Q = (eng.conv_layer_nhwc(a, aq, d["W"], d["A"], c0=d["c0"], n_channels=d["n_ch"]) if conv
+                 else eng.dense_layer(a, aq, d["W"], d["A"], j0=d["j0"], j1=d["j1"]))
+            h2d += a.nbytes + (0 if aq is None else aq.nbytes) + d["W"].nbytes
         else:
-            Q = eng.dense_layer(d["X"], d["Xq"], d["W"], d["A"], j0=d["j0"], j1=d["j1"])
-            d2h += d["N0"] * (d["j1"] - d["j0"]) * 8
+            ad = replicate_leading_axis(a, rank, world, dev)
+            aqd = None if aq is None else replicate_leading_axis(aq, rank, world, dev)
+            Wd = torch.from_numpy(d["W"]).to(dev, non_blocking=True)
+            h2d += h2d_bytes_per_rank(a.shape, 4, world) * (1 if aq is None else 2) + d["W"].nbytes
+            Qd = (eng.conv_layer_nhwc(ad, aqd, Wd, d["A"], c0=d["c0"], n_channels=d["n_ch"]) if conv
+                  else eng.dense_layer(ad, aqd, Wd, d["A"], j0=d["j0"], j1=d["j1"]))
+            Q = (Qd[:, :, d["c0"]:d["c0"] + d["n_ch"]] if conv else Qd[:, d["j0"]:d["j1"]]).cpu().numpy()
+            del ad, aqd, Qd
+        d2h += (9 * d["n_ch"] * d["F"] if conv else d["N0"] * (d["j1"] - d["j0"])) * 8
         if keep is not None:
             keep.append(Q)
-    return d2h
+    return d2h, h2d
 
 
 def host_channel_patches(act, c):
@@ -445,20 +462,23 @@ def main():
     # ---- e2e: host (pinned) buffers through the C ABI, copies inside the timed region ---------------------------
     e2e = None
     if not args.no_e2e:
-        host, h2d_bytes = to_host_pinned(data)
+        host, _ = to_host_pinned(data)
         kept = []
-        run_pass_host(eng, host, kept)  # warm-up (allocates the staging workspaces)
+        run_pass_host(eng, host, kept, rank, world, dev)  # warm-up (allocates the staging workspaces)
         barrier()
         for d, o, Qh in zip(data, outs, kept):   # both entry points must produce the same bits
             Qd = o[0].cpu().numpy()
             if d["kind"] == "conv":
-                assert np.array_equal(Qd[:, :, d["c0"]:d["c0"] + d["n_ch"]], Qh[:, :, d["c0"]:d["c0"] + d["n_ch"]]), d["name"]
+                ref_blk = Qd[:, :, d["c0"]:d["c0"] + d["n_ch"]]
+                assert np.array_equal(ref_blk, Qh[:, :, d["c0"]:d["c0"] + d["n_ch"]] if world == 1 else Qh), d["name"]
             else:
-                assert np.array_equal(Qd[:, d["j0"]:d["j1"]], Qh[:, d["j0"]:d["j1"]]), d["name"]
+                ref_blk = Qd[:, d["j0"]:d["j1"]]
+                assert np.array_equal(ref_blk, Qh[:, d["j0"]:d["j1"]] if world == 1 else Qh), d["name"]
         del kept
+        barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
-            d2h_bytes = run_pass_host(eng, host)
+            d2h_bytes, h2d_bytes = run_pass_host(eng, host, None, rank, world, dev)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if world > 1:
@@ -468,7 +488,9 @@ def main():
         e2e = {"value": total_weights * args.e2e_steps / dt, "unit": "weights/s", "h2d_bytes_per_step": int(h2d_bytes),
                "d2h_bytes_per_step": int(d2h_bytes), "steps": args.e2e_steps, "ms_per_step": dt / args.e2e_steps * 1e3,
                "timing": "host wall clock around synchronous C-ABI calls (copies + kernels), max over ranks",
-               "api": "gpfq_conv_layer_nhwc (host NHWC activations) + gpfq_dense_layer (host matrices)"}
+               "api": "gpfq_conv_layer_nhwc + gpfq_dense_layer from pinned host buffers" +
+                      ("" if world == 1 else f"; per rank 1/{world} of every input over PCIe + one NCCL all-gather over NVLink "
+                                             "(h2d/d2h bytes are per rank)")}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

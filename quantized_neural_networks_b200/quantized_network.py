@@ -24,6 +24,7 @@ from numpy import abs, array, linspace, log2, median, zeros
 
 from . import hostnet
 from .engine import get_engine
+from .replicate import replicate_leading_axis, shard_range
 
 try:  # real Keras if present, the TF-free shim otherwise (same call surface)
     from tensorflow.keras.models import Model as _KModel, clone_model as _kclone  # type: ignore
@@ -85,13 +86,6 @@ class LayerData:
     def __init__(self, wX, qX):
         self.wX, self.qX = wX, qX
         self.same = qX is wX or np.array_equal(wX, qX)
-
-
-def shard_range(n: int, rank: int, world: int):
-    """Contiguous, balanced slice of n independent units (neurons / channels) for `rank` of `world`."""
-    base, rem = divmod(n, world)
-    lo = rank * base + min(rank, rem)
-    return lo, lo + base + (1 if rank < rem else 0)
 
 
 class QuantizedNeuralNetwork:
@@ -209,6 +203,24 @@ class QuantizedNeuralNetwork:
         rad = self.alphabet_scalar * median(abs(W.flatten()))
         return rad * self.alphabet
 
+    def _nccl_job(self):
+        """True when this object is one rank of a torch.distributed job on GPUs (NCCL): layer inputs are then replicated
+        through `replicate_leading_axis` (1 / world of the bytes over each rank's host link + one NVLink all-gather)."""
+        if self.shard[1] == 1:
+            return False
+        try:
+            import torch.distributed as dist
+            return dist.is_available() and dist.is_initialized() and dist.get_backend() == "nccl"
+        except Exception:  # pragma: no cover
+            return False
+
+    def _replicated(self, *arrays):
+        """Device copies of host arrays every rank holds; `None` entries pass through."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        rank, world = self.shard
+        return [None if a is None else replicate_leading_axis(a, rank, world, dev) for a in arrays]
+
     def _gather_columns(self, Q, lo, hi, axis):
         """All-gather the shard's block of Q over the job (multi-GPU); identity for a single rank."""
         rank, world = self.shard
@@ -253,8 +265,15 @@ class QuantizedNeuralNetwork:
         tic = time()
         lo, hi = shard_range(N_ell_plus_1, *self.shard)
         try:
-            Q = self.engine.dense_layer(data.wX, None if data.same else data.qX, np.ascontiguousarray(W),
-                                        np.asarray(layer_alphabet, dtype=np.float64), j0=lo, j1=hi, method=self.method)
+            if self._nccl_job():
+                import torch
+                Xd, Xqd = self._replicated(data.wX, None if data.same else data.qX)
+                Wd = torch.from_numpy(np.ascontiguousarray(W)).to(Xd.device)
+                Q = self.engine.dense_layer(Xd, Xqd, Wd, np.asarray(layer_alphabet, dtype=np.float64), j0=lo, j1=hi,
+                                            method=self.method).cpu().numpy()
+            else:
+                Q = self.engine.dense_layer(data.wX, None if data.same else data.qX, np.ascontiguousarray(W),
+                                            np.asarray(layer_alphabet, dtype=np.float64), j0=lo, j1=hi, method=self.method)
         except Exception as exc:
             self._log(f"\t\tNeurons {lo}:{hi} generated an exception: {exc}")
             raise exc
@@ -362,9 +381,17 @@ class QuantizedCNN(QuantizedNeuralNetwork):
         tic = time()
         if self.conv_path == "nhwc":
             try:
-                Q = self.engine.conv_layer_nhwc(data.wX, None if data.same else data.qX, np.ascontiguousarray(W),
-                                                np.asarray(alphabet, dtype=np.float64), strides=layer.strides,
-                                                padding=layer.padding.upper(), rate=rate, c0=lo, n_channels=hi - lo)
+                if self._nccl_job():
+                    import torch
+                    Ad, Aqd = self._replicated(data.wX, None if data.same else data.qX)
+                    Wd = torch.from_numpy(np.ascontiguousarray(W)).to(Ad.device)
+                    Q = self.engine.conv_layer_nhwc(Ad, Aqd, Wd, np.asarray(alphabet, dtype=np.float64), strides=layer.strides,
+                                                    padding=layer.padding.upper(), rate=rate, c0=lo,
+                                                    n_channels=hi - lo).cpu().numpy()
+                else:
+                    Q = self.engine.conv_layer_nhwc(data.wX, None if data.same else data.qX, np.ascontiguousarray(W),
+                                                    np.asarray(alphabet, dtype=np.float64), strides=layer.strides,
+                                                    padding=layer.padding.upper(), rate=rate, c0=lo, n_channels=hi - lo)
             except Exception as exc:
                 self._log(f"\t\tChannels {lo}:{hi} generated an exception: {exc}")
                 raise exc

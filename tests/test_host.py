@@ -146,3 +146,38 @@ def test_world2_gloo_gather_reassembles_q(axis, shape):
 def test_layerdata_same_detection():
     a = np.ones((3, 4), np.float32)
     assert LayerData(a, a).same and LayerData(a, a.copy()).same and not LayerData(a, a * 2).same
+
+
+def _replicate_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from quantized_neural_networks_b200.replicate import h2d_bytes_per_rank, replicate_leading_axis
+        ok = True
+        for shape in [(7, 3), (8, 2, 2, 3), (1, 5), (5008 // 16, 4)]:
+            a = np.arange(np.prod(shape), dtype=np.float32).reshape(shape) + 1
+            t = replicate_leading_axis(a, rank, world)          # CPU tensors under gloo: same slicing / padding logic
+            ok = ok and np.array_equal(t.numpy(), a)
+            ok = ok and h2d_bytes_per_rank(shape, 4, world) * world >= a.nbytes
+        ret[rank] = ok
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_input_replication_all_gather(world):
+    """N > 1 input replication: each rank contributes 1 / world of the leading axis, one all-gather
+    completes the array on every rank -- ragged and tiny leading axes included."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_replicate_worker, args=(r, world, port, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert dict(ret) == {r: True for r in range(world)}
