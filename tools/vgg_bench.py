@@ -70,6 +70,9 @@ def main():
             W = (torch.rand((3, 3, C, F), device=dev, generator=g) * 2 - 1) * float(np.sqrt(6.0 / (9 * C)))
             A = alph(W)
             lo, hi = shard_range(C, rank, world)
+            if hi == lo:   # fewer channels than ranks: nothing to do for this rank
+                del act, actq, W
+                continue
             out = torch.zeros((1, 3, 3, C, F), dtype=torch.float64, device=dev)
             best = None
             for _ in range(args.reps):
@@ -115,7 +118,9 @@ def main():
                 "ms_sweep": round(best["ms_sweep"], 3), "ms_stream": round(best["ms_stream"], 3),
                 "weights_per_s": round(N0 * nj / (ms * 1e-3))}
         if best["method"] == 2:
-            line["sweep_fp64_pipe_frac"] = round(N0 * N0 * nj / FP64_SLOTS / (best["ms_sweep"] * 1e-3), 3)
+            macs = 3 * m * N0 * nj if best["gram_kernel"] == 3 else N0 * N0 * nj   # residual (low-rank) vs Gram-row outer level
+            line["sweep_form"] = "carried residuals: 3 m N0 N1 MACs" if best["gram_kernel"] == 3 else "Gram rows: N0^2 N1 MACs"
+            line["sweep_fp64_pipe_frac"] = round(macs / FP64_SLOTS / (best["ms_sweep"] * 1e-3), 3)
             if best["gram_kernel"] == 2:
                 tiles = sum((ti >> 1) + 1 for ti in range(-(-N0 // 128)))
                 ops = 15 * tiles * 128 * 256 * 2 * (-(-m // 128) * 128) * 2
