@@ -110,6 +110,21 @@ int gpfq_dense_layer(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx
                      const double *alphabets, const int32_t *K, int32_t n_alphabets,
                      double *Q_out, int64_t ldq, uint32_t flags, gpfq_stats *stats);
 
+/* ---- Dense layer, sweep stage from Gram matrices already on the device ------------------------------
+ * Multi-GPU sample split of the Gram stage (BASELINE north_star): the two m-length contractions of
+ * every greedy step (quantized_network.py:83-89) only enter through G2 = Xq Xq^T and G1 = Xq X^T, which are SUMS over
+ * samples.  Each rank of a job contracts its own m / world samples with gpfq_gram_matrices (device outputs), the
+ * (N0, N0) fp64 partial matrices are summed with ONE all-reduce (NCCL over NVLink), and every rank then walks its own
+ * neurons j0..j1-1 from the summed matrices with this call -- X / Xq are never replicated.
+ *   G1, G2 : (N0, N0) float64 DEVICE pointers (GPFQ_X_DEVICE must be set), contiguous rows, lower triangle +
+ *            diagonal valid; G1 == G2 or G1 == NULL: first layer (X == Xq).
+ *   W, alphabets, K, Q_out, ldq, j0, j1: as gpfq_dense_layer (GPFQ_W_DEVICE / GPFQ_Q_DEVICE say where W / Q_out live).
+ */
+int gpfq_dense_layer_from_gram(gpfq_ctx *ctx, const double *G1, const double *G2, int64_t N0, const float *W,
+                               int64_t ldw, int64_t N1, int64_t j0, int64_t j1, const double *alphabets,
+                               const int32_t *K, int32_t n_alphabets, double *Q_out, int64_t ldq, uint32_t flags,
+                               gpfq_stats *stats);
+
 /* ---- Conv2D / DepthwiseConv2D channels -------------------------------------------------------
  * Replaces the channel loop of QuantizedCNN._quantize_conv2D_layer_parallel_jit (:844-860) and
  * the pool part of _quantize_channel_parallel_jit (:699-721), i.e. _quantize_filter2D_parallel_jit
@@ -155,7 +170,9 @@ int gpfq_bit_round(gpfq_ctx *ctx, const double *t, int64_t n, const double *alph
  * The Gram stage alone: G2 = Xq Xq^T and (if G1_out != NULL) G1 = Xq X^T over the m samples, fp64,
  * (N0, N0) row-major, LOWER triangle + diagonal valid.  These replace the m-length dot/norm calls
  * of quantized_network.py:83-89; tests check them against an fp64 NumPy Gram.
- * GPFQ_X_DEVICE / GPFQ_Q_DEVICE say where X/Xq and the outputs live. */
+ * GPFQ_X_DEVICE / GPFQ_Q_DEVICE say where X/Xq and the outputs live.  With GPFQ_Q_DEVICE the matrices are contracted
+ * in place into the caller's buffers (zeroed first: entries above the diagonal are finite, so partial matrices of a
+ * sample split can be all-reduced whole) and GPFQ_NO_SYNC returns after enqueueing. */
 int gpfq_gram_matrices(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx, int64_t N0,
                        int64_t m, double *G1_out, double *G2_out, uint32_t flags);
 

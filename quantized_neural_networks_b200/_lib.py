@@ -53,6 +53,9 @@ EXPORTS = {
     "gpfq_dense_layer": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64,
                                  c_int64, c_int64, c_int64, POINTER(c_double), POINTER(c_int32), c_int32,
                                  c_void_p, c_int64, c_uint32, POINTER(GpfqStats)]),
+    "gpfq_dense_layer_from_gram": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64,
+                                           c_int64, POINTER(c_double), POINTER(c_int32), c_int32, c_void_p, c_int64,
+                                           c_uint32, POINTER(GpfqStats)]),
     "gpfq_conv_channels": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_void_p), c_int64, c_int32, c_void_p,
                                    c_int64, c_int64, c_int64, c_int64, POINTER(c_double), POINTER(c_int32),
                                    c_int32, c_void_p, c_uint32, POINTER(GpfqStats)]),

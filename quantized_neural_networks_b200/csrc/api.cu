@@ -11,7 +11,7 @@
 // kernels / stages implemented in the other translation units
 int dense_gram_path(gpfq_ctx *, const float *, const float *, int64_t, int64_t, int64_t, const float *, int64_t,
                     int64_t, int64_t, const double *, const int *, const int *, int, double *, int64_t, int64_t,
-                    gpfq_stats *);
+                    gpfq_stats *, const double *G1_pre = nullptr, const double *G2_pre = nullptr);
 int dense_stream_path(gpfq_ctx *, const float *, const float *, int64_t, int64_t, int64_t, const float *, int64_t,
                       int64_t, int64_t, const double *, const int *, const int *, int, double *, int64_t, int64_t,
                       gpfq_stats *);
@@ -434,6 +434,67 @@ extern "C" int gpfq_dense_layer(gpfq_ctx *ctx, const float *X, const float *Xq, 
     return GPFQ_OK;
 }
 
+// Sweep stage alone, from Gram matrices the caller already holds on the device (sample-split Gram stage of a multi-GPU
+// job: every rank contracts its m / world samples with gpfq_gram_matrices, the (N0, N0) partial Grams are summed with
+// one NCCL all-reduce, then each rank sweeps its own neurons from the summed matrices).
+extern "C" int gpfq_dense_layer_from_gram(gpfq_ctx *ctx, const double *G1, const double *G2, int64_t N0, const float *W,
+                                          int64_t ldw, int64_t N1, int64_t j0, int64_t j1, const double *alphabets,
+                                          const int32_t *K, int32_t n_alph, double *Q_out, int64_t ldq, uint32_t flags,
+                                          gpfq_stats *stats) {
+    if (!ctx) return GPFQ_ERR_ARG;
+    ctx->err.clear();
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (!G2 || !W || !Q_out) return gpfq_fail(ctx, GPFQ_ERR_ARG, "NULL G2, W or Q_out");
+    if (N0 < 1 || N1 < 1 || ldw < N1 || ldq < N1 || j0 < 0 || j1 > N1 || j0 > j1)
+        return gpfq_fail(ctx, GPFQ_ERR_ARG, "bad shape: N0=%lld N1=%lld ldw=%lld ldq=%lld j0=%lld j1=%lld", (long long)N0,
+                         (long long)N1, (long long)ldw, (long long)ldq, (long long)j0, (long long)j1);
+    if (!(flags & GPFQ_X_DEVICE)) return gpfq_fail(ctx, GPFQ_ERR_ARG, "G1 / G2 must be device pointers (GPFQ_X_DEVICE)");
+    if ((flags & GPFQ_NO_SYNC) && (flags & GPFQ_ALL_DEVICE) != GPFQ_ALL_DEVICE)
+        return gpfq_fail(ctx, GPFQ_ERR_ARG, "GPFQ_NO_SYNC needs all-device pointers");
+    const int64_t nj = j1 - j0;
+    if (nj == 0) return GPFQ_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    begin_call(ctx, 0);
+    CUDA_TRY(ctx, gpfq_record(ctx, 0, s));
+    Alphabets al;
+    GPFQ_TRY(upload_alphabets(ctx, alphabets, K, n_alph, &al));
+    const float *dW = W;
+    int64_t dldw = ldw, dj0 = j0;
+    if (!(flags & GPFQ_W_DEVICE)) {
+        float *bw = nullptr;
+        GPFQ_TRY(gpfq_ws(ctx, WS_W, (size_t)N0 * nj * sizeof(float), (void **)&bw));
+        CUDA_TRY(ctx, cudaMemcpy2DAsync(bw, nj * sizeof(float), W + j0, ldw * sizeof(float), nj * sizeof(float), N0,
+                                        cudaMemcpyHostToDevice, s));
+        dW = bw;
+        dldw = nj;
+        dj0 = 0;
+    }
+    double *dQ = Q_out;
+    int64_t dldq = ldq, col0 = j0;
+    if (!(flags & GPFQ_Q_DEVICE)) {
+        GPFQ_TRY(gpfq_ws(ctx, WS_Q, (size_t)n_alph * N0 * nj * sizeof(double), (void **)&dQ));
+        dldq = nj;
+        col0 = 0;
+    }
+    CUDA_TRY(ctx, gpfq_record(ctx, 5, s));
+    GPFQ_TRY(dense_gram_path(ctx, nullptr, nullptr, 0, N0, 0, dW, dldw, dj0, nj, al.d_levels, al.d_koff, al.d_flags, n_alph,
+                             dQ, dldq, col0, stats, (G1 == nullptr || G1 == G2) ? nullptr : G1, G2));
+    CUDA_TRY(ctx, gpfq_record(ctx, 6, s));
+    if (!(flags & GPFQ_Q_DEVICE)) {
+        for (int a = 0; a < n_alph; ++a)
+            CUDA_TRY(ctx, cudaMemcpy2DAsync(Q_out + (int64_t)a * N0 * ldq + j0, ldq * sizeof(double),
+                                            dQ + (int64_t)a * N0 * nj, nj * sizeof(double), nj * sizeof(double), N0,
+                                            cudaMemcpyDeviceToHost, s));
+    }
+    CUDA_TRY(ctx, gpfq_record(ctx, 1, s));
+    if (stats) stats->weights = N0 * nj * n_alph;
+    const bool synced = !(flags & GPFQ_NO_SYNC);
+    if (synced) CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    end_call(ctx, stats, synced);
+    return GPFQ_OK;
+}
+
 // Diagnostics: the Gram stage alone (tests check it against an fp64 NumPy Gram).
 // G1_out/G2_out: (N0, N0) fp64, lower triangle + diagonal valid; G1_out may be NULL.
 extern "C" int gpfq_gram_matrices(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx, int64_t N0, int64_t m,
@@ -461,13 +522,26 @@ extern "C" int gpfq_gram_matrices(gpfq_ctx *ctx, const float *X, const float *Xq
         dld = m;
     }
     double *g1 = nullptr, *g2 = nullptr;
+    if (flags & GPFQ_Q_DEVICE) {
+        // device outputs (the sample-split Gram stage of a multi-GPU job): contract straight into the caller's
+        // matrices, zeroed first so that what an all-reduce sums above the diagonal is finite
+        if (!same && !G1_out) return gpfq_fail(ctx, GPFQ_ERR_ARG, "G1_out is NULL but Xq != X");
+        g2 = G2_out;
+        g1 = same ? g2 : G1_out;
+        CUDA_TRY(ctx, cudaMemsetAsync(g2, 0, (size_t)N0 * N0 * sizeof(double), s));
+        if (!same) CUDA_TRY(ctx, cudaMemsetAsync(g1, 0, (size_t)N0 * N0 * sizeof(double), s));
+        GPFQ_TRY(dense_gram_only(ctx, dX, dXq, dld, N0, m, g1, g2));
+        if (same && G1_out && G1_out != G2_out)
+            CUDA_TRY(ctx, cudaMemcpyAsync(G1_out, g2, (size_t)N0 * N0 * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        if (!(flags & GPFQ_NO_SYNC)) CUDA_TRY(ctx, cudaStreamSynchronize(s));
+        return GPFQ_OK;
+    }
     GPFQ_TRY(gpfq_ws(ctx, WS_G2, (size_t)N0 * N0 * sizeof(double), (void **)&g2));
     g1 = g2;
     if (!same) GPFQ_TRY(gpfq_ws(ctx, WS_G1, (size_t)N0 * N0 * sizeof(double), (void **)&g1));
     GPFQ_TRY(dense_gram_only(ctx, dX, dXq, dld, N0, m, g1, g2));
-    const cudaMemcpyKind kind = (flags & GPFQ_Q_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-    CUDA_TRY(ctx, cudaMemcpyAsync(G2_out, g2, (size_t)N0 * N0 * sizeof(double), kind, s));
-    if (G1_out) CUDA_TRY(ctx, cudaMemcpyAsync(G1_out, g1, (size_t)N0 * N0 * sizeof(double), kind, s));
+    CUDA_TRY(ctx, cudaMemcpyAsync(G2_out, g2, (size_t)N0 * N0 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (G1_out) CUDA_TRY(ctx, cudaMemcpyAsync(G1_out, g1, (size_t)N0 * N0 * sizeof(double), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(ctx, cudaStreamSynchronize(s));
     return GPFQ_OK;
 }

@@ -599,10 +599,13 @@ static int dense_lowrank_sweep(gpfq_ctx *ctx, const float *X, const float *Xq, i
 int dense_gram_path(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx, int64_t N0, int64_t m,
                     const float *W, int64_t ldw, int64_t j0, int64_t nj, const double *d_alph,
                     const int *d_koff, const int *d_flags, int n_alph, double *Qd, int64_t ldq, int64_t col0,
-                    gpfq_stats *st) {
-    const bool same = (Xq == X);
+                    gpfq_stats *st, const double *G1_pre, const double *G2_pre) {
+    // G2_pre != NULL: the Gram stage already ran elsewhere (sample-split over the ranks of a job and all-reduced,
+    // gpfq_dense_layer_from_gram); X / Xq / m are then unused and the sweep starts from the given (N0, N0) matrices.
+    const bool pre = (G2_pre != nullptr);
+    const bool same = pre ? (G1_pre == nullptr || G1_pre == G2_pre) : (Xq == X);
     double *G1 = nullptr, *G2 = nullptr, *Wt = nullptr, *Qt = nullptr, *Dt = nullptr;
-    const bool lowrank = dense_uses_lowrank(ctx, N0, m, nj);
+    const bool lowrank = !pre && dense_uses_lowrank(ctx, N0, m, nj);
     // Neurons per CTA of the range walk: the narrowest tile that still fits every CTA on the chip at once (two per SM, so
     // that one CTA's serial walk overlaps another's contraction).
     const int64_t slots = 2LL * ctx->sm_count;
@@ -631,14 +634,20 @@ int dense_gram_path(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx,
         }
         return GPFQ_OK;
     }
-    GPFQ_TRY(gpfq_ws(ctx, WS_G2, (size_t)N0 * N0 * sizeof(double), (void **)&G2));
-    if (same) G1 = G2;
-    else GPFQ_TRY(gpfq_ws(ctx, WS_G1, (size_t)N0 * N0 * sizeof(double), (void **)&G1));
+    if (pre) {
+        G2 = const_cast<double *>(G2_pre);  // read-only below
+        G1 = same ? G2 : const_cast<double *>(G1_pre);
+    } else {
+        GPFQ_TRY(gpfq_ws(ctx, WS_G2, (size_t)N0 * N0 * sizeof(double), (void **)&G2));
+        if (same) G1 = G2;
+        else GPFQ_TRY(gpfq_ws(ctx, WS_G1, (size_t)N0 * N0 * sizeof(double), (void **)&G1));
+    }
     if (ctx->sweep_variant != 0)
         GPFQ_TRY(gpfq_ws(ctx, WS_DT, (size_t)n_alph * nj * SWEEP_B * sizeof(double), (void **)&Dt));
 
     CUDA_TRY(ctx, gpfq_record(ctx, 2, ctx->stream));
-    GPFQ_TRY(dense_gram_only(ctx, X, Xq, ldx, N0, m, G1, G2));
+    if (!pre) GPFQ_TRY(dense_gram_only(ctx, X, Xq, ldx, N0, m, G1, G2));
+    else ctx->last_gram_kernel = 0;
     CUDA_TRY(ctx, gpfq_record(ctx, 3, ctx->stream));
 
     if (ctx->sweep_variant == 0) {
@@ -719,8 +728,8 @@ int dense_gram_path(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx,
     if (st) {
         st->method = GPFQ_METHOD_GRAM >> 4;
         st->gram_kernel = ctx->last_gram_kernel;
-        st->flops_algorithmic = (same ? 1 : 2) * m * N0 * (N0 + 1);  // lower triangles, 2 flops per MAC
-        st->bytes_algorithmic = (same ? 1 : 2) * 4 * N0 * m + (same ? 1 : 2) * 8 * N0 * N0;
+        st->flops_algorithmic = pre ? 2 * N0 * N0 * nj * n_alph : (same ? 1 : 2) * m * N0 * (N0 + 1);  // lower triangles
+        st->bytes_algorithmic = (pre ? 0 : (same ? 1 : 2) * 4 * N0 * m) + (same ? 1 : 2) * 8 * N0 * N0;
     }
     return GPFQ_OK;
 }

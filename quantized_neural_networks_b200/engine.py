@@ -167,8 +167,29 @@ class GpfqEngine:
         self.last_stats = st.as_dict()
         return out[0] if single else out
 
-    def gram_matrices(self, X, Xq=None):
-        """Diagnostics: (G1, G2) fp64 (N0, N0), lower triangle + diagonal valid."""
+    def gram_matrices(self, X, Xq=None, sync=True):
+        """The Gram stage alone: (G1, G2) fp64 (N0, N0), lower triangle + diagonal valid (G1 is G2 when Xq is X / None).
+        NumPy in -> NumPy out (diagnostics); CUDA tensors in -> CUDA tensors out, contracted in place (the per-rank part
+        of a sample-split Gram stage, see `dense_layer_from_gram`)."""
+        if _is_torch(X):
+            X = self._f32(X, "X")
+            same = Xq is None or Xq is X
+            Xq = X if same else self._f32(Xq, "Xq")
+            if tuple(Xq.shape) != tuple(X.shape):
+                raise ValueError("X and Xq must have the same shape")
+            N0, m = int(X.shape[0]), int(X.shape[1])
+            px, ldx = self._rowmajor2d(X, "X")
+            pq, ldq_x = (px, ldx) if same else self._rowmajor2d(Xq, "Xq")
+            if ldq_x != ldx:
+                raise ValueError("X and Xq must share a row stride")
+            G2 = torch.empty((N0, N0), dtype=torch.float64, device=X.device)
+            G1 = G2 if same else torch.empty((N0, N0), dtype=torch.float64, device=X.device)
+            self._bind_stream(True)
+            flags = _lib.X_DEVICE | _lib.Q_DEVICE | (0 if sync else _lib.NO_SYNC)
+            rc = self._lib.gpfq_gram_matrices(self._ctx, c_void_p(px), c_void_p(pq), ldx, N0, m,
+                                              c_void_p(None if same else G1.data_ptr()), c_void_p(G2.data_ptr()), flags)
+            self._check(rc)
+            return G1, G2
         X = np.ascontiguousarray(X, dtype=np.float32)
         same = Xq is None or Xq is X
         Xq = X if same else np.ascontiguousarray(Xq, dtype=np.float32)
@@ -180,6 +201,53 @@ class GpfqEngine:
                                           c_void_p(None if same else G1.ctypes.data), c_void_p(G2.ctypes.data), 0)
         self._check(rc)
         return G1, G2
+
+    def dense_layer_from_gram(self, G1, G2, W, alphabets, j0=0, j1=None, out=None, sync=True):
+        """Sweep stage of a Dense layer from (N0, N0) fp64 Gram matrices on the device (CUDA tensors; G1 None or G2
+        itself for the first layer): what every rank of a sample-split job runs after the all-reduce of the partial
+        Grams.  W: (N0, N1) fp32 NumPy array or CUDA tensor; the result follows W's kind."""
+        flat, K, n_alph, als = _alph_args(alphabets)
+        single = isinstance(alphabets, np.ndarray) and alphabets.ndim == 1
+        if not _is_torch(G2) or G2.dtype != torch.float64 or not G2.is_cuda or not G2.is_contiguous():
+            raise TypeError("G2 must be a contiguous float64 CUDA tensor")
+        same = G1 is None or G1 is G2
+        if not same and (not _is_torch(G1) or G1.dtype != torch.float64 or not G1.is_cuda or not G1.is_contiguous()
+                         or tuple(G1.shape) != tuple(G2.shape)):
+            raise TypeError("G1 must be a contiguous float64 CUDA tensor shaped like G2")
+        N0 = int(G2.shape[0])
+        if G2.dim() != 2 or int(G2.shape[1]) != N0:
+            raise ValueError("G2 must be (N0, N0)")
+        W = self._f32(W, "W")
+        wdev = _is_torch(W)
+        if not wdev and (W.ndim != 2 or W.strides[1] != W.itemsize):
+            W = np.ascontiguousarray(W)
+        if W.shape[0] != N0:
+            raise ValueError(f"W has {W.shape[0]} rows, the Gram matrices have {N0}")
+        N1 = int(W.shape[1])
+        j1 = N1 if j1 is None else int(j1)
+        pw, ldw = self._rowmajor2d(W, "W")
+        self._bind_stream(True)
+        flags = _lib.X_DEVICE
+        if wdev:
+            flags |= _lib.W_DEVICE | _lib.Q_DEVICE
+            if out is None:
+                out = torch.zeros((n_alph, N0, N1), dtype=torch.float64, device=W.device)
+            pout = out.data_ptr()
+            if not sync:
+                flags |= _lib.NO_SYNC
+        else:
+            if out is None:
+                out = np.zeros((n_alph, N0, N1), dtype=np.float64)
+            pout = out.ctypes.data
+        st = _lib.GpfqStats()
+        rc = self._lib.gpfq_dense_layer_from_gram(self._ctx, c_void_p(None if same else G1.data_ptr()),
+                                                  c_void_p(G2.data_ptr()), N0, c_void_p(pw), ldw, N1, int(j0), j1,
+                                                  flat.ctypes.data_as(POINTER(c_double)),
+                                                  K.ctypes.data_as(POINTER(c_int32)), n_alph, c_void_p(pout), N1, flags,
+                                                  byref(st))
+        self._check(rc)
+        self.last_stats = st.as_dict()
+        return out[0] if single else out
 
     # -- Conv -----------------------------------------------------------------------------------
     def conv_channels(self, Xp, Xqp, W, alphabets, c0=0, n_channels=None, out=None, sync=True):

@@ -24,7 +24,7 @@ from numpy import abs, array, linspace, log2, median, zeros
 
 from . import hostnet
 from .engine import get_engine
-from .replicate import replicate_leading_axis, shard_range
+from .replicate import prefer_sample_split, replicate_leading_axis, sample_split_gram, shard_range
 
 try:  # real Keras if present, the TF-free shim otherwise (same call surface)
     from tensorflow.keras.models import Model as _KModel, clone_model as _kclone  # type: ignore
@@ -103,6 +103,7 @@ class QuantizedNeuralNetwork:
         device: int = 0,
         method: str = "auto",
         shard=None,
+        gram_split: str = "auto",
     ):
         """Wrapper of a Keras-style model that quantizes the weights of its Dense layers with GPFQ.
 
@@ -110,7 +111,10 @@ class QuantizedNeuralNetwork:
         `mini_batch_size` are accepted and unused there too (the sample count is
         `len(get_data) * get_data.batch_size`, :467).  Keyword-only extras: `device` (GPU index),
         `method` ("auto" | "stream" | "gram") and `shard=(rank, world)` to split every layer's neurons
-        over the ranks of a torch.distributed job (Q blocks are all-gathered after each layer).
+        over the ranks of a torch.distributed job (Q blocks are all-gathered after each layer), and
+        `gram_split` ("auto" | "samples" | "replicate"): how a multi-GPU job feeds a Dense layer -- "samples" contracts
+        m / world samples per rank and all-reduces the Gram matrices, "replicate" all-gathers the inputs; "auto" picks
+        by bytes moved (`replicate.prefer_sample_split`).
         """
         self.get_data = get_data
         self.trained_net = network
@@ -126,10 +130,12 @@ class QuantizedNeuralNetwork:
         self.alphabet = linspace(-1, 1, num=int(round(2 ** (bits))))
         self.logger = logger
         self.ignore_layers = ignore_layers
-        self._init_device(device, method, shard)
+        self._init_device(device, method, shard, gram_split)
 
-    def _init_device(self, device, method, shard):
-        self.device, self.method = device, method
+    def _init_device(self, device, method, shard, gram_split="auto"):
+        if gram_split not in ("auto", "samples", "replicate"):
+            raise ValueError(f"gram_split must be 'auto', 'samples' or 'replicate', not {gram_split!r}")
+        self.device, self.method, self.gram_split = device, method, gram_split
         self.shard = tuple(shard) if shard else (0, 1)
         self.layer_stats = {}
 
@@ -214,6 +220,12 @@ class QuantizedNeuralNetwork:
         except Exception:  # pragma: no cover
             return False
 
+    def _sample_split(self, N0, m):
+        """Whether a Dense layer of this multi-GPU job runs its Gram stage split over samples (+ all-reduce)."""
+        if self.gram_split == "auto":
+            return self.method in ("auto", "gram") and prefer_sample_split(N0, m, self.shard[1])
+        return self.gram_split == "samples"
+
     def _replicated(self, *arrays):
         """Device copies of host arrays every rank holds; `None` entries pass through."""
         import torch
@@ -265,7 +277,13 @@ class QuantizedNeuralNetwork:
         tic = time()
         lo, hi = shard_range(N_ell_plus_1, *self.shard)
         try:
-            if self._nccl_job():
+            if self._nccl_job() and self._sample_split(N_ell, data.wX.shape[1]):
+                import torch
+                dev = torch.device("cuda", self.device)
+                G1, G2 = sample_split_gram(self.engine, data.wX, None if data.same else data.qX, *self.shard, device=dev)
+                Q = self.engine.dense_layer_from_gram(G1, G2, np.ascontiguousarray(W),
+                                                      np.asarray(layer_alphabet, dtype=np.float64), j0=lo, j1=hi)
+            elif self._nccl_job():
                 import torch
                 Xd, Xqd = self._replicated(data.wX, None if data.same else data.qX)
                 Wd = torch.from_numpy(np.ascontiguousarray(W)).to(Xd.device)
@@ -311,6 +329,7 @@ class QuantizedCNN(QuantizedNeuralNetwork):
         method: str = "auto",
         shard=None,
         conv_path: str = "nhwc",
+        gram_split: str = "auto",
     ):
         """Dense + Conv2D / DepthwiseConv2D quantization (quantized_network.py:594-650).  Like the reference this
         constructor does not take `ignore_layers`.  `conv_path="nhwc"` hands the layer's activation tensors to
@@ -328,7 +347,7 @@ class QuantizedCNN(QuantizedNeuralNetwork):
         self.logger = logger
         self.ignore_layers = []
         self.conv_path = conv_path
-        self._init_device(device, method, shard)
+        self._init_device(device, method, shard, gram_split)
 
     def _build_patch_array(self, channel_idx: int, kernel_size: tuple, strides: tuple, padding: str, rate: tuple,
                            data, mini_batch_size: int):

@@ -47,3 +47,51 @@ def h2d_bytes_per_rank(shape, itemsize: int, world: int) -> int:
     n = shape[0]
     chunk = -(-n // world)
     return int(chunk * int(np.prod(shape[1:], dtype=np.int64)) * itemsize)
+
+
+def sample_split_gram(engine, wX: np.ndarray, qX, rank: int, world: int, device=None, group=None):
+    """Sample-split Gram stage (BASELINE.json north_star): `wX`, `qX` are the (N0, m) feature-major
+    layer inputs every rank holds on the HOST (qX None / wX itself for the first layer).  Rank r moves only the samples
+    `shard_range(m, r, world)` to its GPU, contracts them with `engine.gram_matrices` (libgpfq: tcgen05 / DMMA Gram kernels)
+    and the (N0, N0) fp64 partial matrices are summed with one all-reduce per matrix (NCCL over NVLink; gloo in the CPU
+    tests).  Returns (G1, G2) tensors holding the whole-sample Grams on every rank, G1 is G2 when qX is wX.
+
+    Against input replication this moves 16 N0^2 bytes over NVLink instead of 8 N0 m, never holds more than m / world
+    samples per GPU (the only way a layer with m x N0 beyond one GPU's HBM fits), and divides the Gram stage by `world`.
+    The fp64 sums are associated differently from a one-GPU Gram (partial sums per rank), a 1e-16-relative effect."""
+    import torch
+    import torch.distributed as dist
+    same = qX is None or qX is wX
+    m = wX.shape[1]
+    lo, hi = shard_range(m, rank, world)
+    if hi == lo:                       # fewer samples than ranks: contribute zeros
+        lo, hi = 0, 0
+
+    def to_dev(a):
+        t = torch.from_numpy(np.ascontiguousarray(a[:, lo:hi], dtype=np.float32))
+        return t.to(device, non_blocking=True) if device is not None else t
+
+    N0 = wX.shape[0]
+    if hi > lo:
+        Xd = to_dev(wX)
+        G1, G2 = engine.gram_matrices(Xd, None if same else to_dev(qX))
+        if not isinstance(G2, torch.Tensor):       # an engine returning NumPy (tests)
+            G2 = torch.from_numpy(np.ascontiguousarray(G2))
+            G1 = G2 if same else torch.from_numpy(np.ascontiguousarray(G1))
+    else:
+        G2 = torch.zeros((N0, N0), dtype=torch.float64, device=device)
+        G1 = G2 if same else torch.zeros((N0, N0), dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(G2, group=group)
+        if not same:
+            dist.all_reduce(G1, group=group)
+    return (G2 if same else G1), G2
+
+
+def prefer_sample_split(N0: int, m: int, world: int, hbm_bytes: float = 150e9) -> bool:
+    """Sample split vs input replication for a Dense layer of a `world`-rank job: split when the all-reduce of the Grams
+    (two (N0, N0) fp64 matrices) moves fewer bytes than the all-gather of the inputs (two (N0, m) fp32 matrices), i.e.
+    m > 2 N0 -- the Gram stage then also shrinks by `world` -- or when the replicated inputs would not fit one GPU."""
+    if world <= 1:
+        return False
+    return (8.0 * N0 * m > hbm_bytes) or (m > 2 * N0)

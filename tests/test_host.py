@@ -181,3 +181,63 @@ def test_gloo_input_replication_all_gather(world):
         p.join(120)
         assert p.exitcode == 0
     assert dict(ret) == {r: True for r in range(world)}
+
+
+class _NumpyGramEngine:
+    """Test-only stand-in for GpfqEngine.gram_matrices: fp64 NumPy Grams of the samples it is handed (CPU tensors)."""
+
+    def gram_matrices(self, X, Xq=None, sync=True):
+        x = X.numpy().astype(np.float64)
+        q = x if Xq is None else Xq.numpy().astype(np.float64)
+        G2 = q @ q.T
+        return (G2 if Xq is None else q @ x.T), G2
+
+
+def _split_gram_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from quantized_neural_networks_b200.replicate import sample_split_gram
+        ok = True
+        rng = np.random.default_rng(11)
+        for N0, m, same in [(5, 13, False), (4, 8, True), (3, 1, False), (6, 2, True), (7, 101, False)]:
+            X = rng.standard_normal((N0, m)).astype(np.float32)
+            Xq = X if same else (X + 0.1 * rng.standard_normal((N0, m))).astype(np.float32)
+            G1, G2 = sample_split_gram(_NumpyGramEngine(), X, None if same else Xq, rank, world)
+            x, q = X.astype(np.float64), Xq.astype(np.float64)
+            ok = ok and np.allclose(G2.numpy(), q @ q.T, rtol=1e-13, atol=1e-13)
+            ok = ok and np.allclose(G1.numpy(), q @ x.T, rtol=1e-13, atol=1e-13)
+            ok = ok and ((G1 is G2) == same)
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_sample_split_gram_all_reduce(world):
+    """N > 1 sample-split Gram stage: each rank contracts m / world samples, one all-reduce per
+    matrix gives every rank the whole-sample Grams -- ragged sample counts and fewer samples than ranks included."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_split_gram_worker, args=(r, world, port, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert dict(ret) == {r: True for r in range(world)}
+
+
+def test_prefer_sample_split_rule():
+    from quantized_neural_networks_b200.replicate import prefer_sample_split
+    assert not prefer_sample_split(784, 25000, 1)
+    assert prefer_sample_split(784, 25000, 8)            # MNIST layer: 16 N0^2 = 9.8 MB against 8 N0 m = 157 MB
+    assert not prefer_sample_split(25088, 1504, 8)       # VGG fc1: the Grams would be 10 GB, the inputs 0.3 GB
+    assert prefer_sample_split(16384, 4_000_000, 2)      # inputs beyond one GPU's HBM: split regardless
+    with pytest.raises(ValueError):
+        QuantizedNeuralNetwork(hostnet.mnist_mlp(seed=1, widths=(6,), n_in=4, n_out=3), 1,
+                               hostnet.ArraySequence(np.zeros((1, 2, 2), np.float32), np.zeros(1), 1), gram_split="rows")
