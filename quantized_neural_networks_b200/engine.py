@@ -167,14 +167,18 @@ class GpfqEngine:
         self.last_stats = st.as_dict()
         return out[0] if single else out
 
-    def gram_matrices(self, X, Xq=None, sync=True):
+    def gram_matrices(self, X, Xq=None, sync=True, device_out=False):
         """The Gram stage alone: (G1, G2) fp64 (N0, N0), lower triangle + diagonal valid (G1 is G2 when Xq is X / None).
-        NumPy in -> NumPy out (diagnostics); CUDA tensors in -> CUDA tensors out, contracted in place (the per-rank part
-        of a sample-split Gram stage, see `dense_layer_from_gram`)."""
-        if _is_torch(X):
+        NumPy in -> NumPy out (diagnostics).  CUDA tensors in, or NumPy in with `device_out=True` (rows may be strided
+        views, e.g. a sample range `X[:, lo:hi]`: the library copies them with one pitched H2D transfer) -> CUDA tensors
+        out, contracted in place: the per-rank part of a sample-split Gram stage, see `dense_layer_from_gram`."""
+        if _is_torch(X) or device_out:
+            dev = _is_torch(X)
             X = self._f32(X, "X")
             same = Xq is None or Xq is X
             Xq = X if same else self._f32(Xq, "Xq")
+            if _is_torch(Xq) != dev:
+                raise TypeError("X and Xq must both be NumPy arrays or both be CUDA tensors")
             if tuple(Xq.shape) != tuple(X.shape):
                 raise ValueError("X and Xq must have the same shape")
             N0, m = int(X.shape[0]), int(X.shape[1])
@@ -182,10 +186,11 @@ class GpfqEngine:
             pq, ldq_x = (px, ldx) if same else self._rowmajor2d(Xq, "Xq")
             if ldq_x != ldx:
                 raise ValueError("X and Xq must share a row stride")
-            G2 = torch.empty((N0, N0), dtype=torch.float64, device=X.device)
-            G1 = G2 if same else torch.empty((N0, N0), dtype=torch.float64, device=X.device)
+            tdev = X.device if dev else torch.device("cuda", self.device)
+            G2 = torch.empty((N0, N0), dtype=torch.float64, device=tdev)
+            G1 = G2 if same else torch.empty((N0, N0), dtype=torch.float64, device=tdev)
             self._bind_stream(True)
-            flags = _lib.X_DEVICE | _lib.Q_DEVICE | (0 if sync else _lib.NO_SYNC)
+            flags = (_lib.X_DEVICE if dev else 0) | _lib.Q_DEVICE | (0 if sync or not dev else _lib.NO_SYNC)
             rc = self._lib.gpfq_gram_matrices(self._ctx, c_void_p(px), c_void_p(pq), ldx, N0, m,
                                               c_void_p(None if same else G1.data_ptr()), c_void_p(G2.data_ptr()), flags)
             self._check(rc)

@@ -67,14 +67,10 @@ def sample_split_gram(engine, wX: np.ndarray, qX, rank: int, world: int, device=
     if hi == lo:                       # fewer samples than ranks: contribute zeros
         lo, hi = 0, 0
 
-    def to_dev(a):
-        t = torch.from_numpy(np.ascontiguousarray(a[:, lo:hi], dtype=np.float32))
-        return t.to(device, non_blocking=True) if device is not None else t
-
     N0 = wX.shape[0]
     if hi > lo:
-        Xd = to_dev(wX)
-        G1, G2 = engine.gram_matrices(Xd, None if same else to_dev(qX))
+        # strided views of this rank's sample range: the library moves them with one pitched H2D copy per matrix
+        G1, G2 = engine.gram_matrices(wX[:, lo:hi], None if same else qX[:, lo:hi], device_out=True)
         if not isinstance(G2, torch.Tensor):       # an engine returning NumPy (tests)
             G2 = torch.from_numpy(np.ascontiguousarray(G2))
             G1 = G2 if same else torch.from_numpy(np.ascontiguousarray(G1))

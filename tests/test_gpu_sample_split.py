@@ -25,9 +25,12 @@ def _split_grams(engine, X, Xq, parts):
         lo, hi = (r * m) // parts, ((r + 1) * m) // parts
         if hi == lo:
             continue
-        xd = torch.from_numpy(np.ascontiguousarray(X[:, lo:hi])).cuda()
-        qd = None if same else torch.from_numpy(np.ascontiguousarray(Xq[:, lo:hi])).cuda()
-        g1, g2 = engine.gram_matrices(xd, qd)
+        if r % 2:   # strided host views of the sample range (what `sample_split_gram` hands over), device outputs
+            g1, g2 = engine.gram_matrices(X[:, lo:hi], None if same else Xq[:, lo:hi], device_out=True)
+        else:       # device tensors
+            xd = torch.from_numpy(np.ascontiguousarray(X[:, lo:hi])).cuda()
+            qd = None if same else torch.from_numpy(np.ascontiguousarray(Xq[:, lo:hi])).cuda()
+            g1, g2 = engine.gram_matrices(xd, qd)
         assert g1.is_cuda and g2.dtype == torch.float64 and ((g1 is g2) == same)
         G2 = g2.clone() if G2 is None else G2 + g2
         if not same:

@@ -186,9 +186,10 @@ def test_gloo_input_replication_all_gather(world):
 class _NumpyGramEngine:
     """Test-only stand-in for GpfqEngine.gram_matrices: fp64 NumPy Grams of the samples it is handed (CPU tensors)."""
 
-    def gram_matrices(self, X, Xq=None, sync=True):
-        x = X.numpy().astype(np.float64)
-        q = x if Xq is None else Xq.numpy().astype(np.float64)
+    def gram_matrices(self, X, Xq=None, sync=True, device_out=False):
+        assert device_out and X.dtype == np.float32
+        x = X.astype(np.float64)
+        q = x if Xq is None else Xq.astype(np.float64)
         G2 = q @ q.T
         return (G2 if Xq is None else q @ x.T), G2
 
