@@ -66,7 +66,8 @@ typedef struct gpfq_stats {
     int64_t bytes_algorithmic; /* algorithmic HBM bytes of the dominant kernel */
     int64_t flops_algorithmic; /* algorithmic fp64 flops of the dominant kernel */
     int32_t gram_kernel;     /* Dense Gram stage ran as: 0 none, 1 fp64 DMMA (mma.sync), 2 int8 slices on tcgen05,
-                                3 block-diagonal tiles only (residual form of the sweep's outer level) */
+                                3 block-diagonal tiles only (residual form of the sweep's outer level);
+                                conv NHWC entry point: 4 = correlation form (13 displacement sums per Gram) */
     int32_t reserved;
 } gpfq_stats;
 
@@ -83,7 +84,10 @@ int gpfq_set_stream(gpfq_ctx *ctx, void *cuda_stream);
 /* Tuning / A-B switches (profiling and tests; the defaults pick by shape):
  *   "gram_kernel"  0 auto, 1 fp64 DMMA contraction, 2 int8 slices on tcgen05 (Dense Gram stage)
  *   "i8_pairs_d"   0 default, else keep int8 slice pairs with k + l <= value (2..10; 10 = every pair)
- *   "conv_kernel"  0 TMA-staged / fused NHWC, 1 direct LDG, 2 generic      "sweep_kernel"  0 persistent tile, 1 per block
+ *   "conv_kernel"  0 TMA-staged patch Grams / correlation form from NHWC activations, 1 direct LDG, 2 generic,
+ *                  3 as 0 but the NHWC entry point uses the shared-memory planes kernel (patch form: 126 MACs per column)
+ *   "corr_loads"   correlation form: 0 operands by TMA boxes (falls back to 1 when C % 4 != 0), 1 direct LDG loads
+ *   "sweep_kernel"  0 persistent tile, 1 per block
  *   "sweep_outer"  0 auto, 1 Gram rows of all earlier directions, 2 carried residuals (3 m N0 N1 MACs: wins when m << N0) */
 int gpfq_set_option(gpfq_ctx *ctx, const char *key, int64_t value);
 /* Stage times of an earlier call: calls_back = 0 is the most recent API call, 1 the one before, ...

@@ -27,6 +27,11 @@ int im2col_stage(gpfq_ctx *, const float *, int64_t, int, int, int64_t, int64_t,
                  int, int, int, int, float *, int64_t);
 int msq_stage(gpfq_ctx *, const void *, int, int64_t, const double *, int, int, double *);
 int nhwc9_plan(int, int, int, int, int, int, int, int, int *, int *);
+int corr9_plan(int, int, int, int, int, int, int, int, int, int64_t, int);
+int corr9_pick_slots(gpfq_ctx *, int, int64_t);
+int conv_corr9_stage(gpfq_ctx *, const float *, const float *, bool, int64_t, int64_t, int64_t, int, int, int64_t, int64_t, int,
+                     int, double *, int, int, int, double *, int, int, int);
+int conv_corr9_assemble_stage(gpfq_ctx *, const double *, int, const double *, int, bool, int, double *);
 int conv_gram9_nhwc_stage(gpfq_ctx *, const float *, const float *, bool, int64_t, int64_t, int, int, int64_t, int64_t, int,
                           int, int, int, int, int, int, int, double *, int);
 
@@ -172,8 +177,11 @@ extern "C" int gpfq_set_option(gpfq_ctx *ctx, const char *key, int64_t value) {
     } else if (!strcmp(key, "i8_pairs_d")) {    // 0 default; else keep slice pairs with k + l <= value
         if (value != 0 && (value < 2 || value > 10)) return gpfq_fail(ctx, GPFQ_ERR_ARG, "i8_pairs_d must be 0 or 2..10");
         ctx->i8_pairs_d = (int)value;
-    } else if (!strcmp(key, "conv_kernel")) {   // 0 TMA-staged / fused NHWC, 1 direct LDG, 2 generic
-        if (value < 0 || value > 2) return gpfq_fail(ctx, GPFQ_ERR_ARG, "conv_kernel must be 0, 1 or 2");
+    } else if (!strcmp(key, "corr_loads")) {   // correlation-form conv Grams: 0 TMA boxes, 1 direct LDG
+        if (value < 0 || value > 1) return gpfq_fail(ctx, GPFQ_ERR_ARG, "corr_loads must be 0 or 1");
+        ctx->corr_variant = (int)value;
+    } else if (!strcmp(key, "conv_kernel")) {   // 0 TMA-staged / correlation form, 1 direct LDG, 2 generic, 3 NHWC planes kernel
+        if (value < 0 || value > 3) return gpfq_fail(ctx, GPFQ_ERR_ARG, "conv_kernel must be 0, 1, 2 or 3");
         ctx->conv_variant = (int)value;
     } else if (!strcmp(key, "sweep_outer")) {   // 0 auto, 1 Gram rows, 2 carried residuals (low-rank form, m << N0)
         if (value < 0 || value > 2) return gpfq_fail(ctx, GPFQ_ERR_ARG, "sweep_outer must be 0, 1 or 2");
@@ -551,11 +559,13 @@ extern "C" int gpfq_gram_matrices(gpfq_ctx *ctx, const float *X, const float *Xq
 // ---------------------------------------------------------------------------------------------
 static int conv_finish(gpfq_ctx *ctx, int kk, const double *partial, int n_ch, int n_chunks, bool same,
                        const float *W, int64_t C, int64_t F, int64_t c0, const Alphabets &al, int n_alph,
-                       double *Q_out, uint32_t flags) {
+                       double *Q_out, uint32_t flags, double *gram_ready = nullptr) {
     cudaStream_t s = ctx->stream;
-    double *gram = nullptr;
-    GPFQ_TRY(gpfq_ws(ctx, WS_CG, (size_t)n_ch * 2 * kk * kk * sizeof(double), (void **)&gram));
-    GPFQ_TRY(conv_finalize_stage(ctx, partial, n_ch, n_chunks, kk, same, gram));
+    double *gram = gram_ready;  // per-channel [G1 | G2] already assembled (correlation form): no partials to sum
+    if (!gram) {
+        GPFQ_TRY(gpfq_ws(ctx, WS_CG, (size_t)n_ch * 2 * kk * kk * sizeof(double), (void **)&gram));
+        GPFQ_TRY(conv_finalize_stage(ctx, partial, n_ch, n_chunks, kk, same, gram));
+    }
     const float *dW = W;
     const size_t wcount = (size_t)kk * C * F;
     if (!(flags & GPFQ_W_DEVICE)) {
@@ -766,8 +776,57 @@ extern "C" int gpfq_conv_layer_nhwc(gpfq_ctx *ctx, const float *act, const float
         }
     }
     CUDA_TRY(ctx, gpfq_record(ctx, 5, s));
+    const int corr_rb = ctx->conv_variant == 0 ? corr9_plan(kh, kw, sh, sw, rh, rw, padding_same, (int)H, (int)Wd, C, (int)n_ch) : 0;
+    if (corr_rb) {
+        // ---- correlation form: 13 displacement sums per Gram straight from the activations (conv_corr.cu)
+        const int nbands = (int)ceil_div64(H, corr_rb);
+        const int per_ic = corr9_pick_slots(ctx, (int)n_ch, ipc * nbands);
+        const int bper_ic = 8 * (int)std::max<int64_t>(1, std::min<int64_t>(ipc, per_ic / 8));
+        const int slots = n_ic * per_ic, bslots = n_ic * bper_ic;
+        double *partial = nullptr, *bpartial = nullptr, *gram = nullptr;
+        const size_t part_bytes = (size_t)n_ch * slots * 26 * sizeof(double);
+        const size_t bpart_bytes = (size_t)n_ch * bslots * 26 * sizeof(double);
+        GPFQ_TRY(gpfq_ws(ctx, WS_CPART, part_bytes, (void **)&partial));
+        GPFQ_TRY(gpfq_ws(ctx, WS_CORR_B, bpart_bytes, (void **)&bpartial));
+        GPFQ_TRY(gpfq_ws(ctx, WS_CG, (size_t)n_ch * 2 * kk * kk * sizeof(double), (void **)&gram));
+        CUDA_TRY(ctx, cudaMemsetAsync(partial, 0, part_bytes, s));
+        CUDA_TRY(ctx, cudaMemsetAsync(bpartial, 0, bpart_bytes, s));
+        CUDA_TRY(ctx, gpfq_record(ctx, 2, s));
+        if (host_act) {
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_copy[2], s));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy[2], 0));
+        }
+        for (int ic = 0; ic < n_ic; ++ic) {
+            const int64_t img0 = (int64_t)ic * ipc;
+            const int64_t imgs = std::min<int64_t>(ipc, n_img - img0);
+            if (host_act) {
+                const size_t off = (size_t)img0 * img_elems, bytes = (size_t)imgs * img_elems * sizeof(float);
+                CUDA_TRY(ctx, cudaMemcpyAsync(const_cast<float *>(dA) + off, act + off, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+                if (!same)
+                    CUDA_TRY(ctx, cudaMemcpyAsync(const_cast<float *>(dAq) + off, actq + off, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+                CUDA_TRY(ctx, cudaEventRecord(ctx->ev_copy[ic & 1], ctx->copy_stream));
+                CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->ev_copy[ic & 1], 0));
+            }
+            GPFQ_TRY(conv_corr9_stage(ctx, dA, dAq, same, img0, imgs, n_img, (int)H, (int)Wd, C, c0, (int)n_ch, corr_rb, partial, slots,
+                                      ic * per_ic, per_ic, bpartial, bslots, ic * bper_ic, bper_ic));
+        }
+        GPFQ_TRY(conv_corr9_assemble_stage(ctx, partial, slots, bpartial, bslots, same, (int)n_ch, gram));
+        CUDA_TRY(ctx, gpfq_record(ctx, 3, s));
+        GPFQ_TRY(conv_finish(ctx, kk, nullptr, (int)n_ch, 0, same, W, C, F, c0, al, n_alph, Q_out, flags, gram));
+        CUDA_TRY(ctx, gpfq_record(ctx, 1, s));
+        gpfq_stats local = {};
+        gpfq_stats *st = stats ? stats : &local;
+        conv_stats(ctx, st, kk, n, n_ch, F, same, n_alph);
+        st->bytes_algorithmic = (same ? 1 : 2) * 4LL * n_img * H * Wd * n_ch;  // the activations, once
+        st->flops_algorithmic = (same ? 1 : 2) * 26LL * n_img * H * Wd * n_ch;  // 13 MACs per pixel, channel and Gram
+        st->gram_kernel = 4;
+        const bool synced = !(flags & GPFQ_NO_SYNC);
+        if (synced) CUDA_TRY(ctx, cudaStreamSynchronize(s));
+        end_call(ctx, st, synced);
+        return GPFQ_OK;
+    }
     int planeP = 0, bandR = 0;
-    if (ctx->conv_variant == 0 && nhwc9_plan(kh, kw, sh, sw, rh, rw, Ho, Wo, &planeP, &bandR)) {
+    if ((ctx->conv_variant == 0 || ctx->conv_variant == 3) && nhwc9_plan(kh, kw, sh, sw, rh, rw, Ho, Wo, &planeP, &bandR)) {
         // ---- fused path: Grams straight from the activations, no patch matrices
         const int64_t groups = ceil_div64(n_ch, 8);
         int64_t per_ic = ceil_div64(4LL * 2 * ctx->sm_count, groups * n_ic);  // ~4 waves of two CTAs per SM overall

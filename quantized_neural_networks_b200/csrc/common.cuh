@@ -52,7 +52,9 @@ struct gpfq_ctx {
     cudaEvent_t ev_copy[4] = {};
     std::string err = "";
     int launches = 0;
-    int conv_variant = 0;         // 3x3 patch-Gram kernel: 0 TMA-staged (default), 1 direct LDG, 2 generic
+    int conv_variant = 0;         // 3x3 patch-Gram kernel: 0 TMA-staged / correlation form (default), 1 direct LDG, 2 generic,
+                                  // 3 NHWC entry point: shared-memory planes kernel instead of the correlation form
+    int corr_variant = 0;         // correlation-form conv Grams: 0 TMA-fed (falls back by itself), 1 direct LDG loads
     int sweep_variant = 0;        // triangular sweep: 0 persistent neuron-tile kernel (default), 1 one launch pair per block
     bool stream_literal = false;  // streaming walk: reproduce the reference's fp32-rounded w*X products (set per call)
     int gram_variant = 0;         // Dense Gram stage: 0 auto, 1 fp64 DMMA (mma.sync), 2 int8 slices on tcgen05 (gram_i8.cu)
@@ -71,7 +73,7 @@ struct gpfq_ctx {
 enum WsSlot {
     WS_X = 0, WS_XQ, WS_W, WS_Q, WS_WT, WS_QT, WS_G1, WS_G2, WS_PART, WS_DT, WS_NRM, WS_ALPH,
     WS_U, WS_PTRS, WS_CG, WS_CPART, WS_PATCH_A, WS_PATCH_B, WS_ACT_A, WS_ACT_B, WS_QIDX, WS_MISC,
-    WS_I8_SQ, WS_I8_SX, WS_I8_E, WS_I8_TILES, WS_LR_XD, WS_LR_XT, WS_LR_U
+    WS_I8_SQ, WS_I8_SX, WS_I8_E, WS_I8_TILES, WS_LR_XD, WS_LR_XT, WS_LR_U, WS_CORR_B
 };
 
 int gpfq_fail(gpfq_ctx *ctx, int code, const char *fmt, ...);

@@ -636,7 +636,7 @@ template <int KK>
 static int launch_conv_gram(gpfq_ctx *ctx, ConvPtrs ptrs, bool same, int64_t n, int n_ch, int n_chunks,
                             int64_t chunk_cols, double *partial, bool vec_ok, int slots) {
     dim3 grid((unsigned)n_chunks, (unsigned)n_ch);
-    if (KK == 9 && vec_ok && ctx->conv_variant == 0) {
+    if (KK == 9 && vec_ok && (ctx->conv_variant == 0 || ctx->conv_variant == 3)) {
         using namespace tma9;
         constexpr size_t tail = (size_t)CWARPS * 2 * 81 * sizeof(double) + 2 * STAGES * sizeof(uint64_t);
         const size_t smem = (size_t)STAGES * (same ? 9 : 18) * PITCH * sizeof(float) + tail;
@@ -668,7 +668,7 @@ int conv_supported_kk(int kk) { return kk == 1 || kk == 2 || kk == 3 || kk == 4 
 // Column chunks per channel: grid = n_chunks x n_ch CTAs.  TMA kernel (kk == 9, vectorisable): one CTA per SM, whole
 // waves of sm_count CTAs, chunks a multiple of the 512-column stage; the other kernels: two CTAs per SM.
 int conv_pick_chunks(gpfq_ctx *ctx, int64_t n, int n_ch, int64_t *chunk_cols, int kk, bool vec_ok) {
-    const bool tma = (kk == 9 && vec_ok && ctx->conv_variant == 0);
+    const bool tma = (kk == 9 && vec_ok && (ctx->conv_variant == 0 || ctx->conv_variant == 3));
     const int64_t per_wave = tma ? ctx->sm_count : 2LL * ctx->sm_count;
     const int64_t min_cols = tma ? 32768 : 4096, align = tma ? tma9::COLS : 128;
     int64_t waves = ((int64_t)n * n_ch) / (per_wave * min_cols);

@@ -393,6 +393,86 @@ def test_conv_nhwc_fused_matches_patch_path(n_img, H, Wd, C, F, pad):
     assert np.array_equal(outs["tma"], outs["ldg"]) and np.array_equal(outs["tma_same"], outs["ldg_same"])
 
 
+@pytest.mark.parametrize("n_img,H,Wd,C,F", [(3, 1, 1, 8, 2), (2, 1, 9, 9, 2), (2, 6, 1, 16, 2), (5, 2, 2, 33, 3), (4, 7, 7, 40, 2),
+                                            (3, 14, 14, 64, 4), (2, 28, 28, 96, 2), (2, 16, 16, 32, 3), (1, 45, 37, 8, 2),
+                                            (70, 8, 8, 35, 2), (2, 3, 5, 12, 2)])
+def test_conv_corr9_matches_patch_form(engine, n_img, H, Wd, C, F):
+    """Correlation form of the 3x3 / stride 1 / SAME Grams (conv_corr.cu: 13 displacement sums + border inclusion-exclusion)
+    against the oracle and against the patch-form kernel (shared-memory planes): degenerate images (1 x 1, one row, one
+    column, 2 x 2), ragged bands for every band height, channel counts that are not a multiple of 32, channel shards."""
+    import torch
+    rng = np.random.default_rng(n_img * 131 + H * 7 + C)
+    act = np.maximum(rng.standard_normal((n_img, H, Wd, C)), 0).astype(np.float32)
+    actq = np.maximum(act + 0.05 * rng.standard_normal(act.shape), 0).astype(np.float32)
+    if C >= 12:   # signed activations too: Gram entries with cancellation
+        act[..., 3] = rng.standard_normal((n_img, H, Wd)).astype(np.float32)
+        actq[..., 3] = act[..., 3] + 0.05 * rng.standard_normal((n_img, H, Wd)).astype(np.float32)
+    W = (rng.uniform(-1, 1, (3, 3, C, F)) * 0.3).astype(np.float32)
+    A = O.layer_alphabet(W, 3, O.unit_alphabet(3))
+    patches = lambda ch: (O.channel_patches(act, ch, (3, 3), (1, 1), "SAME"), O.channel_patches(actq, ch, (3, 3), (1, 1), "SAME"))
+    Qref = c_oracle.quantize_conv_layer(W, patches, A)
+    Q = engine.conv_layer_nhwc(act, actq, W, A)
+    corr = H >= 2 and Wd >= 2                               # one-row / one-column images keep the patch form
+    assert (engine.last_stats["gram_kernel"] == 4) == corr  # the correlation form really ran
+    assert O.agreement(Q, Qref) >= AGREE
+    Qs = engine.conv_layer_nhwc(actq, None, W, A)
+    engine.set_option("corr_loads", 1)                      # direct LDG loads instead of TMA boxes: same sums, same order
+    try:
+        assert np.array_equal(engine.conv_layer_nhwc(act, actq, W, A), Q)
+        assert np.array_equal(engine.conv_layer_nhwc(actq, None, W, A), Qs)
+    finally:
+        engine.set_option("corr_loads", 0)
+    dev = engine.conv_layer_nhwc(torch.from_numpy(act).cuda(), torch.from_numpy(actq).cuda(), torch.from_numpy(W).cuda(), A)
+    assert np.array_equal(dev.cpu().numpy(), Q)
+    if C >= 10:
+        part = engine.conv_layer_nhwc(act, actq, W, A, c0=1, n_channels=C - 2)
+        assert np.array_equal(part[:, :, 1:C - 1], Q[:, :, 1:C - 1]) and np.all(part[:, :, 0] == 0)
+    engine.set_option("conv_kernel", 3)
+    try:
+        Qp = engine.conv_layer_nhwc(act, actq, W, A)
+        assert engine.last_stats["gram_kernel"] != 4
+        Qps = engine.conv_layer_nhwc(actq, None, W, A)
+        # a channel that is zero except on its bottom row / right column: tap rows / columns that never sit there are
+        # dead directions (exact zeros in the Gram), the guard of quantized_network.py:83-84 must fire in both forms
+        act2, actq2 = act.copy(), actq.copy()
+        act2[:, :-1, :, 1] = 0
+        actq2[:, :-1, :, 1] = 0
+        act2[:, :, :-1, 2] = 0
+        actq2[:, :, :-1, 2] = 0
+        Qp2 = engine.conv_layer_nhwc(act2, actq2, W, A)
+    finally:
+        engine.set_option("conv_kernel", 0)
+    assert O.agreement(Q, Qp) >= AGREE and O.agreement(Qs, Qps) >= AGREE
+    assert O.agreement(Qp, Qref) >= AGREE
+    Q2 = engine.conv_layer_nhwc(act2, actq2, W, A)
+    assert O.agreement(Q2, Qp2) >= AGREE
+    if corr:
+        assert np.all(Q2[0, :, 1, :] == 0) and np.all(Q2[:, 0, 2, :] == 0)   # dead directions: literal zeros
+
+
+def test_conv_corr9_host_image_chunks(engine):
+    """Host activations larger than one staging chunk (several image chunks, each with its own slot range) and a full
+    VGG-like plane size: correlation form == patch form == device-pointer call."""
+    import torch
+    rng = np.random.default_rng(5)
+    n_img, H, Wd, C, F = 44, 224, 224, 16, 2
+    act = np.maximum(rng.standard_normal((n_img, H, Wd, C), dtype=np.float32), 0)
+    actq = np.maximum(act + 0.05 * rng.standard_normal(act.shape, dtype=np.float32), 0)
+    W = (rng.uniform(-1, 1, (3, 3, C, F)) * 0.3).astype(np.float32)
+    A = O.layer_alphabet(W, 3, O.unit_alphabet(np.log2(3)))
+    Q = engine.conv_layer_nhwc(act, actq, W, A)
+    assert engine.last_stats["gram_kernel"] == 4
+    dev = engine.conv_layer_nhwc(torch.from_numpy(act).cuda(), torch.from_numpy(actq).cuda(), torch.from_numpy(W).cuda(), A)
+    assert np.array_equal(dev.cpu().numpy(), Q) or O.agreement(dev.cpu().numpy(), Q) >= AGREE
+    engine.set_option("conv_kernel", 3)
+    try:
+        Qp = engine.conv_layer_nhwc(act, actq, W, A)
+    finally:
+        engine.set_option("conv_kernel", 0)
+    assert O.agreement(Q, Qp) >= AGREE
+    assert np.all(np.isin(Q, np.concatenate([A, [0.0]])))
+
+
 # ---- Dense Gram stage on tcgen05 (int8 slices, gram_i8.cu) ------------------------------------------------------------
 class _gram_kernel:
     """Force the Dense Gram kernel for a block: 1 = fp64 DMMA contraction, 2 = int8 slices on tcgen05."""

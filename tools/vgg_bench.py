@@ -21,7 +21,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 CONV = [(3, 64, 224), (64, 64, 224), (64, 128, 112), (128, 128, 112), (128, 256, 56), (256, 256, 56), (256, 256, 56),
         (256, 512, 28), (512, 512, 28), (512, 512, 28), (512, 512, 14), (512, 512, 14), (512, 512, 14)]
 DENSE = [(25088, 4096), (4096, 4096), (4096, 1000)]
-FP64_SLOTS = 18.55e12
+FP64_SLOTS = 18.55e12   # DMMA.8x8x4 (profiles/fp64_pipes_r1.txt)
+DFMA_SLOTS = 17.05e12   # DFMA, same pipe
 
 
 def shard_range(n, rank, world):
@@ -36,11 +37,14 @@ def main():
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--shard", default="0/1")
     ap.add_argument("--skip-conv", action="store_true")
+    ap.add_argument("--skip-dense", action="store_true")
+    ap.add_argument("--conv-kernel", type=int, default=0, help="gpfq_set_option conv_kernel: 0 correlation form, 3 planes kernel")
     args = ap.parse_args()
     rank, world = (int(v) for v in args.shard.split("/"))
     import torch
     from quantized_neural_networks_b200 import get_engine
     eng = get_engine(0)
+    eng.set_option("conv_kernel", args.conv_kernel)
     dev = torch.device("cuda", 0)
     peaks = {}
     try:
@@ -81,12 +85,17 @@ def main():
                 if best is None or st["ms_total"] < best["ms_total"]:
                     best = st
             colch = args.n_img * H * H * (hi - lo)
-            slots = colch * (84 if li == 0 else 168)
+            corr = best["gram_kernel"] == 4
+            # patch form: 168 (84 when X == Xq) fp64-pipe slots per patch column and channel at the DMMA rate; correlation
+            # form: 26 (13) DFMAs per pixel and channel at the measured DFMA rate
+            slots = colch * ((13 if li == 0 else 26) if corr else (84 if li == 0 else 168))
+            pipe = DFMA_SLOTS if corr else FP64_SLOTS
             bytes_alg = colch * (4 if li == 0 else 8)
             ms = best["ms_total"]
             print(json.dumps({"layer": f"conv{li}", "C": C, "F": F, "H": H, "channels": [lo, hi], "weights": 9 * (hi - lo) * F,
                               "ms": round(ms, 3), "ms_gram": round(best["ms_gram"], 3),
-                              "fp64_pipe_frac": round(slots / FP64_SLOTS / (best["ms_gram"] * 1e-3), 3),
+                              "form": "correlation (13 DFMA / pixel / Gram)" if corr else "patch (126 MACs / column)",
+                              "fp64_pipe_frac": round(slots / pipe / (best["ms_gram"] * 1e-3), 3),
                               "hbm_frac": round(bytes_alg / hbm / (best["ms_gram"] * 1e-3), 3),
                               "weights_per_s": round(9 * (hi - lo) * F / (ms * 1e-3))}), flush=True)
             total_ms += ms
@@ -95,7 +104,7 @@ def main():
             torch.cuda.empty_cache()
             eng.trim()
     m = args.n_img
-    for li, (N0, N1) in enumerate(DENSE):
+    for li, (N0, N1) in enumerate([] if args.skip_dense else DENSE):
         g = torch.Generator(device=dev).manual_seed(200 + li)
         Z = torch.randn((N0, m), device=dev, generator=g)
         X = torch.relu(Z)
