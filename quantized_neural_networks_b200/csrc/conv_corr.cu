@@ -11,26 +11,27 @@
 // row and/or ONE border column (tap row 0 never reads the bottom image row as its own pixel, tap row 2 never the top
 // row; columns alike).  For s <= t the displacement is lexicographically <= 0: only 13 displacements exist, so a pixel
 // costs 13 exact-product fp64 FMAs per Gram instead of the 81 + 45 of the patch form (126 useful MACs, 168 fp64-pipe
-// slots in conv_gram9_nhwc_kernel).  The pixels s are split into nine disjoint regions -- interior, top / bottom row
-// and left / right column without their ends, four corners -- whose 13 sums are kept apart and ADDED per (a, b) for the
-// regions tap a may sit on.  No subtraction anywhere: a tap direction that only ever reads zeros (a dead channel, an
-// image with black margins) gets an exactly zero Gram row, as in the patch form, so the dead-direction guard of
+// slots in conv_gram9_nhwc_kernel).  The pixels s are split into nine disjoint regions -- {top row, rows between,
+// bottom row} x {left column, columns between, right column} -- whose 13 sums are kept apart and ADDED per (a, b) for
+// the regions tap a may sit on.  No subtraction anywhere: a tap direction that only ever reads zeros (a dead channel,
+// an image with black margins) gets an exactly zero Gram row, as in the patch form, so the dead-direction guard of
 // quantized_network.py:83-84 fires identically.  Sums are exact fp32 x fp32 products accumulated in fp64 in a fixed
 // order (tasks per warp in index order, warps in index order): bit-reproducible, and equal to the patch form up to fp64
 // re-association (1e-16 relative; the parity budget is 1e-9).
 //
-//   conv_corr9_tma_kernel<RB, CROSS>  interior pixels.  lane = channel (NHWC: 32 channels = one 128-byte line per pixel);
-//                                  a warp walks a band of RB image rows left to right with a (RB+2) x 5 fp64 register
-//                                  window of the displaced operand and 13 accumulators per lane.  Operands arrive by TMA
-//                                  (cp.async.bulk.tensor.4d over the (N, H, W, C) tensor, box = 32 channels x 5 columns x
-//                                  RB+2 rows, zero fill outside the image = the 'SAME' padding) into a per-warp mbarrier
-//                                  ring; the warp is its own producer (lane 0 issues the next box before multiplying the
-//                                  current one).  CROSS: xq centre x x window (G1), else xq x xq (G2).  Bound by the fp64
-//                                  pipe: 13 DFMA + ~1.3-2.3 F2F per pixel and pass.
-//   conv_corr9_kernel<RB, CROSS>   the same walk with direct LDG loads (C % 4 != 0 or unaligned tensors: no tensor map)
-//   conv_corr9_border_kernel       the same 13 sums for the eight border regions, bounds-checked loads
+//   conv_corr9_tma_kernel<RB, CROSS>  lane = channel (NHWC: 32 channels = one 128-byte line per pixel); a warp walks a band
+//                                  of RB image rows left to right with a (RB+2) x 5 fp64 register window of the displaced
+//                                  operand and 13 accumulators per lane.  Operands arrive by TMA (cp.async.bulk.tensor.4d
+//                                  over the (N, H, W, C) tensor, box = 32 channels x 5 columns x RB+2 rows, zero fill
+//                                  outside the image = the 'SAME' padding) into a per-warp mbarrier ring; the warp is its
+//                                  own producer (lane 0 issues the next box before multiplying the current one).
+//                                  CROSS: xq centre x x window (G1), else xq x xq (G2).  The first and the last pixel
+//                                  column of a band go to the left / right region records.  One launch with RB in
+//                                  {8, 6, 4} covers rows 1 .. H-2, one with RB = 1 the top and bottom rows.
+//                                  Bound by the fp64 pipe: 13 DFMA + 1.3-2.3 F2F per pixel and pass.
 //   conv_corr9_assemble_kernel     fixed-order slot sums + the per-tap region sums -> [G1 | G2] per channel in the
 //                                  layout conv_sweep_kernel reads
+// Layers the tensor map cannot serve (C < 32, C % 4 != 0, images smaller than a box) keep the patch form.
 #include <cuda.h>
 
 #include <algorithm>
@@ -40,124 +41,19 @@
 namespace corr9 {
 constexpr int ND = 13;        // displacements (dy, dx): dy in {-2, -1} x dx in [-2, 2], then dy = 0 x dx in {-2, -1, 0}
 constexpr int WARPS = 4;      // warps (tasks in flight) per CTA
-constexpr int NCLS = 8;       // border regions: top, bottom row and left, right column (ends excluded), corners TL, TR, BL, BR
 constexpr int WC = 5;         // columns per TMA box = phases of the rotating register window
-constexpr int REC = 2 * ND;   // doubles per (channel, slot): [cross sums | auto sums]
+constexpr int REC = 6 * ND;   // doubles per (channel, slot): [pass: cross, auto][pixel column: first, between, last][13]
 }  // namespace corr9
 
 struct Corr9Geom {
     int H, W;
-    int64_t C;         // channels of the activation tensor
     int64_t c_first;   // first channel of this launch
     int n_ch;          // channels of this launch
     int64_t img0, n_img;
     int slots;         // warps per channel group in this launch
+    int y_first, y_last;  // pixel rows this launch covers; band b of an image starts at y_first + b * RB
+    int two_rows;      // RB = 1 launch over the top and the bottom row: odd slots take y = y_last, even slots y = y_first
 };
-
-// One band of RB image rows of one image, walked left to right.  pb: row y0 - 2, column 0 of the displaced operand
-// (this lane's channel); pa: row y0, column 0 of xq (CROSS only).  EDGE: the band touches the top or the bottom of the
-// image, rows are bounds-checked (interior bands skip the checks: one IMAD.WIDE + LDG per operand).
-template <int RB, bool CROSS, bool EDGE>
-__device__ __forceinline__ void corr9_band(double (&acc)[corr9::ND], const float *__restrict__ pb,
-                                           const float *__restrict__ pa, int rowstride, int Cs, int W, int H, int y0,
-                                           bool chok) {
-    double win[RB + 2][5];
-    double ac[RB];
-    float rawb[RB + 2], rawa[RB];
-#pragma unroll
-    for (int r = 0; r < RB + 2; ++r)
-#pragma unroll
-        for (int c = 0; c < 5; ++c) win[r][c] = 0.0;
-    (void)ac;
-    (void)rawa;
-
-    auto load = [&](int cx) {
-        const bool colok = chok && cx < W;
-        const float *pc = pb + cx * Cs;
-#pragma unroll
-        for (int r = 0; r < RB + 2; ++r) {
-            const bool ok = colok && (!EDGE || (unsigned)(y0 - 2 + r) < (unsigned)H);
-            rawb[r] = ok ? __ldg(pc + r * rowstride) : 0.f;
-        }
-        if (CROSS) {
-            const bool aok = chok && (unsigned)(cx - 2) < (unsigned)W;
-            const float *pac = pa + (cx - 2) * Cs;
-#pragma unroll
-            for (int i = 0; i < RB; ++i) {
-                const bool ok = aok && (!EDGE || (y0 + i) < H);
-                rawa[i] = ok ? __ldg(pac + i * rowstride) : 0.f;
-            }
-        }
-    };
-
-    load(0);
-    for (int cx0 = 0; cx0 < W + 2; cx0 += 5) {
-#pragma unroll
-        for (int ph = 0; ph < 5; ++ph) {
-            const int cx = cx0 + ph;  // newest window column (image column cx) lives in physical slot ph
-            if (cx < W + 2) {
-#pragma unroll
-                for (int r = 0; r < RB + 2; ++r) win[r][ph] = (double)rawb[r];
-                if (CROSS) {
-#pragma unroll
-                    for (int i = 0; i < RB; ++i) ac[i] = (double)rawa[i];
-                }
-                load(cx + 1);  // next column in flight while this one is multiplied
-                if (cx >= 3 && cx <= W) {
-                    // interior pixel column cx - 2 in [1, W - 2] = logical window column 2 = physical slot (ph + 3) % 5
-#pragma unroll
-                    for (int i = 0; i < RB; ++i) {
-                        double a = CROSS ? ac[i] : win[i + 2][(ph + 3) % 5];
-                        if (EDGE && !((unsigned)(y0 + i - 1) < (unsigned)(H - 2))) a = 0.0;  // rows 0 and H - 1: border kernel
-#pragma unroll
-                        for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-                            for (int dx = 0; dx < 5; ++dx)
-                                acc[dy * 5 + dx] = fma(a, win[i + dy][(ph + 1 + dx) % 5], acc[dy * 5 + dx]);
-#pragma unroll
-                        for (int dx = 0; dx < 3; ++dx)
-                            acc[10 + dx] = fma(a, win[i + 2][(ph + 1 + dx) % 5], acc[10 + dx]);
-                    }
-                }
-            }
-        }
-    }
-}
-
-template <int RB, bool CROSS>
-__global__ void __launch_bounds__(corr9::WARPS * 32)
-conv_corr9_kernel(const float *__restrict__ actq, const float *__restrict__ actx, Corr9Geom gm,
-                  double *__restrict__ partial, int slot_stride, int slot0) {
-    using namespace corr9;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int slot = blockIdx.x * WARPS + warp;
-    const int chl = blockIdx.y * 32 + lane;
-    const bool chok = chl < gm.n_ch;
-    const int64_t ch = gm.c_first + (chok ? chl : 0);
-    const int H = gm.H, W = gm.W, Cs = (int)gm.C;
-    const int nbands = (H + RB - 1) / RB;
-    const int64_t ntasks = gm.n_img * nbands;
-    const int rowstride = W * Cs;  // elements per image row (< 2^27, checked by corr9_plan)
-    const float *bsrc = CROSS ? actx : actq;
-    double acc[ND];
-#pragma unroll
-    for (int d = 0; d < ND; ++d) acc[d] = 0.0;
-
-    for (int64_t task = slot; task < ntasks; task += gm.slots) {
-        const int64_t img = gm.img0 + task / nbands;
-        const int y0 = (int)(task % nbands) * RB;
-        // row y0 - 2 of this lane's channel (may lie above the image: never dereferenced then)
-        const float *pb = bsrc + (img * H + (y0 - 2)) * (int64_t)rowstride + ch;
-        const float *pa = actq + (img * H + y0) * (int64_t)rowstride + ch;
-        if (y0 >= 2 && y0 + RB <= H - 1) corr9_band<RB, CROSS, false>(acc, pb, pa, rowstride, Cs, W, H, y0, chok);
-        else corr9_band<RB, CROSS, true>(acc, pb, pa, rowstride, Cs, W, H, y0, chok);
-    }
-    if (chok) {
-        double *out = partial + ((size_t)chl * slot_stride + slot0 + slot) * REC + (CROSS ? 0 : ND);
-#pragma unroll
-        for (int d = 0; d < ND; ++d) out[d] = acc[d];
-    }
-}
 
 // ---- TMA-fed variant ---------------------------------------------------------------------------------------------
 namespace corr9 {
@@ -212,22 +108,29 @@ conv_corr9_tma_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_con
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncwarp();
-    const int H = gm.H, W = gm.W;
+    const int W = gm.W;
     const int c0 = (int)(gm.c_first + (int64_t)blockIdx.y * 32);
-    const int nbands = (H + RB - 1) / RB;
-    const int64_t ntasks = gm.n_img * nbands;
+    const int nrows = gm.y_last - gm.y_first + 1;
+    const int nbands = gm.two_rows ? 1 : (nrows + RB - 1) / RB;
+    // two_rows: this warp's images are slot / 2, slot / 2 + slots / 2, ...; its row is fixed by the slot's parity
+    const int64_t ntasks = gm.two_rows ? gm.n_img : gm.n_img * nbands;
+    const int64_t t_first = gm.two_rows ? slot / 2 : slot, t_step = gm.two_rows ? gm.slots / 2 : gm.slots;
     const int nstages = (W + 2 + WC - 1) / WC;
+    // this lane's record: [pass][first column | between | last column][13]; first / last are read-modify-written in
+    // task order by this lane only (the API zeroes the records), `between` is stored once at the end
+    double *rec = partial + ((size_t)(chok ? chl : 0) * slot_stride + slot0 + slot) * REC + (CROSS ? 0 : 3 * ND);
     uint32_t it = 0;  // boxes this warp has consumed so far: ring position and mbarrier parity
     double acc[ND];
 #pragma unroll
     for (int d = 0; d < ND; ++d) acc[d] = 0.0;
 
-    for (int64_t task = slot; task < ntasks; task += gm.slots) {
-        const int img = (int)(gm.img0 + task / nbands);
-        const int y0 = (int)(task % nbands) * RB;
-        unsigned rowmask = 0;  // bit i: pixel row y0 + i is an interior row (1 .. H - 2)
+    for (int64_t task = t_first; task < ntasks; task += t_step) {
+        const int img = (int)(gm.img0 + (gm.two_rows ? task : task / nbands));
+        const int y0 = gm.two_rows ? ((slot & 1) ? gm.y_last : gm.y_first) : gm.y_first + (int)(task % nbands) * RB;
+        unsigned rowmask = 0;  // bit i: pixel row y0 + i belongs to this launch
 #pragma unroll
-        for (int i = 0; i < RB; ++i) rowmask |= ((unsigned)(y0 + i - 1) < (unsigned)(H - 2)) ? (1u << i) : 0u;
+        for (int i = 0; i < RB; ++i) rowmask |= (y0 + i <= gm.y_last) ? (1u << i) : 0u;
+        const bool allrows = rowmask == (1u << RB) - 1u;
         double win[RB + 2][5];
         double ac[RB];
         (void)ac;
@@ -256,30 +159,69 @@ conv_corr9_tma_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_con
             mbar_wait(&bars[s], (pos / NS) & 1u);
             const float *tb = ring + s * R::STAGE_FLOATS + lane;
             const float *ta = tb + R::B_FLOATS;
+            if (allrows && k >= 1 && k * WC + WC - 1 <= W) {
+                // ---- five pixel columns strictly between the first and the last one, every row live: branch-free
 #pragma unroll
-            for (int ph = 0; ph < WC; ++ph) {
-                const int cx = k * WC + ph;  // newest window column (image column cx) lives in physical slot ph
-                if (cx < W + 2) {
+                for (int ph = 0; ph < WC; ++ph) {
 #pragma unroll
                     for (int r = 0; r < RB + 2; ++r) win[r][ph] = (double)tb[(r * WC + ph) * 32];
                     if (CROSS) {
 #pragma unroll
                         for (int i = 0; i < RB; ++i) ac[i] = (double)ta[(i * WC + ph) * 32];
                     }
-                    if (cx >= 3 && cx <= W) {
-                        // interior pixel column cx - 2 in [1, W - 2] = logical window column 2 = physical slot (ph + 3) % 5
 #pragma unroll
-                        for (int i = 0; i < RB; ++i) {
-                            double a = CROSS ? ac[i] : win[i + 2][(ph + 3) % 5];
-                            a = (rowmask >> i) & 1u ? a : 0.0;
+                    for (int i = 0; i < RB; ++i) {
+                        const double a = CROSS ? ac[i] : win[i + 2][(ph + 3) % 5];
 #pragma unroll
-                            for (int dy = 0; dy < 2; ++dy)
+                        for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
-                                for (int dx = 0; dx < 5; ++dx)
-                                    acc[dy * 5 + dx] = fma(a, win[i + dy][(ph + 1 + dx) % 5], acc[dy * 5 + dx]);
+                            for (int dx = 0; dx < 5; ++dx)
+                                acc[dy * 5 + dx] = fma(a, win[i + dy][(ph + 1 + dx) % 5], acc[dy * 5 + dx]);
 #pragma unroll
-                            for (int dx = 0; dx < 3; ++dx)
-                                acc[10 + dx] = fma(a, win[i + 2][(ph + 1 + dx) % 5], acc[10 + dx]);
+                        for (int dx = 0; dx < 3; ++dx)
+                            acc[10 + dx] = fma(a, win[i + 2][(ph + 1 + dx) % 5], acc[10 + dx]);
+                    }
+                }
+            } else {
+                // ---- band ends, ragged last band: one column at a time into `e`, then to the record it belongs to
+#pragma unroll
+                for (int ph = 0; ph < WC; ++ph) {
+                    const int cx = k * WC + ph;  // newest window column (image column cx) lives in physical slot ph
+                    if (cx < W + 2) {
+#pragma unroll
+                        for (int r = 0; r < RB + 2; ++r) win[r][ph] = (double)tb[(r * WC + ph) * 32];
+                        if (CROSS) {
+#pragma unroll
+                            for (int i = 0; i < RB; ++i) ac[i] = (double)ta[(i * WC + ph) * 32];
+                        }
+                        if (cx >= 2) {
+                            // pixel column cx - 2 = logical window column 2 = physical slot (ph + 3) % 5
+                            double e[ND];
+#pragma unroll
+                            for (int d = 0; d < ND; ++d) e[d] = 0.0;
+#pragma unroll
+                            for (int i = 0; i < RB; ++i) {
+                                double a = CROSS ? ac[i] : win[i + 2][(ph + 3) % 5];
+                                a = (rowmask >> i) & 1u ? a : 0.0;
+#pragma unroll
+                                for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                                    for (int dx = 0; dx < 5; ++dx)
+                                        e[dy * 5 + dx] = fma(a, win[i + dy][(ph + 1 + dx) % 5], e[dy * 5 + dx]);
+#pragma unroll
+                                for (int dx = 0; dx < 3; ++dx)
+                                    e[10 + dx] = fma(a, win[i + 2][(ph + 1 + dx) % 5], e[10 + dx]);
+                            }
+                            if (cx == 2 || cx == W + 1) {
+                                if (chok) {
+                                    double *o = rec + (cx == 2 ? 0 : 2 * ND);
+#pragma unroll
+                                    for (int d = 0; d < ND; ++d) o[d] += e[d];
+                                }
+                            } else {
+#pragma unroll
+                                for (int d = 0; d < ND; ++d) acc[d] += e[d];
+                            }
                         }
                     }
                 }
@@ -288,87 +230,31 @@ conv_corr9_tma_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_con
         it += (uint32_t)nstages;
     }
     if (chok) {
-        double *out = partial + ((size_t)chl * slot_stride + slot0 + slot) * REC + (CROSS ? 0 : ND);
 #pragma unroll
-        for (int d = 0; d < ND; ++d) out[d] = acc[d];
-    }
-}
-
-// Border regions.  Slot s of a launch handles class s % 8 for images s / 8, s / 8 + slots / 8, ...
-template <bool SAME>
-__global__ void __launch_bounds__(corr9::WARPS * 32)
-conv_corr9_border_kernel(const float *__restrict__ actq, const float *__restrict__ actx, Corr9Geom gm,
-                         double *__restrict__ bpartial, int slot_stride, int slot0) {
-    using namespace corr9;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int slot = blockIdx.x * WARPS + warp;
-    const int chl = blockIdx.y * 32 + lane;
-    const bool chok = chl < gm.n_ch;
-    const int64_t ch = gm.c_first + (chok ? chl : 0);
-    const int H = gm.H, W = gm.W;
-    const int64_t Cs = gm.C;
-    const int cls = slot % NCLS;
-    const int64_t first = slot / NCLS, step = gm.slots / NCLS;
-    double a1[ND], a2[ND];
-#pragma unroll
-    for (int d = 0; d < ND; ++d) a1[d] = a2[d] = 0.0;
-    // pixels of the class: (y, x) = (ys + k * yk, xs + k * xk), k < n
-    int ys = 0, xs = 0, yk = 0, xk = 0, n = 1;
-    switch (cls) {
-        case 0: n = W - 2; xk = 1; xs = 1; break;                       // top row without its ends
-        case 1: n = W - 2; xk = 1; xs = 1; ys = H - 1; break;           // bottom row
-        case 2: n = H - 2; yk = 1; ys = 1; break;                       // left column without its ends
-        case 3: n = H - 2; yk = 1; ys = 1; xs = W - 1; break;           // right column
-        case 4: break;                                      // top-left
-        case 5: xs = W - 1; break;                          // top-right
-        case 6: ys = H - 1; break;                          // bottom-left
-        default: ys = H - 1; xs = W - 1; break;             // bottom-right
-    }
-    if (chok) {
-        for (int64_t im = first; im < gm.n_img; im += step) {
-            const float *q = actq + (gm.img0 + im) * (int64_t)H * W * Cs + ch;
-            const float *x = SAME ? q : actx + (gm.img0 + im) * (int64_t)H * W * Cs + ch;
-            for (int k = 0; k < n; ++k) {
-                const int y = ys + k * yk, xx = xs + k * xk;
-                const double a = (double)__ldg(q + ((int64_t)y * W + xx) * Cs);
-#pragma unroll
-                for (int d = 0; d < ND; ++d) {
-                    const int dy = d < 10 ? d / 5 - 2 : 0, dx = d < 10 ? d % 5 - 2 : d - 12;
-                    const int yy = y + dy, xc = xx + dx;
-                    if ((unsigned)yy < (unsigned)H && (unsigned)xc < (unsigned)W) {
-                        const int64_t off = ((int64_t)yy * W + xc) * Cs;
-                        a2[d] = fma(a, (double)__ldg(q + off), a2[d]);
-                        if (!SAME) a1[d] = fma(a, (double)__ldg(x + off), a1[d]);
-                    }
-                }
-            }
-        }
-        double *out = bpartial + ((size_t)chl * slot_stride + slot0 + slot) * REC;
-#pragma unroll
-        for (int d = 0; d < ND; ++d) {
-            out[d] = a1[d];
-            out[ND + d] = a2[d];
-        }
+        for (int d = 0; d < ND; ++d) rec[ND + d] = acc[d];
     }
 }
 
 // gram: (n_channels, 2 * 81): [G1 | G2], lower triangle + diagonal valid, zeros above (conv_finalize_kernel's layout).
+// partial: records of the launch over rows 1 .. H-2 (left column, interior, right column); rpartial: records of the
+// top / bottom row launch (even slots: top-left corner, top row, top-right corner; odd slots: the bottom ones).
 __global__ void __launch_bounds__(96)
-conv_corr9_assemble_kernel(const double *__restrict__ partial, int slots, const double *__restrict__ bpartial, int bslots,
+conv_corr9_assemble_kernel(const double *__restrict__ partial, int slots, const double *__restrict__ rpartial, int rslots,
                            int same, double *__restrict__ gram) {
     using namespace corr9;
-    __shared__ double T[REC], B[NCLS][REC];
+    // S[pass][row class: 0 top, 1 between, 2 bottom][column class: 0 first, 1 between, 2 last][13]
+    __shared__ double S[2][3][3][ND];
     const int ch = blockIdx.x, tid = threadIdx.x;
-    if (tid < REC) {
+    for (int e = tid; e < 2 * 9 * ND; e += blockDim.x) {
+        const int d = e % ND, cc = (e / ND) % 3, rc = (e / (3 * ND)) % 3, pass = e / (9 * ND);
+        const int off = (pass * 3 + cc) * ND + d;
         double tot = 0.0;
-        for (int s = 0; s < slots; ++s) tot += partial[((size_t)ch * slots + s) * REC + tid];  // slots in index order
-        T[tid] = tot;
-    }
-    for (int e = tid; e < NCLS * REC; e += blockDim.x) {
-        const int cls = e / REC, i = e % REC;
-        double tot = 0.0;
-        for (int s = cls; s < bslots; s += NCLS) tot += bpartial[((size_t)ch * bslots + s) * REC + i];
-        B[cls][i] = tot;
+        if (rc == 1) {
+            for (int s = 0; s < slots; ++s) tot += partial[((size_t)ch * slots + s) * REC + off];      // slots in index order
+        } else {
+            for (int s = rc == 0 ? 0 : 1; s < rslots; s += 2) tot += rpartial[((size_t)ch * rslots + s) * REC + off];
+        }
+        S[pass][rc][cc][d] = tot;
     }
     __syncthreads();
     for (int e = tid; e < 162; e += blockDim.x) {
@@ -376,43 +262,41 @@ conv_corr9_assemble_kernel(const double *__restrict__ partial, int slots, const 
         double v = 0.0;
         if (s <= t) {
             const int ar = t / 3, ac = t % 3, dy = s / 3 - ar, dx = s % 3 - ac;
-            const int id = (which == 0 && !same ? 0 : ND) + (dy < 0 ? (dy + 2) * 5 + dx + 2 : 12 + dx);
+            const int id = dy < 0 ? (dy + 2) * 5 + dx + 2 : 12 + dx;
+            const int pass = (which == 0 && !same) ? 0 : 1;
             // tap row 0 never sits on the bottom image row, tap row 2 never on the top row; columns alike
-            const bool top = ar != 2, bot = ar != 0, lef = ac != 2, rig = ac != 0;
-            v = T[id];                       // interior pixels
-            if (top) v += B[0][id];
-            if (bot) v += B[1][id];
-            if (lef) v += B[2][id];
-            if (rig) v += B[3][id];
-            if (top && lef) v += B[4][id];
-            if (top && rig) v += B[5][id];
-            if (bot && lef) v += B[6][id];
-            if (bot && rig) v += B[7][id];
+            const int r_lo = ar == 2 ? 1 : 0, r_hi = ar == 0 ? 1 : 2, c_lo = ac == 2 ? 1 : 0, c_hi = ac == 0 ? 1 : 2;
+            for (int rc = r_lo; rc <= r_hi; ++rc)
+                for (int cc = c_lo; cc <= c_hi; ++cc) v += S[pass][rc][cc][id];
         }
         gram[(size_t)ch * 162 + e] = v;
     }
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------
-// Is the layer eligible, and with how many rows per band?
+// Is the layer eligible, and with how many rows per band?  (0: keep the patch form)
 int corr9_plan(int kh, int kw, int sh, int sw, int rh, int rw, int padding_same, int H, int W, int64_t C, int n_ch) {
     if (kh != 3 || kw != 3 || sh != 1 || sw != 1 || rh != 1 || rw != 1 || !padding_same) return 0;
-    if (H < 2 || W < 2) return 0;                                    // the nine pixel regions must be disjoint
-    if (n_ch < 8 || (int64_t)W * C >= ((int64_t)1 << 27)) return 0;  // few channels: lanes idle (lane = channel)
-    int best = 0, pad = 1 << 30;
-    const int cand[3] = {8, 7, 4};
+    if (H < 6 || W < corr9::WC) return 0;            // a TMA box (RB + 2 >= 6 rows x 5 columns) must fit in the image
+    if (C < 32 || C % 4 != 0 || n_ch < 8) return 0;  // box = 32 channels, 16-byte strides; few channels: lanes idle
+    // rows 1 .. H-2 in bands of RB rows: 13 RB DFMAs + ~4 (RB + 2) conversion slots per band and column
+    int best = 0;
+    long best_cost = 1L << 60;
+    const int cand[3] = {8, 6, 4};
     for (int i = 0; i < 3; ++i) {
-        const int p = (H + cand[i] - 1) / cand[i] * cand[i] - H;
-        if (p < pad) { pad = p; best = cand[i]; }
+        const int rb = cand[i];
+        if (rb + 2 > H) continue;
+        const long cost = (long)((H - 2 + rb - 1) / rb) * (13 * rb + 4 * (rb + 2));
+        if (cost < best_cost) { best_cost = cost; best = rb; }
     }
     return best;
 }
 
-// Slots (warps per channel group) that keep every SM busy for about `waves` rounds.
+// Slots (warps per channel group) that keep two CTAs of four warps resident on every SM.
 int corr9_pick_slots(gpfq_ctx *ctx, int n_ch, int64_t ntasks) {
     using namespace corr9;
     const int64_t groups = ceil_div64(n_ch, 32);
-    int64_t per = ceil_div64((int64_t)ctx->sm_count * 2 * WARPS, groups);  // two CTAs of 4 warps resident per SM (180-200 registers)
+    int64_t per = ceil_div64((int64_t)ctx->sm_count * 2 * WARPS, groups);
     per = std::min<int64_t>(per, std::max<int64_t>(1, ntasks));
     return (int)(ceil_div64(per, WARPS) * WARPS);
 }
@@ -432,10 +316,15 @@ static Corr9EncodeFn corr9_encode_fn() {
     return fn;
 }
 
-// (C, W, H, N) fp32 tensor map with a 32-channel x 5-column x `rows`-row box; false when the tensor cannot be mapped
+// Can the activation tensor be read through a tensor map at all (driver entry point, alignment)?
+int corr9_tensor_ok(const float *act, const float *actq) {
+    return corr9_encode_fn() != nullptr && ((uintptr_t)act & 15) == 0 && ((uintptr_t)actq & 15) == 0;
+}
+
+// (C, W, H, N) fp32 tensor map with a 32-channel x 5-column x `rows`-row box
 static bool corr9_make_map(CUtensorMap *map, const float *act, int64_t n_img_total, int H, int W, int64_t C, int rows) {
     Corr9EncodeFn enc = corr9_encode_fn();
-    if (!enc || C % 4 != 0 || C < 32 || ((uintptr_t)act & 15) != 0 || n_img_total < 1) return false;  // box = 32 channels
+    if (!enc) return false;
     const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img_total};
     const cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};  // bytes, dims 1..3
     const cuuint32_t box[4] = {32u, (cuuint32_t)corr9::WC, (cuuint32_t)rows, 1u};
@@ -446,65 +335,60 @@ static bool corr9_make_map(CUtensorMap *map, const float *act, int64_t n_img_tot
 }
 
 template <int RB>
-static cudaError_t launch_corr9(const float *actq, const float *actx, bool same, const Corr9Geom &gm, int64_t n_img_total,
-                                bool allow_tma, double *partial, int slot_stride, int slot0, cudaStream_t st) {
+static int launch_corr9(gpfq_ctx *ctx, const float *actq, const float *actx, bool same, const Corr9Geom &gm, int64_t C,
+                        int64_t n_img_total, double *partial, int slot_stride, int slot0) {
     using namespace corr9;
+    cudaStream_t st = ctx->stream;
     dim3 grid((unsigned)(gm.slots / WARPS), (unsigned)ceil_div64(gm.n_ch, 32));
     CUtensorMap mq_win, mq_ctr, mx_win;
-    bool tma = allow_tma && corr9_make_map(&mq_win, actq, n_img_total, gm.H, gm.W, gm.C, RB + 2);
-    if (tma && !same)
-        tma = corr9_make_map(&mq_ctr, actq, n_img_total, gm.H, gm.W, gm.C, RB) &&
-              corr9_make_map(&mx_win, actx, n_img_total, gm.H, gm.W, gm.C, RB + 2);
-    if (tma) {
-        cudaError_t e = cudaFuncSetAttribute(conv_corr9_tma_kernel<RB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)Ring<RB, false>::SMEM);
-        if (e != cudaSuccess) return e;
-        conv_corr9_tma_kernel<RB, false><<<grid, WARPS * 32, Ring<RB, false>::SMEM, st>>>(mq_win, mq_win, gm, partial, slot_stride, slot0);
-        if (!same) {
-            e = cudaFuncSetAttribute(conv_corr9_tma_kernel<RB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)Ring<RB, true>::SMEM);
-            if (e != cudaSuccess) return e;
-            conv_corr9_tma_kernel<RB, true><<<grid, WARPS * 32, Ring<RB, true>::SMEM, st>>>(mx_win, mq_ctr, gm, partial, slot_stride, slot0);
-        }
-        return cudaSuccess;
-    }
-    conv_corr9_kernel<RB, false><<<grid, WARPS * 32, 0, st>>>(actq, actq, gm, partial, slot_stride, slot0);
-    if (!same) conv_corr9_kernel<RB, true><<<grid, WARPS * 32, 0, st>>>(actq, actx, gm, partial, slot_stride, slot0);
-    return cudaSuccess;
-}
-
-// Correlation sums of channels [c_first, c_first + n_ch) over images [img0, img0 + n_img): fills main slots
-// [slot0, slot0 + slots) and border slots [bslot0, bslot0 + bslots) of every channel.
-int conv_corr9_stage(gpfq_ctx *ctx, const float *act, const float *actq, bool same, int64_t img0, int64_t n_img,
-                     int64_t n_img_total, int H, int Wd, int64_t C, int64_t c_first, int n_ch, int RB, double *partial,
-                     int slot_stride, int slot0, int slots, double *bpartial, int bslot_stride, int bslot0, int bslots) {
-    using namespace corr9;
-    if (slots % WARPS || bslots % NCLS || bslots % WARPS)
-        return gpfq_fail(ctx, GPFQ_ERR_ARG, "corr9: slot counts must be multiples of %d / %d", WARPS, NCLS);
-    Corr9Geom gm;
-    gm.H = H; gm.W = Wd; gm.C = C; gm.c_first = c_first; gm.n_ch = n_ch; gm.img0 = img0; gm.n_img = n_img;
-    gm.slots = slots;
-    // `act` / `actq` point at image 0 of a tensor of n_img_total images; the tensor maps cover all of it
-    const bool allow_tma = ctx->corr_variant != 1 && n_img_total < ((int64_t)1 << 31);
-    switch (RB) {
-        case 8: CUDA_TRY(ctx, launch_corr9<8>(actq, act, same, gm, n_img_total, allow_tma, partial, slot_stride, slot0, ctx->stream)); break;
-        case 7: CUDA_TRY(ctx, launch_corr9<7>(actq, act, same, gm, n_img_total, allow_tma, partial, slot_stride, slot0, ctx->stream)); break;
-        case 4: CUDA_TRY(ctx, launch_corr9<4>(actq, act, same, gm, n_img_total, allow_tma, partial, slot_stride, slot0, ctx->stream)); break;
-        default: return gpfq_fail(ctx, GPFQ_ERR_ARG, "corr9: no kernel for %d rows per band", RB);
-    }
+    bool ok = corr9_make_map(&mq_win, actq, n_img_total, gm.H, gm.W, C, RB + 2);
+    if (ok && !same)
+        ok = corr9_make_map(&mq_ctr, actq, n_img_total, gm.H, gm.W, C, RB) &&
+             corr9_make_map(&mx_win, actx, n_img_total, gm.H, gm.W, C, RB + 2);
+    if (!ok) return gpfq_fail(ctx, GPFQ_ERR_CUDA, "cuTensorMapEncodeTiled failed for the (%lld, %d, %d, %lld) activations",
+                              (long long)n_img_total, gm.H, gm.W, (long long)C);
+    CUDA_TRY(ctx, cudaFuncSetAttribute(conv_corr9_tma_kernel<RB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)Ring<RB, false>::SMEM));
+    conv_corr9_tma_kernel<RB, false><<<grid, WARPS * 32, Ring<RB, false>::SMEM, st>>>(mq_win, mq_win, gm, partial, slot_stride, slot0);
     KERNEL_CHECK(ctx);
-    if (!same) ctx->launches++;
-    gm.slots = bslots;
-    dim3 bgrid((unsigned)(bslots / WARPS), (unsigned)ceil_div64(n_ch, 32));
-    if (same) conv_corr9_border_kernel<true><<<bgrid, WARPS * 32, 0, ctx->stream>>>(actq, actq, gm, bpartial, bslot_stride, bslot0);
-    else conv_corr9_border_kernel<false><<<bgrid, WARPS * 32, 0, ctx->stream>>>(actq, act, gm, bpartial, bslot_stride, bslot0);
-    KERNEL_CHECK(ctx);
+    if (!same) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(conv_corr9_tma_kernel<RB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)Ring<RB, true>::SMEM));
+        conv_corr9_tma_kernel<RB, true><<<grid, WARPS * 32, Ring<RB, true>::SMEM, st>>>(mx_win, mq_ctr, gm, partial, slot_stride, slot0);
+        KERNEL_CHECK(ctx);
+    }
     return GPFQ_OK;
 }
 
-int conv_corr9_assemble_stage(gpfq_ctx *ctx, const double *partial, int slots, const double *bpartial, int bslots,
+// Correlation sums of channels [c_first, c_first + n_ch) over images [img0, img0 + n_img) of a tensor of n_img_total
+// images: fills slots [slot0, slot0 + slots) of `partial` (rows 1 .. H-2) and [rslot0, rslot0 + rslots) of `rpartial`
+// (top / bottom row) of every channel.  Both record arrays must be zeroed by the caller.
+int conv_corr9_stage(gpfq_ctx *ctx, const float *act, const float *actq, bool same, int64_t img0, int64_t n_img,
+                     int64_t n_img_total, int H, int Wd, int64_t C, int64_t c_first, int n_ch, int RB, double *partial,
+                     int slot_stride, int slot0, int slots, double *rpartial, int rslot_stride, int rslot0, int rslots) {
+    using namespace corr9;
+    if (slots % WARPS || rslots % WARPS || rslots < 2)
+        return gpfq_fail(ctx, GPFQ_ERR_ARG, "corr9: slot counts must be multiples of %d", WARPS);
+    if (n_img_total >= ((int64_t)1 << 31)) return gpfq_fail(ctx, GPFQ_ERR_ARG, "corr9: too many images");
+    Corr9Geom gm;
+    gm.H = H; gm.W = Wd; gm.c_first = c_first; gm.n_ch = n_ch; gm.img0 = img0; gm.n_img = n_img;
+    if (H > 2) {
+        gm.slots = slots; gm.y_first = 1; gm.y_last = H - 2; gm.two_rows = 0;
+        switch (RB) {
+            case 8: GPFQ_TRY(launch_corr9<8>(ctx, actq, act, same, gm, C, n_img_total, partial, slot_stride, slot0)); break;
+            case 6: GPFQ_TRY(launch_corr9<6>(ctx, actq, act, same, gm, C, n_img_total, partial, slot_stride, slot0)); break;
+            case 4: GPFQ_TRY(launch_corr9<4>(ctx, actq, act, same, gm, C, n_img_total, partial, slot_stride, slot0)); break;
+            default: return gpfq_fail(ctx, GPFQ_ERR_ARG, "corr9: no kernel for %d rows per band", RB);
+        }
+    }
+    gm.slots = rslots; gm.y_first = 0; gm.y_last = H - 1; gm.two_rows = 1;
+    GPFQ_TRY(launch_corr9<1>(ctx, actq, act, same, gm, C, n_img_total, rpartial, rslot_stride, rslot0));
+    return GPFQ_OK;
+}
+
+int conv_corr9_assemble_stage(gpfq_ctx *ctx, const double *partial, int slots, const double *rpartial, int rslots,
                               bool same, int n_ch, double *gram) {
-    conv_corr9_assemble_kernel<<<(unsigned)n_ch, 96, 0, ctx->stream>>>(partial, slots, bpartial, bslots, same ? 1 : 0, gram);
+    conv_corr9_assemble_kernel<<<(unsigned)n_ch, 96, 0, ctx->stream>>>(partial, slots, rpartial, rslots, same ? 1 : 0, gram);
     KERNEL_CHECK(ctx);
     return GPFQ_OK;
 }

@@ -393,9 +393,9 @@ def test_conv_nhwc_fused_matches_patch_path(n_img, H, Wd, C, F, pad):
     assert np.array_equal(outs["tma"], outs["ldg"]) and np.array_equal(outs["tma_same"], outs["ldg_same"])
 
 
-@pytest.mark.parametrize("n_img,H,Wd,C,F", [(3, 1, 1, 8, 2), (2, 1, 9, 9, 2), (2, 6, 1, 16, 2), (5, 2, 2, 33, 3), (4, 7, 7, 40, 2),
-                                            (3, 14, 14, 64, 4), (2, 28, 28, 96, 2), (2, 16, 16, 32, 3), (1, 45, 37, 8, 2),
-                                            (70, 8, 8, 35, 2), (2, 3, 5, 12, 2)])
+@pytest.mark.parametrize("n_img,H,Wd,C,F", [(2, 1, 9, 9, 2), (5, 2, 2, 33, 3), (4, 7, 7, 40, 2), (3, 14, 14, 64, 4),
+                                            (2, 28, 28, 96, 2), (2, 16, 16, 32, 3), (1, 45, 37, 36, 2), (70, 8, 8, 44, 2),
+                                            (3, 6, 5, 32, 2), (2, 9, 23, 72, 2), (5, 10, 6, 40, 3), (2, 5, 12, 32, 2)])
 def test_conv_corr9_matches_patch_form(engine, n_img, H, Wd, C, F):
     """Correlation form of the 3x3 / stride 1 / SAME Grams (conv_corr.cu: 13 displacement sums + border inclusion-exclusion)
     against the oracle and against the patch-form kernel (shared-memory planes): degenerate images (1 x 1, one row, one
@@ -412,16 +412,10 @@ def test_conv_corr9_matches_patch_form(engine, n_img, H, Wd, C, F):
     patches = lambda ch: (O.channel_patches(act, ch, (3, 3), (1, 1), "SAME"), O.channel_patches(actq, ch, (3, 3), (1, 1), "SAME"))
     Qref = c_oracle.quantize_conv_layer(W, patches, A)
     Q = engine.conv_layer_nhwc(act, actq, W, A)
-    corr = H >= 2 and Wd >= 2                               # one-row / one-column images keep the patch form
+    corr = H >= 6 and Wd >= 5 and C >= 32 and C % 4 == 0    # what a TMA box of the (N, H, W, C) tensor can serve
     assert (engine.last_stats["gram_kernel"] == 4) == corr  # the correlation form really ran
     assert O.agreement(Q, Qref) >= AGREE
     Qs = engine.conv_layer_nhwc(actq, None, W, A)
-    engine.set_option("corr_loads", 1)                      # direct LDG loads instead of TMA boxes: same sums, same order
-    try:
-        assert np.array_equal(engine.conv_layer_nhwc(act, actq, W, A), Q)
-        assert np.array_equal(engine.conv_layer_nhwc(actq, None, W, A), Qs)
-    finally:
-        engine.set_option("corr_loads", 0)
     dev = engine.conv_layer_nhwc(torch.from_numpy(act).cuda(), torch.from_numpy(actq).cuda(), torch.from_numpy(W).cuda(), A)
     assert np.array_equal(dev.cpu().numpy(), Q)
     if C >= 10:
@@ -455,7 +449,7 @@ def test_conv_corr9_host_image_chunks(engine):
     VGG-like plane size: correlation form == patch form == device-pointer call."""
     import torch
     rng = np.random.default_rng(5)
-    n_img, H, Wd, C, F = 44, 224, 224, 16, 2
+    n_img, H, Wd, C, F = 22, 224, 224, 32, 2
     act = np.maximum(rng.standard_normal((n_img, H, Wd, C), dtype=np.float32), 0)
     actq = np.maximum(act + 0.05 * rng.standard_normal(act.shape, dtype=np.float32), 0)
     W = (rng.uniform(-1, 1, (3, 3, C, F)) * 0.3).astype(np.float32)
