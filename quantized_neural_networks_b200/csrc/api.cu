@@ -28,7 +28,7 @@ int im2col_stage(gpfq_ctx *, const float *, int64_t, int, int, int64_t, int64_t,
 int msq_stage(gpfq_ctx *, const void *, int, int64_t, const double *, int, int, double *);
 int nhwc9_plan(int, int, int, int, int, int, int, int, int *, int *);
 int corr9_plan(int, int, int, int, int, int, int, int, int, int64_t, int);
-int corr9_pick_slots(gpfq_ctx *, int, int64_t);
+int corr9_pick_slots(gpfq_ctx *, int, bool, int, int64_t);
 int corr9_tensor_ok(const float *, const float *);
 int conv_corr9_stage(gpfq_ctx *, const float *, const float *, bool, int64_t, int64_t, int64_t, int, int, int64_t, int64_t, int,
                      int, double *, int, int, int, double *, int, int, int);
@@ -778,8 +778,8 @@ extern "C" int gpfq_conv_layer_nhwc(gpfq_ctx *ctx, const float *act, const float
     if (corr_rb && corr9_tensor_ok(dA, dAq)) {
         // ---- correlation form: 13 displacement sums per Gram straight from the activations (conv_corr.cu)
         const int nbands = (int)ceil_div64(H - 2, corr_rb);                        // rows 1 .. H-2 in bands
-        const int per_ic = corr9_pick_slots(ctx, (int)n_ch, ipc * nbands);
-        const int bper_ic = corr9_pick_slots(ctx, (int)n_ch, 2 * ipc);             // top and bottom row of every image
+        const int per_ic = corr9_pick_slots(ctx, corr_rb, same, (int)n_ch, ipc * nbands);
+        const int bper_ic = corr9_pick_slots(ctx, 1, same, (int)n_ch, 2 * ipc);             // top and bottom row of every image
         const int slots = n_ic * per_ic, bslots = n_ic * bper_ic;
         double *partial = nullptr, *bpartial = nullptr, *gram = nullptr;
         const size_t part_bytes = (size_t)n_ch * slots * 78 * sizeof(double);      // 2 passes x 3 column classes x 13 sums

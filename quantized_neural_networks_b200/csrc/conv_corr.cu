@@ -89,7 +89,7 @@ struct Ring {
 }  // namespace corr9
 
 template <int RB, bool CROSS>
-__global__ void __launch_bounds__(corr9::WARPS * 32)
+__global__ void __launch_bounds__(corr9::WARPS * 32, RB <= 6 ? 3 : 2)
 conv_corr9_tma_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapA, Corr9Geom gm,
                       double *__restrict__ partial, int slot_stride, int slot0) {
     using namespace corr9;
@@ -98,8 +98,10 @@ conv_corr9_tma_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_con
     extern __shared__ __align__(128) unsigned char corr9_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot = blockIdx.x * WARPS + warp;
-    const int chl = blockIdx.y * 32 + lane;
-    const bool chok = chl < gm.n_ch;
+    // a box must start on a 16-byte boundary: channel groups start at c_first rounded down to a multiple of four
+    const int c0 = (int)(gm.c_first & ~(int64_t)3) + (int)blockIdx.y * 32;
+    const int chl = c0 + lane - (int)gm.c_first;  // channel index inside this launch's range
+    const bool chok = chl >= 0 && chl < gm.n_ch;
     float *ring = reinterpret_cast<float *>(corr9_smem + warp * R::WARP_BYTES);
     uint64_t *bars = reinterpret_cast<uint64_t *>(corr9_smem + WARPS * R::WARP_BYTES) + warp * NS;
     if (lane == 0) {
@@ -109,7 +111,6 @@ conv_corr9_tma_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_con
     }
     __syncwarp();
     const int W = gm.W;
-    const int c0 = (int)(gm.c_first + (int64_t)blockIdx.y * 32);
     const int nrows = gm.y_last - gm.y_first + 1;
     const int nbands = gm.two_rows ? 1 : (nrows + RB - 1) / RB;
     // two_rows: this warp's images are slot / 2, slot / 2 + slots / 2, ...; its row is fixed by the slot's parity
@@ -124,9 +125,34 @@ conv_corr9_tma_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_con
 #pragma unroll
     for (int d = 0; d < ND; ++d) acc[d] = 0.0;
 
+    // The boxes of this warp's tasks form one stream (task after task, columns left to right); the producer cursor runs
+    // NS - 1 boxes ahead of the consumer, across task boundaries, so a new band never starts with an empty ring.
+    int64_t ptask = t_first;
+    int pk = 0;
+    uint32_t ppos = 0;
+    auto row_of = [&](int64_t task) {
+        return gm.two_rows ? ((slot & 1) ? gm.y_last : gm.y_first) : gm.y_first + (int)(task % nbands) * RB;
+    };
+    auto produce = [&]() {
+        if (ptask < ntasks) {
+            if (lane == 0) {
+                const int pimg = (int)(gm.img0 + (gm.two_rows ? ptask : ptask / nbands));
+                const int py0 = row_of(ptask);
+                const int s = (int)(ppos % NS);
+                float *dst = ring + s * R::STAGE_FLOATS;
+                mbar_expect_tx(&bars[s], (uint32_t)(R::STAGE_FLOATS * sizeof(float)));
+                tma_load_4d(dst, &mapB, &bars[s], c0, pk * WC, py0 - 2, pimg);
+                if (CROSS) tma_load_4d(dst + R::B_FLOATS, &mapA, &bars[s], c0, pk * WC - 2, py0, pimg);
+            }
+            ++ppos;
+            if (++pk == nstages) { pk = 0; ptask += t_step; }
+        }
+    };
+#pragma unroll
+    for (int p = 0; p < NS - 1; ++p) produce();
+
     for (int64_t task = t_first; task < ntasks; task += t_step) {
-        const int img = (int)(gm.img0 + (gm.two_rows ? task : task / nbands));
-        const int y0 = gm.two_rows ? ((slot & 1) ? gm.y_last : gm.y_first) : gm.y_first + (int)(task % nbands) * RB;
+        const int y0 = row_of(task);
         unsigned rowmask = 0;  // bit i: pixel row y0 + i belongs to this launch
 #pragma unroll
         for (int i = 0; i < RB; ++i) rowmask |= (y0 + i <= gm.y_last) ? (1u << i) : 0u;
@@ -138,22 +164,9 @@ conv_corr9_tma_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_con
         for (int r = 0; r < RB + 2; ++r)
 #pragma unroll
             for (int c = 0; c < 5; ++c) win[r][c] = 0.0;
-        auto issue = [&](int k, uint32_t pos) {
-            if (lane == 0) {
-                const int s = (int)(pos % NS);
-                float *dst = ring + s * R::STAGE_FLOATS;
-                mbar_expect_tx(&bars[s], (uint32_t)(R::STAGE_FLOATS * sizeof(float)));
-                tma_load_4d(dst, &mapB, &bars[s], c0, k * WC, y0 - 2, img);
-                if (CROSS) tma_load_4d(dst + R::B_FLOATS, &mapA, &bars[s], c0, k * WC - 2, y0, img);
-            }
-        };
-        __syncwarp();  // every lane has finished reading the previous task's boxes
-#pragma unroll
-        for (int p = 0; p < NS - 1; ++p)
-            if (p < nstages) issue(p, it + p);
         for (int k = 0; k < nstages; ++k) {
-            __syncwarp();  // the box consumed in iteration k - 1 is free again
-            if (k + NS - 1 < nstages) issue(k + NS - 1, it + k + NS - 1);
+            __syncwarp();  // the box consumed in the previous iteration is free again
+            produce();
             const uint32_t pos = it + k;
             const int s = (int)(pos % NS);
             mbar_wait(&bars[s], (pos / NS) & 1u);
@@ -196,31 +209,33 @@ conv_corr9_tma_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_con
                         }
                         if (cx >= 2) {
                             // pixel column cx - 2 = logical window column 2 = physical slot (ph + 3) % 5
-                            double e[ND];
+                            auto mac = [&](double (&dst)[ND]) {
 #pragma unroll
-                            for (int d = 0; d < ND; ++d) e[d] = 0.0;
+                                for (int i = 0; i < RB; ++i) {
+                                    double a = CROSS ? ac[i] : win[i + 2][(ph + 3) % 5];
+                                    a = (rowmask >> i) & 1u ? a : 0.0;
 #pragma unroll
-                            for (int i = 0; i < RB; ++i) {
-                                double a = CROSS ? ac[i] : win[i + 2][(ph + 3) % 5];
-                                a = (rowmask >> i) & 1u ? a : 0.0;
+                                    for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
-                                for (int dy = 0; dy < 2; ++dy)
+                                        for (int dx = 0; dx < 5; ++dx)
+                                            dst[dy * 5 + dx] = fma(a, win[i + dy][(ph + 1 + dx) % 5], dst[dy * 5 + dx]);
 #pragma unroll
-                                    for (int dx = 0; dx < 5; ++dx)
-                                        e[dy * 5 + dx] = fma(a, win[i + dy][(ph + 1 + dx) % 5], e[dy * 5 + dx]);
+                                    for (int dx = 0; dx < 3; ++dx)
+                                        dst[10 + dx] = fma(a, win[i + 2][(ph + 1 + dx) % 5], dst[10 + dx]);
+                                }
+                            };
+                            if (cx == 2 || cx == W + 1) {   // first / last pixel column: their own records
+                                double e[ND];
 #pragma unroll
-                                for (int dx = 0; dx < 3; ++dx)
-                                    e[10 + dx] = fma(a, win[i + 2][(ph + 1 + dx) % 5], e[10 + dx]);
-                            }
-                            if (cx == 2 || cx == W + 1) {
+                                for (int d = 0; d < ND; ++d) e[d] = 0.0;
+                                mac(e);
                                 if (chok) {
                                     double *o = rec + (cx == 2 ? 0 : 2 * ND);
 #pragma unroll
                                     for (int d = 0; d < ND; ++d) o[d] += e[d];
                                 }
                             } else {
-#pragma unroll
-                                for (int d = 0; d < ND; ++d) acc[d] += e[d];
+                                mac(acc);
                             }
                         }
                     }
@@ -292,11 +307,30 @@ int corr9_plan(int kh, int kw, int sh, int sw, int rh, int rw, int padding_same,
     return best;
 }
 
-// Slots (warps per channel group) that keep two CTAs of four warps resident on every SM.
-int corr9_pick_slots(gpfq_ctx *ctx, int n_ch, int64_t ntasks) {
+template <int RB>
+static int corr9_resident_ctas(bool same) {
     using namespace corr9;
-    const int64_t groups = ceil_div64(n_ch, 32);
-    int64_t per = ceil_div64((int64_t)ctx->sm_count * 2 * WARPS, groups);
+    int a = 0, b = 0;
+    cudaFuncSetAttribute(conv_corr9_tma_kernel<RB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Ring<RB, false>::SMEM);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, conv_corr9_tma_kernel<RB, false>, WARPS * 32, Ring<RB, false>::SMEM);
+    if (same) return a > 0 ? a : 1;
+    cudaFuncSetAttribute(conv_corr9_tma_kernel<RB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Ring<RB, true>::SMEM);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, conv_corr9_tma_kernel<RB, true>, WARPS * 32, Ring<RB, true>::SMEM);
+    a = a < b ? a : b;
+    return a > 0 ? a : 1;
+}
+
+// Slots (warps per channel group) that fill every SM with as many CTAs of four warps as stay resident.
+int corr9_pick_slots(gpfq_ctx *ctx, int RB, bool same, int n_ch, int64_t ntasks) {
+    using namespace corr9;
+    static int occ[2][9] = {};
+    if (RB < 1 || RB > 8) return WARPS;
+    if (!occ[same][RB])
+        occ[same][RB] = RB == 8 ? corr9_resident_ctas<8>(same) : RB == 6 ? corr9_resident_ctas<6>(same)
+                       : RB == 4 ? corr9_resident_ctas<4>(same) : corr9_resident_ctas<1>(same);
+    cudaGetLastError();
+    const int64_t groups = ceil_div64(n_ch + 3, 32);
+    int64_t per = ceil_div64((int64_t)ctx->sm_count * occ[same][RB] * WARPS, groups);
     per = std::min<int64_t>(per, std::max<int64_t>(1, ntasks));
     return (int)(ceil_div64(per, WARPS) * WARPS);
 }
@@ -339,7 +373,7 @@ static int launch_corr9(gpfq_ctx *ctx, const float *actq, const float *actx, boo
                         int64_t n_img_total, double *partial, int slot_stride, int slot0) {
     using namespace corr9;
     cudaStream_t st = ctx->stream;
-    dim3 grid((unsigned)(gm.slots / WARPS), (unsigned)ceil_div64(gm.n_ch, 32));
+    dim3 grid((unsigned)(gm.slots / WARPS), (unsigned)ceil_div64(gm.n_ch + (gm.c_first & 3), 32));
     CUtensorMap mq_win, mq_ctr, mx_win;
     bool ok = corr9_make_map(&mq_win, actq, n_img_total, gm.H, gm.W, C, RB + 2);
     if (ok && !same)
