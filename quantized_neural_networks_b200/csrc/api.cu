@@ -27,8 +27,8 @@ int im2col_stage(gpfq_ctx *, const float *, int64_t, int, int, int64_t, int64_t,
                  int, int, int, int, float *, int64_t);
 int msq_stage(gpfq_ctx *, const void *, int, int64_t, const double *, int, int, double *);
 int nhwc9_plan(int, int, int, int, int, int, int, int, int *, int *);
-int corr9_plan(int, int, int, int, int, int, int, int, int, int64_t, int);
-int corr9_pick_slots(gpfq_ctx *, int, bool, int, int64_t);
+int corr9_plan(int, int, int, int, int, int, int, int, int, int64_t, int, int);
+int corr9_pick_slots(gpfq_ctx *, int, bool, int64_t, int, int64_t);
 int corr9_tensor_ok(const float *, const float *);
 int conv_corr9_stage(gpfq_ctx *, const float *, const float *, bool, int64_t, int64_t, int64_t, int, int, int64_t, int64_t, int,
                      int, double *, int, int, int, double *, int, int, int);
@@ -178,6 +178,9 @@ extern "C" int gpfq_set_option(gpfq_ctx *ctx, const char *key, int64_t value) {
     } else if (!strcmp(key, "i8_pairs_d")) {    // 0 default; else keep slice pairs with k + l <= value
         if (value != 0 && (value < 2 || value > 10)) return gpfq_fail(ctx, GPFQ_ERR_ARG, "i8_pairs_d must be 0 or 2..10");
         ctx->i8_pairs_d = (int)value;
+    } else if (!strcmp(key, "corr_rows")) {   // correlation form: rows per band (0 auto, 4, 6 or 8)
+        if (value != 0 && value != 4 && value != 6 && value != 8) return gpfq_fail(ctx, GPFQ_ERR_ARG, "corr_rows must be 0, 4, 6 or 8");
+        ctx->corr_rb = (int)value;
     } else if (!strcmp(key, "conv_kernel")) {   // 0 TMA-staged / correlation form, 1 direct LDG, 2 generic, 3 NHWC planes kernel
         if (value < 0 || value > 3) return gpfq_fail(ctx, GPFQ_ERR_ARG, "conv_kernel must be 0, 1, 2 or 3");
         ctx->conv_variant = (int)value;
@@ -774,12 +777,12 @@ extern "C" int gpfq_conv_layer_nhwc(gpfq_ctx *ctx, const float *act, const float
         }
     }
     CUDA_TRY(ctx, gpfq_record(ctx, 5, s));
-    const int corr_rb = ctx->conv_variant == 0 ? corr9_plan(kh, kw, sh, sw, rh, rw, padding_same, (int)H, (int)Wd, C, (int)n_ch) : 0;
+    const int corr_rb = ctx->conv_variant == 0 ? corr9_plan(kh, kw, sh, sw, rh, rw, padding_same, (int)H, (int)Wd, C, (int)n_ch, ctx->corr_rb) : 0;
     if (corr_rb && corr9_tensor_ok(dA, dAq)) {
         // ---- correlation form: 13 displacement sums per Gram straight from the activations (conv_corr.cu)
         const int nbands = (int)ceil_div64(H - 2, corr_rb);                        // rows 1 .. H-2 in bands
-        const int per_ic = corr9_pick_slots(ctx, corr_rb, same, (int)n_ch, ipc * nbands);
-        const int bper_ic = corr9_pick_slots(ctx, 1, same, (int)n_ch, 2 * ipc);             // top and bottom row of every image
+        const int per_ic = corr9_pick_slots(ctx, corr_rb, same, c0, (int)n_ch, ipc * nbands);
+        const int bper_ic = corr9_pick_slots(ctx, 1, same, c0, (int)n_ch, 2 * ipc);             // top and bottom row of every image
         const int slots = n_ic * per_ic, bslots = n_ic * bper_ic;
         double *partial = nullptr, *bpartial = nullptr, *gram = nullptr;
         const size_t part_bytes = (size_t)n_ch * slots * 78 * sizeof(double);      // 2 passes x 3 column classes x 13 sums

@@ -127,17 +127,18 @@ conv_corr9_tma_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_con
 
     // The boxes of this warp's tasks form one stream (task after task, columns left to right); the producer cursor runs
     // NS - 1 boxes ahead of the consumer, across task boundaries, so a new band never starts with an empty ring.
+    // (image, band) of a task advance by a fixed step from one task of this warp to its next: no division in the loops
+    const int step_img = (int)(gm.two_rows ? t_step : t_step / nbands), step_band = gm.two_rows ? 0 : (int)(t_step % nbands);
+    const int img_first = (int)(gm.img0 + (gm.two_rows ? t_first : t_first / nbands));
+    const int band_first = gm.two_rows ? 0 : (int)(t_first % nbands);
+    const int row_fixed = (slot & 1) ? gm.y_last : gm.y_first;   // two_rows: this warp's row
     int64_t ptask = t_first;
-    int pk = 0;
+    int pk = 0, pimg = img_first, pband = band_first;
     uint32_t ppos = 0;
-    auto row_of = [&](int64_t task) {
-        return gm.two_rows ? ((slot & 1) ? gm.y_last : gm.y_first) : gm.y_first + (int)(task % nbands) * RB;
-    };
     auto produce = [&]() {
         if (ptask < ntasks) {
             if (lane == 0) {
-                const int pimg = (int)(gm.img0 + (gm.two_rows ? ptask : ptask / nbands));
-                const int py0 = row_of(ptask);
+                const int py0 = gm.two_rows ? row_fixed : gm.y_first + pband * RB;
                 const int s = (int)(ppos % NS);
                 float *dst = ring + s * R::STAGE_FLOATS;
                 mbar_expect_tx(&bars[s], (uint32_t)(R::STAGE_FLOATS * sizeof(float)));
@@ -145,14 +146,23 @@ conv_corr9_tma_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_con
                 if (CROSS) tma_load_4d(dst + R::B_FLOATS, &mapA, &bars[s], c0, pk * WC - 2, py0, pimg);
             }
             ++ppos;
-            if (++pk == nstages) { pk = 0; ptask += t_step; }
+            if (++pk == nstages) {
+                pk = 0;
+                ptask += t_step;
+                pimg += step_img;
+                pband += step_band;
+                if (pband >= nbands) { pband -= nbands; ++pimg; }
+            }
         }
     };
 #pragma unroll
     for (int p = 0; p < NS - 1; ++p) produce();
 
+    int cband = band_first;
     for (int64_t task = t_first; task < ntasks; task += t_step) {
-        const int y0 = row_of(task);
+        const int y0 = gm.two_rows ? row_fixed : gm.y_first + cband * RB;
+        cband += step_band;
+        if (cband >= nbands) cband -= nbands;
         unsigned rowmask = 0;  // bit i: pixel row y0 + i belongs to this launch
 #pragma unroll
         for (int i = 0; i < RB; ++i) rowmask |= (y0 + i <= gm.y_last) ? (1u << i) : 0u;
@@ -209,33 +219,33 @@ conv_corr9_tma_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_con
                         }
                         if (cx >= 2) {
                             // pixel column cx - 2 = logical window column 2 = physical slot (ph + 3) % 5
-                            auto mac = [&](double (&dst)[ND]) {
+                            double e[ND];
 #pragma unroll
-                                for (int i = 0; i < RB; ++i) {
-                                    double a = CROSS ? ac[i] : win[i + 2][(ph + 3) % 5];
-                                    a = (rowmask >> i) & 1u ? a : 0.0;
+                            for (int d = 0; d < ND; ++d) e[d] = 0.0;
 #pragma unroll
-                                    for (int dy = 0; dy < 2; ++dy)
+                            for (int i = 0; i < RB; ++i) {
+                                double a = CROSS ? ac[i] : win[i + 2][(ph + 3) % 5];
+                                a = (rowmask >> i) & 1u ? a : 0.0;
 #pragma unroll
-                                        for (int dx = 0; dx < 5; ++dx)
-                                            dst[dy * 5 + dx] = fma(a, win[i + dy][(ph + 1 + dx) % 5], dst[dy * 5 + dx]);
+                                for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
-                                    for (int dx = 0; dx < 3; ++dx)
-                                        dst[10 + dx] = fma(a, win[i + 2][(ph + 1 + dx) % 5], dst[10 + dx]);
-                                }
-                            };
+                                    for (int dx = 0; dx < 5; ++dx)
+                                        e[dy * 5 + dx] = fma(a, win[i + dy][(ph + 1 + dx) % 5], e[dy * 5 + dx]);
+#pragma unroll
+                                for (int dx = 0; dx < 3; ++dx)
+                                    e[10 + dx] = fma(a, win[i + 2][(ph + 1 + dx) % 5], e[10 + dx]);
+                            }
                             if (cx == 2 || cx == W + 1) {   // first / last pixel column: their own records
-                                double e[ND];
-#pragma unroll
-                                for (int d = 0; d < ND; ++d) e[d] = 0.0;
-                                mac(e);
                                 if (chok) {
+                                    // fire-and-forget reductions (RED.ADD.F64): nothing waits for the round trip to L2;
+                                    // only this lane ever touches the record, and its updates apply in program order
                                     double *o = rec + (cx == 2 ? 0 : 2 * ND);
 #pragma unroll
-                                    for (int d = 0; d < ND; ++d) o[d] += e[d];
+                                    for (int d = 0; d < ND; ++d) atomicAdd(o + d, e[d]);
                                 }
                             } else {
-                                mac(acc);
+#pragma unroll
+                                for (int d = 0; d < ND; ++d) acc[d] += e[d];
                             }
                         }
                     }
@@ -253,7 +263,7 @@ conv_corr9_tma_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_con
 // gram: (n_channels, 2 * 81): [G1 | G2], lower triangle + diagonal valid, zeros above (conv_finalize_kernel's layout).
 // partial: records of the launch over rows 1 .. H-2 (left column, interior, right column); rpartial: records of the
 // top / bottom row launch (even slots: top-left corner, top row, top-right corner; odd slots: the bottom ones).
-__global__ void __launch_bounds__(96)
+__global__ void __launch_bounds__(256)
 conv_corr9_assemble_kernel(const double *__restrict__ partial, int slots, const double *__restrict__ rpartial, int rslots,
                            int same, double *__restrict__ gram) {
     using namespace corr9;
@@ -263,13 +273,22 @@ conv_corr9_assemble_kernel(const double *__restrict__ partial, int slots, const 
     for (int e = tid; e < 2 * 9 * ND; e += blockDim.x) {
         const int d = e % ND, cc = (e / ND) % 3, rc = (e / (3 * ND)) % 3, pass = e / (9 * ND);
         const int off = (pass * 3 + cc) * ND + d;
-        double tot = 0.0;
-        if (rc == 1) {
-            for (int s = 0; s < slots; ++s) tot += partial[((size_t)ch * slots + s) * REC + off];      // slots in index order
-        } else {
-            for (int s = rc == 0 ? 0 : 1; s < rslots; s += 2) tot += rpartial[((size_t)ch * rslots + s) * REC + off];
+        // slots in index order, dealt round-robin to four partial sums (independent loads in flight), combined in order
+        const double *src = rc == 1 ? partial + (size_t)ch * slots * REC + off
+                                    : rpartial + ((size_t)ch * rslots + (rc == 0 ? 0 : 1)) * REC + off;
+        const int n = rc == 1 ? slots : (rslots - (rc == 0 ? 0 : 1) + 1) / 2;
+        const size_t stride = rc == 1 ? REC : 2 * REC;
+        double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+        int s = 0;
+#pragma unroll 2
+        for (; s + 4 <= n; s += 4) {
+            t0 += src[(size_t)s * stride];
+            t1 += src[(size_t)(s + 1) * stride];
+            t2 += src[(size_t)(s + 2) * stride];
+            t3 += src[(size_t)(s + 3) * stride];
         }
-        S[pass][rc][cc][d] = tot;
+        for (; s < n; ++s) t0 += src[(size_t)s * stride];
+        S[pass][rc][cc][d] = (t0 + t1) + (t2 + t3);
     }
     __syncthreads();
     for (int e = tid; e < 162; e += blockDim.x) {
@@ -290,18 +309,20 @@ conv_corr9_assemble_kernel(const double *__restrict__ partial, int slots, const 
 
 // ---- host side ---------------------------------------------------------------------------------------------------
 // Is the layer eligible, and with how many rows per band?  (0: keep the patch form)
-int corr9_plan(int kh, int kw, int sh, int sw, int rh, int rw, int padding_same, int H, int W, int64_t C, int n_ch) {
+int corr9_plan(int kh, int kw, int sh, int sw, int rh, int rw, int padding_same, int H, int W, int64_t C, int n_ch, int force_rb) {
     if (kh != 3 || kw != 3 || sh != 1 || sw != 1 || rh != 1 || rw != 1 || !padding_same) return 0;
     if (H < 6 || W < corr9::WC) return 0;            // a TMA box (RB + 2 >= 6 rows x 5 columns) must fit in the image
     if (C < 32 || C % 4 != 0 || n_ch < 8) return 0;  // box = 32 channels, 16-byte strides; few channels: lanes idle
-    // rows 1 .. H-2 in bands of RB rows: 13 RB DFMAs + ~4 (RB + 2) conversion slots per band and column
+    if ((force_rb == 8 || force_rb == 6 || force_rb == 4) && force_rb + 2 <= H) return force_rb;
+    // rows 1 .. H-2 in bands of RB rows: 13 RB DFMAs + ~4 (RB + 2) conversion slots per band and column, plus a constant
+    // per band (window reset, first / last column stages); calibrated with tools/vgg_bench.py --corr-rows
     int best = 0;
     long best_cost = 1L << 60;
     const int cand[3] = {8, 6, 4};
     for (int i = 0; i < 3; ++i) {
         const int rb = cand[i];
         if (rb + 2 > H) continue;
-        const long cost = (long)((H - 2 + rb - 1) / rb) * (13 * rb + 4 * (rb + 2));
+        const long cost = (long)((H - 2 + rb - 1) / rb) * (13 * rb + 4 * (rb + 2) + 40);  // + per-band start-up (measured)
         if (cost < best_cost) { best_cost = cost; best = rb; }
     }
     return best;
@@ -321,7 +342,7 @@ static int corr9_resident_ctas(bool same) {
 }
 
 // Slots (warps per channel group) that fill every SM with as many CTAs of four warps as stay resident.
-int corr9_pick_slots(gpfq_ctx *ctx, int RB, bool same, int n_ch, int64_t ntasks) {
+int corr9_pick_slots(gpfq_ctx *ctx, int RB, bool same, int64_t c_first, int n_ch, int64_t ntasks) {
     using namespace corr9;
     static int occ[2][9] = {};
     if (RB < 1 || RB > 8) return WARPS;
@@ -329,7 +350,7 @@ int corr9_pick_slots(gpfq_ctx *ctx, int RB, bool same, int n_ch, int64_t ntasks)
         occ[same][RB] = RB == 8 ? corr9_resident_ctas<8>(same) : RB == 6 ? corr9_resident_ctas<6>(same)
                        : RB == 4 ? corr9_resident_ctas<4>(same) : corr9_resident_ctas<1>(same);
     cudaGetLastError();
-    const int64_t groups = ceil_div64(n_ch + 3, 32);
+    const int64_t groups = ceil_div64(n_ch + (c_first & 3), 32);
     int64_t per = ceil_div64((int64_t)ctx->sm_count * occ[same][RB] * WARPS, groups);
     per = std::min<int64_t>(per, std::max<int64_t>(1, ntasks));
     return (int)(ceil_div64(per, WARPS) * WARPS);
@@ -422,7 +443,7 @@ int conv_corr9_stage(gpfq_ctx *ctx, const float *act, const float *actq, bool sa
 
 int conv_corr9_assemble_stage(gpfq_ctx *ctx, const double *partial, int slots, const double *rpartial, int rslots,
                               bool same, int n_ch, double *gram) {
-    conv_corr9_assemble_kernel<<<(unsigned)n_ch, 96, 0, ctx->stream>>>(partial, slots, rpartial, rslots, same ? 1 : 0, gram);
+    conv_corr9_assemble_kernel<<<(unsigned)n_ch, 256, 0, ctx->stream>>>(partial, slots, rpartial, rslots, same ? 1 : 0, gram);
     KERNEL_CHECK(ctx);
     return GPFQ_OK;
 }

@@ -38,6 +38,8 @@ def main():
     ap.add_argument("--shard", default="0/1")
     ap.add_argument("--skip-conv", action="store_true")
     ap.add_argument("--skip-dense", action="store_true")
+    ap.add_argument("--corr-rows", type=int, default=0, help="gpfq_set_option corr_rows (0 auto, 4, 6, 8)")
+    ap.add_argument("--layers", default="", help="comma-separated conv layer indices to run (default: all)")
     ap.add_argument("--conv-kernel", type=int, default=0, help="gpfq_set_option conv_kernel: 0 correlation form, 3 planes kernel")
     args = ap.parse_args()
     rank, world = (int(v) for v in args.shard.split("/"))
@@ -45,6 +47,7 @@ def main():
     from quantized_neural_networks_b200 import get_engine
     eng = get_engine(0)
     eng.set_option("conv_kernel", args.conv_kernel)
+    eng.set_option("corr_rows", args.corr_rows)
     dev = torch.device("cuda", 0)
     peaks = {}
     try:
@@ -56,7 +59,10 @@ def main():
     alph = lambda W: 3 * float(torch.median(W.abs().flatten())) * np.linspace(-1, 1, 3)
     total_ms, total_w = 0.0, 0
     if not args.skip_conv:
+        only = {int(v) for v in args.layers.split(',') if v != ''}
         for li, (C, F, H) in enumerate(CONV):
+            if only and li not in only:
+                continue
             g = torch.Generator(device=dev).manual_seed(100 + li)
             shape = (args.n_img, H, H, C)
             if li == 0:
