@@ -67,7 +67,8 @@ typedef struct gpfq_stats {
     int64_t flops_algorithmic; /* algorithmic fp64 flops of the dominant kernel */
     int32_t gram_kernel;     /* Dense Gram stage ran as: 0 none, 1 fp64 DMMA (mma.sync), 2 int8 slices on tcgen05,
                                 3 block-diagonal tiles only (residual form of the sweep's outer level);
-                                conv NHWC entry point: 4 = correlation form (13 displacement sums per Gram) */
+                                conv NHWC entry point: 4 = correlation form (13 displacement sums per Gram),
+                                5 = correlation form on images packed side by side as virtual channels */
     int32_t reserved;
 } gpfq_stats;
 
@@ -86,6 +87,7 @@ int gpfq_set_stream(gpfq_ctx *ctx, void *cuda_stream);
  *   "i8_pairs_d"   0 default, else keep int8 slice pairs with k + l <= value (2..10; 10 = every pair)
  *   "conv_kernel"  0 TMA-staged patch Grams / correlation form from NHWC activations, 1 direct LDG, 2 generic,
  *                  3 as 0 but the NHWC entry point uses the shared-memory planes kernel (patch form: 126 MACs per column)
+ *   "corr_pack"    correlation form: 0 layers / shards with few channels pack images side by side as virtual channels, 2 never
  *   "corr_rows"    correlation form: image rows per band (0 auto by image height, or 4 / 6 / 8)
  *   "sweep_kernel"  0 persistent tile, 1 per block
  *   "sweep_outer"  0 auto, 1 Gram rows of all earlier directions, 2 carried residuals (3 m N0 N1 MACs: wins when m << N0) */

@@ -27,12 +27,13 @@ int im2col_stage(gpfq_ctx *, const float *, int64_t, int, int, int64_t, int64_t,
                  int, int, int, int, float *, int64_t);
 int msq_stage(gpfq_ctx *, const void *, int, int64_t, const double *, int, int, double *);
 int nhwc9_plan(int, int, int, int, int, int, int, int, int *, int *);
-int corr9_plan(int, int, int, int, int, int, int, int, int, int64_t, int, int);
+int corr9_plan(int, int, int, int, int, int, int, int, int, int);
+int corr9_pack_stage(gpfq_ctx *, const float *, int64_t, int, int, int64_t, int64_t, int, int, int64_t, int64_t, float *);
 int corr9_pick_slots(gpfq_ctx *, int, bool, int64_t, int, int64_t);
 int corr9_tensor_ok(const float *, const float *);
 int conv_corr9_stage(gpfq_ctx *, const float *, const float *, bool, int64_t, int64_t, int64_t, int, int, int64_t, int64_t, int,
                      int, double *, int, int, int, double *, int, int, int);
-int conv_corr9_assemble_stage(gpfq_ctx *, const double *, int, const double *, int, bool, int, double *);
+int conv_corr9_assemble_stage(gpfq_ctx *, const double *, int, const double *, int, bool, int, int, double *);
 int conv_gram9_nhwc_stage(gpfq_ctx *, const float *, const float *, bool, int64_t, int64_t, int, int, int64_t, int64_t, int,
                           int, int, int, int, int, int, int, double *, int);
 
@@ -178,6 +179,9 @@ extern "C" int gpfq_set_option(gpfq_ctx *ctx, const char *key, int64_t value) {
     } else if (!strcmp(key, "i8_pairs_d")) {    // 0 default; else keep slice pairs with k + l <= value
         if (value != 0 && (value < 2 || value > 10)) return gpfq_fail(ctx, GPFQ_ERR_ARG, "i8_pairs_d must be 0 or 2..10");
         ctx->i8_pairs_d = (int)value;
+    } else if (!strcmp(key, "corr_pack")) {   // correlation form, image packing: 0 auto, 2 never
+        if (value != 0 && value != 2) return gpfq_fail(ctx, GPFQ_ERR_ARG, "corr_pack must be 0 or 2");
+        ctx->corr_pack = (int)value;
     } else if (!strcmp(key, "corr_rows")) {   // correlation form: rows per band (0 auto, 4, 6 or 8)
         if (value != 0 && value != 4 && value != 6 && value != 8) return gpfq_fail(ctx, GPFQ_ERR_ARG, "corr_rows must be 0, 4, 6 or 8");
         ctx->corr_rb = (int)value;
@@ -777,19 +781,46 @@ extern "C" int gpfq_conv_layer_nhwc(gpfq_ctx *ctx, const float *act, const float
         }
     }
     CUDA_TRY(ctx, gpfq_record(ctx, 5, s));
-    const int corr_rb = ctx->conv_variant == 0 ? corr9_plan(kh, kw, sh, sw, rh, rw, padding_same, (int)H, (int)Wd, C, (int)n_ch, ctx->corr_rb) : 0;
-    if (corr_rb && corr9_tensor_ok(dA, dAq)) {
+    const int corr_rb = ctx->conv_variant == 0 ? corr9_plan(kh, kw, sh, sw, rh, rw, padding_same, (int)H, (int)Wd, ctx->corr_rb) : 0;
+    // what a tensor map of the activations needs: 32-channel boxes on a 16-byte channel pitch; and lane = channel wants a
+    // full warp of channels.  Otherwise G images are packed side by side as virtual channels first (conv_corr.cu).
+    const bool corr_direct = C >= 32 && C % 4 == 0 && n_ch >= 8;
+    int corr_G = 1;
+    if (corr_rb && (!corr_direct || n_ch <= 16) && ctx->corr_pack != 2) {
+        int g = 32, a = (int)(n_ch % 32);
+        while (a) { const int t = g % a; g = a; a = t; }   // g = gcd(n_ch, 32)
+        corr_G = 32 / g;
+        const double packed = (double)ceil_div64(n_img, corr_G) * corr_G * H * Wd * n_ch * sizeof(float) * (same ? 1 : 2);
+        if (corr_G * n_ch > 4096 || packed > 32e9) corr_G = 1;   // keep the patch form / the direct tensor map
+    }
+    if (corr_rb && (corr_G > 1 || corr_direct) && corr9_tensor_ok(dA, dAq)) {
         // ---- correlation form: 13 displacement sums per Gram straight from the activations (conv_corr.cu)
+        const bool pack = corr_G > 1;
+        const int64_t VC = pack ? (int64_t)corr_G * n_ch : C;            // channels of the tensor the kernels see
+        const int vch = pack ? (int)VC : (int)n_ch;                       // channels (records) of this call
+        const int64_t vc0 = pack ? 0 : c0;
+        int64_t cipc = ipc;                                               // images per host chunk: whole groups when packing
+        if (pack) cipc = std::min<int64_t>(ceil_div64(cipc, corr_G) * corr_G, ceil_div64(n_img, corr_G) * corr_G);
+        const int cn_ic = (int)ceil_div64(n_img, cipc);
+        const int64_t units_per_chunk = pack ? cipc / corr_G : cipc;      // tensor "images" per chunk
+        const int64_t units_total = pack ? ceil_div64(n_img, corr_G) : n_img;
         const int nbands = (int)ceil_div64(H - 2, corr_rb);                        // rows 1 .. H-2 in bands
-        const int per_ic = corr9_pick_slots(ctx, corr_rb, same, c0, (int)n_ch, ipc * nbands);
-        const int bper_ic = corr9_pick_slots(ctx, 1, same, c0, (int)n_ch, 2 * ipc);             // top and bottom row of every image
-        const int slots = n_ic * per_ic, bslots = n_ic * bper_ic;
+        const int per_ic = corr9_pick_slots(ctx, corr_rb, same, vc0, vch, units_per_chunk * nbands);
+        const int bper_ic = corr9_pick_slots(ctx, 1, same, vc0, vch, 2 * units_per_chunk);   // top and bottom row of every image
+        const int slots = cn_ic * per_ic, bslots = cn_ic * bper_ic;
         double *partial = nullptr, *bpartial = nullptr, *gram = nullptr;
-        const size_t part_bytes = (size_t)n_ch * slots * 78 * sizeof(double);      // 2 passes x 3 column classes x 13 sums
-        const size_t bpart_bytes = (size_t)n_ch * bslots * 78 * sizeof(double);
+        float *pkA = nullptr, *pkQ = nullptr;
+        const size_t part_bytes = (size_t)vch * slots * 78 * sizeof(double);      // 2 passes x 3 column classes x 13 sums
+        const size_t bpart_bytes = (size_t)vch * bslots * 78 * sizeof(double);
         GPFQ_TRY(gpfq_ws(ctx, WS_CPART, part_bytes, (void **)&partial));
         GPFQ_TRY(gpfq_ws(ctx, WS_CORR_B, bpart_bytes, (void **)&bpartial));
         GPFQ_TRY(gpfq_ws(ctx, WS_CG, (size_t)n_ch * 2 * kk * kk * sizeof(double), (void **)&gram));
+        if (pack) {
+            const size_t pk_bytes = (size_t)units_total * H * Wd * VC * sizeof(float);
+            GPFQ_TRY(gpfq_ws(ctx, WS_PATCH_A, pk_bytes, (void **)&pkA));
+            pkQ = pkA;
+            if (!same) GPFQ_TRY(gpfq_ws(ctx, WS_PATCH_B, pk_bytes, (void **)&pkQ));
+        }
         CUDA_TRY(ctx, cudaMemsetAsync(partial, 0, part_bytes, s));
         CUDA_TRY(ctx, cudaMemsetAsync(bpartial, 0, bpart_bytes, s));
         CUDA_TRY(ctx, gpfq_record(ctx, 2, s));
@@ -797,9 +828,9 @@ extern "C" int gpfq_conv_layer_nhwc(gpfq_ctx *ctx, const float *act, const float
             CUDA_TRY(ctx, cudaEventRecord(ctx->ev_copy[2], s));
             CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy[2], 0));
         }
-        for (int ic = 0; ic < n_ic; ++ic) {
-            const int64_t img0 = (int64_t)ic * ipc;
-            const int64_t imgs = std::min<int64_t>(ipc, n_img - img0);
+        for (int ic = 0; ic < cn_ic; ++ic) {
+            const int64_t img0 = (int64_t)ic * cipc;
+            const int64_t imgs = std::min<int64_t>(cipc, n_img - img0);
             if (host_act) {
                 const size_t off = (size_t)img0 * img_elems, bytes = (size_t)imgs * img_elems * sizeof(float);
                 CUDA_TRY(ctx, cudaMemcpyAsync(const_cast<float *>(dA) + off, act + off, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
@@ -808,10 +839,17 @@ extern "C" int gpfq_conv_layer_nhwc(gpfq_ctx *ctx, const float *act, const float
                 CUDA_TRY(ctx, cudaEventRecord(ctx->ev_copy[ic & 1], ctx->copy_stream));
                 CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->ev_copy[ic & 1], 0));
             }
-            GPFQ_TRY(conv_corr9_stage(ctx, dA, dAq, same, img0, imgs, n_img, (int)H, (int)Wd, C, c0, (int)n_ch, corr_rb, partial, slots,
-                                      ic * per_ic, per_ic, bpartial, bslots, ic * bper_ic, bper_ic));
+            if (pack) {
+                GPFQ_TRY(corr9_pack_stage(ctx, dA, n_img, (int)H, (int)Wd, C, c0, (int)n_ch, corr_G, img0, imgs, pkA));
+                if (!same) GPFQ_TRY(corr9_pack_stage(ctx, dAq, n_img, (int)H, (int)Wd, C, c0, (int)n_ch, corr_G, img0, imgs, pkQ));
+                GPFQ_TRY(conv_corr9_stage(ctx, pkA, pkQ, same, img0 / corr_G, ceil_div64(imgs, corr_G), units_total, (int)H, (int)Wd, VC,
+                                          0, vch, corr_rb, partial, slots, ic * per_ic, per_ic, bpartial, bslots, ic * bper_ic, bper_ic));
+            } else {
+                GPFQ_TRY(conv_corr9_stage(ctx, dA, dAq, same, img0, imgs, n_img, (int)H, (int)Wd, C, c0, (int)n_ch, corr_rb, partial, slots,
+                                          ic * per_ic, per_ic, bpartial, bslots, ic * bper_ic, bper_ic));
+            }
         }
-        GPFQ_TRY(conv_corr9_assemble_stage(ctx, partial, slots, bpartial, bslots, same, (int)n_ch, gram));
+        GPFQ_TRY(conv_corr9_assemble_stage(ctx, partial, slots, bpartial, bslots, same, (int)n_ch, pack ? corr_G : 1, gram));
         CUDA_TRY(ctx, gpfq_record(ctx, 3, s));
         GPFQ_TRY(conv_finish(ctx, kk, nullptr, (int)n_ch, 0, same, W, C, F, c0, al, n_alph, Q_out, flags, gram));
         CUDA_TRY(ctx, gpfq_record(ctx, 1, s));
@@ -820,7 +858,7 @@ extern "C" int gpfq_conv_layer_nhwc(gpfq_ctx *ctx, const float *act, const float
         conv_stats(ctx, st, kk, n, n_ch, F, same, n_alph);
         st->bytes_algorithmic = (same ? 1 : 2) * 4LL * n_img * H * Wd * n_ch;  // the activations, once
         st->flops_algorithmic = (same ? 1 : 2) * 26LL * n_img * H * Wd * n_ch;  // 13 MACs per pixel, channel and Gram
-        st->gram_kernel = 4;
+        st->gram_kernel = pack ? 5 : 4;
         const bool synced = !(flags & GPFQ_NO_SYNC);
         if (synced) CUDA_TRY(ctx, cudaStreamSynchronize(s));
         end_call(ctx, st, synced);

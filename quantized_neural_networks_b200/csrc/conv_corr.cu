@@ -265,7 +265,7 @@ conv_corr9_tma_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_con
 // top / bottom row launch (even slots: top-left corner, top row, top-right corner; odd slots: the bottom ones).
 __global__ void __launch_bounds__(256)
 conv_corr9_assemble_kernel(const double *__restrict__ partial, int slots, const double *__restrict__ rpartial, int rslots,
-                           int same, double *__restrict__ gram) {
+                           int same, int n_ch, int G, double *__restrict__ gram) {
     using namespace corr9;
     // S[pass][row class: 0 top, 1 between, 2 bottom][column class: 0 first, 1 between, 2 last][13]
     __shared__ double S[2][3][3][ND];
@@ -273,21 +273,25 @@ conv_corr9_assemble_kernel(const double *__restrict__ partial, int slots, const 
     for (int e = tid; e < 2 * 9 * ND; e += blockDim.x) {
         const int d = e % ND, cc = (e / ND) % 3, rc = (e / (3 * ND)) % 3, pass = e / (9 * ND);
         const int off = (pass * 3 + cc) * ND + d;
-        // slots in index order, dealt round-robin to four partial sums (independent loads in flight), combined in order
-        const double *src = rc == 1 ? partial + (size_t)ch * slots * REC + off
-                                    : rpartial + ((size_t)ch * rslots + (rc == 0 ? 0 : 1)) * REC + off;
+        // slots in index order, dealt round-robin to four partial sums (independent loads in flight), combined in order;
+        // packed layers: the G virtual channels g * n_ch + ch of this channel, g in index order
         const int n = rc == 1 ? slots : (rslots - (rc == 0 ? 0 : 1) + 1) / 2;
         const size_t stride = rc == 1 ? REC : 2 * REC;
         double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
-        int s = 0;
+        for (int g = 0; g < G; ++g) {
+            const size_t vch = (size_t)g * n_ch + ch;
+            const double *src = rc == 1 ? partial + vch * slots * REC + off
+                                        : rpartial + (vch * rslots + (rc == 0 ? 0 : 1)) * REC + off;
+            int s = 0;
 #pragma unroll 2
-        for (; s + 4 <= n; s += 4) {
-            t0 += src[(size_t)s * stride];
-            t1 += src[(size_t)(s + 1) * stride];
-            t2 += src[(size_t)(s + 2) * stride];
-            t3 += src[(size_t)(s + 3) * stride];
+            for (; s + 4 <= n; s += 4) {
+                t0 += src[(size_t)s * stride];
+                t1 += src[(size_t)(s + 1) * stride];
+                t2 += src[(size_t)(s + 2) * stride];
+                t3 += src[(size_t)(s + 3) * stride];
+            }
+            for (; s < n; ++s) t0 += src[(size_t)s * stride];
         }
-        for (; s < n; ++s) t0 += src[(size_t)s * stride];
         S[pass][rc][cc][d] = (t0 + t1) + (t2 + t3);
     }
     __syncthreads();
@@ -308,11 +312,12 @@ conv_corr9_assemble_kernel(const double *__restrict__ partial, int slots, const 
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------
-// Is the layer eligible, and with how many rows per band?  (0: keep the patch form)
-int corr9_plan(int kh, int kw, int sh, int sw, int rh, int rw, int padding_same, int H, int W, int64_t C, int n_ch, int force_rb) {
+// Is the geometry eligible, and with how many rows per band?  (0: keep the patch form.)  The channel conditions of the
+// tensor map (C >= 32, C % 4 == 0) are the caller's: it can meet them by packing images side by side (corr9_pack_kernel).
+int corr9_plan(int kh, int kw, int sh, int sw, int rh, int rw, int padding_same, int H, int W, int force_rb) {
     if (kh != 3 || kw != 3 || sh != 1 || sw != 1 || rh != 1 || rw != 1 || !padding_same) return 0;
     if (H < 6 || W < corr9::WC) return 0;            // a TMA box (RB + 2 >= 6 rows x 5 columns) must fit in the image
-    if (C < 32 || C % 4 != 0 || n_ch < 8) return 0;  // box = 32 channels, 16-byte strides; few channels: lanes idle
+    if ((int64_t)H * W >= ((int64_t)1 << 28)) return 0;
     if ((force_rb == 8 || force_rb == 6 || force_rb == 4) && force_rb + 2 <= H) return force_rb;
     // rows 1 .. H-2 in bands of RB rows: 13 RB DFMAs + ~4 (RB + 2) conversion slots per band and column, plus a constant
     // per band (window reset, first / last column stages); calibrated with tools/vgg_bench.py --corr-rows
@@ -326,6 +331,39 @@ int corr9_plan(int kh, int kw, int sh, int sw, int rh, int rw, int padding_same,
         if (cost < best_cost) { best_cost = cost; best = rb; }
     }
     return best;
+}
+
+// ---- image packing ---------------------------------------------------------------------------------------------------
+// lane = channel needs 32 channels per warp and a 16-byte channel pitch.  Layers with few channels (the first conv layer:
+// C = 3; a rank of a multi-GPU job that owns 8 of 64 channels) are repacked so that G = 32 / gcd(n_ch, 32) images sit side
+// by side as "virtual channels": out[(ng, y, x, g * n_ch + c)] = act[(ng * G + g, y, x, c_first + c)], zeros past the last
+// image.  Every virtual channel is an ordinary channel of an ordinary (n / G, H, W, G n_ch) tensor for the correlation
+// kernels; conv_corr9_assemble_kernel adds the G records of a real channel (g in index order).
+__global__ void __launch_bounds__(256)
+corr9_pack_kernel(const float *__restrict__ act, int64_t n_img, int64_t hw, int64_t C, int64_t c_first, int n_ch, int G,
+                  int64_t img0, int64_t n_out, float *__restrict__ out) {
+    const int VC = G * n_ch;
+    // out is indexed from group img0 / G on: element e = ((ng - ng0) * hw + p) * VC + v
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_out; e += (int64_t)gridDim.x * blockDim.x) {
+        const int v = (int)(e % VC);
+        const int64_t t = e / VC, p = t % hw, ng = t / hw;
+        const int g = v / n_ch, c = v - g * n_ch;
+        const int64_t n = img0 + ng * G + g;
+        out[e] = n < n_img ? __ldg(act + (n * hw + p) * C + c_first + c) : 0.f;
+    }
+}
+
+// Packs images [img0, img0 + imgs) (img0 a multiple of G) of channels [c_first, c_first + n_ch) into `out`, which holds
+// the packed tensor of ALL images: groups [img0 / G, ceil((img0 + imgs) / G)) are written.
+int corr9_pack_stage(gpfq_ctx *ctx, const float *act, int64_t n_img, int H, int Wd, int64_t C, int64_t c_first, int n_ch, int G,
+                     int64_t img0, int64_t imgs, float *out) {
+    const int64_t hw = (int64_t)H * Wd, VC = (int64_t)G * n_ch;
+    const int64_t ngrp = ceil_div64(imgs, G), n_out = ngrp * hw * VC;
+    const int blocks = (int)std::min<int64_t>(ceil_div64(n_out, 256), (int64_t)ctx->sm_count * 16);
+    corr9_pack_kernel<<<blocks, 256, 0, ctx->stream>>>(act, std::min<int64_t>(n_img, img0 + imgs), hw, C, c_first, n_ch, G, img0,
+                                                       n_out, out + (img0 / G) * hw * VC);
+    KERNEL_CHECK(ctx);
+    return GPFQ_OK;
 }
 
 template <int RB>
@@ -441,9 +479,10 @@ int conv_corr9_stage(gpfq_ctx *ctx, const float *act, const float *actq, bool sa
     return GPFQ_OK;
 }
 
+// n_ch real channels; G > 1: the records belong to G * n_ch virtual channels of a packed tensor
 int conv_corr9_assemble_stage(gpfq_ctx *ctx, const double *partial, int slots, const double *rpartial, int rslots,
-                              bool same, int n_ch, double *gram) {
-    conv_corr9_assemble_kernel<<<(unsigned)n_ch, 256, 0, ctx->stream>>>(partial, slots, rpartial, rslots, same ? 1 : 0, gram);
+                              bool same, int n_ch, int G, double *gram) {
+    conv_corr9_assemble_kernel<<<(unsigned)n_ch, 256, 0, ctx->stream>>>(partial, slots, rpartial, rslots, same ? 1 : 0, n_ch, G, gram);
     KERNEL_CHECK(ctx);
     return GPFQ_OK;
 }

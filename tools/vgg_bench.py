@@ -91,7 +91,7 @@ def main():
                 if best is None or st["ms_total"] < best["ms_total"]:
                     best = st
             colch = args.n_img * H * H * (hi - lo)
-            corr = best["gram_kernel"] == 4
+            corr = best["gram_kernel"] in (4, 5)
             # patch form: 168 (84 when X == Xq) fp64-pipe slots per patch column and channel at the DMMA rate; correlation
             # form: 26 (13) DFMAs per pixel and channel at the measured DFMA rate
             slots = colch * ((13 if li == 0 else 26) if corr else (84 if li == 0 else 168))
@@ -100,7 +100,7 @@ def main():
             ms = best["ms_total"]
             print(json.dumps({"layer": f"conv{li}", "C": C, "F": F, "H": H, "channels": [lo, hi], "weights": 9 * (hi - lo) * F,
                               "ms": round(ms, 3), "ms_gram": round(best["ms_gram"], 3),
-                              "form": "correlation (13 DFMA / pixel / Gram)" if corr else "patch (126 MACs / column)",
+                              "form": ("correlation, packed images" if best["gram_kernel"] == 5 else "correlation (13 DFMA / pixel / Gram)") if corr else "patch (126 MACs / column)",
                               "fp64_pipe_frac": round(slots / pipe / (best["ms_gram"] * 1e-3), 3),
                               "hbm_frac": round(bytes_alg / hbm / (best["ms_gram"] * 1e-3), 3),
                               "weights_per_s": round(9 * (hi - lo) * F / (ms * 1e-3))}), flush=True)
