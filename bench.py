@@ -17,6 +17,9 @@ One "step" = one pass of the hot path over all eight layers.
           than per-channel patch matrices), Dense layers through gpfq_dense_layer; every Q comes back to the host.
   roofline  the dominant kernel (conv_gram9_tma_kernel, HBM-bound, 74 % of the step): algorithmic bytes / CUDA-event time
           of that stage.  roofline_tensor_stage: the Dense Gram stage on tcgen05 (int8 slices), against 2 x measured bf16.
+  from_activations  the same device-resident pass with every conv layer handed over as its NHWC activation tensor (no
+          patch matrices: the 9 x 9 Grams are 13 displacement sums of the activations, conv_corr.cu) -- value, ms/step and
+          the roofline of conv_corr9_tma_kernel.
   cpu_baseline  the oracle's NumPy restatement of the reference walk (kind "port": the reference is Python and does
           not travel to the GPU box), one process per host core exactly like the reference's ProcessPoolExecutor, on a
           bounded sample of every layer, extrapolated linearly in the number of neurons/filters.
@@ -130,6 +133,16 @@ def run_pass_device(eng, data, outs, sync=False):
     for d, o in zip(data, outs):
         if d["kind"] == "conv":
             eng.conv_channels(d["Xp"], d["Xqp"], d["W"], d["A"], c0=d["c0"], n_channels=d["n_ch"], out=o, sync=sync)
+        else:
+            eng.dense_layer(d["X"], d["Xq"], d["W"], d["A"], j0=d["j0"], j1=d["j1"], out=o, sync=sync)
+
+
+def run_pass_device_nhwc(eng, data, outs, sync=False):
+    """The same pass with the conv layers handed over as NHWC activation tensors (the coarser override point of
+    INTEGRATION.md: `_quantize_conv2D_layer_parallel_jit` before `_build_patch_array`), still device-resident."""
+    for d, o in zip(data, outs):
+        if d["kind"] == "conv":
+            eng.conv_layer_nhwc(d["act"], d["actq"], d["W"], d["A"], c0=d["c0"], n_channels=d["n_ch"], out=o, sync=sync)
         else:
             eng.dense_layer(d["X"], d["Xq"], d["W"], d["A"], j0=d["j0"], j1=d["j1"], out=o, sync=sync)
 
@@ -459,6 +472,53 @@ def main():
                       "fp64_equivalent_tflops": (1 if d["first"] else 2) * m * N0 * (N0 + 1) / (ms_g * 1e-3) / 1e12,
                       "note": "stage time includes the slicing and exponent kernels; a 0.5 ms stage is mostly fill/drain"}
 
+    # ---- the same pass from the layers' NHWC activations (device-resident): no patch matrices anywhere -----------------
+    nhwc = None
+    if args.workload == "cifar10_cnn":
+        outs2 = [torch.zeros_like(o) for o in outs]
+        for _ in range(max(args.warmup, 3)):
+            run_pass_device_nhwc(eng, data, outs2)
+        barrier()
+        agree = min(float((a == b).double().mean()) for a, b in zip(outs, outs2))
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        f0.record()
+        for _ in range(args.steps):
+            run_pass_device_nhwc(eng, data, outs2)
+        f1.record()
+        barrier()
+        ms2 = f0.elapsed_time(f1)
+        if world > 1:
+            t = torch.tensor([ms2], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms2 = float(t.item())
+        ms2 /= args.steps
+        cb = cm = cf = 0.0
+        kinds = {}
+        for back in range(min(len(layers) * args.steps, 120)):
+            st = eng.query_stats(back)
+            lname, lkind = layers[(len(layers) - 1 - back) % len(layers)][:2]
+            if lkind == "conv" and st.get("gram_kernel") in (4, 5):
+                cb += st["bytes_algorithmic"]
+                cf += st["flops_algorithmic"]
+                cm += st["ms_gram"]
+            if lkind == "conv":
+                kinds[lname] = {0: "patch form (shared-memory planes)", 4: "correlation form", 5: "correlation form, packed images"}.get(
+                    st.get("gram_kernel"), str(st.get("gram_kernel")))
+        nhwc = {"value": total_weights / (ms2 * 1e-3), "unit": "weights/s", "ms_per_step": ms2,
+                "inputs": "NHWC activations of every conv layer resident in HBM (2.9 GB per pass, larger than L2) instead of "
+                          "per-channel patch matrices (25.7 GB)",
+                "agreement_with_patch_matrix_pass": agree, "conv_gram_form": kinds,
+                "roofline": None if cm <= 0 else {
+                    "kernel": "conv_corr9_tma_kernel (13 displacement sums per Gram; TMA boxes -> per-warp mbarrier ring -> "
+                              "fp64 register window, DFMA)", "bound": "hbm", "achieved": cb / (cm * 1e-3) / 1e9,
+                    "peak": hbm_peak, "unit": "GB/s", "frac": cb / (cm * 1e-3) / 1e9 / hbm_peak,
+                    "algorithmic_bytes": "4 B per pixel and channel per tensor (the activations, read once)",
+                    "dfma_pipe_frac": cf / 2 / (cm * 1e-3) / 17.05e12,
+                    "dfma_pipe_note": "13 DFMA per pixel, channel and Gram against the measured 17.05e12 DFMA/s "
+                                      "(profiles/fp64_pipes_r1.txt); the stage time includes image packing, row launches and assembly"}}
+        del outs2
+
     # ---- e2e: host (pinned) buffers through the C ABI, copies inside the timed region ---------------------------
     e2e = None
     if not args.no_e2e:
@@ -466,14 +526,15 @@ def main():
         kept = []
         run_pass_host(eng, host, kept, rank, world, dev)  # warm-up (allocates the staging workspaces)
         barrier()
-        for d, o, Qh in zip(data, outs, kept):   # both entry points must produce the same bits
-            Qd = o[0].cpu().numpy()
+        for d, o, Qh in zip(data, outs, kept):   # both entry points must agree (north-star gate: >= 99.99 % of entries;
+            Qd = o[0].cpu().numpy()               # the correlation form re-associates fp64 sums, so not always bit for bit)
             if d["kind"] == "conv":
                 ref_blk = Qd[:, :, d["c0"]:d["c0"] + d["n_ch"]]
-                assert np.array_equal(ref_blk, Qh[:, :, d["c0"]:d["c0"] + d["n_ch"]] if world == 1 else Qh), d["name"]
+                got = Qh[:, :, d["c0"]:d["c0"] + d["n_ch"]] if world == 1 else Qh
             else:
                 ref_blk = Qd[:, d["j0"]:d["j1"]]
-                assert np.array_equal(ref_blk, Qh[:, d["j0"]:d["j1"]] if world == 1 else Qh), d["name"]
+                got = Qh[:, d["j0"]:d["j1"]] if world == 1 else Qh
+            assert ref_blk.size == 0 or float(np.mean(ref_blk == got)) >= 0.9999, d["name"]
         del kept
         barrier()
         t0 = time.perf_counter()
@@ -505,7 +566,8 @@ def main():
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
-                "roofline": roofline, "roofline_tensor_stage": tensor, "cpu_baseline": cpu, "layers": layer_report}
+                "roofline": roofline, "roofline_tensor_stage": tensor, "from_activations": nhwc, "cpu_baseline": cpu,
+                "layers": layer_report}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

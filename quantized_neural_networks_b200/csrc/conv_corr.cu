@@ -340,16 +340,43 @@ int corr9_plan(int kh, int kw, int sh, int sw, int rh, int rw, int padding_same,
 // image.  Every virtual channel is an ordinary channel of an ordinary (n / G, H, W, G n_ch) tensor for the correlation
 // kernels; conv_corr9_assemble_kernel adds the G records of a real channel (g in index order).
 __global__ void __launch_bounds__(256)
-corr9_pack_kernel(const float *__restrict__ act, int64_t n_img, int64_t hw, int64_t C, int64_t c_first, int n_ch, int G,
-                  int64_t img0, int64_t n_out, float *__restrict__ out) {
-    const int VC = G * n_ch;
-    // out is indexed from group img0 / G on: element e = ((ng - ng0) * hw + p) * VC + v
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_out; e += (int64_t)gridDim.x * blockDim.x) {
-        const int v = (int)(e % VC);
-        const int64_t t = e / VC, p = t % hw, ng = t / hw;
+corr9_pack_kernel(const float *__restrict__ act, int64_t n_valid, int hw, int64_t C, int64_t c_first, int n_ch, int G,
+                  int64_t img0, int pix_per_warp, float *__restrict__ out) {
+    // blockIdx.y: group of G images; every warp copies a run of pixels, 32 virtual channels (one 128-byte line) at a time
+    const int lane = threadIdx.x & 31, VC = G * n_ch;
+    const int64_t ng = blockIdx.y;
+    const int p0 = (int)((blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * pix_per_warp);
+    const int p1 = min(hw, p0 + pix_per_warp);
+    if (p0 >= p1) return;
+    for (int vb = 0; vb < VC; vb += 32) {
+        const int v = vb + lane;
+        if (v >= VC) continue;
         const int g = v / n_ch, c = v - g * n_ch;
         const int64_t n = img0 + ng * G + g;
-        out[e] = n < n_img ? __ldg(act + (n * hw + p) * C + c_first + c) : 0.f;
+        float *dst = out + (ng * hw + p0) * VC + v;
+        if (n < n_valid) {
+            const float *src = act + (n * hw + p0) * C + c_first + c;
+            int p = p0;
+            for (; p + 8 <= p1; p += 8) {
+                float t[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) t[u] = __ldg(src + (int64_t)u * C);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) dst[(int64_t)u * VC] = t[u];
+                src += 8 * C;
+                dst += (int64_t)8 * VC;
+            }
+            for (; p < p1; ++p) {
+                *dst = __ldg(src);
+                src += C;
+                dst += VC;
+            }
+        } else {
+            for (int p = p0; p < p1; ++p) {
+                *dst = 0.f;
+                dst += VC;
+            }
+        }
     }
 }
 
@@ -357,12 +384,19 @@ corr9_pack_kernel(const float *__restrict__ act, int64_t n_img, int64_t hw, int6
 // the packed tensor of ALL images: groups [img0 / G, ceil((img0 + imgs) / G)) are written.
 int corr9_pack_stage(gpfq_ctx *ctx, const float *act, int64_t n_img, int H, int Wd, int64_t C, int64_t c_first, int n_ch, int G,
                      int64_t img0, int64_t imgs, float *out) {
-    const int64_t hw = (int64_t)H * Wd, VC = (int64_t)G * n_ch;
-    const int64_t ngrp = ceil_div64(imgs, G), n_out = ngrp * hw * VC;
-    const int blocks = (int)std::min<int64_t>(ceil_div64(n_out, 256), (int64_t)ctx->sm_count * 16);
-    corr9_pack_kernel<<<blocks, 256, 0, ctx->stream>>>(act, std::min<int64_t>(n_img, img0 + imgs), hw, C, c_first, n_ch, G, img0,
-                                                       n_out, out + (img0 / G) * hw * VC);
-    KERNEL_CHECK(ctx);
+    const int hw = H * Wd;
+    const int64_t VC = (int64_t)G * n_ch, ngrp = ceil_div64(imgs, G);
+    // enough warps for ~8 CTAs per SM over the whole launch, at least 32 pixels per warp
+    int64_t ppw = ceil_div64((int64_t)hw * ngrp, (int64_t)ctx->sm_count * 64);
+    ppw = std::max<int64_t>(32, std::min<int64_t>(ppw, hw));
+    const int64_t warps = ceil_div64(hw, ppw);
+    for (int64_t g0 = 0; g0 < ngrp; g0 += 65535) {   // gridDim.y limit
+        const int64_t gn = std::min<int64_t>(65535, ngrp - g0);
+        dim3 grid((unsigned)ceil_div64(warps, 8), (unsigned)gn);
+        corr9_pack_kernel<<<grid, 256, 0, ctx->stream>>>(act, std::min<int64_t>(n_img, img0 + imgs), hw, C, c_first, n_ch, G,
+                                                         img0 + g0 * G, (int)ppw, out + (img0 / G + g0) * hw * VC);
+        KERNEL_CHECK(ctx);
+    }
     return GPFQ_OK;
 }
 
