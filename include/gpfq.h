@@ -87,7 +87,9 @@ int gpfq_set_stream(gpfq_ctx *ctx, void *cuda_stream);
  *   "i8_pairs_d"   0 default, else keep int8 slice pairs with k + l <= value (2..10; 10 = every pair)
  *   "conv_kernel"  0 TMA-staged patch Grams / correlation form from NHWC activations, 1 direct LDG, 2 generic,
  *                  3 as 0 but the NHWC entry point uses the shared-memory planes kernel (patch form: 126 MACs per column)
- *   "corr_pack"    correlation form: 0 layers / shards with few channels pack images side by side as virtual channels, 2 never
+ *   "corr_pack"    correlation form, images packed side by side as virtual channels: 0 when the channel count cannot be
+ *                  mapped (C < 32 or C % 4 != 0) and the images are large, 1 always, 2 never
+ *   "corr_small"   1: correlation form also on images below 128 pixels (default: the planes kernel is faster there)
  *   "corr_rows"    correlation form: image rows per band (0 auto by image height, or 4 / 6 / 8)
  *   "sweep_kernel"  0 persistent tile, 1 per block
  *   "sweep_outer"  0 auto, 1 Gram rows of all earlier directions, 2 carried residuals (3 m N0 N1 MACs: wins when m << N0) */

@@ -179,9 +179,11 @@ extern "C" int gpfq_set_option(gpfq_ctx *ctx, const char *key, int64_t value) {
     } else if (!strcmp(key, "i8_pairs_d")) {    // 0 default; else keep slice pairs with k + l <= value
         if (value != 0 && (value < 2 || value > 10)) return gpfq_fail(ctx, GPFQ_ERR_ARG, "i8_pairs_d must be 0 or 2..10");
         ctx->i8_pairs_d = (int)value;
-    } else if (!strcmp(key, "corr_pack")) {   // correlation form, image packing: 0 auto, 2 never
-        if (value != 0 && value != 2) return gpfq_fail(ctx, GPFQ_ERR_ARG, "corr_pack must be 0 or 2");
+    } else if (!strcmp(key, "corr_pack")) {   // correlation form, image packing: 0 auto, 1 always (tests), 2 never
+        if (value < 0 || value > 2) return gpfq_fail(ctx, GPFQ_ERR_ARG, "corr_pack must be 0, 1 or 2");
         ctx->corr_pack = (int)value;
+    } else if (!strcmp(key, "corr_small")) {   // correlation form also on images below 128 pixels (tests)
+        ctx->corr_direct_small = value != 0;
     } else if (!strcmp(key, "corr_rows")) {   // correlation form: rows per band (0 auto, 4, 6 or 8)
         if (value != 0 && value != 4 && value != 6 && value != 8) return gpfq_fail(ctx, GPFQ_ERR_ARG, "corr_rows must be 0, 4, 6 or 8");
         ctx->corr_rb = (int)value;
@@ -784,16 +786,27 @@ extern "C" int gpfq_conv_layer_nhwc(gpfq_ctx *ctx, const float *act, const float
     const int corr_rb = ctx->conv_variant == 0 ? corr9_plan(kh, kw, sh, sw, rh, rw, padding_same, (int)H, (int)Wd, ctx->corr_rb) : 0;
     // what a tensor map of the activations needs: 32-channel boxes on a 16-byte channel pitch; and lane = channel wants a
     // full warp of channels.  Otherwise G images are packed side by side as virtual channels first (conv_corr.cu).
-    const bool corr_direct = C >= 32 && C % 4 == 0 && n_ch >= 8;
+    // Measured (tools/vgg_bench.py --net cifar / --conv-kernel 3): on 8 x 8 images the per-band start-up outweighs the 6.5x
+    // fewer MACs and the shared-memory planes kernel wins; packing pays for itself only on large images whose channel
+    // count cannot be mapped directly (VGG's first layer: 7.0 -> 3.6 ms); channel shards of 8-16 channels run faster
+    // unpacked with idle lanes.
+    const bool corr_direct = C >= 32 && C % 4 == 0 && n_ch >= 8 && H * Wd >= 128;
     int corr_G = 1;
-    if (corr_rb && (!corr_direct || n_ch <= 16) && ctx->corr_pack != 2) {
+    if (corr_rb && !(C >= 32 && C % 4 == 0) && H * Wd >= 4096 && ctx->corr_pack != 2) {
         int g = 32, a = (int)(n_ch % 32);
         while (a) { const int t = g % a; g = a; a = t; }   // g = gcd(n_ch, 32)
         corr_G = 32 / g;
         const double packed = (double)ceil_div64(n_img, corr_G) * corr_G * H * Wd * n_ch * sizeof(float) * (same ? 1 : 2);
-        if (corr_G * n_ch > 4096 || packed > 32e9) corr_G = 1;   // keep the patch form / the direct tensor map
+        if (corr_G * n_ch > 4096 || packed > 32e9) corr_G = 1;   // keep the patch form
     }
-    if (corr_rb && (corr_G > 1 || corr_direct) && corr9_tensor_ok(dA, dAq)) {
+    if (ctx->corr_pack == 1 && corr_rb) {   // tests: pack whatever the shape
+        int g = 32, a = (int)(n_ch % 32);
+        while (a) { const int t = g % a; g = a; a = t; }
+        corr_G = 32 / g;
+        if (corr_G == 1 || corr_G * n_ch > 4096) corr_G = (corr_G * n_ch > 4096) ? 1 : 2;
+    }
+    if (corr_rb && (corr_G > 1 || (corr_direct && ctx->corr_pack != 1) || (ctx->corr_direct_small && C >= 32 && C % 4 == 0 && n_ch >= 8)) &&
+        corr9_tensor_ok(dA, dAq)) {
         // ---- correlation form: 13 displacement sums per Gram straight from the activations (conv_corr.cu)
         const bool pack = corr_G > 1;
         const int64_t VC = pack ? (int64_t)corr_G * n_ch : C;            // channels of the tensor the kernels see

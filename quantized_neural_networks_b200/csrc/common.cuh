@@ -54,7 +54,8 @@ struct gpfq_ctx {
     int launches = 0;
     int conv_variant = 0;         // 3x3 patch-Gram kernel: 0 TMA-staged / correlation form (default), 1 direct LDG, 2 generic,
                                   // 3 NHWC entry point: shared-memory planes kernel instead of the correlation form
-    int corr_pack = 0;            // correlation form: 0 pack images as virtual channels when few channels, 2 never pack
+    int corr_pack = 0;            // correlation form, images packed as virtual channels: 0 by shape, 1 always (tests), 2 never
+    bool corr_direct_small = false;  // correlation form also on images below 128 pixels (tests)
     int corr_rb = 0;              // correlation-form conv Grams: rows per band (0: chosen per image height)
     int sweep_variant = 0;        // triangular sweep: 0 persistent neuron-tile kernel (default), 1 one launch pair per block
     bool stream_literal = false;  // streaming walk: reproduce the reference's fp32-rounded w*X products (set per call)

@@ -393,15 +393,32 @@ def test_conv_nhwc_fused_matches_patch_path(n_img, H, Wd, C, F, pad):
     assert np.array_equal(outs["tma"], outs["ldg"]) and np.array_equal(outs["tma_same"], outs["ldg_same"])
 
 
+class _conv_options:
+    """Planner overrides of the NHWC conv entry point for a block (gpfq_set_option), restored on exit."""
+
+    def __init__(self, engine, **opts):
+        self.engine, self.opts = engine, opts
+
+    def __enter__(self):
+        for k, v in self.opts.items():
+            self.engine.set_option(k, v)
+
+    def __exit__(self, *exc):
+        for k in self.opts:
+            self.engine.set_option(k, 0)
+
+
 @pytest.mark.parametrize("n_img,H,Wd,C,F", [(2, 1, 9, 9, 2), (5, 2, 2, 33, 3), (4, 7, 7, 40, 2), (3, 14, 14, 64, 4),
                                             (2, 28, 28, 96, 2), (2, 16, 16, 32, 3), (1, 45, 37, 36, 2), (70, 8, 8, 44, 2),
                                             (3, 6, 5, 32, 2), (2, 9, 23, 72, 2), (5, 10, 6, 40, 3), (2, 5, 12, 32, 2),
                                             (5, 9, 11, 3, 4), (40, 12, 12, 8, 2), (7, 8, 8, 12, 2), (3, 10, 10, 33, 2),
-                                            (33, 6, 7, 16, 2)])
+                                            (33, 6, 7, 16, 2), (2, 70, 66, 3, 2)])
 def test_conv_corr9_matches_patch_form(engine, n_img, H, Wd, C, F):
-    """Correlation form of the 3x3 / stride 1 / SAME Grams (conv_corr.cu: 13 displacement sums + border inclusion-exclusion)
-    against the oracle and against the patch-form kernel (shared-memory planes): degenerate images (1 x 1, one row, one
-    column, 2 x 2), ragged bands for every band height, channel counts that are not a multiple of 32, channel shards."""
+    """Correlation form of the 3x3 / stride 1 / SAME Grams (conv_corr.cu: 13 displacement sums per pixel region, added per
+    tap) against the oracle and against the patch-form kernel (shared-memory planes), with the planner's choice and with
+    both variants forced: TMA boxes straight on the activations, and images packed side by side as virtual channels.
+    Degenerate images keep the patch form; ragged bands for every band height, channel counts that are not a multiple of
+    32, channel shards that start off a 16-byte boundary, channels that are zero except on one border (dead directions)."""
     import torch
     rng = np.random.default_rng(n_img * 131 + H * 7 + C)
     act = np.maximum(rng.standard_normal((n_img, H, Wd, C)), 0).astype(np.float32)
@@ -413,39 +430,39 @@ def test_conv_corr9_matches_patch_form(engine, n_img, H, Wd, C, F):
     A = O.layer_alphabet(W, 3, O.unit_alphabet(3))
     patches = lambda ch: (O.channel_patches(act, ch, (3, 3), (1, 1), "SAME"), O.channel_patches(actq, ch, (3, 3), (1, 1), "SAME"))
     Qref = c_oracle.quantize_conv_layer(W, patches, A)
-    Q = engine.conv_layer_nhwc(act, actq, W, A)
-    corr = H >= 6 and Wd >= 5                               # a TMA box (6 rows x 5 columns) fits in the image
-    packed = C < 32 or C % 4 != 0 or C <= 16                # few / unaligned channels: images packed as virtual channels
-    assert engine.last_stats["gram_kernel"] == ((5 if packed else 4) if corr else 0)  # the correlation form really ran
-    assert O.agreement(Q, Qref) >= AGREE
-    Qs = engine.conv_layer_nhwc(actq, None, W, A)
-    dev = engine.conv_layer_nhwc(torch.from_numpy(act).cuda(), torch.from_numpy(actq).cuda(), torch.from_numpy(W).cuda(), A)
-    assert np.array_equal(dev.cpu().numpy(), Q)
-    if C >= 10:
-        part = engine.conv_layer_nhwc(act, actq, W, A, c0=1, n_channels=C - 2)
-        assert engine.last_stats["gram_kernel"] in ((4, 5) if corr else (0,))
-        assert np.array_equal(part[:, :, 1:C - 1], Q[:, :, 1:C - 1]) and np.all(part[:, :, 0] == 0)
-    engine.set_option("conv_kernel", 3)
-    try:
-        Qp = engine.conv_layer_nhwc(act, actq, W, A)
-        assert engine.last_stats["gram_kernel"] == 0
-        Qps = engine.conv_layer_nhwc(actq, None, W, A)
-        # a channel that is zero except on its bottom row / right column: tap rows / columns that never sit there are
-        # dead directions (exact zeros in the Gram), the guard of quantized_network.py:83-84 must fire in both forms
-        act2, actq2 = act.copy(), actq.copy()
-        act2[:, :-1, :, 1] = 0
-        actq2[:, :-1, :, 1] = 0
-        act2[:, :, :-1, 2] = 0
-        actq2[:, :, :-1, 2] = 0
-        Qp2 = engine.conv_layer_nhwc(act2, actq2, W, A)
-    finally:
-        engine.set_option("conv_kernel", 0)
-    assert O.agreement(Q, Qp) >= AGREE and O.agreement(Qs, Qps) >= AGREE
-    assert O.agreement(Qp, Qref) >= AGREE
-    Q2 = engine.conv_layer_nhwc(act2, actq2, W, A)
-    assert O.agreement(Q2, Qp2) >= AGREE
-    if corr:
-        assert np.all(Q2[0, :, 1, :] == 0) and np.all(Q2[:, 0, 2, :] == 0)   # dead directions: literal zeros
+    # a second input: channels 1 and 2 are zero except on the bottom row / right column, so tap rows / columns that never
+    # sit there are dead directions (exact zeros in the Gram) and the guard of quantized_network.py:83-84 must fire
+    act2, actq2 = act.copy(), actq.copy()
+    act2[:, :-1, :, 1] = 0
+    actq2[:, :-1, :, 1] = 0
+    act2[:, :, :-1, 2] = 0
+    actq2[:, :, :-1, 2] = 0
+    geom = H >= 6 and Wd >= 5                    # a TMA box (6 rows x 5 columns) fits in the image
+    mappable = C >= 32 and C % 4 == 0            # 32-channel boxes on a 16-byte channel pitch
+    runs = {"planner": (dict(), {0, 4, 5}), "planes": (dict(conv_kernel=3), {0})}
+    if geom and mappable:
+        runs["direct"] = (dict(corr_small=1, corr_pack=2), {4})
+    if geom:
+        runs["packed"] = (dict(corr_pack=1), {5})
+    out = {}
+    for name, (opts, kernels) in runs.items():
+        with _conv_options(engine, **opts):
+            Q = engine.conv_layer_nhwc(act, actq, W, A)
+            assert engine.last_stats["gram_kernel"] in kernels, (name, engine.last_stats["gram_kernel"])
+            assert O.agreement(Q, Qref) >= AGREE, name
+            Qs = engine.conv_layer_nhwc(actq, None, W, A)
+            dev = engine.conv_layer_nhwc(torch.from_numpy(act).cuda(), torch.from_numpy(actq).cuda(), torch.from_numpy(W).cuda(), A)
+            assert np.array_equal(dev.cpu().numpy(), Q), name
+            if C >= 10:   # a shard that starts at channel 1
+                part = engine.conv_layer_nhwc(act, actq, W, A, c0=1, n_channels=C - 2)
+                assert O.agreement(part[:, :, 1:C - 1], Q[:, :, 1:C - 1]) >= AGREE and np.all(part[:, :, 0] == 0), name
+            Q2 = engine.conv_layer_nhwc(act2, actq2, W, A)
+            if H >= 2 and Wd >= 2:
+                assert np.all(Q2[0, :, 1, :] == 0) and np.all(Q2[:, 0, 2, :] == 0), name   # dead directions: literal zeros
+            out[name] = (Q, Qs, Q2)
+    for name in out:
+        for x, y in zip(out[name], out["planes"]):
+            assert O.agreement(x, y) >= AGREE, name
 
 
 @pytest.mark.parametrize("n_img,C", [(22, 32), (200, 3)])

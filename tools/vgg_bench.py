@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--n-img", type=int, default=1504)
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--shard", default="0/1")
+    ap.add_argument("--net", default="vgg16", choices=["vgg16", "cifar"], help="layer shapes: VGG16 (default) or the CIFAR10 CNN of config 2 (use --n-img 5008)")
     ap.add_argument("--skip-conv", action="store_true")
     ap.add_argument("--skip-dense", action="store_true")
     ap.add_argument("--corr-rows", type=int, default=0, help="gpfq_set_option corr_rows (0 auto, 4, 6, 8)")
@@ -43,6 +44,10 @@ def main():
     ap.add_argument("--conv-kernel", type=int, default=0, help="gpfq_set_option conv_kernel: 0 correlation form, 3 planes kernel")
     args = ap.parse_args()
     rank, world = (int(v) for v in args.shard.split("/"))
+    global CONV, DENSE
+    if args.net == "cifar":
+        CONV = [(3, 32, 32), (32, 32, 32), (32, 64, 16), (64, 64, 16), (64, 128, 8), (128, 128, 8)]
+        DENSE = [(2048, 128), (128, 10)]
     import torch
     from quantized_neural_networks_b200 import get_engine
     eng = get_engine(0)
