@@ -334,6 +334,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-activations-leg", action="store_true", help="skip the from_activations leg (profiling the value leg)")
+    ap.add_argument("--profile-activations-leg", action="store_true",
+                    help="profiling only: run nothing but warm-up + timed passes of the from_activations leg")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -398,6 +401,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.profile_activations_leg:
+        for _ in range(max(args.warmup, 3) + args.steps):
+            run_pass_device_nhwc(eng, data, outs)
+        barrier()
+        return
     for _ in range(max(args.warmup, 3)):
         run_pass_device(eng, data, outs)
     barrier()
@@ -474,7 +482,7 @@ def main():
 
     # ---- the same pass from the layers' NHWC activations (device-resident): no patch matrices anywhere -----------------
     nhwc = None
-    if args.workload == "cifar10_cnn":
+    if args.workload == "cifar10_cnn" and not args.no_activations_leg:
         outs2 = [torch.zeros_like(o) for o in outs]
         for _ in range(max(args.warmup, 3)):
             run_pass_device_nhwc(eng, data, outs2)

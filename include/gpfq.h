@@ -163,6 +163,26 @@ int gpfq_conv_layer_nhwc(gpfq_ctx *ctx, const float *act, const float *actq, int
                          const double *alphabets, const int32_t *K, int32_t n_alphabets,
                          double *Q_out, uint32_t flags, gpfq_stats *stats);
 
+/* ---- Conv2D layer split over IMAGES (multi-GPU) -------------------------------------------------------------------
+ * The 9-step walk of a channel (quantized_network.py:219-228) sees its patch matrices only through the kk x kk matrices
+ * G1 = Xq X^T, G2 = Xq Xq^T, which are sums over patches, i.e. over images.  A multi-GPU job therefore gives each rank
+ * n_img / world images of EVERY channel (1 / world of the activations over its own PCIe link, no replication):
+ *   gpfq_conv_gram_nhwc        per-channel [G1 | G2] (2 kk^2 float64 per channel, lower triangles + diagonals valid, G1 == G2
+ *                              when actq == act / NULL) of channels c0 .. c0+n_ch-1 over the given images.  gram_out lives
+ *                              on the device when GPFQ_Q_DEVICE is set, else on the host.
+ *   (one all-reduce of the n_ch x 2 kk^2 doubles, e.g. NCCL over NVLink: 83 KB for 64 channels)
+ *   gpfq_conv_layer_from_gram  the walks of every filter of channels c0 .. c0+n_ch-1 from such matrices (device pointer,
+ *                              GPFQ_X_DEVICE; channel i of the range at gram + i * 2 kk^2).  W / Q_out as in
+ *                              gpfq_conv_channels (GPFQ_W_DEVICE / GPFQ_Q_DEVICE say where they live).
+ */
+int gpfq_conv_gram_nhwc(gpfq_ctx *ctx, const float *act, const float *actq, int64_t n_img, int64_t H, int64_t Wd,
+                        int64_t C, int32_t kh, int32_t kw, int32_t stride_h, int32_t stride_w, int32_t rate_h,
+                        int32_t rate_w, int32_t padding_same, int64_t c0, int64_t n_channels, double *gram_out,
+                        uint32_t flags);
+int gpfq_conv_layer_from_gram(gpfq_ctx *ctx, const double *gram, int32_t kk, const float *W, int64_t C, int64_t F,
+                              int64_t c0, int64_t n_channels, const double *alphabets, const int32_t *K,
+                              int32_t n_alphabets, double *Q_out, uint32_t flags, gpfq_stats *stats);
+
 /* ---- MSQ baseline ---------------------------------------------------------------------------
  * Plain nearest-level rounding of every weight (_bit_round_parallel :40-57 applied elementwise,
  * as in quantize_pretrained_mlp.py:97-117).  n elements, contiguous. */

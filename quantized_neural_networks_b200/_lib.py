@@ -63,6 +63,11 @@ EXPORTS = {
                                      c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int64,
                                      c_int64, c_int64, POINTER(c_double), POINTER(c_int32), c_int32, c_void_p,
                                      c_uint32, POINTER(GpfqStats)]),
+    "gpfq_conv_gram_nhwc": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32, c_int32,
+                                    c_int32, c_int32, c_int32, c_int32, c_int32, c_int64, c_int64, c_void_p, c_uint32]),
+    "gpfq_conv_layer_from_gram": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_int64, c_int64, c_int64,
+                                          POINTER(c_double), POINTER(c_int32), c_int32, c_void_p, c_uint32,
+                                          POINTER(GpfqStats)]),
     "gpfq_msq": (c_int, [c_void_p, c_void_p, c_int64, POINTER(c_double), c_int32, c_void_p, c_uint32]),
     "gpfq_bit_round": (c_int, [c_void_p, c_void_p, c_int64, POINTER(c_double), c_int32, c_void_p, c_uint32]),
     "gpfq_gram_matrices": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,

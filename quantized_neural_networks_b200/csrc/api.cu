@@ -573,6 +573,14 @@ static int conv_finish(gpfq_ctx *ctx, int kk, const double *partial, int n_ch, i
         GPFQ_TRY(gpfq_ws(ctx, WS_CG, (size_t)n_ch * 2 * kk * kk * sizeof(double), (void **)&gram));
         GPFQ_TRY(conv_finalize_stage(ctx, partial, n_ch, n_chunks, kk, same, gram));
     }
+    if (ctx->gram_only_out) {
+        // gpfq_conv_gram_nhwc: the caller wants the per-channel [G1 | G2] of these images, not the walk (image split of a
+        // multi-GPU job: the matrices of all ranks are summed first)
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->gram_only_out, gram, (size_t)n_ch * 2 * kk * kk * sizeof(double),
+                                      (flags & GPFQ_Q_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(ctx, gpfq_record(ctx, 4, s));
+        return GPFQ_OK;
+    }
     const float *dW = W;
     const size_t wcount = (size_t)kk * C * F;
     if (!(flags & GPFQ_W_DEVICE)) {
@@ -986,6 +994,57 @@ extern "C" int gpfq_conv_layer_nhwc(gpfq_ctx *ctx, const float *act, const float
     const bool synced = !(flags & GPFQ_NO_SYNC);
     if (synced) CUDA_TRY(ctx, cudaStreamSynchronize(s));
     end_call(ctx, stats ? stats : &local, synced);
+    return GPFQ_OK;
+}
+
+// Gram stage of a conv layer alone (see include/gpfq.h): the same planner and kernels as gpfq_conv_layer_nhwc, stopped
+// before the walk.
+extern "C" int gpfq_conv_gram_nhwc(gpfq_ctx *ctx, const float *act, const float *actq, int64_t n_img, int64_t H, int64_t Wd,
+                                   int64_t C, int32_t kh, int32_t kw, int32_t sh, int32_t sw, int32_t rh, int32_t rw,
+                                   int32_t padding_same, int64_t c0, int64_t n_ch, double *gram_out, uint32_t flags) {
+    if (!ctx) return GPFQ_ERR_ARG;
+    if (!gram_out) return gpfq_fail(ctx, GPFQ_ERR_ARG, "NULL gram_out");
+    static const double unit[2] = {-1.0, 1.0};   // the walk never runs: any alphabet / kernel pointer will do
+    static const int32_t two = 2;
+    static const float w_dummy = 0.f;
+    ctx->gram_only_out = gram_out;
+    // W_DEVICE keeps the (unused) kernel from being copied; Q_DEVICE in `flags` says where gram_out lives
+    const int rc = gpfq_conv_layer_nhwc(ctx, act, actq, n_img, H, Wd, C, kh, kw, sh, sw, rh, rw, padding_same, &w_dummy, 1, c0, n_ch,
+                                        unit, &two, 1, gram_out, (flags | GPFQ_W_DEVICE) & ~GPFQ_NO_SYNC, nullptr);
+    ctx->gram_only_out = nullptr;
+    return rc;
+}
+
+// Walk stage of a conv layer from per-channel Gram matrices on the device (see include/gpfq.h).
+extern "C" int gpfq_conv_layer_from_gram(gpfq_ctx *ctx, const double *gram, int32_t kk, const float *W, int64_t C, int64_t F,
+                                         int64_t c0, int64_t n_ch, const double *alphabets, const int32_t *K, int32_t n_alph,
+                                         double *Q_out, uint32_t flags, gpfq_stats *stats) {
+    if (!ctx) return GPFQ_ERR_ARG;
+    ctx->err.clear();
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (!gram || !W || !Q_out) return gpfq_fail(ctx, GPFQ_ERR_ARG, "NULL gram, W or Q_out");
+    if (!(flags & GPFQ_X_DEVICE)) return gpfq_fail(ctx, GPFQ_ERR_ARG, "gram must be a device pointer (GPFQ_X_DEVICE)");
+    if (C < 1 || F < 1 || c0 < 0 || n_ch < 0 || c0 + n_ch > C) return gpfq_fail(ctx, GPFQ_ERR_ARG, "bad channel range");
+    if (!conv_supported_kk(kk)) return gpfq_fail(ctx, GPFQ_ERR_UNSUPPORTED, "kernel size kk=%d has no walk kernel", kk);
+    if (n_ch == 0) return GPFQ_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    begin_call(ctx, 2);
+    CUDA_TRY(ctx, gpfq_record(ctx, 0, s));
+    Alphabets al;
+    GPFQ_TRY(upload_alphabets(ctx, alphabets, K, n_alph, &al));
+    CUDA_TRY(ctx, gpfq_record(ctx, 5, s));
+    CUDA_TRY(ctx, gpfq_record(ctx, 2, s));
+    CUDA_TRY(ctx, gpfq_record(ctx, 3, s));
+    GPFQ_TRY(conv_finish(ctx, kk, nullptr, (int)n_ch, 0, false, W, C, F, c0, al, n_alph, Q_out, flags, const_cast<double *>(gram)));
+    CUDA_TRY(ctx, gpfq_record(ctx, 1, s));
+    gpfq_stats local = {};
+    gpfq_stats *st = stats ? stats : &local;
+    st->weights = (int64_t)kk * n_ch * F * n_alph;
+    st->method = GPFQ_METHOD_GRAM >> 4;
+    const bool synced = !(flags & GPFQ_NO_SYNC);
+    if (synced) CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    end_call(ctx, st, synced);
     return GPFQ_OK;
 }
 

@@ -354,6 +354,75 @@ class GpfqEngine:
         self.last_stats = st.as_dict()
         return out[0] if single else out
 
+    def conv_gram_nhwc(self, act, actq, kernel_size=(3, 3), strides=(1, 1), padding="SAME", rate=(1, 1), c0=0, n_channels=None):
+        """Gram stage of a conv layer alone: per-channel [G1 | G2] of channels c0..c0+n_channels-1 over the given images,
+        as a float64 CUDA tensor (n_channels, 2, kh*kw, kh*kw) (lower triangles + diagonals valid).  act / actq: NHWC
+        NumPy arrays or CUDA tensors.  The per-rank part of an image-split multi-GPU job (`conv_layer_from_gram`)."""
+        act = self._f32(act, "act")
+        same = actq is None or actq is act
+        actq = act if same else self._f32(actq, "actq")
+        dev = _is_torch(act)
+        if _is_torch(actq) != dev:
+            raise TypeError("act and actq must both be NumPy arrays or both be CUDA tensors")
+        if not dev:
+            act = np.ascontiguousarray(act)
+            actq = act if same else np.ascontiguousarray(actq)
+        elif not (act.is_contiguous() and actq.is_contiguous()):
+            raise ValueError("device tensors must be contiguous")
+        if tuple(actq.shape) != tuple(act.shape):
+            raise ValueError("act and actq must have the same shape")
+        n_img, H, Wd, C = (int(v) for v in act.shape)
+        kh, kw = (int(v) for v in kernel_size)
+        n_channels = (C - c0) if n_channels is None else int(n_channels)
+        rate = tuple(rate) if rate else (1, 1)
+        ptr = (lambda t: t.data_ptr()) if dev else (lambda t: t.ctypes.data)
+        gram = torch.zeros((n_channels, 2, kh * kw, kh * kw), dtype=torch.float64,
+                           device=act.device if dev else torch.device("cuda", self.device))
+        self._bind_stream(True)
+        flags = (_lib.X_DEVICE if dev else 0) | _lib.Q_DEVICE
+        rc = self._lib.gpfq_conv_gram_nhwc(self._ctx, c_void_p(ptr(act)), c_void_p(ptr(actq)), n_img, H, Wd, C, kh, kw,
+                                           int(strides[0]), int(strides[1]), int(rate[0]), int(rate[1]),
+                                           1 if str(padding).upper() == "SAME" else 0, int(c0), n_channels,
+                                           c_void_p(gram.data_ptr()), flags)
+        self._check(rc)
+        self.last_stats = self.query_stats(0)
+        return gram
+
+    def conv_layer_from_gram(self, gram, W, alphabets, c0=0, n_channels=None, out=None, sync=True):
+        """Walks of every filter of channels c0..c0+n_channels-1 from per-channel Gram matrices on the device
+        (`conv_gram_nhwc`, summed over the ranks of an image-split job).  W: (kh, kw, C, F) NumPy array or CUDA tensor."""
+        flat, K, n_alph, als = _alph_args(alphabets)
+        single = isinstance(alphabets, np.ndarray) and alphabets.ndim == 1
+        W = self._f32(W, "W")
+        wdev = _is_torch(W)
+        W = W.contiguous() if wdev else np.ascontiguousarray(W)
+        kh, kw, C, F = (int(v) for v in W.shape)
+        kk = kh * kw
+        n_channels = (C - c0) if n_channels is None else int(n_channels)
+        if (not _is_torch(gram) or gram.dtype != torch.float64 or not gram.is_cuda or not gram.is_contiguous()
+                or gram.numel() != n_channels * 2 * kk * kk):
+            raise TypeError(f"gram must be a contiguous float64 CUDA tensor of {n_channels} x 2 x {kk} x {kk} entries")
+        self._bind_stream(True)
+        flags = _lib.X_DEVICE
+        if wdev:
+            flags |= _lib.W_DEVICE | _lib.Q_DEVICE
+            if out is None:
+                out = torch.zeros((n_alph, kh, kw, C, F), dtype=torch.float64, device=W.device)
+            pout, pw = out.data_ptr(), W.data_ptr()
+            if not sync:
+                flags |= _lib.NO_SYNC
+        else:
+            if out is None:
+                out = np.zeros((n_alph, kh, kw, C, F), dtype=np.float64)
+            pout, pw = out.ctypes.data, W.ctypes.data
+        st = _lib.GpfqStats()
+        rc = self._lib.gpfq_conv_layer_from_gram(self._ctx, c_void_p(gram.data_ptr()), kk, c_void_p(pw), C, F, int(c0),
+                                                 n_channels, flat.ctypes.data_as(POINTER(c_double)),
+                                                 K.ctypes.data_as(POINTER(c_int32)), n_alph, c_void_p(pout), flags, byref(st))
+        self._check(rc)
+        self.last_stats = st.as_dict()
+        return out[0] if single else out
+
     def msq(self, W, alphabet):
         """Plain nearest-level rounding of every weight (the MSQ baseline of the reference's drivers)."""
         W = np.ascontiguousarray(W, dtype=np.float32)

@@ -24,7 +24,7 @@ from numpy import abs, array, linspace, log2, median, zeros
 
 from . import hostnet
 from .engine import get_engine
-from .replicate import prefer_sample_split, replicate_leading_axis, sample_split_gram, shard_range
+from .replicate import image_split_conv_gram, prefer_sample_split, replicate_leading_axis, sample_split_gram, shard_range
 
 try:  # real Keras if present, the TF-free shim otherwise (same call surface)
     from tensorflow.keras.models import Model as _KModel, clone_model as _kclone  # type: ignore
@@ -400,7 +400,15 @@ class QuantizedCNN(QuantizedNeuralNetwork):
         tic = time()
         if self.conv_path == "nhwc":
             try:
-                if self._nccl_job():
+                if self._nccl_job() and self.gram_split != "replicate":
+                    # image split: every rank contracts n_img / world images of ALL channels, one tiny all-reduce sums the
+                    # per-channel Grams, then every rank walks every channel (cheap: kk steps per filter) -- no Q gather
+                    gram = image_split_conv_gram(self.engine, data.wX, None if data.same else data.qX, W.shape[:2],
+                                                 layer.strides, layer.padding.upper(), rate, *self.shard)
+                    self.layer_stats[layer_idx] = dict(self.engine.last_stats)
+                    Q = self.engine.conv_layer_from_gram(gram, np.ascontiguousarray(W), np.asarray(alphabet, dtype=np.float64))
+                    lo, hi = 0, num_channels
+                elif self._nccl_job():
                     import torch
                     Ad, Aqd = self._replicated(data.wX, None if data.same else data.qX)
                     Wd = torch.from_numpy(np.ascontiguousarray(W)).to(Ad.device)
@@ -414,14 +422,15 @@ class QuantizedCNN(QuantizedNeuralNetwork):
             except Exception as exc:
                 self._log(f"\t\tChannels {lo}:{hi} generated an exception: {exc}")
                 raise exc
-            self.layer_stats[layer_idx] = dict(self.engine.last_stats)
+            self.layer_stats.setdefault(layer_idx, dict(self.engine.last_stats))
         else:
             Q = zeros(W.shape)
             for channel_idx in range(lo, hi):
                 Q[:, :, channel_idx, :] = self._quantize_channel_parallel_jit(
                     channel_idx, W[:, :, channel_idx, :], data, strides=layer.strides, padding=layer.padding.upper(),
                     rate=rate, alphabet=alphabet, patch_mini_batch_size=self.patch_mini_batch_size)
-        Q = self._gather_columns(Q, lo, hi, axis=2)
+        if (lo, hi) != (0, num_channels):
+            Q = self._gather_columns(Q, lo, hi, axis=2)
         self._log(f"\t\t{num_channels} channels x {W.shape[-1]} filters quantized in {time()-tic:.2f} seconds.")
         self._update_weights(layer_idx, Q)
 

@@ -91,3 +91,28 @@ def prefer_sample_split(N0: int, m: int, world: int, hbm_bytes: float = 150e9) -
     if world <= 1:
         return False
     return (8.0 * N0 * m > hbm_bytes) or (m > 2 * N0)
+
+
+def image_split_conv_gram(engine, act: np.ndarray, actq, kernel_size, strides, padding, rate, rank: int, world: int,
+                          group=None):
+    """Image-split Gram stage of a conv layer: `act`, `actq` are the (n_img, H, W, C) layer inputs every rank holds on the
+    HOST (actq None / act itself for the first layer).  Rank r hands only the images `shard_range(n_img, r, world)` to its
+    GPU (`engine.conv_gram_nhwc`: the per-channel kk x kk Grams are sums over images) and the (C, 2, kk, kk) fp64 partial
+    matrices are summed with ONE all-reduce (83 KB for 64 channels).  Returns the whole-batch Grams of ALL channels on
+    every rank: 1 / world of the activations per host link and per GPU, no replication, no other collective."""
+    import torch
+    import torch.distributed as dist
+    same = actq is None or actq is act
+    n_img = act.shape[0]
+    lo, hi = shard_range(n_img, rank, world)
+    kk = int(kernel_size[0]) * int(kernel_size[1])
+    if hi > lo:
+        gram = engine.conv_gram_nhwc(act[lo:hi], None if same else actq[lo:hi], kernel_size, strides, padding, rate)
+        if not isinstance(gram, torch.Tensor):       # an engine returning NumPy (tests)
+            gram = torch.from_numpy(np.ascontiguousarray(gram))
+    else:                                            # fewer images than ranks: contribute zeros
+        dev = None if getattr(engine, "device", None) is None else torch.device("cuda", engine.device)
+        gram = torch.zeros((act.shape[3], 2, kk, kk), dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(gram, group=group)
+    return gram

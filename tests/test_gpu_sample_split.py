@@ -119,3 +119,58 @@ def test_two_gpu_nccl_sample_split_job():
                          timeout=600, cwd=ROOT)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "MULTI_GPU_CHECK PASS" in res.stdout
+
+
+@pytest.mark.parametrize("n_img,H,Wd,C,F,pad,parts", [(6, 9, 11, 8, 3, "SAME", 3), (5, 14, 14, 64, 2, "SAME", 2),
+                                                      (7, 8, 8, 5, 2, "VALID", 4), (3, 70, 66, 3, 2, "SAME", 2)])
+def test_conv_from_image_split_grams(engine, n_img, H, Wd, C, F, pad, parts):
+    """Conv layer split over images (what the ranks of a multi-GPU job do): per-channel Grams of image chunks summed by
+    hand (= the all-reduce), walks from the sum through gpfq_conv_layer_from_gram -- against the oracle and the one-call
+    entry point; every Gram kernel the planner can pick (planes, correlation form, packed, im2col + patch Grams)."""
+    import torch
+    rng = np.random.default_rng(n_img * 17 + C)
+    act = np.maximum(rng.standard_normal((n_img, H, Wd, C)), 0).astype(np.float32)
+    actq = np.maximum(act + 0.05 * rng.standard_normal(act.shape), 0).astype(np.float32)
+    W = (rng.uniform(-1, 1, (3, 3, C, F)) * 0.3).astype(np.float32)
+    A = O.layer_alphabet(W, 3, O.unit_alphabet(3))
+    patches = lambda ch: (O.channel_patches(act, ch, (3, 3), (1, 1), pad), O.channel_patches(actq, ch, (3, 3), (1, 1), pad))
+    Qref = c_oracle.quantize_conv_layer(W, patches, A)
+    for same in (False, True):
+        gram = None
+        for r in range(parts):
+            lo, hi = (r * n_img) // parts, ((r + 1) * n_img) // parts
+            if hi == lo:
+                continue
+            if r % 2:   # host arrays in, device Grams out
+                g = engine.conv_gram_nhwc(actq[lo:hi] if same else act[lo:hi], None if same else actq[lo:hi], (3, 3), padding=pad)
+            else:       # device tensors
+                a = torch.from_numpy(np.ascontiguousarray(actq[lo:hi] if same else act[lo:hi])).cuda()
+                g = engine.conv_gram_nhwc(a, None if same else torch.from_numpy(np.ascontiguousarray(actq[lo:hi])).cuda(), (3, 3),
+                                          padding=pad)
+            assert g.is_cuda and tuple(g.shape) == (C, 2, 9, 9)
+            gram = g.clone() if gram is None else gram + g
+        Q = engine.conv_layer_from_gram(gram, W, A)
+        Q1 = engine.conv_layer_nhwc(actq if same else act, None if same else actq, W, A, padding=pad)
+        assert O.agreement(Q, Q1) >= 0.9999
+        if not same:
+            assert O.agreement(Q, Qref) >= 0.9999
+        # channel shards of the walk and device W / Q
+        Wd_ = torch.from_numpy(W).cuda()
+        out = torch.zeros((1, 3, 3, C, F), dtype=torch.float64, device="cuda")
+        cut = max(1, C // 3)
+        engine.conv_layer_from_gram(gram[:cut].contiguous(), Wd_, A, c0=0, n_channels=cut, out=out)
+        engine.conv_layer_from_gram(gram[cut:].contiguous(), Wd_, A, c0=cut, n_channels=C - cut, out=out)
+        assert np.array_equal(out[0].cpu().numpy(), Q)
+
+
+def test_golden_conv_from_gram(engine):
+    """Golden conv fixture of the unmodified reference through the Gram-only + from-Gram entry points, the Grams summed over
+    two image chunks: exact."""
+    z = golden("conv3x3_small")
+    act, actq, W = z["act"], z["actq"], z["W"]
+    half = act.shape[0] // 2
+    gram = engine.conv_gram_nhwc(act[:half], actq[:half], (3, 3)) + engine.conv_gram_nhwc(act[half:], actq[half:], (3, 3))
+    for tag in ("k16", "k3", "k4"):
+        assert np.array_equal(engine.conv_layer_from_gram(gram, W, z["A_" + tag]), z["Q_" + tag]), tag
+    g1 = engine.conv_gram_nhwc(act[:half], None, (3, 3)) + engine.conv_gram_nhwc(act[half:], None, (3, 3))
+    assert np.array_equal(engine.conv_layer_from_gram(g1, W, z["A_first"]), z["Q_first"])

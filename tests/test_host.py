@@ -242,3 +242,57 @@ def test_prefer_sample_split_rule():
     with pytest.raises(ValueError):
         QuantizedNeuralNetwork(hostnet.mnist_mlp(seed=1, widths=(6,), n_in=4, n_out=3), 1,
                                hostnet.ArraySequence(np.zeros((1, 2, 2), np.float32), np.zeros(1), 1), gram_split="rows")
+
+
+class _NumpyConvGramEngine:
+    """Test-only stand-in for GpfqEngine.conv_gram_nhwc: fp64 NumPy Grams of the oracle's patch matrices."""
+
+    device = None
+
+    def conv_gram_nhwc(self, act, actq, kernel_size=(3, 3), strides=(1, 1), padding="SAME", rate=(1, 1), c0=0, n_channels=None):
+        actq = act if actq is None else actq
+        C, kk = act.shape[3], kernel_size[0] * kernel_size[1]
+        g = np.zeros((C, 2, kk, kk))
+        for c in range(C):
+            X = O.channel_patches(act, c, tuple(kernel_size), tuple(strides), padding, tuple(rate)).astype(np.float64)
+            Xq = O.channel_patches(actq, c, tuple(kernel_size), tuple(strides), padding, tuple(rate)).astype(np.float64)
+            g[c, 0], g[c, 1] = Xq @ X.T, Xq @ Xq.T
+        return g
+
+
+def _image_split_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from quantized_neural_networks_b200.replicate import image_split_conv_gram
+        ok = True
+        rng = np.random.default_rng(17)
+        eng = _NumpyConvGramEngine()
+        for n_img, H, Wd, C, same, pad in [(5, 6, 5, 3, False, "SAME"), (2, 4, 4, 2, True, "VALID"), (1, 5, 5, 2, False, "SAME")]:
+            act = rng.standard_normal((n_img, H, Wd, C)).astype(np.float32)
+            actq = act if same else (act + 0.1 * rng.standard_normal(act.shape)).astype(np.float32)
+            g = image_split_conv_gram(eng, act, None if same else actq, (3, 3), (1, 1), pad, (1, 1), rank, world)
+            full = eng.conv_gram_nhwc(act, actq, (3, 3), (1, 1), pad, (1, 1))
+            ok = ok and np.allclose(g.numpy(), full, rtol=1e-12, atol=1e-12)
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_image_split_conv_gram_all_reduce(world):
+    """N > 1 conv layers: every rank contracts n_img / world images of all channels, one all-reduce of the per-channel
+    kk x kk Grams gives every rank the whole-batch matrices -- ragged image counts, fewer images than ranks."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_image_split_worker, args=(r, world, port, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert dict(ret) == {r: True for r in range(world)}

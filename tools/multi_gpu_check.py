@@ -17,7 +17,7 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from quantized_neural_networks_b200 import QuantizedNeuralNetwork, get_engine, hostnet  # noqa: E402
+from quantized_neural_networks_b200 import QuantizedCNN, QuantizedNeuralNetwork, get_engine, hostnet  # noqa: E402
 from quantized_neural_networks_b200.replicate import replicate_leading_axis, sample_split_gram, shard_range  # noqa: E402
 
 
@@ -65,6 +65,35 @@ def main():
     # the split really ran: the sweep-only entry point reports no Gram kernel of its own
     ok = ok and all(spl.layer_stats[i]["gram_kernel"] == 0 for i in spl.layer_dims)
     ok = ok and auto.layer_stats[1]["gram_kernel"] == 0          # 784 x 2400: m > 2 N0 -> split
+
+    # ---- a CNN: conv layers split over images (per-channel Grams + one tiny all-reduce), Dense layers as above -----------
+    xi = rng.random((320, 16, 16, 3)).astype(np.float32)
+    xi_eval = rng.random((256, 16, 16, 3)).astype(np.float32)
+
+    def run_cnn(**kw):
+        net = hostnet.cifar10_cnn(seed=5, size=16, widths=(32, 32, 64), dense=64, n_out=10)
+        q = QuantizedCNN(net, 32, hostnet.ArraySequence(xi, np.zeros(320), 32), logger=quiet, bits=2, alphabet_scalar=3,
+                         device=local, **kw)
+        q.quantize_network()
+        return q
+
+    c_one = run_cnn()
+    c_img = run_cnn(shard=(rank, world))
+    c_rep = run_cnn(shard=(rank, world), gram_split="replicate")
+    pc = c_one.quantized_net.predict(xi_eval).argmax(-1)
+    for name, q, exact in (("image split", c_img, False), ("replicate", c_rep, True)):
+        for idx, layer in enumerate(c_one.trained_net.layers):
+            if layer.__class__.__name__ not in ("Conv2D", "Dense"):
+                continue
+            a = c_one.quantized_net.layers[idx].get_weights()[0]
+            b = q.quantized_net.layers[idx].get_weights()[0]
+            agree = float(np.mean(a == b))
+            good = agree == 1.0 if exact else agree >= 0.9999
+            ok = ok and good
+            log(f"[cnn {name}] layer {idx} {layer.__class__.__name__} {a.shape}: agreement {agree:.6f} {'ok' if good else 'FAIL'}")
+        same_pred = bool(np.array_equal(pc, q.quantized_net.predict(xi_eval).argmax(-1)))
+        ok = ok and same_pred
+        log(f"[cnn {name}] predictions identical: {same_pred}")
 
     # ---- timing of the two feeds on one larger layer (host inputs, all transfers inside) -------------------
     N0, N1, m = 2048, 2048, 40000
