@@ -137,11 +137,19 @@ def run_pass_device(eng, data, outs, sync=False):
             eng.dense_layer(d["X"], d["Xq"], d["W"], d["A"], j0=d["j0"], j1=d["j1"], out=o, sync=sync)
 
 
-def run_pass_device_nhwc(eng, data, outs, sync=False):
+def run_pass_device_nhwc(eng, data, outs, sync=False, rank=0, world=1):
     """The same pass with the conv layers handed over as NHWC activation tensors (the coarser override point of
-    INTEGRATION.md: `_quantize_conv2D_layer_parallel_jit` before `_build_patch_array`), still device-resident."""
+    INTEGRATION.md: `_quantize_conv2D_layer_parallel_jit` before `_build_patch_array`), still device-resident.
+    world > 1: conv layers split over IMAGES -- every rank contracts its n_img / world images of all channels, one NCCL
+    all-reduce sums the per-channel 9 x 9 Grams (C x 162 doubles), every rank then walks every channel."""
+    import torch.distributed as dist
     for d, o in zip(data, outs):
-        if d["kind"] == "conv":
+        if d["kind"] == "conv" and world > 1:
+            lo, hi = shard_range(d["act"].shape[0], rank, world)
+            gram = eng.conv_gram_nhwc(d["act"][lo:hi], None if d["actq"] is None else d["actq"][lo:hi], (3, 3))
+            dist.all_reduce(gram)
+            eng.conv_layer_from_gram(gram, d["W"], d["A"], out=o, sync=sync)
+        elif d["kind"] == "conv":
             eng.conv_layer_nhwc(d["act"], d["actq"], d["W"], d["A"], c0=d["c0"], n_channels=d["n_ch"], out=o, sync=sync)
         else:
             eng.dense_layer(d["X"], d["Xq"], d["W"], d["A"], j0=d["j0"], j1=d["j1"], out=o, sync=sync)
@@ -177,11 +185,13 @@ def to_host_pinned(data):
 def run_pass_host(eng, host, keep=None, rank=0, world=1, dev=None):
     """One pass from HOST buffers.  world == 1: host pointers straight into the C ABI (the library overlaps its chunked
     H2D copies with the Gram kernels).  world > 1: every rank needs the whole layer input, so each copies 1/world of the
-    leading axis over its own PCIe link and ONE NCCL all-gather over NVLink completes it (replicate.py), then the
-    device-pointer entry points run on the rank's shard of channels / neurons; Q blocks go back to the host.
+    leading axis over its own PCIe link: conv layers are split over images and Dense layers with m > 2 N0 over samples
+    (the Gram matrices are sums over samples: one NCCL all-reduce of them, replicate.py), the remaining Dense layers are
+    completed by ONE all-gather over NVLink; the walks run on the rank's shard of channels / neurons.
     Returns (d2h bytes, h2d bytes that crossed this rank's host link)."""
     import torch
-    from quantized_neural_networks_b200.replicate import h2d_bytes_per_rank, replicate_leading_axis
+    from quantized_neural_networks_b200.replicate import (h2d_bytes_per_rank, image_split_conv_gram, prefer_sample_split,
+                                                            replicate_leading_axis, sample_split_gram)
     d2h = h2d = 0
     for d in host:
         conv = d["kind"] == "conv"
@@ -190,14 +200,26 @@ def run_pass_host(eng, host, keep=None, rank=0, world=1, dev=None):
             Q = (eng.conv_layer_nhwc(a, aq, d["W"], d["A"], c0=d["c0"], n_channels=d["n_ch"]) if conv
                  else eng.dense_layer(a, aq, d["W"], d["A"], j0=d["j0"], j1=d["j1"]))
             h2d += a.nbytes + (0 if aq is None else aq.nbytes) + d["W"].nbytes
+        elif conv:
+            # image split: this rank's n_img / world images of every channel over its own PCIe link, one all-reduce of the
+            # per-channel Grams, every channel walked on every rank (no replication, no Q exchange)
+            gram = image_split_conv_gram(eng, a, aq, (3, 3), (1, 1), "SAME", (1, 1), rank, world)
+            Q = eng.conv_layer_from_gram(gram, d["W"], d["A"])[:, :, d["c0"]:d["c0"] + d["n_ch"]]
+            lo, hi = shard_range(a.shape[0], rank, world)
+            h2d += (hi - lo) * int(np.prod(a.shape[1:])) * 4 * (1 if aq is None else 2) + d["W"].nbytes
+        elif prefer_sample_split(d["N0"], d["m"], world):
+            # Dense, m > 2 N0: this rank's m / world samples, all-reduce of the (N0, N0) Grams, walk of this rank's neurons
+            G1, G2 = sample_split_gram(eng, a, aq, rank, world, device=dev)
+            Q = eng.dense_layer_from_gram(G1, G2, d["W"], d["A"], j0=d["j0"], j1=d["j1"])[:, d["j0"]:d["j1"]]
+            lo, hi = shard_range(a.shape[1], rank, world)
+            h2d += d["N0"] * (hi - lo) * 4 * (1 if aq is None else 2) + d["W"].nbytes
         else:
             ad = replicate_leading_axis(a, rank, world, dev)
             aqd = None if aq is None else replicate_leading_axis(aq, rank, world, dev)
             Wd = torch.from_numpy(d["W"]).to(dev, non_blocking=True)
-            h2d += h2d_bytes_per_rank(a.shape, 4, world) * (1 if aq is None else 2) + d["W"].nbytes
-            Qd = (eng.conv_layer_nhwc(ad, aqd, Wd, d["A"], c0=d["c0"], n_channels=d["n_ch"]) if conv
-                  else eng.dense_layer(ad, aqd, Wd, d["A"], j0=d["j0"], j1=d["j1"]))
-            Q = (Qd[:, :, d["c0"]:d["c0"] + d["n_ch"]] if conv else Qd[:, d["j0"]:d["j1"]]).cpu().numpy()
+            h2d += h2d_bytes_per_rank(a.shape, 4, world) * 2 + d["W"].nbytes
+            Qd = eng.dense_layer(ad, aqd, Wd, d["A"], j0=d["j0"], j1=d["j1"])
+            Q = Qd[:, d["j0"]:d["j1"]].cpu().numpy()
             del ad, aqd, Qd
         d2h += (9 * d["n_ch"] * d["F"] if conv else d["N0"] * (d["j1"] - d["j0"])) * 8
         if keep is not None:
@@ -485,14 +507,17 @@ def main():
     if args.workload == "cifar10_cnn" and not args.no_activations_leg:
         outs2 = [torch.zeros_like(o) for o in outs]
         for _ in range(max(args.warmup, 3)):
-            run_pass_device_nhwc(eng, data, outs2)
+            run_pass_device_nhwc(eng, data, outs2, rank=rank, world=world)
         barrier()
-        agree = min(float((a == b).double().mean()) for a, b in zip(outs, outs2))
+        def _agree(a, b):   # world > 1: `outs` holds this rank's channels / neurons only, the image-split pass every channel
+            m = (a != 0) if world > 1 else torch.ones_like(a, dtype=torch.bool)
+            return float((a == b)[m].double().mean()) if bool(m.any()) else 1.0
+        agree = min(_agree(a, b) for a, b in zip(outs, outs2))
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         f0.record()
         for _ in range(args.steps):
-            run_pass_device_nhwc(eng, data, outs2)
+            run_pass_device_nhwc(eng, data, outs2, rank=rank, world=world)
         f1.record()
         barrier()
         ms2 = f0.elapsed_time(f1)
@@ -558,8 +583,9 @@ def main():
                "d2h_bytes_per_step": int(d2h_bytes), "steps": args.e2e_steps, "ms_per_step": dt / args.e2e_steps * 1e3,
                "timing": "host wall clock around synchronous C-ABI calls (copies + kernels), max over ranks",
                "api": "gpfq_conv_layer_nhwc + gpfq_dense_layer from pinned host buffers" +
-                      ("" if world == 1 else f"; per rank 1/{world} of every input over PCIe + one NCCL all-gather over NVLink "
-                                             "(h2d/d2h bytes are per rank)")}
+                      ("" if world == 1 else f"; per rank 1/{world} of every input over PCIe: conv layers split over images and Dense "
+                                             "layers with m > 2 N0 over samples (one NCCL all-reduce of the Gram matrices each), other "
+                                             "Dense layers replicated by one all-gather over NVLink (h2d/d2h bytes are per rank)")}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
