@@ -538,14 +538,32 @@ static int dense_lowrank_sweep(gpfq_ctx *ctx, const float *X, const float *Xq, i
             KERNEL_CHECK(ctx);
         }
     }
-    // block-diagonal Gram tiles, compact: Gc[t][s - tb(t)], row stride R (exact fp32 x fp32 products, fp64 sums)
-    for (int64_t tb = 0; tb < N0; tb += R) {
-        const int64_t te = tb + R < N0 ? tb + R : N0;
-        for (int which = 0; which < (same ? 1 : 2); ++which) {
+    // block-diagonal Gram tiles, compact: Gc[t][s - tb(t)], row stride R (exact fp32 x fp32 products, fp64 sums).  All full
+    // ranges go down as the batches of ONE launch per Gram (a 512 x 512 lower triangle alone is ~20 CTAs), a ragged last
+    // range as one more.
+    const int64_t nfull = N0 / R;
+    for (int which = 0; which < (same ? 1 : 2); ++which) {
+        for (int64_t b0 = 0; b0 < nfull; b0 += 65535) {
+            const int64_t nb = std::min<int64_t>(65535, nfull - b0), tb = b0 * R;
             GemmArgs g = {};
             g.seg[0] = {Xq + tb * ldx, (which ? X : Xq) + tb * ldx, ldx, ldx, m, 1.0};
             g.nseg = 1;
-            g.M = g.N = te - tb;
+            g.M = g.N = R;
+            g.C = (which ? Gc1 : Gc2) + tb * R;
+            g.ldc = R;
+            g.nsplit = 1;
+            g.lower_only = 1;
+            g.batch_strideA0 = R * ldx;
+            g.batch_strideB = R * ldx;
+            g.batch_strideC = R * R;
+            GPFQ_TRY((launch_gemm_nt<float, 128, 64, 32>(ctx, g, (int)nb)));
+        }
+        if (nfull * R < N0) {
+            const int64_t tb = nfull * R;
+            GemmArgs g = {};
+            g.seg[0] = {Xq + tb * ldx, (which ? X : Xq) + tb * ldx, ldx, ldx, m, 1.0};
+            g.nseg = 1;
+            g.M = g.N = N0 - tb;
             g.C = (which ? Gc1 : Gc2) + tb * R;
             g.ldc = R;
             g.nsplit = 1;
@@ -584,7 +602,24 @@ static int dense_lowrank_sweep(gpfq_ctx *ctx, const float *X, const float *Xq, i
                 g.nsplit = 1;
                 g.batch_strideA0 = nj * m;
                 g.batch_strideC = nj * R;
-                GPFQ_TRY((launch_gemm_nt<double, 128, 64, 16>(ctx, g, n_alph)));
+                // few neurons (one rank of a multi-GPU job): split the samples so that every SM gets a CTA; fixed-order sum
+                const int64_t tiles = ceil_div64(nj, 128) * n_alph * ceil_div64(te - tb, 64);
+                int64_t ns = tiles >= ctx->sm_count ? 1 : ctx->sm_count / tiles;
+                ns = std::min<int64_t>(std::min<int64_t>(ns, 8), std::max<int64_t>(1, m / 256));
+                if (ns > 1) {
+                    const size_t one = (size_t)n_alph * nj * R;
+                    double *Dpart = nullptr;
+                    GPFQ_TRY(gpfq_ws(ctx, WS_PART, (size_t)ns * one * sizeof(double), (void **)&Dpart));
+                    g.C = Dpart;
+                    g.nsplit = (int)ns;
+                    g.split_stride = (int64_t)one;
+                    GPFQ_TRY((launch_gemm_nt<double, 128, 64, 16>(ctx, g, n_alph)));
+                    const int blocks = (int)std::min<int64_t>(ceil_div64((int64_t)one, 256), 4096);
+                    reduce_splits_kernel<<<blocks, 256, 0, ctx->stream>>>(Dpart, (int)ns, (int64_t)one, Do, (int64_t)one);
+                    KERNEL_CHECK(ctx);
+                } else {
+                    GPFQ_TRY((launch_gemm_nt<double, 128, 64, 16>(ctx, g, n_alph)));
+                }
             }
         }
         // the compact tiles are addressed like the full matrices: column s of row t lives at Gc[t * R + (s - tb)]

@@ -33,6 +33,7 @@ struct GemmArgs {
     int64_t batch_strideA1, batch_strideC;  // blockIdx.z batches (multi-alphabet panels): seg[1].A and C
     int64_t batch_strideA0;                 // ... and seg[0].A (0: shared by the batches)
     int accumulate;                         // C += result instead of C = result (nsplit must be 1)
+    int64_t batch_strideB;                  // ... and B of both segments (0: shared): batched block-diagonal Gram tiles
 };
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src_bytes) {
@@ -131,7 +132,7 @@ gemm_nt_kernel(const GemmArgs g) {
             const int kt = (s == 0) ? it : it - ntile[0];
             const int64_t k0 = kbeg[s] + (int64_t)kt * BK;
             const T *A = reinterpret_cast<const T *>(g.seg[s].A) + batch * (s == 1 ? g.batch_strideA1 : g.batch_strideA0);
-            const T *B = reinterpret_cast<const T *>(g.seg[s].B);
+            const T *B = reinterpret_cast<const T *>(g.seg[s].B) + batch * g.batch_strideB;
             const int st = it % STAGES;
             load_tile<T, BM, BK, THREADS, ALIGNED>(As + st * BM * LD, A, g.seg[s].lda, i0, g.M, k0, kend[s]);
             load_tile<T, BN, BK, THREADS, ALIGNED>(Bs + st * BN * LD, B, g.seg[s].ldb, j0, g.N, k0, kend[s]);
@@ -206,7 +207,9 @@ static int launch_gemm_nt(gpfq_ctx *ctx, GemmArgs g, int nbatch) {
         aligned = aligned && ((uintptr_t)g.seg[s].A % 16 == 0) && ((uintptr_t)g.seg[s].B % 16 == 0) &&
                   ((g.seg[s].lda * sizeof(T)) % 16 == 0) && ((g.seg[s].ldb * sizeof(T)) % 16 == 0);
     }
-    if (nbatch > 1) aligned = aligned && ((g.batch_strideA1 * sizeof(T)) % 16 == 0) && ((g.batch_strideA0 * sizeof(T)) % 16 == 0);
+    if (nbatch > 1)
+        aligned = aligned && ((g.batch_strideA1 * sizeof(T)) % 16 == 0) && ((g.batch_strideA0 * sizeof(T)) % 16 == 0) &&
+                  ((g.batch_strideB * sizeof(T)) % 16 == 0);
     const int tiles_m = (int)ceil_div64(g.M, BM);
     g.tiles_n = (int)ceil_div64(g.N, BN);
     dim3 grid((unsigned)(tiles_m * g.tiles_n), (unsigned)g.nsplit, (unsigned)nbatch);

@@ -37,6 +37,9 @@ def main():
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--shard", default="0/1")
     ap.add_argument("--net", default="vgg16", choices=["vgg16", "cifar"], help="layer shapes: VGG16 (default) or the CIFAR10 CNN of config 2 (use --n-img 5008)")
+    ap.add_argument("--conv-split", default="images", choices=["images", "channels"],
+                    help="with --shard r/w: conv layers split over images (Gram-only call on n_img / w images of every channel + "
+                         "the walks of every channel; the all-reduce of C x 162 doubles is not emulated) or over channels")
     ap.add_argument("--skip-conv", action="store_true")
     ap.add_argument("--skip-dense", action="store_true")
     ap.add_argument("--corr-rows", type=int, default=0, help="gpfq_set_option corr_rows (0 auto, 4, 6, 8)")
@@ -85,17 +88,27 @@ def main():
             W = (torch.rand((3, 3, C, F), device=dev, generator=g) * 2 - 1) * float(np.sqrt(6.0 / (9 * C)))
             A = alph(W)
             lo, hi = shard_range(C, rank, world)
-            if hi == lo:   # fewer channels than ranks: nothing to do for this rank
+            if hi == lo and not (world > 1 and args.conv_split == "images"):   # fewer channels than ranks: nothing to do
                 del act, actq, W
                 continue
             out = torch.zeros((1, 3, 3, C, F), dtype=torch.float64, device=dev)
             best = None
+            img_split = world > 1 and args.conv_split == "images"
+            ilo, ihi = shard_range(args.n_img, rank, world)
             for _ in range(args.reps):
-                eng.conv_layer_nhwc(act, actq, W, A, c0=lo, n_channels=hi - lo, out=out, sync=True)
-                st = dict(eng.last_stats)
+                if img_split:
+                    gram = eng.conv_gram_nhwc(act[ilo:ihi], None if actq is None else actq[ilo:ihi], (3, 3))
+                    st = dict(eng.last_stats)
+                    eng.conv_layer_from_gram(gram, W, A, out=out, sync=True)
+                    st["ms_total"] += eng.last_stats["ms_total"]
+                else:
+                    eng.conv_layer_nhwc(act, actq, W, A, c0=lo, n_channels=hi - lo, out=out, sync=True)
+                    st = dict(eng.last_stats)
                 if best is None or st["ms_total"] < best["ms_total"]:
                     best = st
-            colch = args.n_img * H * H * (hi - lo)
+            if img_split:
+                lo, hi = 0, C
+            colch = (ihi - ilo if img_split else args.n_img) * H * H * (hi - lo)
             corr = best["gram_kernel"] in (4, 5)
             # patch form: 168 (84 when X == Xq) fp64-pipe slots per patch column and channel at the DMMA rate; correlation
             # form: 26 (13) DFMAs per pixel and channel at the measured DFMA rate
@@ -103,7 +116,8 @@ def main():
             pipe = DFMA_SLOTS if corr else FP64_SLOTS
             bytes_alg = colch * (4 if li == 0 else 8)
             ms = best["ms_total"]
-            print(json.dumps({"layer": f"conv{li}", "C": C, "F": F, "H": H, "channels": [lo, hi], "weights": 9 * (hi - lo) * F,
+            print(json.dumps({"layer": f"conv{li}", "C": C, "F": F, "H": H, "channels": [lo, hi],
+                              "images": [ilo, ihi] if img_split else [0, args.n_img], "weights": 9 * (hi - lo) * F,
                               "ms": round(ms, 3), "ms_gram": round(best["ms_gram"], 3),
                               "form": ("correlation, packed images" if best["gram_kernel"] == 5 else "correlation (13 DFMA / pixel / Gram)") if corr else "patch (126 MACs / column)",
                               "fp64_pipe_frac": round(slots / pipe / (best["ms_gram"] * 1e-3), 3),
