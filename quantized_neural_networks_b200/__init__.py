@@ -5,6 +5,7 @@ Host-side mirror of elybrand/quantized_neural_networks' `scripts/quantized_netwo
 a C-ABI library of hand-written sm_100a CUDA kernels (include/gpfq.h)."""
 from ._lib import GpfqError, build  # noqa: F401
 from .engine import GpfqEngine, get_engine  # noqa: F401
+from .grid import QuantizedCNNGrid, pack_levels, unpack_levels  # noqa: F401
 from .quantized_network import (  # noqa: F401
     QuantizedCNN,
     QuantizedNeuralNetwork,
@@ -13,4 +14,5 @@ from .quantized_network import (  # noqa: F401
     _quantize_neuron_parallel,
 )
 
-__all__ = ["GpfqEngine", "GpfqError", "QuantizedCNN", "QuantizedNeuralNetwork", "build", "get_engine"]
+__all__ = ["GpfqEngine", "GpfqError", "QuantizedCNN", "QuantizedCNNGrid", "QuantizedNeuralNetwork", "build", "get_engine",
+           "pack_levels", "unpack_levels"]

@@ -107,3 +107,52 @@ def test_vgg_like_full_network_matches_the_oracle_walk():
     qo = _with_oracle(QuantizedCNN, net, 16, seq, bits=np.log2(3), alphabet_scalar=3)
     qo.quantize_network()
     _compare(qg, qo, x[:32], {"Dense", "Conv2D"})
+
+
+def test_grid_runner_matches_point_by_point_runs():
+    """BASELINE config 5 (quantize_pretrained_cnn.py:32-48): the (bits x alphabet_scalar) grid walked in lock-step -- analog
+    inputs collected once per layer, the first layer's grid points in ONE multi-alphabet call -- gives every grid point the
+    weights of its own QuantizedCNN run; MSQ baselines, the CSV schema and the level-index packing of the drivers."""
+    from quantized_neural_networks_b200 import QuantizedCNNGrid, get_engine, pack_levels, unpack_levels
+    rng = np.random.default_rng(21)
+    net = hostnet.cifar10_cnn(seed=9, size=16, widths=(4, 6, 8), dense=24, n_out=5)
+    x = rng.random((96, 16, 16, 3)).astype(np.float32)
+    y = rng.integers(0, 5, 96)
+    seq = hostnet.ArraySequence(x, y, 32)
+    quiet = type("L", (), {"info": staticmethod(lambda m: None)})()
+    bits_list, scalars = [np.log2(3), 2, 4], [2, 5]
+    grid = QuantizedCNNGrid(net, 32, seq, bits_list, scalars, logger=quiet).quantize_network()
+    assert grid.grid == [(b, c) for b in bits_list for c in scalars]
+    first = grid.calls[0]
+    assert first == (first[0], len(grid.grid))               # X == Xq at the first quantized layer: one batched call
+    assert all(n == 1 for _, n in grid.calls[1:])             # deeper layers: one twin, one Xq, one call per grid point
+    for (b, c), qnet in zip(grid.grid, grid.quantized_nets):
+        single = QuantizedCNN(net, 32, seq, logger=quiet, bits=b, alphabet_scalar=c)
+        single.quantize_network()
+        for idx, layer in enumerate(net.layers):
+            if layer.__class__.__name__ in ("Dense", "Conv2D"):
+                Wg, Ws = qnet.layers[idx].get_weights()[0], single.quantized_net.layers[idx].get_weights()[0]
+                assert float(np.mean(Wg == Ws)) >= 0.9999, (b, c, idx)
+                assert not np.array_equal(Wg, layer.get_weights()[0])
+        assert np.array_equal(qnet.predict(x[:64]).argmax(-1), single.quantized_net.predict(x[:64]).argmax(-1))
+    # MSQ baselines: plain rounding to the same per-layer alphabets (quantize_pretrained_cnn.py:97-117)
+    msq = grid.msq_networks()
+    for (b, c), mnet, p in zip(grid.grid, msq, grid.points):
+        for idx, layer in enumerate(net.layers):
+            if layer.__class__.__name__ in ("Dense", "Conv2D"):
+                W = layer.get_weights()[0]
+                A = O.layer_alphabet(W, c, O.unit_alphabet(b))
+                ref = np.array([O.bit_round(w, A) for w in W.flatten()]).reshape(W.shape)   # the driver's own loop (:104-106)
+                assert np.array_equal(np.asarray(mnet.layers[idx].get_weights()[0], dtype=np.float64), ref.astype(np.float32).astype(np.float64))
+    rows = grid.metrics(x, y)
+    assert len(rows) == len(grid.grid)
+    assert list(rows[0]) == ["data_set", "serialized_model", "q_train_size", "ignore_layers", "bits", "alphabet_scalar",
+                             "analog_test_acc", "sd_test_acc", "msq_test_acc", "quantization_time"]
+    assert all(0.0 <= r["sd_test_acc"] <= 1.0 and r["q_train_size"] == 96 for r in rows)
+    # int8 level indices + alphabet: the storage format of a quantized kernel
+    p = grid.points[-1]
+    idx_last = [i for i, l in enumerate(net.layers) if l.__class__.__name__ == "Dense"][0]
+    W = net.layers[idx_last].get_weights()[0]
+    Q = get_engine(0).dense_layer(x[:64].reshape(64, -1)[:, :W.shape[0]].T.copy(), None, W, np.asarray(p._layer_alphabet(W), dtype=np.float64))
+    lev, A = pack_levels(Q, p._layer_alphabet(W))
+    assert lev.dtype == np.int8 and np.array_equal(unpack_levels(lev, A), Q)

@@ -296,3 +296,22 @@ def test_gloo_image_split_conv_gram_all_reduce(world):
         p.join(120)
         assert p.exitcode == 0
     assert dict(ret) == {r: True for r in range(world)}
+
+
+def test_grid_runner_host_logic_and_level_packing():
+    """Grid enumeration in the driver's order, grouping of grid points with identical quantized inputs, int8 level packing."""
+    from quantized_neural_networks_b200 import QuantizedCNNGrid, pack_levels, unpack_levels
+    net = hostnet.cifar10_cnn(seed=2, size=8, widths=(2, 3, 4), dense=5, n_out=3)
+    seq = hostnet.ArraySequence(np.zeros((4, 8, 8, 3), np.float32), np.zeros(4), 2)
+    g = QuantizedCNNGrid(net, 2, seq, [np.log2(3), 2, 3, 4], [2, 3, 4, 5, 6])
+    assert len(g.grid) == 20 and g.grid[0] == (np.log2(3), 2) and g.grid[1] == (np.log2(3), 3) and g.grid[-1] == (4, 6)
+    assert [len(p.alphabet) for p in g.points][::5] == [3, 4, 8, 16] and g.q_train_size == 4
+    a = np.arange(6, dtype=np.float32).reshape(2, 3)
+    groups = g._groups([a, a.copy(), a + 1, a + 1, a], a)
+    assert [(q is None, m) for q, m in groups] == [(True, [0, 1, 4]), (False, [2, 3])]
+    A = 0.3 * np.linspace(-1, 1, 4)
+    Q = np.array([[A[0], A[3], 0.0], [A[2], A[1], A[1]]])
+    lev, A2 = pack_levels(Q, A)
+    assert lev.tolist() == [[0, 3, -1], [2, 1, 1]] and np.array_equal(unpack_levels(lev, A2), Q)
+    with pytest.raises(ValueError):
+        pack_levels(np.array([0.123]), A)
