@@ -164,3 +164,12 @@ class QuantizedCNNGrid:
         df = pd.DataFrame(self.metrics(x_test, y_test))
         df.to_csv(path)
         return df
+
+
+def top_k_accuracy(pred: np.ndarray, labels: np.ndarray, k: int = 1) -> float:
+    """Top-k accuracy of class scores `pred` (n, classes) against integer or one-hot labels -- the top-1 / top-5 figures
+    of quantize_pretrained_imagenet.py:203-226."""
+    labels = np.asarray(labels)
+    lab = labels.argmax(-1) if labels.ndim > 1 else labels.astype(int)
+    top = np.argpartition(-np.asarray(pred), min(k, pred.shape[1]) - 1, axis=1)[:, :k]
+    return float(np.mean((top == lab[:, None]).any(axis=1)))
