@@ -263,18 +263,22 @@ conv_corr9_tma_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_con
 // gram: (n_channels, 2 * 81): [G1 | G2], lower triangle + diagonal valid, zeros above (conv_finalize_kernel's layout).
 // partial: records of the launch over rows 1 .. H-2 (left column, interior, right column); rpartial: records of the
 // top / bottom row launch (even slots: top-left corner, top row, top-right corner; odd slots: the bottom ones).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 conv_corr9_assemble_kernel(const double *__restrict__ partial, int slots, const double *__restrict__ rpartial, int rslots,
                            int same, int n_ch, int G, double *__restrict__ gram) {
     using namespace corr9;
     // S[pass][row class: 0 top, 1 between, 2 bottom][column class: 0 first, 1 between, 2 last][13]
+    constexpr int NV = 2 * 9 * ND, NP = 4;            // values per channel; slot partitions (one quarter of the CTA each)
     __shared__ double S[2][3][3][ND];
+    __shared__ double P[NP][NV];
     const int ch = blockIdx.x, tid = threadIdx.x;
-    for (int e = tid; e < 2 * 9 * ND; e += blockDim.x) {
+    const int e = tid % 256, part = tid / 256;        // 1024 threads: value e (< 234) x partition `part`
+    if (e < NV) {
         const int d = e % ND, cc = (e / ND) % 3, rc = (e / (3 * ND)) % 3, pass = e / (9 * ND);
         const int off = (pass * 3 + cc) * ND + d;
-        // slots in index order, dealt round-robin to four partial sums (independent loads in flight), combined in order;
-        // packed layers: the G virtual channels g * n_ch + ch of this channel, g in index order
+        // The records of a value are summed in a FIXED order whatever the launch geometry: slots in index order dealt
+        // round-robin to 16 chains (4 partitions x 4 interleaved sums, independent loads in flight), chains combined in
+        // index order; packed layers: the G virtual channels g * n_ch + ch of this channel, g in index order.
         const int n = rc == 1 ? slots : (rslots - (rc == 0 ? 0 : 1) + 1) / 2;
         const size_t stride = rc == 1 ? REC : 2 * REC;
         double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
@@ -282,21 +286,30 @@ conv_corr9_assemble_kernel(const double *__restrict__ partial, int slots, const 
             const size_t vch = (size_t)g * n_ch + ch;
             const double *src = rc == 1 ? partial + vch * slots * REC + off
                                         : rpartial + (vch * rslots + (rc == 0 ? 0 : 1)) * REC + off;
-            int s = 0;
+            int s = part * 4;
 #pragma unroll 2
-            for (; s + 4 <= n; s += 4) {
+            for (; s + 4 <= n; s += 4 * NP) {
                 t0 += src[(size_t)s * stride];
                 t1 += src[(size_t)(s + 1) * stride];
                 t2 += src[(size_t)(s + 2) * stride];
                 t3 += src[(size_t)(s + 3) * stride];
             }
-            for (; s < n; ++s) t0 += src[(size_t)s * stride];
+            if (s < n) {   // the ragged last group of four belongs to exactly one partition
+                t0 += src[(size_t)s * stride];
+                if (s + 1 < n) t1 += src[(size_t)(s + 1) * stride];
+                if (s + 2 < n) t2 += src[(size_t)(s + 2) * stride];
+            }
         }
-        S[pass][rc][cc][d] = (t0 + t1) + (t2 + t3);
+        P[part][e] = (t0 + t1) + (t2 + t3);
     }
     __syncthreads();
-    for (int e = tid; e < 162; e += blockDim.x) {
-        const int which = e / 81, t = (e % 81) / 9, s = e % 9;
+    if (tid < NV) {
+        const int d = tid % ND, cc = (tid / ND) % 3, rc = (tid / (3 * ND)) % 3, pass = tid / (9 * ND);
+        S[pass][rc][cc][d] = (P[0][tid] + P[1][tid]) + (P[2][tid] + P[3][tid]);
+    }
+    __syncthreads();
+    for (int e2 = tid; e2 < 162; e2 += blockDim.x) {
+        const int which = e2 / 81, t = (e2 % 81) / 9, s = e2 % 9;
         double v = 0.0;
         if (s <= t) {
             const int ar = t / 3, ac = t % 3, dy = s / 3 - ar, dx = s % 3 - ac;
@@ -307,7 +320,7 @@ conv_corr9_assemble_kernel(const double *__restrict__ partial, int slots, const 
             for (int rc = r_lo; rc <= r_hi; ++rc)
                 for (int cc = c_lo; cc <= c_hi; ++cc) v += S[pass][rc][cc][id];
         }
-        gram[(size_t)ch * 162 + e] = v;
+        gram[(size_t)ch * 162 + e2] = v;
     }
 }
 
@@ -516,7 +529,7 @@ int conv_corr9_stage(gpfq_ctx *ctx, const float *act, const float *actq, bool sa
 // n_ch real channels; G > 1: the records belong to G * n_ch virtual channels of a packed tensor
 int conv_corr9_assemble_stage(gpfq_ctx *ctx, const double *partial, int slots, const double *rpartial, int rslots,
                               bool same, int n_ch, int G, double *gram) {
-    conv_corr9_assemble_kernel<<<(unsigned)n_ch, 256, 0, ctx->stream>>>(partial, slots, rpartial, rslots, same ? 1 : 0, n_ch, G, gram);
+    conv_corr9_assemble_kernel<<<(unsigned)n_ch, 1024, 0, ctx->stream>>>(partial, slots, rpartial, rslots, same ? 1 : 0, n_ch, G, gram);
     KERNEL_CHECK(ctx);
     return GPFQ_OK;
 }
