@@ -129,28 +129,12 @@ def build_device_inputs(layers, n_img, rank, world, dev):
     return out
 
 
-def dense_device(eng, d, o, sync, rank, world):
-    """One Dense layer from device-resident inputs.  world > 1 and m > 2 N0: the Gram stage split over samples -- this rank's
-    m / world columns of X, X~ on tcgen05, one NCCL all-reduce per (N0, N0) Gram matrix, the walks of this rank's neurons."""
-    from quantized_neural_networks_b200.replicate import prefer_sample_split
-    if world > 1 and prefer_sample_split(d["N0"], d["m"], world):
-        import torch.distributed as dist
-        lo, hi = shard_range(d["m"], rank, world)
-        G1, G2 = eng.gram_matrices(d["X"][:, lo:hi], None if d["Xq"] is None else d["Xq"][:, lo:hi], sync=False)
-        dist.all_reduce(G2)
-        if G1 is not G2:
-            dist.all_reduce(G1)
-        eng.dense_layer_from_gram(G1, G2, d["W"], d["A"], j0=d["j0"], j1=d["j1"], out=o, sync=sync)
-    else:
-        eng.dense_layer(d["X"], d["Xq"], d["W"], d["A"], j0=d["j0"], j1=d["j1"], out=o, sync=sync)
-
-
-def run_pass_device(eng, data, outs, sync=False, rank=0, world=1):
+def run_pass_device(eng, data, outs, sync=False):
     for d, o in zip(data, outs):
         if d["kind"] == "conv":
             eng.conv_channels(d["Xp"], d["Xqp"], d["W"], d["A"], c0=d["c0"], n_channels=d["n_ch"], out=o, sync=sync)
         else:
-            dense_device(eng, d, o, sync, rank, world)
+            eng.dense_layer(d["X"], d["Xq"], d["W"], d["A"], j0=d["j0"], j1=d["j1"], out=o, sync=sync)
 
 
 def run_pass_device_nhwc(eng, data, outs, sync=False, rank=0, world=1):
@@ -168,7 +152,7 @@ def run_pass_device_nhwc(eng, data, outs, sync=False, rank=0, world=1):
         elif d["kind"] == "conv":
             eng.conv_layer_nhwc(d["act"], d["actq"], d["W"], d["A"], c0=d["c0"], n_channels=d["n_ch"], out=o, sync=sync)
         else:
-            dense_device(eng, d, o, sync, rank, world)
+            eng.dense_layer(d["X"], d["Xq"], d["W"], d["A"], j0=d["j0"], j1=d["j1"], out=o, sync=sync)
 
 
 def to_host_pinned(data):
@@ -387,8 +371,7 @@ def main():
     config = {"workload": f"{args.workload}: " + ("CIFAR10 CNN 6x Conv2D 3x3 (per-channel patch matrices 9 x n_patches) + Dense 2048->128->10"
                                                     if args.workload == "cifar10_cnn" else "MNIST MLP 784-500-300-10"),
               "samples": n_img, "alphabet": f"bits={BITS} (K=16), alphabet_scalar={CSCALAR}" if args.workload == "cifar10_cnn"
-              else "ternary", "weights_per_step": total_weights, "sharding": f"conv channels / dense neurons over {world} rank(s)" + ("" if world == 1 else
-              "; Dense Gram stages with m > 2 N0 split over samples + NCCL all-reduce; from_activations / e2e legs: conv layers split over images"),
+              else "ternary", "weights_per_step": total_weights, "sharding": f"conv channels / dense neurons over {world} rank(s)",
               "l2": "inputs (>= 25 GB per pass) exceed L2; no flush needed"}
 
     import torch
@@ -446,14 +429,14 @@ def main():
         barrier()
         return
     for _ in range(max(args.warmup, 3)):
-        run_pass_device(eng, data, outs, rank=rank, world=world)
+        run_pass_device(eng, data, outs)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
         barrier()
         e0.record()
         for _ in range(args.steps):
-            run_pass_device(eng, data, outs, rank=rank, world=world)
+            run_pass_device(eng, data, outs)
         e1.record()
         barrier()
     ms = e0.elapsed_time(e1)
