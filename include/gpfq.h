@@ -90,7 +90,6 @@ int gpfq_set_stream(gpfq_ctx *ctx, void *cuda_stream);
  *   "corr_pack"    correlation form, images packed side by side as virtual channels: 0 when the channel count cannot be
  *                  mapped (C < 32 or C % 4 != 0) and the images are large, 1 always, 2 never
  *   "corr_small"   1: correlation form also on images below 128 pixels (default: the planes kernel is faster there)
- *   "corr_quad"    correlation form: 0 the four warps of a CTA share one 128-channel TMA box when C >= 128, 2 one 32-channel box per warp
  *   "corr_rows"    correlation form: image rows per band (0 auto by image height, or 4 / 6 / 8)
  *   "sweep_kernel"  0 persistent tile, 1 per block
  *   "sweep_outer"  0 auto, 1 Gram rows of all earlier directions, 2 carried residuals (3 m N0 N1 MACs: wins when m << N0) */

@@ -29,7 +29,7 @@ int msq_stage(gpfq_ctx *, const void *, int, int64_t, const double *, int, int, 
 int nhwc9_plan(int, int, int, int, int, int, int, int, int *, int *);
 int corr9_plan(int, int, int, int, int, int, int, int, int, int);
 int corr9_pack_stage(gpfq_ctx *, const float *, int64_t, int, int, int64_t, int64_t, int, int, int64_t, int64_t, float *);
-int corr9_pick_slots(gpfq_ctx *, int, bool, int64_t, int64_t, int, int64_t);
+int corr9_pick_slots(gpfq_ctx *, int, bool, int64_t, int, int64_t);
 int corr9_tensor_ok(const float *, const float *);
 int conv_corr9_stage(gpfq_ctx *, const float *, const float *, bool, int64_t, int64_t, int64_t, int, int, int64_t, int64_t, int,
                      int, double *, int, int, int, double *, int, int, int);
@@ -182,9 +182,6 @@ extern "C" int gpfq_set_option(gpfq_ctx *ctx, const char *key, int64_t value) {
     } else if (!strcmp(key, "corr_pack")) {   // correlation form, image packing: 0 auto, 1 always (tests), 2 never
         if (value < 0 || value > 2) return gpfq_fail(ctx, GPFQ_ERR_ARG, "corr_pack must be 0, 1 or 2");
         ctx->corr_pack = (int)value;
-    } else if (!strcmp(key, "corr_quad")) {    // correlation form: 0 four channel groups per CTA when C >= 128, 2 never
-        if (value != 0 && value != 2) return gpfq_fail(ctx, GPFQ_ERR_ARG, "corr_quad must be 0 or 2");
-        ctx->corr_quad = (int)value;
     } else if (!strcmp(key, "corr_small")) {   // correlation form also on images below 128 pixels (tests)
         ctx->corr_direct_small = value != 0;
     } else if (!strcmp(key, "corr_rows")) {   // correlation form: rows per band (0 auto, 4, 6 or 8)
@@ -829,8 +826,8 @@ extern "C" int gpfq_conv_layer_nhwc(gpfq_ctx *ctx, const float *act, const float
         const int64_t units_per_chunk = pack ? cipc / corr_G : cipc;      // tensor "images" per chunk
         const int64_t units_total = pack ? ceil_div64(n_img, corr_G) : n_img;
         const int nbands = (int)ceil_div64(H - 2, corr_rb);                        // rows 1 .. H-2 in bands
-        const int per_ic = corr9_pick_slots(ctx, corr_rb, same, VC, vc0, vch, units_per_chunk * nbands);
-        const int bper_ic = corr9_pick_slots(ctx, 1, same, VC, vc0, vch, 2 * units_per_chunk);   // top and bottom row of every image
+        const int per_ic = corr9_pick_slots(ctx, corr_rb, same, vc0, vch, units_per_chunk * nbands);
+        const int bper_ic = corr9_pick_slots(ctx, 1, same, vc0, vch, 2 * units_per_chunk);   // top and bottom row of every image
         const int slots = cn_ic * per_ic, bslots = cn_ic * bper_ic;
         double *partial = nullptr, *bpartial = nullptr, *gram = nullptr;
         float *pkA = nullptr, *pkQ = nullptr;

@@ -56,7 +56,6 @@ struct gpfq_ctx {
                                   // 3 NHWC entry point: shared-memory planes kernel instead of the correlation form
     int corr_pack = 0;            // correlation form, images packed as virtual channels: 0 by shape, 1 always (tests), 2 never
     bool corr_direct_small = false;  // correlation form also on images below 128 pixels (tests)
-    int corr_quad = 0;            // correlation form: 0 one 128-channel box per CTA when C >= 128, 2 always 32-channel boxes per warp
     int corr_rb = 0;              // correlation-form conv Grams: rows per band (0: chosen per image height)
     int sweep_variant = 0;        // triangular sweep: 0 persistent neuron-tile kernel (default), 1 one launch pair per block
     bool stream_literal = false;  // streaming walk: reproduce the reference's fp32-rounded w*X products (set per call)

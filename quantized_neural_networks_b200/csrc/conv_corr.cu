@@ -88,39 +88,28 @@ struct Ring {
 };
 }  // namespace corr9
 
-// QUAD = false: the four warps of a CTA walk four different (image, band) streams of ONE 32-channel group, each with its own
-// ring.  QUAD = true (layers with >= 128 channels): the four warps walk the SAME stream for four ADJACENT channel groups;
-// thread 0 fetches one box of 128 channels (512 contiguous bytes per pixel instead of four 128-byte pieces requested at
-// unrelated times: the DRAM pages of a pixel are opened once) into a ring the whole CTA shares.
-template <int RB, bool CROSS, bool QUAD>
+template <int RB, bool CROSS>
 __global__ void __launch_bounds__(corr9::WARPS * 32, RB <= 6 ? 3 : 2)
 conv_corr9_tma_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapA, Corr9Geom gm,
                       double *__restrict__ partial, int slot_stride, int slot0) {
     using namespace corr9;
     using R = Ring<RB, CROSS>;
     constexpr int NS = R::NS;
-    constexpr int CW = QUAD ? 4 : 1;                       // channel groups per box
-    constexpr int STAGE = R::STAGE_FLOATS * CW, BOX_B = R::B_FLOATS * CW, PITCH = 32 * CW;
     extern __shared__ __align__(128) unsigned char corr9_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int slot = QUAD ? (int)blockIdx.x : (int)blockIdx.x * WARPS + warp;
+    const int slot = blockIdx.x * WARPS + warp;
     // a box must start on a 16-byte boundary: channel groups start at c_first rounded down to a multiple of four
-    const int c0 = (int)(gm.c_first & ~(int64_t)3) + (int)blockIdx.y * PITCH;
-    const int chl = c0 + (QUAD ? warp * 32 : 0) + lane - (int)gm.c_first;  // channel index inside this launch's range
+    const int c0 = (int)(gm.c_first & ~(int64_t)3) + (int)blockIdx.y * 32;
+    const int chl = c0 + lane - (int)gm.c_first;  // channel index inside this launch's range
     const bool chok = chl >= 0 && chl < gm.n_ch;
-    const bool producer = QUAD ? threadIdx.x == 0 : lane == 0;
-    float *ring = reinterpret_cast<float *>(corr9_smem + (QUAD ? 0 : warp * R::WARP_BYTES));
-    uint64_t *bars = reinterpret_cast<uint64_t *>(corr9_smem + WARPS * R::WARP_BYTES) + (QUAD ? 0 : warp * NS);
-    auto sync = [&]() {
-        if (QUAD) __syncthreads();
-        else __syncwarp();
-    };
-    if (producer) {
+    float *ring = reinterpret_cast<float *>(corr9_smem + warp * R::WARP_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(corr9_smem + WARPS * R::WARP_BYTES) + warp * NS;
+    if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < NS; ++s) mbar_init(&bars[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    sync();
+    __syncwarp();
     const int W = gm.W;
     const int nrows = gm.y_last - gm.y_first + 1;
     const int nbands = gm.two_rows ? 1 : (nrows + RB - 1) / RB;
@@ -148,13 +137,13 @@ conv_corr9_tma_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_con
     uint32_t ppos = 0;
     auto produce = [&]() {
         if (ptask < ntasks) {
-            if (producer) {
+            if (lane == 0) {
                 const int py0 = gm.two_rows ? row_fixed : gm.y_first + pband * RB;
                 const int s = (int)(ppos % NS);
-                float *dst = ring + s * STAGE;
-                mbar_expect_tx(&bars[s], (uint32_t)(STAGE * sizeof(float)));
+                float *dst = ring + s * R::STAGE_FLOATS;
+                mbar_expect_tx(&bars[s], (uint32_t)(R::STAGE_FLOATS * sizeof(float)));
                 tma_load_4d(dst, &mapB, &bars[s], c0, pk * WC, py0 - 2, pimg);
-                if (CROSS) tma_load_4d(dst + BOX_B, &mapA, &bars[s], c0, pk * WC - 2, py0, pimg);
+                if (CROSS) tma_load_4d(dst + R::B_FLOATS, &mapA, &bars[s], c0, pk * WC - 2, py0, pimg);
             }
             ++ppos;
             if (++pk == nstages) {
@@ -186,22 +175,22 @@ conv_corr9_tma_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_con
 #pragma unroll
             for (int c = 0; c < 5; ++c) win[r][c] = 0.0;
         for (int k = 0; k < nstages; ++k) {
-            sync();  // the box consumed in the previous iteration is free again
+            __syncwarp();  // the box consumed in the previous iteration is free again
             produce();
             const uint32_t pos = it + k;
             const int s = (int)(pos % NS);
             mbar_wait(&bars[s], (pos / NS) & 1u);
-            const float *tb = ring + s * STAGE + (QUAD ? warp * 32 : 0) + lane;
-            const float *ta = tb + BOX_B;
+            const float *tb = ring + s * R::STAGE_FLOATS + lane;
+            const float *ta = tb + R::B_FLOATS;
             if (allrows && k >= 1 && k * WC + WC - 1 <= W) {
                 // ---- five pixel columns strictly between the first and the last one, every row live: branch-free
 #pragma unroll
                 for (int ph = 0; ph < WC; ++ph) {
 #pragma unroll
-                    for (int r = 0; r < RB + 2; ++r) win[r][ph] = (double)tb[(r * WC + ph) * PITCH];
+                    for (int r = 0; r < RB + 2; ++r) win[r][ph] = (double)tb[(r * WC + ph) * 32];
                     if (CROSS) {
 #pragma unroll
-                        for (int i = 0; i < RB; ++i) ac[i] = (double)ta[(i * WC + ph) * PITCH];
+                        for (int i = 0; i < RB; ++i) ac[i] = (double)ta[(i * WC + ph) * 32];
                     }
 #pragma unroll
                     for (int i = 0; i < RB; ++i) {
@@ -223,10 +212,10 @@ conv_corr9_tma_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_con
                     const int cx = k * WC + ph;  // newest window column (image column cx) lives in physical slot ph
                     if (cx < W + 2) {
 #pragma unroll
-                        for (int r = 0; r < RB + 2; ++r) win[r][ph] = (double)tb[(r * WC + ph) * PITCH];
+                        for (int r = 0; r < RB + 2; ++r) win[r][ph] = (double)tb[(r * WC + ph) * 32];
                         if (CROSS) {
 #pragma unroll
-                            for (int i = 0; i < RB; ++i) ac[i] = (double)ta[(i * WC + ph) * PITCH];
+                            for (int i = 0; i < RB; ++i) ac[i] = (double)ta[(i * WC + ph) * 32];
                         }
                         if (cx >= 2) {
                             // pixel column cx - 2 = logical window column 2 = physical slot (ph + 3) % 5
@@ -424,42 +413,30 @@ int corr9_pack_stage(gpfq_ctx *ctx, const float *act, int64_t n_img, int H, int 
     return GPFQ_OK;
 }
 
-// Four adjacent channel groups per CTA (QUAD) when the call has them and a 128-channel box fits in the tensor.
-static bool corr9_quad(int64_t C, int64_t c_first, int n_ch) { return C >= 128 && ceil_div64(n_ch + (c_first & 3), 32) >= 4; }
-static bool corr9_quad_enabled(gpfq_ctx *ctx, int64_t C, int64_t c_first, int n_ch) { return ctx->corr_quad != 2 && corr9_quad(C, c_first, n_ch); }
-
-template <int RB, bool QUAD>
+template <int RB>
 static int corr9_resident_ctas(bool same) {
     using namespace corr9;
     int a = 0, b = 0;
-    cudaFuncSetAttribute(conv_corr9_tma_kernel<RB, false, QUAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Ring<RB, false>::SMEM);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, conv_corr9_tma_kernel<RB, false, QUAD>, WARPS * 32, Ring<RB, false>::SMEM);
+    cudaFuncSetAttribute(conv_corr9_tma_kernel<RB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Ring<RB, false>::SMEM);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, conv_corr9_tma_kernel<RB, false>, WARPS * 32, Ring<RB, false>::SMEM);
     if (same) return a > 0 ? a : 1;
-    cudaFuncSetAttribute(conv_corr9_tma_kernel<RB, true, QUAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Ring<RB, true>::SMEM);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, conv_corr9_tma_kernel<RB, true, QUAD>, WARPS * 32, Ring<RB, true>::SMEM);
+    cudaFuncSetAttribute(conv_corr9_tma_kernel<RB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Ring<RB, true>::SMEM);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, conv_corr9_tma_kernel<RB, true>, WARPS * 32, Ring<RB, true>::SMEM);
     a = a < b ? a : b;
     return a > 0 ? a : 1;
 }
 
-// Slots (task streams per channel group / quad = records per channel) that fill every SM with as many CTAs as stay resident.
-// Always a multiple of four (the two-row launch pairs slots; non-QUAD CTAs carry four).
-int corr9_pick_slots(gpfq_ctx *ctx, int RB, bool same, int64_t C, int64_t c_first, int n_ch, int64_t ntasks) {
+// Slots (warps per channel group) that fill every SM with as many CTAs of four warps as stay resident.
+int corr9_pick_slots(gpfq_ctx *ctx, int RB, bool same, int64_t c_first, int n_ch, int64_t ntasks) {
     using namespace corr9;
-    static int occ[2][2][9] = {};
+    static int occ[2][9] = {};
     if (RB < 1 || RB > 8) return WARPS;
-    const bool quad = corr9_quad_enabled(ctx, C, c_first, n_ch);
-    int &o = occ[quad][same][RB];
-    if (!o) {
-        if (quad) o = RB == 8 ? corr9_resident_ctas<8, true>(same) : RB == 6 ? corr9_resident_ctas<6, true>(same)
-                    : RB == 4 ? corr9_resident_ctas<4, true>(same) : corr9_resident_ctas<1, true>(same);
-        else o = RB == 8 ? corr9_resident_ctas<8, false>(same) : RB == 6 ? corr9_resident_ctas<6, false>(same)
-                 : RB == 4 ? corr9_resident_ctas<4, false>(same) : corr9_resident_ctas<1, false>(same);
-    }
+    if (!occ[same][RB])
+        occ[same][RB] = RB == 8 ? corr9_resident_ctas<8>(same) : RB == 6 ? corr9_resident_ctas<6>(same)
+                       : RB == 4 ? corr9_resident_ctas<4>(same) : corr9_resident_ctas<1>(same);
     cudaGetLastError();
     const int64_t groups = ceil_div64(n_ch + (c_first & 3), 32);
-    // streams per group: QUAD -> one per CTA and quad of groups; else four per CTA and group
-    int64_t per = quad ? ceil_div64((int64_t)ctx->sm_count * o, ceil_div64(groups, 4))
-                       : ceil_div64((int64_t)ctx->sm_count * o * WARPS, groups);
+    int64_t per = ceil_div64((int64_t)ctx->sm_count * occ[same][RB] * WARPS, groups);
     per = std::min<int64_t>(per, std::max<int64_t>(1, ntasks));
     return (int)(ceil_div64(per, WARPS) * WARPS);
 }
@@ -485,52 +462,42 @@ int corr9_tensor_ok(const float *act, const float *actq) {
 }
 
 // (C, W, H, N) fp32 tensor map with a 32-channel x 5-column x `rows`-row box
-static bool corr9_make_map(CUtensorMap *map, const float *act, int64_t n_img_total, int H, int W, int64_t C, int rows, int box_ch) {
+static bool corr9_make_map(CUtensorMap *map, const float *act, int64_t n_img_total, int H, int W, int64_t C, int rows) {
     Corr9EncodeFn enc = corr9_encode_fn();
     if (!enc) return false;
     const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img_total};
     const cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};  // bytes, dims 1..3
-    const cuuint32_t box[4] = {(cuuint32_t)box_ch, (cuuint32_t)corr9::WC, (cuuint32_t)rows, 1u};
+    const cuuint32_t box[4] = {32u, (cuuint32_t)corr9::WC, (cuuint32_t)rows, 1u};
     const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(act), dims, strides, box, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int RB, bool QUAD>
-static int launch_corr9_variant(gpfq_ctx *ctx, const float *actq, const float *actx, bool same, const Corr9Geom &gm, int64_t C,
-                                int64_t n_img_total, double *partial, int slot_stride, int slot0) {
-    using namespace corr9;
-    cudaStream_t st = ctx->stream;
-    const int64_t groups = ceil_div64(gm.n_ch + (gm.c_first & 3), 32);
-    dim3 grid(QUAD ? (unsigned)gm.slots : (unsigned)(gm.slots / WARPS), QUAD ? (unsigned)ceil_div64(groups, 4) : (unsigned)groups);
-    const int box_ch = QUAD ? 128 : 32;
-    CUtensorMap mq_win, mq_ctr, mx_win;
-    bool ok = corr9_make_map(&mq_win, actq, n_img_total, gm.H, gm.W, C, RB + 2, box_ch);
-    if (ok && !same)
-        ok = corr9_make_map(&mq_ctr, actq, n_img_total, gm.H, gm.W, C, RB, box_ch) &&
-             corr9_make_map(&mx_win, actx, n_img_total, gm.H, gm.W, C, RB + 2, box_ch);
-    if (!ok) return gpfq_fail(ctx, GPFQ_ERR_CUDA, "cuTensorMapEncodeTiled failed for the (%lld, %d, %d, %lld) activations",
-                              (long long)n_img_total, gm.H, gm.W, (long long)C);
-    CUDA_TRY(ctx, cudaFuncSetAttribute(conv_corr9_tma_kernel<RB, false, QUAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)Ring<RB, false>::SMEM));
-    conv_corr9_tma_kernel<RB, false, QUAD><<<grid, WARPS * 32, Ring<RB, false>::SMEM, st>>>(mq_win, mq_win, gm, partial, slot_stride, slot0);
-    KERNEL_CHECK(ctx);
-    if (!same) {
-        CUDA_TRY(ctx, cudaFuncSetAttribute(conv_corr9_tma_kernel<RB, true, QUAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)Ring<RB, true>::SMEM));
-        conv_corr9_tma_kernel<RB, true, QUAD><<<grid, WARPS * 32, Ring<RB, true>::SMEM, st>>>(mx_win, mq_ctr, gm, partial, slot_stride, slot0);
-        KERNEL_CHECK(ctx);
-    }
-    return GPFQ_OK;
-}
-
 template <int RB>
 static int launch_corr9(gpfq_ctx *ctx, const float *actq, const float *actx, bool same, const Corr9Geom &gm, int64_t C,
                         int64_t n_img_total, double *partial, int slot_stride, int slot0) {
-    if (corr9_quad_enabled(ctx, C, gm.c_first, gm.n_ch))
-        return launch_corr9_variant<RB, true>(ctx, actq, actx, same, gm, C, n_img_total, partial, slot_stride, slot0);
-    return launch_corr9_variant<RB, false>(ctx, actq, actx, same, gm, C, n_img_total, partial, slot_stride, slot0);
+    using namespace corr9;
+    cudaStream_t st = ctx->stream;
+    dim3 grid((unsigned)(gm.slots / WARPS), (unsigned)ceil_div64(gm.n_ch + (gm.c_first & 3), 32));
+    CUtensorMap mq_win, mq_ctr, mx_win;
+    bool ok = corr9_make_map(&mq_win, actq, n_img_total, gm.H, gm.W, C, RB + 2);
+    if (ok && !same)
+        ok = corr9_make_map(&mq_ctr, actq, n_img_total, gm.H, gm.W, C, RB) &&
+             corr9_make_map(&mx_win, actx, n_img_total, gm.H, gm.W, C, RB + 2);
+    if (!ok) return gpfq_fail(ctx, GPFQ_ERR_CUDA, "cuTensorMapEncodeTiled failed for the (%lld, %d, %d, %lld) activations",
+                              (long long)n_img_total, gm.H, gm.W, (long long)C);
+    CUDA_TRY(ctx, cudaFuncSetAttribute(conv_corr9_tma_kernel<RB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)Ring<RB, false>::SMEM));
+    conv_corr9_tma_kernel<RB, false><<<grid, WARPS * 32, Ring<RB, false>::SMEM, st>>>(mq_win, mq_win, gm, partial, slot_stride, slot0);
+    KERNEL_CHECK(ctx);
+    if (!same) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(conv_corr9_tma_kernel<RB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)Ring<RB, true>::SMEM));
+        conv_corr9_tma_kernel<RB, true><<<grid, WARPS * 32, Ring<RB, true>::SMEM, st>>>(mx_win, mq_ctr, gm, partial, slot_stride, slot0);
+        KERNEL_CHECK(ctx);
+    }
+    return GPFQ_OK;
 }
 
 // Correlation sums of channels [c_first, c_first + n_ch) over images [img0, img0 + n_img) of a tensor of n_img_total

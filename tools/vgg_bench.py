@@ -43,7 +43,6 @@ def main():
     ap.add_argument("--skip-conv", action="store_true")
     ap.add_argument("--skip-dense", action="store_true")
     ap.add_argument("--corr-rows", type=int, default=0, help="gpfq_set_option corr_rows (0 auto, 4, 6, 8)")
-    ap.add_argument("--corr-quad", type=int, default=0, help="gpfq_set_option corr_quad (0 auto, 2 never)")
     ap.add_argument("--layers", default="", help="comma-separated conv layer indices to run (default: all)")
     ap.add_argument("--conv-kernel", type=int, default=0, help="gpfq_set_option conv_kernel: 0 correlation form, 3 planes kernel")
     args = ap.parse_args()
@@ -57,7 +56,6 @@ def main():
     eng = get_engine(0)
     eng.set_option("conv_kernel", args.conv_kernel)
     eng.set_option("corr_rows", args.corr_rows)
-    eng.set_option("corr_quad", args.corr_quad)
     dev = torch.device("cuda", 0)
     peaks = {}
     try:
