@@ -89,7 +89,7 @@ struct Ring {
 }  // namespace corr9
 
 template <int RB, bool CROSS>
-__global__ void __launch_bounds__(corr9::WARPS * 32, RB <= 6 ? 3 : 2)
+__global__ void __launch_bounds__(corr9::WARPS * 32, RB <= 4 ? 3 : 2)
 conv_corr9_tma_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapA, Corr9Geom gm,
                       double *__restrict__ partial, int slot_stride, int slot0) {
     using namespace corr9;
@@ -206,17 +206,31 @@ conv_corr9_tma_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_con
                     }
                 }
             } else {
-                // ---- band ends, ragged last band: one column at a time into `e`, then to the record it belongs to
+                // ---- band ends, ragged last band: one column at a time into `e`, then to the record it belongs to.  The raw
+                // fp32 values of a column are read from the box one column ahead (the branches between the columns keep the
+                // compiler from hoisting the loads itself, and LDS -> F2F -> DFMA back to back is all latency: ncu, conv10)
+                float rawb[RB + 2], rawa[RB];
+                (void)rawa;
+                auto fetch = [&](int ph) {
+#pragma unroll
+                    for (int r = 0; r < RB + 2; ++r) rawb[r] = tb[(r * WC + ph) * 32];
+                    if (CROSS) {
+#pragma unroll
+                        for (int i = 0; i < RB; ++i) rawa[i] = ta[(i * WC + ph) * 32];
+                    }
+                };
+                fetch(0);
 #pragma unroll
                 for (int ph = 0; ph < WC; ++ph) {
                     const int cx = k * WC + ph;  // newest window column (image column cx) lives in physical slot ph
                     if (cx < W + 2) {
 #pragma unroll
-                        for (int r = 0; r < RB + 2; ++r) win[r][ph] = (double)tb[(r * WC + ph) * 32];
+                        for (int r = 0; r < RB + 2; ++r) win[r][ph] = (double)rawb[r];
                         if (CROSS) {
 #pragma unroll
-                            for (int i = 0; i < RB; ++i) ac[i] = (double)ta[(i * WC + ph) * 32];
+                            for (int i = 0; i < RB; ++i) ac[i] = (double)rawa[i];
                         }
+                        if (ph + 1 < WC) fetch(ph + 1);   // inside the box even when that column lies past the image (zeros)
                         if (cx >= 2) {
                             // pixel column cx - 2 = logical window column 2 = physical slot (ph + 3) % 5
                             double e[ND];
