@@ -372,7 +372,8 @@ def main():
                                                     if args.workload == "cifar10_cnn" else "MNIST MLP 784-500-300-10"),
               "samples": n_img, "alphabet": f"bits={BITS} (K=16), alphabet_scalar={CSCALAR}" if args.workload == "cifar10_cnn"
               else "ternary", "weights_per_step": total_weights, "sharding": f"conv channels / dense neurons over {world} rank(s)",
-              "l2": "inputs (>= 25 GB per pass) exceed L2; no flush needed"}
+              "l2": ("inputs (25.7 GB of patch matrices per pass) exceed L2; no flush needed" if args.workload == "cifar10_cnn"
+                     else "inputs (240 MB per pass) exceed the 126 MB L2; no flush needed")}
 
     import torch
     if args.impl == "reference":
