@@ -573,24 +573,36 @@ static int dense_lowrank_sweep(gpfq_ctx *ctx, const float *X, const float *Xq, i
     }
     CUDA_TRY(ctx, gpfq_record(ctx, 3, st));
     CUDA_TRY(ctx, cudaMemsetAsync(Ut, 0, (size_t)n_alph * nj * m * sizeof(double), st));
+    // The W part of the residual update, U += W[range] X[range], does not depend on the range's decisions: it runs on the
+    // side stream WHILE the range is walked (the walk is a latency-bound chain on one CTA per neuron tile and leaves the
+    // DMMA pipe idle); only the Q part, U -= Q[range] X~[range], waits for the walk.  Order on U: D(range) reads it, then the
+    // W part (side stream, after D), then the Q part (main stream, after the walk and the W part) -- events 0 / 1.
+    cudaStream_t side = ctx->copy_stream;
+    auto residual_update = [&](int64_t lo, int64_t hi, bool w_part, cudaStream_t on) -> int {
+        GemmArgs g = {};
+        if (w_part) g.seg[0] = {Wt + lo, Xt + lo, N0, N0, hi - lo, 1.0};
+        else g.seg[0] = {Qt + lo, Xqt + lo, N0, N0, hi - lo, -1.0};
+        g.nseg = 1;
+        g.M = nj;
+        g.N = m;
+        g.C = Ut;
+        g.ldc = m;
+        g.nsplit = 1;
+        g.accumulate = 1;
+        g.batch_strideA0 = w_part ? 0 : nj * N0;   // W is shared by the alphabets of a batch, Q is per alphabet
+        g.batch_strideC = nj * m;
+        cudaStream_t keep = ctx->stream;
+        ctx->stream = on;
+        const int rc = launch_gemm_nt<double, 128, 64, 16>(ctx, g, n_alph);
+        ctx->stream = keep;
+        return rc;
+    };
     for (int64_t tb = 0, pb = 0; tb < N0; pb = tb, tb += R) {
         const int64_t te = tb + R < N0 ? tb + R : N0;
         if (tb > 0) {
-            {   // U += W[pb:tb] X[pb:tb] - Q[pb:tb] X~[pb:tb]
-                GemmArgs g = {};
-                g.seg[0] = {Wt + pb, Xt + pb, N0, N0, tb - pb, 1.0};
-                g.seg[1] = {Qt + pb, Xqt + pb, N0, N0, tb - pb, -1.0};
-                g.nseg = 2;
-                g.M = nj;
-                g.N = m;
-                g.C = Ut;
-                g.ldc = m;
-                g.nsplit = 1;
-                g.accumulate = 1;
-                g.batch_strideA1 = nj * N0;
-                g.batch_strideC = nj * m;
-                GPFQ_TRY((launch_gemm_nt<double, 128, 64, 16>(ctx, g, n_alph)));
-            }
+            // U -= Q[pb:tb] X~[pb:tb], after the W part of the same range (side stream) has landed
+            CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_copy[1], 0));
+            GPFQ_TRY(residual_update(pb, tb, false, st));
             {   // D[range] = U X~[range]^T
                 GemmArgs g = {};
                 g.seg[0] = {Ut, Xqd + tb * m, m, m, m, 1.0};
@@ -621,6 +633,12 @@ static int dense_lowrank_sweep(gpfq_ctx *ctx, const float *X, const float *Xq, i
                     GPFQ_TRY((launch_gemm_nt<double, 128, 64, 16>(ctx, g, n_alph)));
                 }
             }
+        }
+        if (te < N0) {   // the W part of THIS range for the ranges after it: side stream, once D(range) has read U
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_copy[0], st));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(side, ctx->ev_copy[0], 0));
+            GPFQ_TRY(residual_update(tb, te, true, side));
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_copy[1], side));
         }
         // the compact tiles are addressed like the full matrices: column s of row t lives at Gc[t * R + (s - tb)]
         GPFQ_TRY(dispatch_sweep_tile(ctx, NT, Gc1 - tb, Gc2 - tb, R, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph, tb, te,
