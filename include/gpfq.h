@@ -92,7 +92,9 @@ int gpfq_set_stream(gpfq_ctx *ctx, void *cuda_stream);
  *   "corr_small"   1: correlation form also on images below 128 pixels (default: the planes kernel is faster there)
  *   "corr_rows"    correlation form: image rows per band (0 auto by image height, or 4 / 6 / 8)
  *   "sweep_kernel"  0 persistent tile, 1 per block
- *   "sweep_outer"  0 auto, 1 Gram rows of all earlier directions, 2 carried residuals (3 m N0 N1 MACs: wins when m << N0) */
+ *   "sweep_outer"  0 auto, 1 Gram rows of all earlier directions, 2 carried residuals (3 m N0 N1 MACs: wins when m << N0),
+ *                  3 carried residuals as one chain (default: two halves of the neurons on two streams, so that one half's
+ *                  contractions fill the other half's latency-bound walk) */
 int gpfq_set_option(gpfq_ctx *ctx, const char *key, int64_t value);
 /* Stage times of an earlier call: calls_back = 0 is the most recent API call, 1 the one before, ...
  * (a ring of 128).  For GPFQ_NO_SYNC calls, synchronise the stream first; unfinished events read 0. */

@@ -190,8 +190,9 @@ extern "C" int gpfq_set_option(gpfq_ctx *ctx, const char *key, int64_t value) {
     } else if (!strcmp(key, "conv_kernel")) {   // 0 TMA-staged / correlation form, 1 direct LDG, 2 generic, 3 NHWC planes kernel
         if (value < 0 || value > 3) return gpfq_fail(ctx, GPFQ_ERR_ARG, "conv_kernel must be 0, 1, 2 or 3");
         ctx->conv_variant = (int)value;
-    } else if (!strcmp(key, "sweep_outer")) {   // 0 auto, 1 Gram rows, 2 carried residuals (low-rank form, m << N0)
-        if (value < 0 || value > 2) return gpfq_fail(ctx, GPFQ_ERR_ARG, "sweep_outer must be 0, 1 or 2");
+    } else if (!strcmp(key, "sweep_outer")) {   // 0 auto, 1 Gram rows, 2 carried residuals (low-rank form, m << N0),
+        // 3 carried residuals as ONE chain (no two-stream split of the neurons)
+        if (value < 0 || value > 3) return gpfq_fail(ctx, GPFQ_ERR_ARG, "sweep_outer must be 0, 1, 2 or 3");
         ctx->lowrank_variant = (int)value;
     } else if (!strcmp(key, "sweep_kernel")) {  // 0 persistent neuron-tile kernel, 1 one launch pair per block
         if (value < 0 || value > 1) return gpfq_fail(ctx, GPFQ_ERR_ARG, "sweep_kernel must be 0 or 1");

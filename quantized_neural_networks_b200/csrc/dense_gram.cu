@@ -482,7 +482,7 @@ __global__ void widen_transpose_kernel(const float *__restrict__ X, int64_t ldx,
 
 static bool dense_uses_lowrank(gpfq_ctx *ctx, int64_t N0, int64_t m, int64_t nj) {
     if (ctx->sweep_variant != 0 || ctx->lowrank_variant == 1) return false;
-    if (ctx->lowrank_variant == 2) return N0 > 64;
+    if (ctx->lowrank_variant >= 2) return N0 > 64;
     return 3 * m < N0 && N0 >= 4096 && nj >= 256;
 }
 
@@ -573,11 +573,77 @@ static int dense_lowrank_sweep(gpfq_ctx *ctx, const float *X, const float *Xq, i
     }
     CUDA_TRY(ctx, gpfq_record(ctx, 3, st));
     CUDA_TRY(ctx, cudaMemsetAsync(Ut, 0, (size_t)n_alph * nj * m * sizeof(double), st));
-    // The W part of the residual update, U += W[range] X[range], does not depend on the range's decisions: it runs on the
+    cudaStream_t side = ctx->copy_stream;
+    if (n_alph == 1 && nj >= 512 && ctx->lowrank_variant != 3) {
+        // Two independent half-problems on two streams: neurons are independent, so while one half sits in the
+        // latency-bound walk of a range (one CTA per neuron tile, DMMA pipe idle) the other half's contractions run,
+        // and vice versa -- the hardware interleaves the two chains, nothing else synchronises them.
+        const int64_t half = ceil_div64(ceil_div64(nj, 2), 128) * 128;
+        const int64_t one = nj * R;
+        const int64_t tiles_h = ceil_div64(half, 128) * ceil_div64(R, 64);
+        int64_t ns = tiles_h >= ctx->sm_count ? 1 : ctx->sm_count / tiles_h;
+        ns = std::min<int64_t>(std::min<int64_t>(ns, 8), std::max<int64_t>(1, m / 256));
+        double *Dpart = nullptr;
+        if (ns > 1) GPFQ_TRY(gpfq_ws(ctx, WS_PART, (size_t)ns * one * sizeof(double), (void **)&Dpart));
+        auto chain = [&](cudaStream_t on, int64_t j_lo, int64_t njh) -> int {
+            cudaStream_t keep = ctx->stream;
+            ctx->stream = on;
+            int rc = GPFQ_OK;
+            for (int64_t tb = 0, pb = 0; tb < N0 && rc == GPFQ_OK; pb = tb, tb += R) {
+                const int64_t te = tb + R < N0 ? tb + R : N0;
+                if (tb > 0) {
+                    GemmArgs g = {};   // U += W[pb:tb] X[pb:tb] - Q[pb:tb] X~[pb:tb]
+                    g.seg[0] = {Wt + j_lo * N0 + pb, Xt + pb, N0, N0, tb - pb, 1.0};
+                    g.seg[1] = {Qt + j_lo * N0 + pb, Xqt + pb, N0, N0, tb - pb, -1.0};
+                    g.nseg = 2;
+                    g.M = njh;
+                    g.N = m;
+                    g.C = Ut + j_lo * m;
+                    g.ldc = m;
+                    g.nsplit = 1;
+                    g.accumulate = 1;
+                    rc = launch_gemm_nt<double, 128, 64, 16>(ctx, g, 1);
+                    if (rc != GPFQ_OK) break;
+                    GemmArgs d = {};   // D[range] = U X~[range]^T
+                    d.seg[0] = {Ut + j_lo * m, Xqd + tb * m, m, m, m, 1.0};
+                    d.nseg = 1;
+                    d.M = njh;
+                    d.N = te - tb;
+                    d.C = Do + j_lo * R;
+                    d.ldc = R;
+                    d.nsplit = 1;
+                    if (ns > 1) {
+                        d.C = Dpart + j_lo * R;
+                        d.nsplit = (int)ns;
+                        d.split_stride = one;
+                        rc = launch_gemm_nt<double, 128, 64, 16>(ctx, d, 1);
+                        if (rc != GPFQ_OK) break;
+                        const int blocks = (int)std::min<int64_t>(ceil_div64(njh * R, 256), 4096);
+                        reduce_splits_kernel<<<blocks, 256, 0, on>>>(Dpart + j_lo * R, (int)ns, one, Do + j_lo * R, njh * R);
+                        ctx->launches++;
+                    } else {
+                        rc = launch_gemm_nt<double, 128, 64, 16>(ctx, d, 1);
+                        if (rc != GPFQ_OK) break;
+                    }
+                }
+                rc = dispatch_sweep_tile(ctx, NT, Gc1 - tb, Gc2 - tb, R, N0, Wt + j_lo * N0, Qt + j_lo * N0, njh, d_alph, d_koff,
+                                         d_flags, 1, tb, te, tb > 0 ? Do + j_lo * R : nullptr, R);
+            }
+            ctx->stream = keep;
+            return rc;
+        };
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_copy[0], st));          // Gram tiles, widened inputs and U = 0 are ready
+        CUDA_TRY(ctx, cudaStreamWaitEvent(side, ctx->ev_copy[0], 0));
+        GPFQ_TRY(chain(st, 0, half));
+        GPFQ_TRY(chain(side, half, nj - half));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_copy[1], side));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_copy[1], 0));
+        return GPFQ_OK;
+    }
+    // One chain (several alphabets, or few neurons).  The W part of the residual update, U += W[range] X[range], does not depend on the range's decisions: it runs on the
     // side stream WHILE the range is walked (the walk is a latency-bound chain on one CTA per neuron tile and leaves the
     // DMMA pipe idle); only the Q part, U -= Q[range] X~[range], waits for the walk.  Order on U: D(range) reads it, then the
     // W part (side stream, after D), then the Q part (main stream, after the walk and the W part) -- events 0 / 1.
-    cudaStream_t side = ctx->copy_stream;
     auto residual_update = [&](int64_t lo, int64_t hi, bool w_part, cudaStream_t on) -> int {
         GemmArgs g = {};
         if (w_part) g.seg[0] = {Wt + lo, Xt + lo, N0, N0, hi - lo, 1.0};
