@@ -574,7 +574,7 @@ static int dense_lowrank_sweep(gpfq_ctx *ctx, const float *X, const float *Xq, i
     CUDA_TRY(ctx, gpfq_record(ctx, 3, st));
     CUDA_TRY(ctx, cudaMemsetAsync(Ut, 0, (size_t)n_alph * nj * m * sizeof(double), st));
     cudaStream_t side = ctx->copy_stream;
-    if (n_alph == 1 && nj >= 512 && ctx->lowrank_variant != 3) {
+    if (n_alph == 1 && nj >= 2048 && ctx->lowrank_variant != 3) {   // measured: 512 neurons run faster as one chain
         // Two independent half-problems on two streams: neurons are independent, so while one half sits in the
         // latency-bound walk of a range (one CTA per neuron tile, DMMA pipe idle) the other half's contractions run,
         // and vice versa -- the hardware interleaves the two chains, nothing else synchronises them.
