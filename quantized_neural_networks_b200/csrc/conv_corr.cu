@@ -31,7 +31,10 @@
 //                                  Bound by the fp64 pipe: 13 DFMA + 1.3-2.3 F2F per pixel and pass.
 //   conv_corr9_assemble_kernel     fixed-order slot sums + the per-tap region sums -> [G1 | G2] per channel in the
 //                                  layout conv_sweep_kernel reads
-// Layers the tensor map cannot serve (C < 32, C % 4 != 0, images smaller than a box) keep the patch form.
+//   corr9_pack_kernel              channel counts a tensor map cannot serve (C < 32, C % 4 != 0) on large images: G images
+//                                  side by side as virtual channels of an ordinary tensor; the assembly adds their records
+// Images smaller than a box (H < 6 or W < 5) and, by measurement, images below 128 pixels keep the patch form (the
+// planner is in gpfq_conv_layer_nhwc, api.cu).
 #include <cuda.h>
 
 #include <algorithm>
