@@ -349,16 +349,21 @@ int corr9_plan(int kh, int kw, int sh, int sw, int rh, int rw, int padding_same,
     if (H < 6 || W < corr9::WC) return 0;            // a TMA box (RB + 2 >= 6 rows x 5 columns) must fit in the image
     if ((int64_t)H * W >= ((int64_t)1 << 28)) return 0;
     if ((force_rb == 8 || force_rb == 6 || force_rb == 4) && force_rb + 2 <= H) return force_rb;
-    // rows 1 .. H-2 in bands of RB rows: 13 RB DFMAs + ~4 (RB + 2) conversion slots per band and column, plus a constant
-    // per band (window reset, first / last column stages); calibrated with tools/vgg_bench.py --corr-rows
+    // Rows 1 .. H-2 in bands of RB rows.  Measured (tools/vgg_bench.py --corr-rows, VGG16 and CIFAR10 shapes): RB = 8 wins
+    // whenever at least 85 % of its band rows are live (224, 112, 56, 32, 16 rows high), otherwise the band height that
+    // wastes fewest rows, with RB = 4 handicapped by 0.1 (more conversions and box traffic per DFMA: on 28 x 28 it wastes
+    // least and is still the slowest; RB = 6 is 6 % faster than RB = 8 there; 14 x 14: RB = 6).
+    const int rows = H - 2;
+    auto live = [&](int rb) { return (double)rows / (double)((rows + rb - 1) / rb * rb); };
+    if (8 + 2 <= H && live(8) >= 0.85) return 8;
     int best = 0;
-    long best_cost = 1L << 60;
+    double best_live = -1.0;
     const int cand[3] = {8, 6, 4};
     for (int i = 0; i < 3; ++i) {
         const int rb = cand[i];
         if (rb + 2 > H) continue;
-        const long cost = (long)((H - 2 + rb - 1) / rb) * (13 * rb + 4 * (rb + 2) + 40);  // + per-band start-up (measured)
-        if (cost < best_cost) { best_cost = cost; best = rb; }
+        const double score = live(rb) - (rb == 4 ? 0.1 : 0.0);
+        if (score > best_live + 1e-9) { best_live = score; best = rb; }
     }
     return best;
 }
