@@ -4,34 +4,44 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # the reference's NumPy path on the host cores
 
-Workload (config.workload): BASELINE.json configs[1], the CIFAR10 CNN of train_cifar10_cnn.py -- six 3x3 'same'
-Conv2D layers handed over as per-channel patch matrices (9 x n_patches, m_img = 5008 images) and two Dense layers
-(2048->128, 128->10, m = 5008), 4-bit alphabet (K = 16), synthetic activations, random-init weights.
-One "step" = one pass of the hot path over all eight layers.
+Default workload (config.workload): BASELINE.json configs[2], the north-star target -- a VGG16-shaped full-network GPFQ
+ternary pass (quantize_pretrained_imagenet.py:43-50: ternary, 1504 images): thirteen 3x3 'same' Conv2D layers handed over
+as their NHWC activation tensors (what _get_layer_data_generator collects, quantized_network.py:468; 109 GB resident) and
+three Dense layers (25088->4096->4096->1000, m = 1504), synthetic activations, random-init weights.
+One "step" = one pass of the hot path over all sixteen layers.  --workload cifar10_cnn | mnist_mlp | dense_sweep run
+BASELINE configs[1], [0] and [3] the same way (configs[4], the 20-alphabet grid: tools/grid_bench.py).
 
-  value   whole-job weights/s with every input resident in HBM when the timed region starts (CUDA events on the
-          launching stream, max over ranks).  Inputs (25.7 GB) are far larger than L2, so no flush is needed.
-  e2e     the same pass through the reference-facing C ABI with HOST (pinned) buffers, copies inside the timed region.
-          Conv layers go through gpfq_conv_layer_nhwc (the coarser override point of INTEGRATION.md: the layer's
-          (n_img, H, W, C) activations are handed over, patches are extracted on the device -- 9x fewer PCIe bytes
-          than per-channel patch matrices), Dense layers through gpfq_dense_layer; every Q comes back to the host.
-  roofline  the dominant kernel (conv_gram9_tma_kernel, HBM-bound, 74 % of the step): algorithmic bytes / CUDA-event time
-          of that stage.  roofline_tensor_stage: the Dense Gram stage on tcgen05 (int8 slices), against 2 x measured bf16.
-  from_activations  the same device-resident pass with every conv layer handed over as its NHWC activation tensor (no
-          patch matrices: the 9 x 9 Grams are 13 displacement sums of the activations, conv_corr.cu) -- value, ms/step and
-          the roofline of conv_corr9_tma_kernel.
-  cpu_baseline  the oracle's NumPy restatement of the reference walk (kind "port": the reference is Python and does
-          not travel to the GPU box), one process per host core exactly like the reference's ProcessPoolExecutor, on a
-          bounded sample of every layer, extrapolated linearly in the number of neurons/filters.
-Multi-GPU: conv channels and Dense neurons shard over ranks (no data-path collective); total work is fixed => "strong".
+  value     whole-job weights/s with every input resident in HBM when the timed region starts (CUDA events on the
+            launching stream, max over ranks).  N > 1: conv layers are split over IMAGES (each rank contracts its
+            n_img / N images of every channel, one NCCL all-reduce of the per-channel 9 x 9 Grams, every rank walks every
+            channel), Dense neurons are sharded with the inputs replicated and the Q blocks all-gathered (fp32, what
+            Keras set_weights stores) -- all of it inside the timed region.  Total work is fixed => "strong".
+  e2e       the same pass through the reference-facing C ABI with HOST (pinned) buffers, layer by layer: H2D copies,
+            kernels and the D2H copy of Q inside the timed region (host wall clock around the synchronous calls).
+  per_layer every layer's time, weights/s and fraction of its governing roofline (conv: fp64 DFMA pipe / HBM; Dense: the
+            stage that takes the most time).
+  roofline  the kernel that takes the largest share of the step.
+  parity    (N = 1) the literal C oracle run on a sample of neurons / filters of EVERY layer at full size, on the very host
+            buffers the e2e leg hands to the C ABI, compared with the Q the C ABI returned: agreement, relative-residual
+            delta, entries checked.  The run fails below 99.99 % / above 1e-6.
+  cpu_baseline  the oracle's NumPy restatement of the reference walk (kind "port": the reference is Python and does not
+            travel to the GPU box), one process per host core like the reference's ProcessPoolExecutor, on a bounded
+            sample of every layer (conv layers: one channel, `cores` filters, a subset of the images), extrapolated
+            linearly in filters x channels x images / neurons.
 """
 from __future__ import annotations
 
+import os
+
+os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")   # the CPU-baseline workers are one process per core (SURVEY.md 8d)
+os.environ.setdefault("OMP_NUM_THREADS", "1")
+
 import argparse
 import json
-import os
+import shutil
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -40,15 +50,43 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_IMG = 5008
-BITS, CSCALAR = 4, 4
-# (name, kind, C or N0, F or N1, H)   -- SURVEY.md App. B, config 2
-CIFAR_LAYERS = [
-    ("conv0", "conv", 3, 32, 32), ("conv2", "conv", 32, 32, 32), ("conv6", "conv", 32, 64, 16),
-    ("conv8", "conv", 64, 64, 16), ("conv12", "conv", 64, 128, 8), ("conv14", "conv", 128, 128, 8),
-    ("dense19", "dense", 2048, 128, 0), ("dense22", "dense", 128, 10, 0),
-]
-MNIST_LAYERS = [("dense1", "dense", 784, 500, 0), ("dense3", "dense", 500, 300, 0), ("dense5", "dense", 300, 10, 0)]
+DFMA_RATE = 17.05e12     # DFMA / s, measured on this pool's B200 (profiles/fp64_pipes_r1.txt)
+DMMA_RATE = 18.55e12     # fp64 MACs / s through DMMA.8x8x4 (same pipe)
+
+
+def conv(name, C, F, H):
+    return dict(name=name, kind="conv", C=C, F=F, H=H)
+
+
+def dense(name, N0, N1, m=None):
+    return dict(name=name, kind="dense", N0=N0, N1=N1, m=m)
+
+
+# SURVEY.md App. B.  VGG16: Keras VGG16() as instantiated by quantize_pretrained_imagenet.py:43,89
+VGG_LAYERS = [conv("conv0", 3, 64, 224), conv("conv1", 64, 64, 224), conv("conv2", 64, 128, 112), conv("conv3", 128, 128, 112),
+              conv("conv4", 128, 256, 56), conv("conv5", 256, 256, 56), conv("conv6", 256, 256, 56), conv("conv7", 256, 512, 28),
+              conv("conv8", 512, 512, 28), conv("conv9", 512, 512, 28), conv("conv10", 512, 512, 14), conv("conv11", 512, 512, 14),
+              conv("conv12", 512, 512, 14), dense("fc1", 25088, 4096), dense("fc2", 4096, 4096), dense("fc3", 4096, 1000)]
+CIFAR_LAYERS = [conv("conv0", 3, 32, 32), conv("conv2", 32, 32, 32), conv("conv6", 32, 64, 16), conv("conv8", 64, 64, 16),
+                conv("conv12", 64, 128, 8), conv("conv14", 128, 128, 8), dense("dense19", 2048, 128), dense("dense22", 128, 10)]
+MNIST_LAYERS = [dense("dense1", 784, 500), dense("dense3", 500, 300), dense("dense5", 300, 10)]
+SWEEP_LAYERS = [dense(f"dense_{n}_{m // 1000}k", n, n, m) for n in (1024, 4096, 16384) for m in (5000, 25000, 100000)]
+
+WORKLOADS = {
+    "vgg16": dict(layers=VGG_LAYERS, n_img=1504, bits=np.log2(3), c=3,
+                  desc="VGG16 (BASELINE configs[2]): 13x Conv2D 3x3 'same' from NHWC activations + Dense 25088->4096->4096->1000, "
+                       "ternary (quantize_pretrained_imagenet.py:43-50)",
+                  l2="109 GB of layer inputs per pass stream through HBM between two uses of any buffer; no flush needed"),
+    "cifar10_cnn": dict(layers=CIFAR_LAYERS, n_img=5008, bits=4, c=4,
+                        desc="CIFAR10 CNN (BASELINE configs[1]): 6x Conv2D 3x3 from NHWC activations + Dense 2048->128->10, 4-bit",
+                        l2="2.9 GB of layer inputs per pass exceed the 126 MB L2; no flush needed"),
+    "mnist_mlp": dict(layers=MNIST_LAYERS, n_img=25000, bits=np.log2(3), c=3,
+                      desc="MNIST MLP 784-500-300-10 (BASELINE configs[0]), ternary, m = 25000",
+                      l2="240 MB of layer inputs per pass exceed the 126 MB L2; no flush needed"),
+    "dense_sweep": dict(layers=SWEEP_LAYERS, n_img=0, bits=np.log2(3), c=3,
+                        desc="synthetic Dense sweep (BASELINE configs[3]): N0 = N1 in {1024, 4096, 16384} x m in {5k, 25k, 100k}, ternary",
+                        l2="28 GB of layer inputs per pass exceed L2; no flush needed"),
+}
 
 
 def shard_range(n, rank, world):
@@ -57,186 +95,98 @@ def shard_range(n, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def layer_weights(layer):
-    name, kind, a, b, H = layer
-    return 9 * a * b if kind == "conv" else a * b
+def layer_weights(l):
+    return 9 * l["C"] * l["F"] if l["kind"] == "conv" else l["N0"] * l["N1"]
 
 
-def make_alphabet(W_abs_median, bits=BITS, c=CSCALAR):
-    return c * float(W_abs_median) * np.linspace(-1, 1, int(round(2 ** bits)))
+def make_alphabet(W_abs_median, wl):
+    """rad * linspace(-1, 1, K) (quantized_network.py:396, :544-545)."""
+    return wl["c"] * float(W_abs_median) * np.linspace(-1, 1, int(round(2 ** wl["bits"])))
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# synthetic data (device side, torch is only the buffer/generator)
+# synthetic data (device side; torch is only the buffer / generator)
 # ----------------------------------------------------------------------------------------------------------------
-def build_device_inputs(layers, n_img, rank, world, dev):
-    """Per layer: dict with device tensors.  conv: NHWC activations act/actq (what the reference's host code collects,
-    quantized_network.py:468) and, derived from them, Xp/Xqp = per-channel (9, n) patch matrices of this rank's channels
-    (what _build_patch_array hands to the workers, :789-797)."""
+def build_device_inputs(wl, n_img, rank, world, dev):
+    """Per layer a dict of device tensors.  conv: NHWC activations act / actq of THIS RANK's images (the image split of a
+    multi-GPU job; all images when world == 1); dense: (N0, m) X / Xq replicated, neurons j0..j1 are this rank's."""
     import torch
     out = []
-    for li, (name, kind, a, b, H) in enumerate(layers):
+    for li, l in enumerate(wl["layers"]):
         g = torch.Generator(device=dev).manual_seed(1000 + li)
-        if kind == "conv":
-            C, F = a, b
+        first = li == 0 and wl is not WORKLOADS["dense_sweep"]
+        if l["kind"] == "conv":
+            C, F, H = l["C"], l["F"], l["H"]
             W = (torch.rand((3, 3, C, F), device=dev, generator=g) * 2 - 1) * float(np.sqrt(6.0 / (9 * C)))
-            A = make_alphabet(torch.median(W.abs().flatten()))
-            lo, hi = shard_range(C, rank, world)
-            n = n_img * H * H
-            first = li == 0
-            shape = (n_img, H, H, C)
-            if first:   # image-like: uniform[0,1) with half the pixels zero; X == Xq
-                act = torch.rand(shape, device=dev, generator=g) * (torch.rand(shape, device=dev, generator=g) < 0.5)
-                actq = None
-            else:       # hidden: X = relu(Z), Xq = relu(Z + 0.05 N)
-                Z = torch.randn(shape, device=dev, generator=g)
-                act = torch.relu(Z)
-                actq = torch.relu(Z + 0.05 * torch.randn(shape, device=dev, generator=g))
-                del Z
-            Xp, Xqp = [], []
-            cb = max(1, min(hi - lo, int(1.5e9 // (36 * n))))
-            for c0 in range(lo, hi, cb):
-                c1 = min(hi, c0 + cb)
-                mats = []
-                for t in ((act,) if first else (act, actq)):
-                    tc = t[..., c0:c1].permute(3, 0, 1, 2).reshape(-1, 1, H, H)
-                    p = torch.nn.functional.unfold(tc, 3, padding=1)                          # (cb*n_img, 9, H*H)
-                    p = p.reshape(c1 - c0, n_img, 9, H * H).permute(0, 2, 1, 3).reshape(c1 - c0, 9, n).contiguous()
-                    mats.append(p)
-                    del tc
-                Xp += list(mats[0])
-                Xqp += list(mats[0] if first else mats[1])
-                del p, mats
-            out.append(dict(name=name, kind=kind, W=W, A=A, Xp=Xp, Xqp=None if first else Xqp, c0=lo, n_ch=hi - lo,
-                            n=n, C=C, F=F, first=first, act=act, actq=actq))
+            A = make_alphabet(torch.median(W.abs().flatten()), wl)
+            lo, hi = shard_range(n_img, rank, world)
+            g.manual_seed(1000 + li + 7919 * (rank + 1))
+            shape = (hi - lo, H, H, C)
+            act = torch.empty(shape, device=dev)
+            actq = None if first else torch.empty(shape, device=dev)
+            step = max(1, int(2 ** 28 // (H * H * C)))      # chunked: temporaries of a 19 GB randn would double the footprint
+            for i0 in range(0, hi - lo, step):
+                n = min(step, hi - lo - i0)
+                if first:   # image-like input, X == Xq
+                    z = torch.rand((n, H, H, C), device=dev, generator=g)
+                    if wl is not WORKLOADS["vgg16"]:    # MNIST / CIFAR-like sparsity (SURVEY.md 8d)
+                        z = z * (torch.rand((n, H, H, C), device=dev, generator=g) < 0.5)
+                    act[i0:i0 + n] = z
+                else:       # hidden: X = relu(Z), Xq = relu(Z + 0.05 N)
+                    z = torch.randn((n, H, H, C), device=dev, generator=g)
+                    act[i0:i0 + n] = torch.relu(z)
+                    actq[i0:i0 + n] = torch.relu(z + 0.05 * torch.randn((n, H, H, C), device=dev, generator=g))
+                del z
+            out.append(dict(l, W=W, A=A, act=act, actq=actq, first=first, img_lo=lo, img_hi=hi, n_img=n_img,
+                            out=torch.zeros((1, 3, 3, C, F), dtype=torch.float64, device=dev)))
         else:
-            N0, N1 = a, b
-            m = n_img if n_img else 25000
+            N0, N1 = l["N0"], l["N1"]
+            m = l["m"] or n_img
             W = (torch.rand((N0, N1), device=dev, generator=g) * 2 - 1) * float(np.sqrt(6.0 / N0))
-            A = make_alphabet(torch.median(W.abs().flatten()))
-            first = (li == 0)
-            if first:
-                X = torch.rand((N0, m), device=dev, generator=g) * (torch.rand((N0, m), device=dev, generator=g) < 0.5)
-                Xq = None
-            else:
-                Z = torch.randn((N0, m), device=dev, generator=g)
-                X = torch.relu(Z)
-                Xq = torch.relu(Z + 0.05 * torch.randn((N0, m), device=dev, generator=g))
-                del Z
+            A = make_alphabet(torch.median(W.abs().flatten()), wl)
+            X = torch.empty((N0, m), device=dev)
+            Xq = None if first else torch.empty((N0, m), device=dev)
+            step = max(1, int(2 ** 28 // m))
+            for t0 in range(0, N0, step):
+                n = min(step, N0 - t0)
+                if first:
+                    X[t0:t0 + n] = torch.rand((n, m), device=dev, generator=g) * (torch.rand((n, m), device=dev, generator=g) < 0.5)
+                else:
+                    z = torch.randn((n, m), device=dev, generator=g)
+                    X[t0:t0 + n] = torch.relu(z)
+                    Xq[t0:t0 + n] = torch.relu(z + 0.05 * torch.randn((n, m), device=dev, generator=g))
+                    del z
             lo, hi = shard_range(N1, rank, world)
-            out.append(dict(name=name, kind=kind, W=W, A=A, X=X, Xq=Xq, j0=lo, j1=hi, N0=N0, N1=N1, m=m, first=first))
+            d = dict(l, W=W, A=A, X=X, Xq=Xq, j0=lo, j1=hi, m=m, first=first,
+                     out=torch.zeros((1, N0, N1), dtype=torch.float64, device=dev))
+            if world > 1:   # Q exchange buffers (fp32, what set_weights stores): equal-width column blocks
+                width = -(-N1 // world)
+                d["gblk"] = torch.zeros((N0, width), dtype=torch.float32, device=dev)
+                d["gout"] = torch.empty((world, N0, width), dtype=torch.float32, device=dev)
+            out.append(d)
         torch.cuda.empty_cache()
     return out
 
 
-def run_pass_device(eng, data, outs, sync=False):
-    for d, o in zip(data, outs):
-        if d["kind"] == "conv":
-            eng.conv_channels(d["Xp"], d["Xqp"], d["W"], d["A"], c0=d["c0"], n_channels=d["n_ch"], out=o, sync=sync)
-        else:
-            eng.dense_layer(d["X"], d["Xq"], d["W"], d["A"], j0=d["j0"], j1=d["j1"], out=o, sync=sync)
+def api_calls(d, world):
+    return 2 if (d["kind"] == "conv" and world > 1) else 1
 
 
-def run_pass_device_nhwc(eng, data, outs, sync=False, rank=0, world=1):
-    """The same pass with the conv layers handed over as NHWC activation tensors (the coarser override point of
-    INTEGRATION.md: `_quantize_conv2D_layer_parallel_jit` before `_build_patch_array`), still device-resident.
-    world > 1: conv layers split over IMAGES -- every rank contracts its n_img / world images of all channels, one NCCL
-    all-reduce sums the per-channel 9 x 9 Grams (C x 162 doubles), every rank then walks every channel."""
+def run_layer_device(eng, d, world):
+    """One layer of the device-resident pass (asynchronous on torch's current stream)."""
     import torch.distributed as dist
-    for d, o in zip(data, outs):
-        if d["kind"] == "conv" and world > 1:
-            lo, hi = shard_range(d["act"].shape[0], rank, world)
-            gram = eng.conv_gram_nhwc(d["act"][lo:hi], None if d["actq"] is None else d["actq"][lo:hi], (3, 3))
+    if d["kind"] == "conv":
+        if world > 1:
+            gram = eng.conv_gram_nhwc(d["act"], d["actq"], (3, 3), sync=False)
             dist.all_reduce(gram)
-            eng.conv_layer_from_gram(gram, d["W"], d["A"], out=o, sync=sync)
-        elif d["kind"] == "conv":
-            eng.conv_layer_nhwc(d["act"], d["actq"], d["W"], d["A"], c0=d["c0"], n_channels=d["n_ch"], out=o, sync=sync)
+            eng.conv_layer_from_gram(gram, d["W"], d["A"], out=d["out"], sync=False)
         else:
-            eng.dense_layer(d["X"], d["Xq"], d["W"], d["A"], j0=d["j0"], j1=d["j1"], out=o, sync=sync)
-
-
-def to_host_pinned(data):
-    """Pinned host copies of what the reference's host code holds: NHWC activations per conv layer, (N0, m) matrices per
-    Dense layer, the kernels."""
-    import torch
-
-    def pin(t):
-        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-        h.copy_(t)
-        return h.numpy()
-
-    host, nbytes = [], 0
-    for d in data:
-        if d["kind"] == "conv":
-            act = pin(d["act"])
-            actq = None if d["actq"] is None else pin(d["actq"])
-            nbytes += act.nbytes + (0 if actq is None else actq.nbytes)
-            h = dict(d, act=act, actq=actq, W=d["W"].cpu().numpy(), Xp=None, Xqp=None)
-        else:
-            X = pin(d["X"])
-            Xq = None if d["Xq"] is None else pin(d["Xq"])
-            nbytes += X.nbytes + (0 if Xq is None else Xq.nbytes)
-            h = dict(d, X=X, Xq=Xq, W=d["W"].cpu().numpy())
-        nbytes += h["W"].nbytes
-        host.append(h)
-    return host, nbytes
-
-
-def run_pass_host(eng, host, keep=None, rank=0, world=1, dev=None):
-    """One pass from HOST buffers.  world == 1: host pointers straight into the C ABI (the library overlaps its chunked
-    H2D copies with the Gram kernels).  world > 1: every rank needs the whole layer input, so each copies 1/world of the
-    leading axis over its own PCIe link: conv layers are split over images and Dense layers with m > 2 N0 over samples
-    (the Gram matrices are sums over samples: one NCCL all-reduce of them, replicate.py), the remaining Dense layers are
-    completed by ONE all-gather over NVLink; the walks run on the rank's shard of channels / neurons.
-    Returns (d2h bytes, h2d bytes that crossed this rank's host link)."""
-    import torch
-    from quantized_neural_networks_b200.replicate import (h2d_bytes_per_rank, image_split_conv_gram, prefer_sample_split,
-                                                            replicate_leading_axis, sample_split_gram)
-    d2h = h2d = 0
-    for d in host:
-        conv = d["kind"] == "conv"
-        a, aq = (d["act"], d["actq"]) if conv else (d["X"], d["Xq"])
-        if world == 1:
-            Q = (eng.conv_layer_nhwc(a, aq, d["W"], d["A"], c0=d["c0"], n_channels=d["n_ch"]) if conv
-                 else eng.dense_layer(a, aq, d["W"], d["A"], j0=d["j0"], j1=d["j1"]))
-            h2d += a.nbytes + (0 if aq is None else aq.nbytes) + d["W"].nbytes
-        elif conv:
-            # image split: this rank's n_img / world images of every channel over its own PCIe link, one all-reduce of the
-            # per-channel Grams, every channel walked on every rank (no replication, no Q exchange)
-            gram = image_split_conv_gram(eng, a, aq, (3, 3), (1, 1), "SAME", (1, 1), rank, world)
-            Q = eng.conv_layer_from_gram(gram, d["W"], d["A"])[:, :, d["c0"]:d["c0"] + d["n_ch"]]
-            lo, hi = shard_range(a.shape[0], rank, world)
-            h2d += (hi - lo) * int(np.prod(a.shape[1:])) * 4 * (1 if aq is None else 2) + d["W"].nbytes
-        elif prefer_sample_split(d["N0"], d["m"], world):
-            # Dense, m > 2 N0: this rank's m / world samples, all-reduce of the (N0, N0) Grams, walk of this rank's neurons
-            G1, G2 = sample_split_gram(eng, a, aq, rank, world, device=dev)
-            Q = eng.dense_layer_from_gram(G1, G2, d["W"], d["A"], j0=d["j0"], j1=d["j1"])[:, d["j0"]:d["j1"]]
-            lo, hi = shard_range(a.shape[1], rank, world)
-            h2d += d["N0"] * (hi - lo) * 4 * (1 if aq is None else 2) + d["W"].nbytes
-        else:
-            ad = replicate_leading_axis(a, rank, world, dev)
-            aqd = None if aq is None else replicate_leading_axis(aq, rank, world, dev)
-            Wd = torch.from_numpy(d["W"]).to(dev, non_blocking=True)
-            h2d += h2d_bytes_per_rank(a.shape, 4, world) * 2 + d["W"].nbytes
-            Qd = eng.dense_layer(ad, aqd, Wd, d["A"], j0=d["j0"], j1=d["j1"])
-            Q = Qd[:, d["j0"]:d["j1"]].cpu().numpy()
-            del ad, aqd, Qd
-        d2h += (9 * d["n_ch"] * d["F"] if conv else d["N0"] * (d["j1"] - d["j0"])) * 8
-        if keep is not None:
-            keep.append(Q)
-    return d2h, h2d
-
-
-def host_channel_patches(act, c):
-    """(9, n) patch matrix of channel c of an NHWC host array, 3x3 'same' stride 1 -- what _build_patch_array yields."""
-    n_img, H = act.shape[0], act.shape[1]
-    p = np.zeros((n_img, H + 2, H + 2), np.float32)
-    p[:, 1:-1, 1:-1] = act[..., c]
-    cols = np.empty((9, n_img * H * H), np.float32)
-    for r in range(3):
-        for cc in range(3):
-            cols[r * 3 + cc] = p[:, r:r + H, cc:cc + H].reshape(-1)
-    return cols
+            eng.conv_layer_nhwc(d["act"], d["actq"], d["W"], d["A"], out=d["out"], sync=False)
+    else:
+        eng.dense_layer(d["X"], d["Xq"], d["W"], d["A"], j0=d["j0"], j1=d["j1"], out=d["out"], sync=False)
+        if world > 1:
+            d["gblk"][:, :d["j1"] - d["j0"]].copy_(d["out"][0][:, d["j0"]:d["j1"]])
+            dist.all_gather_into_tensor(d["gout"], d["gblk"])
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -252,9 +202,10 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            time.sleep(0.3)   # nvidia-smi needs a moment before its first sample
         except Exception:
             self.proc = None
         return self
@@ -282,66 +233,170 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# CPU baseline: the oracle's NumPy walk in a fork pool, one process per core (the reference's own fan-out)
+# CPU side: the oracle.  A pool of one worker process per core, forked BEFORE CUDA is initialised; the sample of a layer
+# reaches the workers as .npy files they memory-map (the reference hands its workers an HDF5 file name the same way).
 # ----------------------------------------------------------------------------------------------------------------
-_CPU = {}
+_MM = {}
 
 
-def _cpu_neuron(args):
-    key, j = args
+def _cpu_unit(args):
+    tag, j = args
     from oracle import gpfq_oracle as O
-    d = _CPU[key]
-    return O.quantize_neuron(d["W"][:, j], d["X"], d["Xq"], d["A"])
+    if _MM.get("tag") != tag:
+        _MM.clear()
+        _MM.update(tag=tag, W=np.load(tag + "_W.npy", mmap_mode="r"), X=np.load(tag + "_X.npy", mmap_mode="r"),
+                   A=np.load(tag + "_A.npy"))
+        _MM["Xq"] = np.load(tag + "_Xq.npy", mmap_mode="r") if os.path.exists(tag + "_Xq.npy") else _MM["X"]
+    return O.quantize_neuron(np.asarray(_MM["W"][:, j]), _MM["X"], _MM["Xq"], _MM["A"])
 
 
-def cpu_sample_pass(host_layers, cores, budget_per_layer=2.5):
-    """Times a bounded sample of every layer with `cores` worker processes; returns (extrapolated full-net seconds,
-    description).  Neurons / filters are independent and equal-cost, so the extrapolation is linear in their count."""
-    import concurrent.futures as cf
-    import multiprocessing as mp
-    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
-    os.environ.setdefault("OMP_NUM_THREADS", "1")
-    try:
-        from threadpoolctl import threadpool_limits
-        limiter = threadpool_limits(limits=1)
-    except Exception:
-        limiter = None
-    _CPU.clear()
-    jobs = []
-    for li, d in enumerate(host_layers):
-        if d["kind"] == "conv":
-            if d.get("Xp"):
-                X = d["Xp"][0]
-                Xq = X if d["Xqp"] is None else d["Xqp"][0]
+def _cpu_noop(_):
+    return os.getpid()
+
+
+class CpuPool:
+    def __init__(self, cores):
+        import concurrent.futures as cf
+        import multiprocessing as mp
+        self.cores = cores
+        base = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > (2 << 30) else None
+        self.dir = tempfile.mkdtemp(prefix="gpfq_bench_", dir=base)
+        self.ex = cf.ProcessPoolExecutor(max_workers=cores, mp_context=mp.get_context("fork"))
+        list(self.ex.map(_cpu_noop, range(4 * cores)))   # start every worker now
+        self.n = 0
+
+    def time_units(self, W, X, Xq, A, units):
+        """Walks neurons `units` of the (N0, N1) problem (W, X, Xq) on the pool; returns (seconds, Q columns)."""
+        self.n += 1
+        tag = os.path.join(self.dir, f"s{self.n}")
+        np.save(tag + "_W.npy", np.ascontiguousarray(W, dtype=np.float32))
+        np.save(tag + "_X.npy", np.ascontiguousarray(X, dtype=np.float32))
+        if Xq is not None and Xq is not X:
+            np.save(tag + "_Xq.npy", np.ascontiguousarray(Xq, dtype=np.float32))
+        np.save(tag + "_A.npy", np.asarray(A, dtype=np.float64))
+        t0 = time.perf_counter()
+        cols = list(self.ex.map(_cpu_unit, [(tag, int(j)) for j in units]))
+        dt = time.perf_counter() - t0
+        for f in os.listdir(self.dir):
+            if f.startswith(f"s{self.n}_"):
+                os.remove(os.path.join(self.dir, f))
+        return dt, cols
+
+    def close(self):
+        self.ex.shutdown(wait=True, cancel_futures=True)
+        shutil.rmtree(self.dir, ignore_errors=True)
+
+
+def plane_patches(plane):
+    """(9, n) patch matrix of one channel plane (n_img, H, H): 3x3 'same' stride 1, row r*3+c, patches in image-major
+    order -- what _build_patch_array writes to channel{c}_patch_array.h5 (quantized_network.py:789-797)."""
+    n_img, H = plane.shape[0], plane.shape[1]
+    p = np.zeros((n_img, H + 2, H + 2), np.float32)
+    p[:, 1:-1, 1:-1] = plane
+    cols = np.empty((9, n_img * H * H), np.float32)
+    for r in range(3):
+        for cc in range(3):
+            cols[r * 3 + cc] = p[:, r:r + H, cc:cc + H].reshape(-1)
+    return cols
+
+
+def cpu_time_layer(pool, l, W, A, planes=None, X=None, Xq=None, max_patches=600_000):
+    """NumPy port of the reference walk on a bounded sample of layer `l`; returns (extrapolated seconds for the whole layer
+    on pool.cores processes, weights actually walked, description).  conv: `planes` = (plane, planeq or None) of ONE
+    channel, (n_img, H, H); the first images up to ~max_patches patch columns, `cores` filters; cost is linear in patch
+    columns, filters and channels.  dense: 2 x cores neurons at full size; linear in neurons."""
+    cores = pool.cores
+    if l["kind"] == "conv":
+        plane, planeq = planes
+        n_img, H = plane.shape[0], plane.shape[1]
+        n_s = max(1, min(n_img, max_patches // (H * H)))
+        Xp = plane_patches(plane[:n_s])
+        Xqp = Xp if planeq is None else plane_patches(planeq[:n_s])
+        take = min(l["F"], cores)
+        Wc = np.ascontiguousarray(W.reshape(9, -1)[:, :take])
+        dt, _ = pool.time_units(Wc, Xp, Xqp, A, range(take))
+        scale = (l["n_img_total"] / n_s) * (l["C"] * l["F"] / take)
+        return dt * scale, 9 * take, f"{l['name']}:{take}f/{l['C'] * l['F']}x{n_s}img/{l['n_img_total']}"
+    N1 = W.shape[1]
+    take = min(N1, 2 * cores if l["N0"] >= 1024 else 4 * cores)
+    dt, _ = pool.time_units(W[:, :take], X, Xq, A, range(take))
+    return dt * (l["N1"] / take), l["N0"] * take, f"{l['name']}:{take}n/{l['N1']}"
+
+
+def residual_rel(W, Q, X, Xq):
+    """||X^T w - Xq^T q|| / ||X^T w|| per column (fp64)."""
+    Xd, Xqd = np.asarray(X, dtype=np.float64), np.asarray(Xq, dtype=np.float64)
+    a = Xd.T @ np.asarray(W, dtype=np.float64)
+    r = a - Xqd.T @ Q
+    return np.linalg.norm(r, axis=0) / np.maximum(np.linalg.norm(a, axis=0), 1e-300)
+
+
+def parity_layer(l, W, A, Qgpu, X, Xq, units, cores):
+    """Literal C oracle (oracle/gpfq_oracle.c, quantized_network.py:91-121 / :185-233) on columns `units` of the (N0, N1)
+    problem at FULL size vs the same columns of the GPU result.  Returns the parity record of the layer."""
+    from oracle import c_oracle
+    units = list(units)
+    Ws = np.ascontiguousarray(W[:, units])
+    Qref = c_oracle.quantize_layer(Ws, X, X if Xq is None else Xq, A, nthreads=cores)
+    Qg = np.asarray(Qgpu)[:, units]
+    agree = float(np.mean(Qref == Qg))
+    delta = 0.0
+    if agree < 1.0:   # identical Q => identical residual; only mismatching columns can differ
+        bad = [i for i in range(len(units)) if not np.array_equal(Qref[:, i], Qg[:, i])]
+        r_ref = residual_rel(Ws[:, bad], Qref[:, bad], X, X if Xq is None else Xq)
+        r_gpu = residual_rel(Ws[:, bad], Qg[:, bad], X, X if Xq is None else Xq)
+        delta = float(np.max(np.abs(r_gpu - r_ref) / np.maximum(r_ref, 1e-300)))
+    return {"agreement": agree, "resid_rel_delta": delta, "n_checked": int(Qref.size), "units": len(units)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# per-layer roofline
+# ----------------------------------------------------------------------------------------------------------------
+def layer_roofline(d, sts, ms, hbm_peak, i8_peak):
+    """Fraction of the governing roofline of one layer from the library's stage times (gpfq_query_stats) of its call(s)."""
+    st = sts[0]
+    rec = {"ms": round(ms, 4), "weights_per_s": round(layer_weights(d) / (ms * 1e-3)) if ms > 0 else None}
+    if d["kind"] == "conv":
+        gk = st.get("gram_kernel")
+        ms_g = st["ms_gram"] if st["ms_gram"] > 0 else ms
+        rec["form"] = {0: "patch form (shared-memory planes, 126 MACs / column)", 4: "correlation form (13 DFMA / pixel / Gram)",
+                       5: "correlation form, packed images"}.get(gk, str(gk))
+        hbm = st["bytes_algorithmic"] / (ms_g * 1e-3) / 1e9 / hbm_peak
+        pipe = st["flops_algorithmic"] / 2 / (ms_g * 1e-3) / (DFMA_RATE if gk in (4, 5) else DMMA_RATE)
+        rec.update(ms_gram=round(ms_g, 4), hbm_frac=round(hbm, 3), fp64_pipe_frac=round(pipe, 3),
+                   bound="fp64 pipe (DFMA)" if pipe >= hbm else "hbm", frac=round(max(pipe, hbm), 3))
+    else:
+        rec["method"] = {1: "stream", 2: "gram", 3: "stream_fast"}.get(st["method"])
+        rec["gram_kernel"] = {1: "dmma", 2: "i8_tcgen05", 3: "residual form (block-diagonal tiles)"}.get(st.get("gram_kernel"))
+        rec.update(ms_gram=round(st["ms_gram"], 4), ms_sweep=round(st["ms_sweep"], 4), ms_stream=round(st["ms_stream"], 4))
+        nj, N0, m = d["j1"] - d["j0"], d["N0"], d["m"]
+        if st["method"] == 2:
+            macs = 3.0 * m * N0 * nj if st.get("gram_kernel") == 3 else float(N0) * N0 * nj
+            i8 = st.get("reserved", 0)
+            if i8 & 1:      # sweep contractions on tcgen05 (int8 slices): reported against the int8 tensor peak
+                ops = float(st["flops_algorithmic"])
+                rec.update(bound="tensor (int8 slices on tcgen05)", frac=round(ops / (st["ms_sweep"] * 1e-3) / 1e12 / i8_peak, 3),
+                           sweep_form="carried residuals, int8-slice contractions" if st.get("gram_kernel") == 3 else "Gram rows")
             else:
-                X = host_channel_patches(d["act"], d["c0"])
-                Xq = X if d["actq"] is None else host_channel_patches(d["actq"], d["c0"])
-            Wc = np.ascontiguousarray(d["W"][:, :, d["c0"], :].reshape(9, d["F"]))
-            units_total = d["n_ch"] * d["F"]
-            take = min(d["F"], cores)
-            weights_per_unit = 9
+                rec.update(bound="fp64 pipe (DMMA)", frac=round(macs / DMMA_RATE / (max(st["ms_sweep"], 1e-6) * 1e-3), 3),
+                           sweep_form="carried residuals: 3 m N0 N1 MACs" if st.get("gram_kernel") == 3 else "Gram rows: N0^2 N1 MACs")
+            if st.get("gram_kernel") == 2 and st["ms_gram"] > 0:
+                tiles = sum((ti >> 1) + 1 for ti in range(-(-N0 // 128)))
+                ops = 15 * tiles * 128 * 256 * 2 * (-(-m // 128) * 128) * (1 if d["first"] else 2)
+                rec["gram_int8_frac"] = round(ops / (st["ms_gram"] * 1e-3) / 1e12 / i8_peak, 3)
         else:
-            X, Xq = d["X"], (d["X"] if d["Xq"] is None else d["Xq"])
-            Wc = d["W"]
-            units_total = d["j1"] - d["j0"]
-            take = min(units_total, 2 * cores if d["N0"] >= 1024 else 4 * cores)
-            weights_per_unit = d["N0"]
-        _CPU[li] = dict(W=Wc, X=X, Xq=Xq, A=np.asarray(d["A"], dtype=np.float64))
-        jobs.append((li, d["name"], take, units_total, weights_per_unit))
-    total_s, desc, sampled_w = 0.0, [], 0
-    ctx = mp.get_context("fork")
-    with cf.ProcessPoolExecutor(max_workers=cores, mp_context=ctx) as ex:
-        list(ex.map(_cpu_neuron, [(jobs[-1][0], 0)] * cores))  # start the workers before timing
-        for li, name, take, units_total, wpu in jobs:
-            t0 = time.perf_counter()
-            list(ex.map(_cpu_neuron, [(li, j) for j in range(take)]))
-            dt = time.perf_counter() - t0
-            total_s += dt * units_total / take
-            sampled_w += take * wpu
-            desc.append(f"{name}:{take}/{units_total}")
-    if limiter is not None:
-        limiter.restore_original_limits()
-    return total_s, sampled_w, "units timed per layer " + " ".join(desc)
+            rec.update(bound="fp64 pipe (DFMA)", frac=round(3.0 * m * N0 * nj / DFMA_RATE / (max(st["ms_stream"], 1e-6) * 1e-3), 3))
+    return rec
+
+
+def load_traffic(kernel):
+    """Per-launch DRAM bytes of `kernel` from the committed ncu --set full capture of this round (profiles/r2_traffic.json,
+    written by tools/ncu_summary.py --traffic); None when no capture is committed."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+        return t.get(kernel)
+    except Exception:
+        return None
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -351,56 +406,39 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gpfq", choices=["gpfq", "reference"])
-    ap.add_argument("--workload", default="cifar10_cnn", choices=["cifar10_cnn", "mnist_mlp"])
-    ap.add_argument("--n-img", type=int, default=0, help="override the image/sample count (debug only)")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--workload", default="vgg16", choices=sorted(WORKLOADS))
+    ap.add_argument("--n-img", type=int, default=0, help="override the image / sample count (debug only)")
+    ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-activations-leg", action="store_true", help="skip the from_activations leg (profiling the value leg)")
-    ap.add_argument("--profile-activations-leg", action="store_true",
-                    help="profiling only: run nothing but warm-up + timed passes of the from_activations leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline and parity legs")
+    ap.add_argument("--profile", action="store_true", help="profiling only: warm-up + timed passes of the value leg, nothing else")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    layers = CIFAR_LAYERS if args.workload == "cifar10_cnn" else MNIST_LAYERS
-    n_img = args.n_img or (N_IMG if args.workload == "cifar10_cnn" else 25000)
+    wl = WORKLOADS[args.workload]
+    layers = wl["layers"]
+    n_img = args.n_img or wl["n_img"]
     total_weights = sum(layer_weights(l) for l in layers)
     cores = len(os.sched_getaffinity(0))
-    config = {"workload": f"{args.workload}: " + ("CIFAR10 CNN 6x Conv2D 3x3 (per-channel patch matrices 9 x n_patches) + Dense 2048->128->10"
-                                                    if args.workload == "cifar10_cnn" else "MNIST MLP 784-500-300-10"),
-              "samples": n_img, "alphabet": f"bits={BITS} (K=16), alphabet_scalar={CSCALAR}" if args.workload == "cifar10_cnn"
-              else "ternary", "weights_per_step": total_weights, "sharding": f"conv channels / dense neurons over {world} rank(s)",
-              "l2": ("inputs (25.7 GB of patch matrices per pass) exceed L2; no flush needed" if args.workload == "cifar10_cnn"
-                     else "inputs (240 MB per pass) exceed the 126 MB L2; no flush needed")}
+    config = {"workload": f"{args.workload}: {wl['desc']}", "samples": n_img or "per layer",
+              "alphabet": f"K={int(round(2 ** wl['bits']))} levels, alphabet_scalar={wl['c']}",
+              "weights_per_step": total_weights,
+              "sharding": f"conv layers over images + all-reduce of the Grams, Dense neurons over {world} rank(s) + all-gather of Q",
+              "l2": wl["l2"]}
+    metric = "quantized weights/s, full-network GPFQ pass"
 
-    import torch
     if args.impl == "reference":
-        # The reference's own CPU implementation of the path: Python/NumPy, does not travel -> the oracle port, run
-        # exactly as BASELINE.md section 3 prescribes.  Rank 0 alone works.
         if rank != 0:
             return
-        dev = torch.device("cuda", local_rank) if torch.cuda.is_available() else torch.device("cpu")
-        data = build_inputs_for_cpu(layers, n_img)
-        vals = []
-        for it in range(args.warmup + args.steps):
-            sec, sampled_w, desc = cpu_sample_pass(data, cores, 2.0)
-            if it >= args.warmup:
-                vals.append(total_weights / sec)
-            if it == 0 and args.warmup + args.steps > 2 and sec > 0:
-                pass
-        v = float(np.mean(vals))
-        line = {"impl": "reference", "metric": "quantized weights/s, full-network GPFQ pass", "value": v, "unit": "weights/s",
-                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_weights / v * 1e3,
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": config,
-                "cpu_baseline": {"value": v, "unit": "weights/s", "cores": cores, "kind": "port",
-                                 "sample": desc + "; extrapolated linearly in neurons/filters; HDF5 I/O excluded"},
-                "e2e": {"value": v, "unit": "weights/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        reference_arm(args, wl, layers, n_img, total_weights, cores, config, metric)
         return
 
+    want_cpu = rank == 0 and world == 1 and not args.no_cpu and not args.no_e2e and not args.profile
+    pool = CpuPool(cores) if want_cpu else None      # forked before CUDA exists in this process
+
+    import torch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: there is no CPU fallback for the GPFQ hot path")
     torch.cuda.set_device(local_rank)
@@ -411,242 +449,264 @@ def main():
     from quantized_neural_networks_b200 import get_engine
     eng = get_engine(local_rank)
 
-    data = build_device_inputs(layers, n_img, rank, world, dev)
-    outs = []
-    for d in data:
-        if d["kind"] == "conv":
-            outs.append(torch.zeros((1, 3, 3, d["C"], d["F"]), dtype=torch.float64, device=dev))
-        else:
-            outs.append(torch.zeros((1, d["N0"], d["N1"]), dtype=torch.float64, device=dev))
+    data = build_device_inputs(wl, n_img, rank, world, dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    if args.profile_activations_leg:
-        for _ in range(max(args.warmup, 3) + args.steps):
-            run_pass_device_nhwc(eng, data, outs)
+    W_ = max(args.warmup, 3)
+    for _ in range(W_):
+        for d in data:
+            run_layer_device(eng, d, world)
+    barrier()
+    if args.profile:
+        for _ in range(args.steps):
+            for d in data:
+                run_layer_device(eng, d, world)
         barrier()
         return
-    for _ in range(max(args.warmup, 3)):
-        run_pass_device(eng, data, outs)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(len(data) + 1)] for _ in range(args.steps)]
     with ClockSampler(local_rank) as clocks:
         barrier()
-        e0.record()
-        for _ in range(args.steps):
-            run_pass_device(eng, data, outs)
-        e1.record()
+        for s in range(args.steps):
+            ev[s][0].record()
+            for i, d in enumerate(data):
+                run_layer_device(eng, d, world)
+                ev[s][i + 1].record()
         barrier()
-    ms = e0.elapsed_time(e1)
+    ms = ev[0][0].elapsed_time(ev[-1][-1])
+    layer_ms = [float(np.mean([ev[s][i].elapsed_time(ev[s][i + 1]) for s in range(args.steps)])) for i in range(len(data))]
     if world > 1:
-        t = torch.tensor([ms], device=dev)
+        t = torch.tensor([ms] + layer_ms, device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        ms, layer_ms = float(t[0].item()), [float(v) for v in t[1:].tolist()]
     ms_per_step = ms / args.steps
     value = total_weights / (ms_per_step * 1e-3)
 
-    # per-call stage times of the timed region (most recent calls first)
-    ncall = min(len(layers) * args.steps, 120)
-    per_layer = {}
-    launches_per_step = 0
-    for back in range(ncall):
-        st = eng.query_stats(back)
-        name = layers[(len(layers) - 1 - back) % len(layers)][0]
-        per_layer.setdefault(name, []).append(st)
-    conv_bytes = conv_ms = 0.0
-    layer_report = {}
-    for name, sts in per_layer.items():
-        kind = dict((l[0], l[1]) for l in layers)[name]
-        launches_per_step += sts[0]["kernel_launches"]
-        msl = float(np.mean([s["ms_total"] for s in sts]))
-        layer_report[name] = {"ms": round(msl, 4), "weights_per_s": round(sts[0]["weights"] / (msl * 1e-3)) if msl > 0 else None,
-                              "method": {1: "stream", 2: "gram", 3: "stream_fast"}.get(sts[0]["method"]),
-                              "gram_kernel": {1: "dmma", 2: "i8_tcgen05", 3: "block_diagonal"}.get(sts[0].get("gram_kernel"))}
-        if kind == "conv":
-            conv_bytes += sum(s["bytes_algorithmic"] for s in sts)
-            conv_ms += sum(s["ms_gram"] for s in sts)
+    # stage times of the LAST step's calls (most recent call first)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = conv_bytes / (conv_ms * 1e-3) / 1e9 if conv_ms > 0 else None
-    # DRAM bytes ncu measured for three launches of this kernel (conv8, conv12, conv14; profiles/r1c_conv_gram9_tma.md)
-    # against their algorithmic bytes: 10.352e9 vs 10.339e9 -- every byte is read exactly once
-    roofline = {"kernel": "conv_gram9_tma_kernel (3x3 per-channel patch Grams: UBLKCP/mbarrier ring, DMMA corners + DFMA edge; "
-                          "74 % of the step, profiles/r1g_bench_launches.md)", "bound": "hbm",
-                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": (achieved / hbm_peak) if achieved else None,
-                "traffic": 10.352e9, "traffic_note": "dram read+write of the conv8+conv12+conv14 launches (ncu --set full); "
-                                                     "algorithmic bytes of the same launches: 10.339e9",
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy)" if peaks else "fallback (B200_PROFILING.md)",
-                "algorithmic_bytes": "72 B per patch column per channel (36 when X == Xq); the stage time is CUDA events around "
-                                     "the Gram launches of every conv call of the timed region"}
-    # the one tensor-core stage of the pass: the Dense Gram (dense19, 2048 x 2048 over m = 5008) as int8 slices on tcgen05
-    tensor = None
-    for name, sts in per_layer.items():
-        kind = dict((l[0], l[1]) for l in layers)[name]
-        if kind == "dense" and sts[0].get("gram_kernel") == 2 and sts[0]["ms_gram"] > 0:
-            d = [x for x in data if x["name"] == name][0]
-            N0, m = d["N0"], d["m"]
-            tiles = sum((ti >> 1) + 1 for ti in range(-(-N0 // 128)))
-            ops = 15 * tiles * 128 * 256 * 2 * (-(-m // 128) * 128) * (1 if d["first"] else 2)
-            ms_g = float(np.mean([x["ms_gram"] for x in sts]))
-            peak_i8 = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
-            tensor = {"kernel": "gram_i8_kernel (tcgen05.mma kind::i8 + TMA + TMEM; 15 int8 slice pairs)", "layer": name, "bound": "tensor",
-                      "achieved": ops / (ms_g * 1e-3) / 1e12, "peak": peak_i8, "unit": "TOP/s (int8)",
-                      "frac": ops / (ms_g * 1e-3) / 1e12 / peak_i8,
-                      "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops (int8 issues at twice the bf16 rate; no int8 peak is measured)",
-                      "fp64_equivalent_tflops": (1 if d["first"] else 2) * m * N0 * (N0 + 1) / (ms_g * 1e-3) / 1e12,
-                      "note": "stage time includes the slicing and exponent kernels; a 0.5 ms stage is mostly fill/drain"}
+    i8_peak = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
+    back, launches_per_step, per_layer, stage = 0, 0, {}, {}
+    for i in range(len(data) - 1, -1, -1):
+        d = data[i]
+        sts = []
+        for _ in range(api_calls(d, world)):
+            sts.append(eng.query_stats(back))
+            back += 1
+        sts.reverse()
+        launches_per_step += sum(s["kernel_launches"] for s in sts)
+        stage[d["name"]] = sts
+        per_layer[d["name"]] = layer_roofline(d, sts, layer_ms[i], hbm_peak, i8_peak)
+    per_layer = {d["name"]: per_layer[d["name"]] for d in data}
 
-    # ---- the same pass from the layers' NHWC activations (device-resident): no patch matrices anywhere -----------------
-    nhwc = None
-    if args.workload == "cifar10_cnn" and not args.no_activations_leg:
-        outs2 = [torch.zeros_like(o) for o in outs]
-        for _ in range(max(args.warmup, 3)):
-            run_pass_device_nhwc(eng, data, outs2, rank=rank, world=world)
-        barrier()
-        def _agree(a, b):   # world > 1: `outs` holds this rank's channels / neurons only, the image-split pass every channel
-            m = (a != 0) if world > 1 else torch.ones_like(a, dtype=torch.bool)
-            return float((a == b)[m].double().mean()) if bool(m.any()) else 1.0
-        agree = min(_agree(a, b) for a, b in zip(outs, outs2))
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        f0.record()
-        for _ in range(args.steps):
-            run_pass_device_nhwc(eng, data, outs2, rank=rank, world=world)
-        f1.record()
-        barrier()
-        ms2 = f0.elapsed_time(f1)
-        if world > 1:
-            t = torch.tensor([ms2], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms2 = float(t.item())
-        ms2 /= args.steps
-        cb = cm = cf = 0.0
-        kinds = {}
-        for back in range(min(len(layers) * args.steps, 120)):
-            st = eng.query_stats(back)
-            lname, lkind = layers[(len(layers) - 1 - back) % len(layers)][:2]
-            if lkind == "conv" and st.get("gram_kernel") in (4, 5):
-                cb += st["bytes_algorithmic"]
-                cf += st["flops_algorithmic"]
-                cm += st["ms_gram"]
-            if lkind == "conv":
-                kinds[lname] = {0: "patch form (shared-memory planes)", 4: "correlation form", 5: "correlation form, packed images"}.get(
-                    st.get("gram_kernel"), str(st.get("gram_kernel")))
-        nhwc = {"value": total_weights / (ms2 * 1e-3), "unit": "weights/s", "ms_per_step": ms2,
-                "inputs": "NHWC activations of every conv layer resident in HBM (2.9 GB per pass, larger than L2) instead of "
-                          "per-channel patch matrices (25.7 GB)",
-                "agreement_with_patch_matrix_pass": agree, "conv_gram_form": kinds,
-                "roofline": None if cm <= 0 else {
-                    "kernel": "conv_corr9_tma_kernel (13 displacement sums per Gram; TMA boxes -> per-warp mbarrier ring -> "
-                              "fp64 register window, DFMA)", "bound": "hbm", "achieved": cb / (cm * 1e-3) / 1e9,
-                    "peak": hbm_peak, "unit": "GB/s", "frac": cb / (cm * 1e-3) / 1e9 / hbm_peak,
-                    "algorithmic_bytes": "4 B per pixel and channel per tensor (the activations, read once)",
-                    "dfma_pipe_frac": cf / 2 / (cm * 1e-3) / 17.05e12,
-                    "dfma_pipe_note": "13 DFMA per pixel, channel and Gram against the measured 17.05e12 DFMA/s "
-                                      "(profiles/fp64_pipes_r1.txt); the stage time includes image packing, row launches and assembly"}}
-        del outs2
+    # the dominant kernel family of the step
+    conv_ms = sum(stage[d["name"]][0]["ms_gram"] for d in data if d["kind"] == "conv" and stage[d["name"]][0].get("gram_kernel") in (4, 5))
+    conv_bytes = sum(stage[d["name"]][0]["bytes_algorithmic"] for d in data if d["kind"] == "conv" and stage[d["name"]][0].get("gram_kernel") in (4, 5))
+    conv_dfma = sum(stage[d["name"]][0]["flops_algorithmic"] / 2 for d in data if d["kind"] == "conv" and stage[d["name"]][0].get("gram_kernel") in (4, 5))
+    roofline = None
+    if conv_ms > 0:
+        ach = conv_bytes / (conv_ms * 1e-3) / 1e9
+        roofline = {"kernel": "conv_corr9_tma_kernel (3x3 per-channel Grams as 13 displacement sums straight from the NHWC activations: "
+                              "TMA 4-D boxes -> per-warp mbarrier ring -> fp64 register window, DFMA)",
+                    "share_of_step": round(conv_ms / ms_per_step, 3), "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": ach / hbm_peak, "traffic": load_traffic("conv_corr9_tma_kernel"),
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy)" if peaks else "fallback (B200_PROFILING.md)",
+                    "algorithmic_bytes": "4 B per pixel and channel per tensor (X and Xq activations, each read once) over the CUDA-event "
+                                         "time of the Gram stage of every conv call of the last step",
+                    "dfma_pipe_frac": conv_dfma / (conv_ms * 1e-3) / DFMA_RATE,
+                    "dfma_pipe_note": "the kernel issues 13 DFMA per pixel, channel and Gram; the fp64 pipe (17.05e12 DFMA/s measured, "
+                                      "profiles/fp64_pipes_r1.txt) saturates before HBM does"}
 
-    # ---- e2e: host (pinned) buffers through the C ABI, copies inside the timed region ---------------------------
-    e2e = None
+    # ---- e2e + parity + cpu baseline: host (pinned) buffers through the C ABI, layer by layer ----------------------
+    e2e, parity, cpu = None, None, None
     if not args.no_e2e:
-        host, _ = to_host_pinned(data)
-        kept = []
-        run_pass_host(eng, host, kept, rank, world, dev)  # warm-up (allocates the staging workspaces)
-        barrier()
-        for d, o, Qh in zip(data, outs, kept):   # both entry points must agree (north-star gate: >= 99.99 % of entries;
-            Qd = o[0].cpu().numpy()               # the correlation form re-associates fp64 sums, so not always bit for bit)
-            if d["kind"] == "conv":
-                ref_blk = Qd[:, :, d["c0"]:d["c0"] + d["n_ch"]]
-                got = Qh[:, :, d["c0"]:d["c0"] + d["n_ch"]] if world == 1 else Qh
-            else:
-                ref_blk = Qd[:, d["j0"]:d["j1"]]
-                got = Qh[:, d["j0"]:d["j1"]] if world == 1 else Qh
-            assert ref_blk.size == 0 or float(np.mean(ref_blk == got)) >= 0.9999, d["name"]
-        del kept
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            d2h_bytes, h2d_bytes = run_pass_host(eng, host, None, rank, world, dev)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        e2e = {"value": total_weights * args.e2e_steps / dt, "unit": "weights/s", "h2d_bytes_per_step": int(h2d_bytes),
-               "d2h_bytes_per_step": int(d2h_bytes), "steps": args.e2e_steps, "ms_per_step": dt / args.e2e_steps * 1e3,
-               "timing": "host wall clock around synchronous C-ABI calls (copies + kernels), max over ranks",
-               "api": "gpfq_conv_layer_nhwc + gpfq_dense_layer from pinned host buffers" +
-                      ("" if world == 1 else f"; per rank 1/{world} of every input over PCIe: conv layers split over images and Dense "
-                                             "layers with m > 2 N0 over samples (one NCCL all-reduce of the Gram matrices each), other "
-                                             "Dense layers replicated by one all-gather over NVLink (h2d/d2h bytes are per rank)")}
-
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        host_cpu = host if e2e is not None else to_host_pinned(data)[0]
-        sec, sampled_w, desc = cpu_sample_pass(host_cpu, cores)
-        cpu = {"value": total_weights / sec, "unit": "weights/s", "cores": cores, "kind": "port",
-               "sample": desc + "; extrapolated linearly in neurons/filters; HDF5 I/O excluded",
-               "extrapolated_full_pass_s": sec}
+        e2e, parity, cpu = e2e_leg(args, eng, data, rank, world, dev, pool, cores, total_weights, barrier)
+    if pool is not None:
+        pool.close()
 
     if rank == 0:
-        line = {"metric": "quantized weights/s, full-network GPFQ pass", "value": value, "unit": "weights/s", "n_gpus": world,
-                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-                "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
-                "roofline": roofline, "roofline_tensor_stage": tensor, "from_activations": nhwc, "cpu_baseline": cpu,
-                "layers": layer_report}
+        line = {"metric": metric, "value": value, "unit": "weights/s", "n_gpus": world, "steps": args.steps, "warmup": W_,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": config, "clocks": clocks.summary(), "e2e": e2e,
+                "gpu_launches": int(launches_per_step * args.steps), "roofline": roofline, "parity": parity, "cpu_baseline": cpu,
+                "per_layer": per_layer}
         print(json.dumps(line))
+        if parity is not None:
+            bad = {k: v for k, v in parity.items() if v["agreement"] < 0.9999 or v["resid_rel_delta"] > 1e-6}
+            if bad:
+                raise SystemExit(f"parity gate failed: {bad}")
     if world > 1:
         dist.destroy_process_group()
 
 
-def build_inputs_for_cpu(layers, n_img):
-    """Host-only synthetic inputs for the reference arm: one channel of patches per conv layer is enough for the sample."""
-    rng = np.random.default_rng(0)
-    out = []
-    for li, (name, kind, a, b, H) in enumerate(layers):
-        if kind == "conv":
-            C, F = a, b
-            W = (rng.uniform(-1, 1, (3, 3, C, F)) * np.sqrt(6.0 / (9 * C))).astype(np.float32)
-            A = make_alphabet(np.median(np.abs(W)))
-            n = n_img * H * H
-            first = li == 0
-            shape = (n_img, H, H)
-            if first:
-                act = (rng.random(shape, dtype=np.float32) * (rng.random(shape, dtype=np.float32) < 0.5)).astype(np.float32)
-                acts = [act]
+def e2e_leg(args, eng, data, rank, world, dev, pool, cores, total_weights, barrier):
+    """The pass from HOST buffers.  One pinned buffer pair, refilled per layer from the device tensors OUTSIDE the timed
+    region (the reference's host code holds one layer's activations at a time too: layer{idx}_data.h5 is written, used and
+    removed per layer, quantized_network.py:471-500, :574); the timed region of a layer is the synchronous C-ABI call(s):
+    H2D copies, kernels, D2H of Q.  world > 1: every rank hands over only its own images (conv: image split, one all-reduce
+    of the Grams) / samples or a 1 / world slice of the replicated inputs (Dense), see replicate.py."""
+    import torch
+    import torch.distributed as dist
+    from quantized_neural_networks_b200.replicate import prefer_sample_split, replicate_leading_axis, sample_split_gram
+    need = max((d["act"].numel() if d["kind"] == "conv" else d["X"].numel()) for d in data)
+    pin = [torch.empty(need, dtype=torch.float32, pin_memory=True) for _ in range(2)]
+
+    def host_view(t, which):
+        h = pin[which][:t.numel()].view(t.shape)
+        h.copy_(t)
+        return h.numpy()
+
+    parity = {} if pool is not None else None
+    cpu_s, cpu_w, cpu_desc = 0.0, 0, []
+    total_s, h2d, d2h = 0.0, 0, 0
+    for it in range(1 + args.e2e_steps):      # pass 0: warm-up (allocates the staging workspaces) + parity + CPU sample
+        timed = it > 0
+        for d in data:
+            convl = d["kind"] == "conv"
+            a = host_view(d["act"] if convl else d["X"], 0)
+            src_q = d["actq"] if convl else d["Xq"]
+            aq = None if src_q is None else host_view(src_q, 1)
+            Wh = d["W"].cpu().numpy()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            if convl and world == 1:
+                Q = eng.conv_layer_nhwc(a, aq, Wh, d["A"])
+                nb = a.nbytes * (1 if aq is None else 2)
+            elif convl:
+                gram = eng.conv_gram_nhwc(a, aq, (3, 3))
+                dist.all_reduce(gram)
+                Q = eng.conv_layer_from_gram(gram, Wh, d["A"])
+                nb = a.nbytes * (1 if aq is None else 2)
+            elif world == 1:
+                Q = eng.dense_layer(a, aq, Wh, d["A"])
+                nb = a.nbytes * (1 if aq is None else 2)
+            elif prefer_sample_split(d["N0"], d["m"], world):
+                G1, G2 = sample_split_gram(eng, a, aq, rank, world, device=dev)
+                Q = eng.dense_layer_from_gram(G1, G2, Wh, d["A"], j0=d["j0"], j1=d["j1"])
+                lo, hi = shard_range(d["m"], rank, world)
+                nb = d["N0"] * (hi - lo) * 4 * (1 if aq is None else 2)
             else:
-                Z = rng.standard_normal(shape, dtype=np.float32)
-                acts = [np.maximum(Z, 0), np.maximum(Z + 0.05 * rng.standard_normal(shape, dtype=np.float32), 0)]
-            mats = []
-            for t in acts:
-                p = np.zeros((n_img, H + 2, H + 2), np.float32)
-                p[:, 1:-1, 1:-1] = t
-                cols = np.empty((9, n), np.float32)
-                for r in range(3):
-                    for c in range(3):
-                        cols[r * 3 + c] = p[:, r:r + H, c:c + H].reshape(-1)
-                mats.append(cols)
-            out.append(dict(name=name, kind=kind, W=W, A=A, Xp=[mats[0]], Xqp=None if first else [mats[1]], c0=0, n_ch=C,
-                            n=n, C=C, F=F))
+                ad = replicate_leading_axis(a, rank, world, dev)
+                aqd = None if aq is None else replicate_leading_axis(aq, rank, world, dev)
+                Wd = torch.from_numpy(Wh).to(dev, non_blocking=True)
+                Q = eng.dense_layer(ad, aqd, Wd, d["A"], j0=d["j0"], j1=d["j1"])[..., d["j0"]:d["j1"]].cpu().numpy()
+                nb = -(-d["N0"] // world) * d["m"] * 4 * (1 if aq is None else 2)
+                del ad, aqd
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if timed:
+                total_s += dt
+                if it == 1:
+                    h2d += nb + Wh.nbytes
+                    d2h += (layer_weights(d) if world == 1 or convl else d["N0"] * (d["j1"] - d["j0"])) * 8
+            elif pool is not None:
+                # ---- parity at full size on the host buffers just handed to the C ABI, and the CPU-baseline sample
+                Q0 = Q
+                if convl:
+                    c = d["C"] // 2
+                    plane = np.ascontiguousarray(a[..., c])
+                    planeq = None if aq is None else np.ascontiguousarray(aq[..., c])
+                    Xp = plane_patches(plane)
+                    Xqp = None if planeq is None else plane_patches(planeq)
+                    units = range(min(d["F"], 16 if Xp.shape[1] > 10_000_000 else 32))
+                    parity[d["name"]] = parity_layer(d, Wh[:, :, c, :].reshape(9, -1), d["A"], Q0[:, :, c, :].reshape(9, -1), Xp, Xqp, units, cores)
+                    del Xp, Xqp
+                    sec, w, desc = cpu_time_layer(pool, dict(d, n_img_total=d["n_img"]), Wh[:, :, c, :], d["A"], planes=(plane, planeq))
+                else:
+                    units = range(min(d["N1"], 2 * cores if d["N0"] * d["m"] > 3e7 else 4 * cores))
+                    parity[d["name"]] = parity_layer(d, Wh, d["A"], Q0, a, aq, units, cores)
+                    sec, w, desc = cpu_time_layer(pool, d, Wh, d["A"], X=a, Xq=aq)
+                cpu_s += sec
+                cpu_w += w
+                cpu_desc.append(desc)
+            del Q
+    if world > 1:
+        t = torch.tensor([total_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_s = float(t.item())
+    e2e = {"value": total_weights * args.e2e_steps / total_s, "unit": "weights/s", "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps, "ms_per_step": total_s / args.e2e_steps * 1e3,
+           "timing": "host wall clock around the synchronous C-ABI call(s) of every layer (H2D copies + kernels + D2H of Q), "
+                     "summed over the layers, max over ranks; the pinned host buffers are refilled between layers outside the timed region",
+           "api": ("gpfq_conv_layer_nhwc + gpfq_dense_layer from pinned host buffers" if world == 1 else
+                   f"per rank 1/{world} of every input over PCIe: gpfq_conv_gram_nhwc on the rank's images + all-reduce + "
+                   "gpfq_conv_layer_from_gram; Dense: sample split (gpfq_gram_matrices + all-reduce + gpfq_dense_layer_from_gram) when "
+                   "m > 2 N0, else inputs replicated by one all-gather over NVLink (bytes are per rank)")}
+    cpu = None
+    if pool is not None:
+        cpu = {"value": total_weights / cpu_s, "unit": "weights/s", "cores": cores, "kind": "port",
+               "sample": "NumPy port of the reference walk, one process per core; per layer [filters or neurons timed / total x images "
+                         "used / total]: " + " ".join(cpu_desc) + "; extrapolated linearly; HDF5 I/O excluded",
+               "sampled_weights": int(cpu_w), "extrapolated_full_pass_s": cpu_s}
+    return e2e, parity, cpu
+
+
+def reference_arm(args, wl, layers, n_img, total_weights, cores, config, metric):
+    """The reference's own CPU implementation of the path: Python / NumPy, does not travel to the GPU box -> the oracle's
+    NumPy port, run exactly as BASELINE.md section 3 prescribes (one process per core, single-threaded BLAS).  A step is a
+    bounded sample of every layer; `value` extrapolates it linearly to the whole pass, `ms_per_step` is the sample itself."""
+    pool = CpuPool(cores)
+    rng = np.random.default_rng(0)
+    samples = []
+    for li, l in enumerate(layers):
+        first = li == 0
+        if l["kind"] == "conv":
+            C, F, H = l["C"], l["F"], l["H"]
+            W = (rng.uniform(-1, 1, (3, 3, F)) * np.sqrt(6.0 / (9 * C))).astype(np.float32)   # the filters of ONE channel
+            n_s = max(1, min(n_img, 600_000 // (H * H)))
+            if first:
+                plane = rng.random((n_s, H, H), dtype=np.float32)
+                planes = (plane, None)
+            else:
+                Z = rng.standard_normal((n_s, H, H), dtype=np.float32)
+                planes = (np.maximum(Z, 0), np.maximum(Z + 0.05 * rng.standard_normal((n_s, H, H), dtype=np.float32), 0))
+            A = make_alphabet(np.median(np.abs(W)), wl)
+            samples.append((dict(l, n_img_total=n_img), W, A, dict(planes=planes)))
         else:
-            N0, N1 = a, b
-            m = n_img
-            W = (rng.uniform(-1, 1, (N0, N1)) * np.sqrt(6.0 / N0)).astype(np.float32)
-            A = make_alphabet(np.median(np.abs(W)))
+            N0, N1 = l["N0"], l["N1"]
+            m = l["m"] or n_img
+            take = min(N1, 2 * cores if N0 >= 1024 else 4 * cores)
+            W = (rng.uniform(-1, 1, (N0, take)) * np.sqrt(6.0 / N0)).astype(np.float32)
             Z = rng.standard_normal((N0, m), dtype=np.float32)
             X = np.maximum(Z, 0)
-            Xq = np.maximum(Z + 0.05 * rng.standard_normal((N0, m), dtype=np.float32), 0)
-            out.append(dict(name=name, kind=kind, W=W, A=A, X=X, Xq=Xq, j0=0, j1=N1, N0=N0, N1=N1, m=m))
-    return out
+            Xq = None if first else np.maximum(Z + 0.05 * rng.standard_normal((N0, m), dtype=np.float32), 0)
+            del Z
+            A = make_alphabet(np.median(np.abs(W)), wl)
+            samples.append((dict(l), W, A, dict(X=X, Xq=Xq)))
+    vals, walls, desc = [], [], ""
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        sec, descs = 0.0, []
+        for l, W, A, kw in samples:
+            s, w, dsc = cpu_time_layer(pool, l, W, A, **kw)
+            sec += s
+            descs.append(dsc)
+        if it >= args.warmup:
+            vals.append(total_weights / sec)
+            walls.append(time.perf_counter() - t0)
+        desc = " ".join(descs)
+    pool.close()
+    v = float(np.mean(vals))
+    line = {"impl": "reference", "metric": metric, "value": v, "unit": "weights/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": float(np.mean(walls)) * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "value_note": "whole-pass weights/s extrapolated linearly from the sample each step walks; ms_per_step is the wall time "
+                          "of that sample; extrapolated_full_pass_s the whole pass at this rate",
+            "cpu_baseline": {"value": v, "unit": "weights/s", "cores": cores, "kind": "port",
+                             "sample": "NumPy port of the reference walk, one process per core; per layer [filters or neurons timed / "
+                                       "total x images used / total]: " + desc + "; extrapolated linearly; HDF5 I/O excluded",
+                             "extrapolated_full_pass_s": total_weights / v},
+            "e2e": {"value": v, "unit": "weights/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
 
 
 if __name__ == "__main__":

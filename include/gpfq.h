@@ -92,6 +92,7 @@ int gpfq_set_stream(gpfq_ctx *ctx, void *cuda_stream);
  *   "corr_small"   1: correlation form also on images below 128 pixels (default: the planes kernel is faster there)
  *   "corr_rows"    correlation form: image rows per band (0 auto by image height, or 4 / 6 / 8)
  *   "sweep_kernel"  0 persistent tile, 1 per block
+ *   "sweep_i8"     contractions of the residual-form sweep: 0 auto, 1 int8 slices on tcgen05, 2 fp64 DMMA
  *   "sweep_outer"  0 auto, 1 Gram rows of all earlier directions, 2 carried residuals (3 m N0 N1 MACs: wins when m << N0),
  *                  3 carried residuals as one chain (default: two halves of the neurons on two streams, so that one half's
  *                  contractions fill the other half's latency-bound walk) */
@@ -171,7 +172,9 @@ int gpfq_conv_layer_nhwc(gpfq_ctx *ctx, const float *act, const float *actq, int
  * n_img / world images of EVERY channel (1 / world of the activations over its own PCIe link, no replication):
  *   gpfq_conv_gram_nhwc        per-channel [G1 | G2] (2 kk^2 float64 per channel, lower triangles + diagonals valid, G1 == G2
  *                              when actq == act / NULL) of channels c0 .. c0+n_ch-1 over the given images.  gram_out lives
- *                              on the device when GPFQ_Q_DEVICE is set, else on the host.
+ *                              on the device when GPFQ_Q_DEVICE is set, else on the host.  With device activations AND a
+ *                              device gram_out, GPFQ_NO_SYNC returns after enqueueing (the all-reduce that follows is
+ *                              ordered on the same stream).
  *   (one all-reduce of the n_ch x 2 kk^2 doubles, e.g. NCCL over NVLink: 83 KB for 64 channels)
  *   gpfq_conv_layer_from_gram  the walks of every filter of channels c0 .. c0+n_ch-1 from such matrices (device pointer,
  *                              GPFQ_X_DEVICE; channel i of the range at gram + i * 2 kk^2).  W / Q_out as in

@@ -194,6 +194,9 @@ extern "C" int gpfq_set_option(gpfq_ctx *ctx, const char *key, int64_t value) {
         // 3 carried residuals as ONE chain (no two-stream split of the neurons)
         if (value < 0 || value > 3) return gpfq_fail(ctx, GPFQ_ERR_ARG, "sweep_outer must be 0, 1, 2 or 3");
         ctx->lowrank_variant = (int)value;
+    } else if (!strcmp(key, "sweep_i8")) {      // residual-form sweep contractions: 0 auto, 1 int8 slices on tcgen05, 2 fp64 DMMA
+        if (value < 0 || value > 2) return gpfq_fail(ctx, GPFQ_ERR_ARG, "sweep_i8 must be 0, 1 or 2");
+        ctx->sweep_i8 = (int)value;
     } else if (!strcmp(key, "sweep_kernel")) {  // 0 persistent neuron-tile kernel, 1 one launch pair per block
         if (value < 0 || value > 1) return gpfq_fail(ctx, GPFQ_ERR_ARG, "sweep_kernel must be 0 or 1");
         ctx->sweep_variant = (int)value;
@@ -1009,9 +1012,12 @@ extern "C" int gpfq_conv_gram_nhwc(gpfq_ctx *ctx, const float *act, const float 
     static const int32_t two = 2;
     static const float w_dummy = 0.f;
     ctx->gram_only_out = gram_out;
-    // W_DEVICE keeps the (unused) kernel from being copied; Q_DEVICE in `flags` says where gram_out lives
+    // W_DEVICE keeps the (unused) kernel from being copied; Q_DEVICE in `flags` says where gram_out lives; GPFQ_NO_SYNC
+    // (device inputs and outputs only) returns after enqueueing: the copy into gram_out is ordered on the stream
+    uint32_t f = flags | GPFQ_W_DEVICE;
+    if ((f & GPFQ_ALL_DEVICE) != GPFQ_ALL_DEVICE) f &= ~GPFQ_NO_SYNC;
     const int rc = gpfq_conv_layer_nhwc(ctx, act, actq, n_img, H, Wd, C, kh, kw, sh, sw, rh, rw, padding_same, &w_dummy, 1, c0, n_ch,
-                                        unit, &two, 1, gram_out, (flags | GPFQ_W_DEVICE) & ~GPFQ_NO_SYNC, nullptr);
+                                        unit, &two, 1, gram_out, f, nullptr);
     ctx->gram_only_out = nullptr;
     return rc;
 }

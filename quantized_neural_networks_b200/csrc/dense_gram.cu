@@ -621,6 +621,10 @@ static int dense_lowrank_sweep(gpfq_ctx *ctx, const float *X, const float *Xq, i
                         const int blocks = (int)std::min<int64_t>(ceil_div64(njh * R, 256), 4096);
                         reduce_splits_kernel<<<blocks, 256, 0, on>>>(Dpart + j_lo * R, (int)ns, one, Do + j_lo * R, njh * R);
                         ctx->launches++;
+                        if (cudaError_t e = cudaGetLastError(); e != cudaSuccess) {
+                            rc = gpfq_fail(ctx, GPFQ_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e), __FILE__, __LINE__);
+                            break;
+                        }
                     } else {
                         rc = launch_gemm_nt<double, 128, 64, 16>(ctx, d, 1);
                         if (rc != GPFQ_OK) break;

@@ -354,7 +354,8 @@ class GpfqEngine:
         self.last_stats = st.as_dict()
         return out[0] if single else out
 
-    def conv_gram_nhwc(self, act, actq, kernel_size=(3, 3), strides=(1, 1), padding="SAME", rate=(1, 1), c0=0, n_channels=None):
+    def conv_gram_nhwc(self, act, actq, kernel_size=(3, 3), strides=(1, 1), padding="SAME", rate=(1, 1), c0=0, n_channels=None,
+                       sync=True):
         """Gram stage of a conv layer alone: per-channel [G1 | G2] of channels c0..c0+n_channels-1 over the given images,
         as a float64 CUDA tensor (n_channels, 2, kh*kw, kh*kw) (lower triangles + diagonals valid).  act / actq: NHWC
         NumPy arrays or CUDA tensors.  The per-rank part of an image-split multi-GPU job (`conv_layer_from_gram`)."""
@@ -379,7 +380,7 @@ class GpfqEngine:
         gram = torch.zeros((n_channels, 2, kh * kw, kh * kw), dtype=torch.float64,
                            device=act.device if dev else torch.device("cuda", self.device))
         self._bind_stream(True)
-        flags = (_lib.X_DEVICE if dev else 0) | _lib.Q_DEVICE
+        flags = (_lib.X_DEVICE if dev else 0) | _lib.Q_DEVICE | (_lib.NO_SYNC if dev and not sync else 0)
         rc = self._lib.gpfq_conv_gram_nhwc(self._ctx, c_void_p(ptr(act)), c_void_p(ptr(actq)), n_img, H, Wd, C, kh, kw,
                                            int(strides[0]), int(strides[1]), int(rate[0]), int(rate[1]),
                                            1 if str(padding).upper() == "SAME" else 0, int(c0), n_channels,
