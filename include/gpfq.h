@@ -209,6 +209,13 @@ int gpfq_bit_round(gpfq_ctx *ctx, const double *t, int64_t n, const double *alph
 int gpfq_gram_matrices(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx, int64_t N0,
                        int64_t m, double *G1_out, double *G2_out, uint32_t flags);
 
+/* The int8-slice tcgen05 contraction the residual-form sweep uses for U += W_r X_r - Q_r Xq_r and D_r = U Xq_r^T
+ * (whole ranges of the updates / dots of quantized_network.py:119, :86-89), exposed for tests: C = A B^T with
+ * A (M, K) float64 and B (N, K) float32 host arrays -- or, with transposed_b, B given as (K, N) (the X^T slicing path) --
+ * keeping digit-slice pairs with s_a + s_b <= D (2..10).  C_out: (M, N) float64 host array. */
+int gpfq_debug_slgemm(gpfq_ctx *ctx, const double *A, const float *B, int64_t M, int64_t N, int64_t K, int32_t D,
+                      int32_t transposed_b, double *C_out);
+
 #ifdef __cplusplus
 }
 #endif

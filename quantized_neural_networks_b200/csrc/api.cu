@@ -277,6 +277,9 @@ static int upload_alphabets(gpfq_ctx *ctx, const double *alphabets, const int32_
         CUDA_TRY(ctx, cudaMemcpyAsync(d + e.off, e.blob.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
         hit = &e;
     }
+    ctx->h_alph = alphabets;   // host view for the duration of the call (the int8 sweep contractions need the level spacing)
+    ctx->h_koff = out->h_koff.data();
+    ctx->h_flags = out->h_flags.data();
     out->d_levels = reinterpret_cast<const double *>(d + hit->off);
     out->d_koff = reinterpret_cast<const int *>(d + hit->off + lev_bytes);
     out->d_flags = reinterpret_cast<const int *>(d + hit->off + lev_bytes + koff_bytes);
@@ -745,7 +748,6 @@ extern "C" int gpfq_conv_layer_nhwc(gpfq_ctx *ctx, const float *act, const float
         c0 < 0 || n_ch < 0 || c0 + n_ch > C || H > 65535 || Wd > 65535)
         return gpfq_fail(ctx, GPFQ_ERR_ARG, "bad conv geometry");
     const int kk = kh * kw;
-    if (!conv_supported_kk(kk)) return gpfq_fail(ctx, GPFQ_ERR_UNSUPPORTED, "kernel %dx%d: use gpfq_conv_channels", kh, kw);
     if (n_ch == 0) return GPFQ_OK;
     // TensorFlow extract_patches geometry (quantized_network.py:158-172)
     const int keh = (kh - 1) * rh + 1, kew = (kw - 1) * rw + 1;
@@ -766,6 +768,42 @@ extern "C" int gpfq_conv_layer_nhwc(gpfq_ctx *ctx, const float *act, const float
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     const bool same = (actq == nullptr || actq == act);
+    if (!conv_supported_kk(kk)) {
+        // Kernel sizes without a dedicated Gram / walk kernel (5 x 5, 7 x 7, ...; the reference takes any size,
+        // quantized_network.py:686-727): patches of one channel at a time on the device (im2col), then that channel is a
+        // (kk, F) Dense problem over n patches -- what gpfq_conv_channels does for such sizes from host patch matrices.
+        if (ctx->gram_only_out) return gpfq_fail(ctx, GPFQ_ERR_UNSUPPORTED, "kernel %dx%d has no Gram-only (image split) path", kh, kw);
+        const size_t abytes_g = (size_t)n_img * H * Wd * C * sizeof(float);
+        const float *gA = act, *gAq = same ? act : actq;
+        if (!(flags & GPFQ_X_DEVICE)) {
+            float *ba = nullptr, *bq = nullptr;
+            GPFQ_TRY(gpfq_ws(ctx, WS_ACT_A, abytes_g, (void **)&ba));
+            CUDA_TRY(ctx, cudaMemcpyAsync(ba, act, abytes_g, cudaMemcpyHostToDevice, s));
+            gA = gAq = ba;
+            if (!same) {
+                GPFQ_TRY(gpfq_ws(ctx, WS_ACT_B, abytes_g, (void **)&bq));
+                CUDA_TRY(ctx, cudaMemcpyAsync(bq, actq, abytes_g, cudaMemcpyHostToDevice, s));
+                gAq = bq;
+            }
+        }
+        float *pa = nullptr, *pq = nullptr;
+        GPFQ_TRY(gpfq_ws(ctx, WS_PATCH_A, (size_t)kk * n * sizeof(float), (void **)&pa));
+        pq = pa;
+        if (!same) GPFQ_TRY(gpfq_ws(ctx, WS_PATCH_B, (size_t)kk * n * sizeof(float), (void **)&pq));
+        int64_t launches = 0;
+        for (int64_t i = 0; i < n_ch; ++i) {
+            const int64_t c = c0 + i;
+            GPFQ_TRY(im2col_stage(ctx, gA, n_img, (int)H, (int)Wd, C, c, 1, kh, kw, sh, sw, rh, rw, pt, pl, Ho, Wo, pa, (int64_t)kk * n));
+            if (!same)
+                GPFQ_TRY(im2col_stage(ctx, gAq, n_img, (int)H, (int)Wd, C, c, 1, kh, kw, sh, sw, rh, rw, pt, pl, Ho, Wo, pq, (int64_t)kk * n));
+            // per-alphabet outputs are kk*C*F apart, which is exactly N0*ldq for N0 = kk, ldq = C*F
+            GPFQ_TRY(gpfq_dense_layer(ctx, pa, same ? pa : pq, n, kk, n, W + c * F, C * F, F, 0, F, alphabets, K, n_alph, Q_out + c * F,
+                                      C * F, ((flags & ~GPFQ_NO_SYNC) | GPFQ_X_DEVICE | GPFQ_METHOD_GRAM), stats));
+            launches += (stats ? stats->kernel_launches : 0) + (same ? 1 : 2);
+        }
+        if (stats) { stats->kernel_launches = (int)launches; stats->weights = (int64_t)kk * n_ch * F * n_alph; }
+        return GPFQ_OK;
+    }
     begin_call(ctx, 2);
     CUDA_TRY(ctx, gpfq_record(ctx, 0, s));
     Alphabets al;

@@ -63,11 +63,14 @@ struct gpfq_ctx {
     int lowrank_variant = 0;      // sweep outer level: 0 auto, 1 Gram rows, 2 residual (low-rank) form
     int sweep_i8 = 0;             // sweep contractions of the residual form: 0 auto, 1 int8 slices on tcgen05, 2 fp64 DMMA
     int i8_pairs_d = 0;           // int8 Gram: keep slice pairs with k + l <= this (0: the default of gram_i8.cu)
+    const double *h_alph = nullptr;  // host copy of the current call's alphabets (levels back to back) and their offsets
+    const int *h_koff = nullptr, *h_flags = nullptr;
+    int last_sweep_i8 = 0;        // the last residual-form sweep ran its contractions on tcgen05 (int8 slices)
     double *gram_only_out = nullptr;  // set for the duration of gpfq_conv_gram_nhwc: conv_finish hands the Grams out, no walk
     int last_gram_kernel = 0;     // what the last Dense Gram stage ran (1 DMMA, 2 int8 tcgen05)
     size_t i8_oom_bytes = 0;      // smallest int8-Gram workspace that failed to allocate (0: none yet)
     // grow-only named workspaces
-    DevBuf ws[32];
+    DevBuf ws[48];
     DevBuf pinned[4];
     // alphabets already resident on the device (steady-state calls re-use them: no copy, no sync)
     std::vector<AlphEntry> alph_cache;
@@ -77,7 +80,8 @@ struct gpfq_ctx {
 enum WsSlot {
     WS_X = 0, WS_XQ, WS_W, WS_Q, WS_WT, WS_QT, WS_G1, WS_G2, WS_PART, WS_DT, WS_NRM, WS_ALPH,
     WS_U, WS_PTRS, WS_CG, WS_CPART, WS_PATCH_A, WS_PATCH_B, WS_ACT_A, WS_ACT_B, WS_QIDX, WS_MISC,
-    WS_I8_SQ, WS_I8_SX, WS_I8_E, WS_I8_TILES, WS_LR_XD, WS_LR_XT, WS_LR_U, WS_CORR_B
+    WS_I8_SQ, WS_I8_SX, WS_I8_E, WS_I8_TILES, WS_LR_XD, WS_LR_XT, WS_LR_U, WS_CORR_B,
+    WS_SL_W, WS_SL_XT, WS_SL_XQT, WS_SL_XQ, WS_SL_U, WS_SL_KQ, WS_SL_E
 };
 
 int gpfq_fail(gpfq_ctx *ctx, int code, const char *fmt, ...);

@@ -11,6 +11,7 @@
 #include <algorithm>
 
 #include "gemm_nt.cuh"
+#include "slgemm_i8.cuh"
 
 static constexpr int SWEEP_B = 32;
 static constexpr int64_t SWEEP_OUTER = 512;  // directions per range of the two-level sweep
@@ -480,10 +481,17 @@ __global__ void widen_transpose_kernel(const float *__restrict__ X, int64_t ldx,
     }
 }
 
-static bool dense_uses_lowrank(gpfq_ctx *ctx, int64_t N0, int64_t m, int64_t nj) {
+static bool dense_uses_lowrank(gpfq_ctx *ctx, int64_t N0, int64_t m, int64_t nj, int n_alph, bool same, bool i8_ok) {
     if (ctx->sweep_variant != 0 || ctx->lowrank_variant == 1) return false;
     if (ctx->lowrank_variant >= 2) return N0 > 64;
-    return 3 * m < N0 && N0 >= 4096 && nj >= 256;
+    if (!i8_ok) return 3 * m < N0 && N0 >= 4096 && nj >= 256;   // fp64 (DMMA) contractions: the measured rule of round 1
+    // int8-slice contractions (slgemm_i8.cu): 39 slice-pair products of nj x m x N0 at ~2e15 int8 op/s plus the block-diagonal
+    // Gram tiles, against N0^2 nj fp64 MACs at ~1e13 /s plus the full tcgen05 Gram stage (15 pairs per Gram)
+    if (N0 < 1024 || nj < 256) return false;
+    const double grams = same ? 1.0 : 2.0;
+    const double t_lr = 78.0 * nj * (double)m * N0 / 2.0e15 + grams * (double)m * N0 * 512.0 / 1.3e13;
+    const double t_gr = (double)N0 * N0 * nj / 1.0e13 + grams * 15.0 * (double)N0 * N0 * m / 2.0e15;
+    return t_lr < t_gr;
 }
 
 static int64_t pick_range_length(gpfq_ctx *ctx, int64_t nj, int n_alph) {
@@ -717,6 +725,149 @@ static int dense_lowrank_sweep(gpfq_ctx *ctx, const float *X, const float *Xq, i
     return GPFQ_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same residual-form sweep with its contractions on the 5th-generation tensor cores (slgemm_i8.cu): X, X~ and W as five
+// int8 digit slices each (sliced ONCE per layer; X^T / X~^T with one exponent per sample, X~ and W with one per row), the
+// decisions of a range as ONE slice of level indices k' = q / h (symmetric equispaced alphabets: q = h k', |k'| <= K - 1,
+// the literal 0 of a dead direction is k' = 0), the fp64 residuals U re-sliced after every range.  Per range:
+//     U += W_r X_r  (19 slice pairs, dropped terms < 2^-46 of 2^(eW + eX) per direction)  -  h K'_r X~_r  (5 pairs, exact)
+//     D_r = U X~_r^T (15 pairs, < 2^-38 of 2^(eU + eX~) per sample: ~1e-11 of the decision argument, as the tcgen05 Gram)
+// every slice-pair sum is an exact integer in TMEM, the fp64 combination has a fixed order: bit-reproducible.
+// ---------------------------------------------------------------------------------------------
+static bool alphabet_symmetric_equispaced(const double *a, int K, int flag, double *h) {
+    if (!flag || K < 2 || !(a[K - 1] > 0.0)) return false;
+    if (!(fabs(a[0] + a[K - 1]) <= 1e-13 * a[K - 1])) return false;
+    *h = a[K - 1] / (double)(K - 1);
+    return K - 1 <= 127;
+}
+
+static bool dense_lowrank_uses_i8(gpfq_ctx *ctx, int64_t N0, int64_t m, int64_t nj, int n_alph, double *h) {
+    if (ctx->sweep_i8 == 2 || n_alph != 1 || !ctx->h_alph || !ctx->h_koff || !ctx->h_flags) return false;
+    if (m > 204 * 128 || N0 >= ((int64_t)1 << 30)) return false;   // one K chunk of the s32 accumulators
+    return alphabet_symmetric_equispaced(ctx->h_alph + ctx->h_koff[0], ctx->h_koff[1] - ctx->h_koff[0], ctx->h_flags[0], h);
+}
+
+static int dense_lowrank_sweep_i8(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx, int64_t N0, int64_t m,
+                                  const double *Wt, double *Qt, int64_t nj, const double *d_alph, const int *d_koff,
+                                  const int *d_flags, int NT, double h, gpfq_stats *stats) {
+    const bool same = (Xq == X);
+    cudaStream_t st = ctx->stream, side = ctx->copy_stream;
+    int64_t R = pick_range_length(ctx, nj, 1);
+    R = std::max<int64_t>(128, R / 128 * 128);      // K blocks of the update are 128 directions
+    const int64_t N0P = ceil_div64(N0, 128) * 128, mP = ceil_div64(m, 128) * 128, njP = ceil_div64(nj, 128) * 128;
+    constexpr int S = 5;
+    int8_t *sW = nullptr, *sXT = nullptr, *sXqT = nullptr, *sXq = nullptr, *sU = nullptr, *sKq = nullptr;
+    int32_t *e = nullptr;
+    double *Ut = nullptr, *Gc1 = nullptr, *Gc2 = nullptr, *Do = nullptr;
+    GPFQ_TRY(gpfq_ws(ctx, WS_SL_W, (size_t)S * njP * N0P, (void **)&sW));
+    GPFQ_TRY(gpfq_ws(ctx, WS_SL_XT, (size_t)S * mP * N0P, (void **)&sXT));
+    if (same) sXqT = sXT;
+    else GPFQ_TRY(gpfq_ws(ctx, WS_SL_XQT, (size_t)S * mP * N0P, (void **)&sXqT));
+    GPFQ_TRY(gpfq_ws(ctx, WS_SL_XQ, (size_t)S * N0P * mP, (void **)&sXq));
+    GPFQ_TRY(gpfq_ws(ctx, WS_SL_U, (size_t)S * njP * mP, (void **)&sU));
+    GPFQ_TRY(gpfq_ws(ctx, WS_SL_KQ, (size_t)njP * N0P, (void **)&sKq));
+    GPFQ_TRY(gpfq_ws(ctx, WS_SL_E, (size_t)(2 * njP + N0P + 3 * mP + 16) * sizeof(int32_t), (void **)&e));
+    int32_t *eW = e, *eU = eW + njP, *eXq = eU + njP, *eXT = eXq + N0P, *eXqT = same ? eXT : eXT + mP;
+    int *scratch = eXT + 2 * mP;
+    GPFQ_TRY(gpfq_ws(ctx, WS_LR_U, (size_t)nj * m * sizeof(double), (void **)&Ut));
+    GPFQ_TRY(gpfq_ws(ctx, WS_G2, (size_t)N0 * R * sizeof(double), (void **)&Gc2));
+    if (same) Gc1 = Gc2;
+    else GPFQ_TRY(gpfq_ws(ctx, WS_G1, (size_t)N0 * R * sizeof(double), (void **)&Gc1));
+    GPFQ_TRY(gpfq_ws(ctx, WS_DT, (size_t)nj * R * sizeof(double), (void **)&Do));
+
+    CUDA_TRY(ctx, gpfq_record(ctx, 2, st));
+    // slicing, once per layer
+    GPFQ_TRY(sl_rowsplit<float>(ctx, Xq, ldx, N0, m, eXq, sXq, N0P, mP, N0P));
+    GPFQ_TRY(sl_transsplit(ctx, X, ldx, N0, m, eXT, scratch, sXT, mP, N0P));
+    if (!same) GPFQ_TRY(sl_transsplit(ctx, Xq, ldx, N0, m, eXqT, scratch, sXqT, mP, N0P));
+    GPFQ_TRY(sl_rowsplit<double>(ctx, Wt, N0, nj, N0, eW, sW, njP, N0P, njP));
+    // block-diagonal Gram tiles, compact: Gc[t][s - tb(t)], row stride R (exact fp32 x fp32 products, fp64 sums)
+    const int64_t nfull = N0 / R;
+    for (int which = 0; which < (same ? 1 : 2); ++which) {
+        for (int64_t b0 = 0; b0 < nfull; b0 += 65535) {
+            const int64_t nb = std::min<int64_t>(65535, nfull - b0), tb = b0 * R;
+            GemmArgs g = {};
+            g.seg[0] = {Xq + tb * ldx, (which ? X : Xq) + tb * ldx, ldx, ldx, m, 1.0};
+            g.nseg = 1;
+            g.M = g.N = R;
+            g.C = (which ? Gc1 : Gc2) + tb * R;
+            g.ldc = R;
+            g.nsplit = 1;
+            g.lower_only = 1;
+            g.batch_strideA0 = R * ldx;
+            g.batch_strideB = R * ldx;
+            g.batch_strideC = R * R;
+            GPFQ_TRY((launch_gemm_nt<float, 128, 64, 32>(ctx, g, (int)nb)));
+        }
+        if (nfull * R < N0) {
+            const int64_t tb = nfull * R;
+            GemmArgs g = {};
+            g.seg[0] = {Xq + tb * ldx, (which ? X : Xq) + tb * ldx, ldx, ldx, m, 1.0};
+            g.nseg = 1;
+            g.M = g.N = N0 - tb;
+            g.C = (which ? Gc1 : Gc2) + tb * R;
+            g.ldc = R;
+            g.nsplit = 1;
+            g.lower_only = 1;
+            GPFQ_TRY((launch_gemm_nt<float, 128, 64, 32>(ctx, g, 1)));
+        }
+    }
+    CUDA_TRY(ctx, gpfq_record(ctx, 3, st));
+    CUDA_TRY(ctx, cudaMemsetAsync(Ut, 0, (size_t)nj * m * sizeof(double), st));
+    SlOperand oW, oXT, oXqT, oXq, oU, oKq;
+    GPFQ_TRY(sl_make_operand(ctx, &oW, sW, njP, N0P, S, eW, 0));
+    GPFQ_TRY(sl_make_operand(ctx, &oXT, sXT, mP, N0P, S, eXT, 0));
+    GPFQ_TRY(sl_make_operand(ctx, &oXqT, sXqT, mP, N0P, S, eXqT, 0));
+    GPFQ_TRY(sl_make_operand(ctx, &oXq, sXq, N0P, mP, S, eXq, 0));
+    GPFQ_TRY(sl_make_operand(ctx, &oU, sU, njP, mP, S, eU, 0));
+    GPFQ_TRY(sl_make_operand(ctx, &oKq, sKq, njP, N0P, 1, nullptr, 6));   // single digit b: value = b 2^(e - 6) = b
+    const int D_UPDATE = 7, D_DOTS = 6;
+
+    auto chain = [&](cudaStream_t on, int64_t j_lo, int64_t njh) -> int {
+        cudaStream_t keep = ctx->stream;
+        ctx->stream = on;
+        int rc = GPFQ_OK;
+        const int64_t rows_h = ceil_div64(njh, 128) * 128;
+        for (int64_t tb = 0, pb = 0; tb < N0 && rc == GPFQ_OK; pb = tb, tb += R) {
+            const int64_t te = tb + R < N0 ? tb + R : N0;
+            if (tb > 0) {
+                const int64_t Kp = ceil_div64(tb - pb, 128) * 128;
+                rc = sl_qindex(ctx, Qt + j_lo * N0, N0, njh, pb, tb, 1.0 / h, sKq + j_lo * N0P, rows_h, N0P, Kp);
+                if (rc != GPFQ_OK) break;
+                SlProduct up[2] = {{&oW, &oXT, j_lo, 0, pb, Kp, D_UPDATE, 1.0}, {&oKq, &oXqT, j_lo, 0, pb, Kp, 6, -h}};
+                rc = slgemm_i8(ctx, up, 2, Ut + j_lo * m, m, njh, m, true);        // U += W_r X_r - h K'_r X~_r
+                if (rc != GPFQ_OK) break;
+                rc = sl_rowsplit<double>(ctx, Ut + j_lo * m, m, njh, m, eU + j_lo, sU + j_lo * mP, njP, mP, rows_h);
+                if (rc != GPFQ_OK) break;
+                SlProduct dp = {&oU, &oXq, j_lo, tb, 0, mP, D_DOTS, 1.0};
+                rc = slgemm_i8(ctx, &dp, 1, Do + j_lo * R, R, njh, te - tb, false);   // D_r = U X~_r^T
+                if (rc != GPFQ_OK) break;
+            }
+            rc = dispatch_sweep_tile(ctx, NT, Gc1 - tb, Gc2 - tb, R, N0, Wt + j_lo * N0, Qt + j_lo * N0, njh, d_alph, d_koff,
+                                     d_flags, 1, tb, te, tb > 0 ? Do + j_lo * R : nullptr, R);
+        }
+        ctx->stream = keep;
+        return rc;
+    };
+    if (stats) {
+        stats->flops_algorithmic = 2LL * (19 + 5 + 15) * nj * m * N0;   // int8 operations of the 39 slice-pair products
+        stats->reserved |= 1;
+    }
+    ctx->last_sweep_i8 = 1;
+    if (nj >= 2048 && ctx->lowrank_variant != 3) {
+        // two independent halves of the neurons on two streams: one half's contractions fill the other half's serial walk
+        const int64_t half = ceil_div64(ceil_div64(nj, 2), 128) * 128;
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_copy[0], st));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(side, ctx->ev_copy[0], 0));
+        GPFQ_TRY(chain(st, 0, half));
+        GPFQ_TRY(chain(side, half, nj - half));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_copy[1], side));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_copy[1], 0));
+        return GPFQ_OK;
+    }
+    return chain(st, 0, nj);
+}
+
 // Dense layer by Gram + sweep.  All pointers are device pointers.
 //   Qd: (n_alph, N0, ldq) fp64 device output, columns col0..col0+nj-1 written.
 int dense_gram_path(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx, int64_t N0, int64_t m,
@@ -728,7 +879,9 @@ int dense_gram_path(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx,
     const bool pre = (G2_pre != nullptr);
     const bool same = pre ? (G1_pre == nullptr || G1_pre == G2_pre) : (Xq == X);
     double *G1 = nullptr, *G2 = nullptr, *Wt = nullptr, *Qt = nullptr, *Dt = nullptr;
-    const bool lowrank = !pre && dense_uses_lowrank(ctx, N0, m, nj);
+    double h_step = 0.0;
+    const bool i8_sweep = !pre && dense_lowrank_uses_i8(ctx, N0, m, nj, n_alph, &h_step);
+    const bool lowrank = !pre && dense_uses_lowrank(ctx, N0, m, nj, n_alph, same, i8_sweep);
     // Neurons per CTA of the range walk: the narrowest tile that still fits every CTA on the chip at once (two per SM, so
     // that one CTA's serial walk overlaps another's contraction).
     const int64_t slots = 2LL * ctx->sm_count;
@@ -741,7 +894,11 @@ int dense_gram_path(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx,
         KERNEL_CHECK(ctx);
     }
     if (lowrank) {
-        GPFQ_TRY(dense_lowrank_sweep(ctx, X, Xq, ldx, N0, m, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph, NT));
+        ctx->last_sweep_i8 = 0;
+        if (i8_sweep)
+            GPFQ_TRY(dense_lowrank_sweep_i8(ctx, X, Xq, ldx, N0, m, Wt, Qt, nj, d_alph, d_koff, d_flags, NT, h_step, st));
+        else
+            GPFQ_TRY(dense_lowrank_sweep(ctx, X, Xq, ldx, N0, m, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph, NT));
         for (int a = 0; a < n_alph; ++a) {
             dim3 grid((unsigned)ceil_div64(N0, 32), (unsigned)ceil_div64(nj, 32));
             transpose_q_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(Qt + (int64_t)a * nj * N0, N0, nj,
@@ -752,7 +909,7 @@ int dense_gram_path(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx,
         if (st) {
             st->method = GPFQ_METHOD_GRAM >> 4;
             st->gram_kernel = 3;
-            st->flops_algorithmic = 6 * m * N0 * nj * n_alph;
+            if (!ctx->last_sweep_i8) st->flops_algorithmic = 6 * m * N0 * nj * n_alph;
             st->bytes_algorithmic = (same ? 1 : 2) * 4 * N0 * m;
         }
         return GPFQ_OK;

@@ -424,6 +424,21 @@ class GpfqEngine:
         self.last_stats = st.as_dict()
         return out[0] if single else out
 
+    def debug_slgemm(self, A, B, D=7, transposed_b=False):
+        """C = A B^T through the int8-slice tcgen05 contraction of the residual-form sweep (diagnostics / tests).
+        A: (M, K) float64; B: (N, K) float32, or (K, N) with `transposed_b`."""
+        A = np.ascontiguousarray(A, dtype=np.float64)
+        B = np.ascontiguousarray(B, dtype=np.float32)
+        M, K = A.shape
+        N = B.shape[1] if transposed_b else B.shape[0]
+        if (B.shape[0] if transposed_b else B.shape[1]) != K:
+            raise ValueError("A and B disagree on K")
+        C = np.zeros((M, N), dtype=np.float64)
+        self._bind_stream(False)
+        self._check(self._lib.gpfq_debug_slgemm(self._ctx, c_void_p(A.ctypes.data), c_void_p(B.ctypes.data), M, N, K, int(D),
+                                                1 if transposed_b else 0, c_void_p(C.ctypes.data)))
+        return C
+
     def msq(self, W, alphabet):
         """Plain nearest-level rounding of every weight (the MSQ baseline of the reference's drivers)."""
         W = np.ascontiguousarray(W, dtype=np.float32)

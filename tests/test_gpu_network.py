@@ -95,6 +95,23 @@ def test_cnn_full_network_matches_the_oracle_walk(conv_path):
     _compare(qg, qo, x[:64], {"Dense", "Conv2D"})
 
 
+def test_cnn_with_5x5_and_7x7_kernels_through_the_default_path():
+    """Kernel sizes without a dedicated kernel (the 7 x 7 / stride 2 stem of ResNet50, 5 x 5 layers) go through the default
+    conv_path="nhwc" like any other: the reference handles every kernel size (quantized_network.py:686-727)."""
+    rng = np.random.default_rng(14)
+    L = hostnet
+    net = L.Sequential([L.Conv2D(6, 7, strides=2, padding="same", activation="relu"), L.BatchNormalization(),
+                        L.Conv2D(8, 5, padding="valid", activation="relu"), L.MaxPooling2D(2), L.Flatten(),
+                        L.Dense(10, activation="softmax")], input_shape=(24, 24, 3), seed=4)
+    x = rng.random((64, 24, 24, 3)).astype(np.float32)
+    seq = hostnet.ArraySequence(x, rng.integers(0, 10, 64), 16)
+    qg = QuantizedCNN(net, 16, seq, bits=3, alphabet_scalar=3)
+    qg.quantize_network()
+    qo = _with_oracle(QuantizedCNN, net, 16, seq, bits=3, alphabet_scalar=3)
+    qo.quantize_network()
+    _compare(qg, qo, x[:32], {"Dense", "Conv2D"})
+
+
 def test_vgg_like_full_network_matches_the_oracle_walk():
     """BASELINE config 3 shape family (Keras VGG16, quantize_pretrained_imagenet.py:43-50): InputLayer, 13 conv 3x3
     'same', 5 pools, fc1 / fc2 / predictions -- a thin copy (channels / 16, 32 x 32 inputs), ternary alphabet."""

@@ -215,8 +215,16 @@ def test_conv_1x1_and_2x2_and_generic_kernel_sizes(engine):
         Xp = [patches(ch)[0] for ch in range(C)]
         Xqp = [patches(ch)[1] for ch in range(C)]
         assert np.array_equal(engine.conv_channels(Xp, Xqp, W, A), Qref), k
-        if k in (1, 2):
-            assert np.array_equal(engine.conv_layer_nhwc(act, actq, W, A), Qref), k
+        # the NHWC entry point takes every kernel size too (5 x 5: device im2col + one Dense problem per channel)
+        assert np.array_equal(engine.conv_layer_nhwc(act, actq, W, A), Qref), k
+    # 7 x 7 / stride 2 / VALID (the ResNet50 stem geometry) and a channel shard, first layer (X == Xq)
+    act = np.maximum(rng.standard_normal((4, 20, 20, 3)), 0).astype(np.float32)
+    W = (rng.uniform(-1, 1, (7, 7, 3, 5)) * 0.2).astype(np.float32)
+    A = O.layer_alphabet(W, 3, O.unit_alphabet(2))
+    patches = lambda ch: (O.channel_patches(act, ch, (7, 7), (2, 2), "VALID"),) * 2
+    Qref = c_oracle.quantize_conv_layer(W, patches, A)
+    Q = engine.conv_layer_nhwc(act, None, W, A, strides=(2, 2), padding="VALID", c0=1, n_channels=2)
+    assert np.array_equal(Q[:, :, 1:3], Qref[:, :, 1:3]) and not Q[:, :, 0].any()
 
 
 def test_msq_and_bit_round(engine):
@@ -598,8 +606,15 @@ def test_sweep_lowrank_outer_level_matches_the_oracle(engine, N0, N1, m, first):
     Qref = c_oracle.quantize_layer(W, X, Xq, A)
     engine.set_option("sweep_outer", 2)
     try:
-        Q = engine.dense_layer(X, None if first else Xq, W, A, method="gram")
-        assert engine.last_stats["gram_kernel"] == 3
+        Q = engine.dense_layer(X, None if first else Xq, W, A, method="gram")       # contractions on tcgen05 (int8 slices)
+        assert engine.last_stats["gram_kernel"] == 3 and engine.last_stats["reserved"] & 1
+        engine.set_option("sweep_i8", 2)                                            # the same on the fp64 DMMA pipe
+        try:
+            Qf = engine.dense_layer(X, None if first else Xq, W, A, method="gram")
+            assert engine.last_stats["gram_kernel"] == 3 and not engine.last_stats["reserved"] & 1
+        finally:
+            engine.set_option("sweep_i8", 0)
+        assert np.array_equal(Q, Qf)
         A2 = O.layer_alphabet(W, 4, O.unit_alphabet(3))
         Qm = engine.dense_layer(X, None if first else Xq, W, [A, A2], method="gram", j0=1, j1=N1 - 1)
     finally:
@@ -619,3 +634,25 @@ def test_sweep_lowrank_outer_level_matches_the_oracle(engine, N0, N1, m, first):
         finally:
             engine.set_option("sweep_outer", 0)
     assert np.array_equal(Qm[1][:, 1:N1 - 1], c_oracle.quantize_layer(W, X, Xq, A2)[:, 1:N1 - 1])
+
+
+# ---- the int8-slice tcgen05 contraction of the residual-form sweep (slgemm_i8.cu) ---------------------------------------
+@pytest.mark.parametrize("M,N,K,tb", [(128, 128, 128, False), (200, 300, 1000, False), (130, 260, 5000, True), (64, 70, 30000, False),
+                                      (257, 129, 384, True), (1, 1, 1, False)])
+def test_slgemm_i8_matches_fp64(engine, M, N, K, tb):
+    """C = A B^T, A fp64 (residual-like: wide dynamic range inside a row), B fp32: D = 7 keeps the dropped slice pairs below
+    2^-46 of 2^(eA + eB) per K position; D = 10 (every pair) leaves only the 2^-38 slice rounding; integer data is exact."""
+    rng = np.random.default_rng(M * N + K)
+    A = rng.standard_normal((M, K)) * np.exp(rng.uniform(-3, 3, (M, K)))
+    B = np.maximum(rng.standard_normal((N, K)), 0).astype(np.float32)
+    Bin = np.ascontiguousarray(B.T) if tb else B
+    ref = A @ B.astype(np.float64).T
+    scale = np.abs(A) @ np.abs(B).astype(np.float64).T + 1e-300
+    for D, tol in ((6, 5e-9), (7, 5e-11), (10, 5e-11)):
+        C = engine.debug_slgemm(A, Bin, D=D, transposed_b=tb)
+        err = float(np.max(np.abs(C - ref) / scale))
+        assert err <= tol, (D, err)
+    Ai = rng.integers(-100, 100, (M, K)).astype(np.float64)
+    Bi = rng.integers(0, 255, (N, K)).astype(np.float32)
+    Ci = engine.debug_slgemm(Ai, np.ascontiguousarray(Bi.T) if tb else Bi, D=10, transposed_b=tb)
+    assert np.array_equal(Ci, Ai @ Bi.astype(np.float64).T)
