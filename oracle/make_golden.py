@@ -166,5 +166,35 @@ def main():
     save("ties_and_dead", X=X, W=W, A3=A3, Q3=ref_dense(W, X, X, A3), A4=A4, Q4=ref_dense(W, X, X, A4))
 
 
+def network_goldens():
+    """Whole-network fixtures: the reference's OWN host code (`QuantizedNeuralNetwork(...).quantize_network()` :576-590;
+    for conv layers `_get_layer_data_generator` + `_build_patch_array` + `_quantize_channel_parallel_jit`) run unmodified
+    over the hostnet stand-ins, on the seeded cases of tests/test_reference_host.py."""
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_reference_host as T
+    cwd = os.getcwd()
+    os.chdir(tempfile.mkdtemp())
+    try:
+        out = {}
+        for tag, bits, c in (("ternary_c2", np.log2(3), 2), ("bits3_c4", 3, 4)):
+            net, seq, x, q = T.run_reference_mlp(bits, c)
+            for idx, layer in enumerate(net.layers):
+                if layer.__class__.__name__ == "Dense":
+                    out[f"{tag}_Q{idx}"] = np.array(q.quantized_net.layers[idx].get_weights()[0])
+            out[f"{tag}_pred"] = q.quantized_net.predict(x).argmax(-1)
+        save("ref_network_mlp", **out)
+        net, seq, x, q, Qr = T.run_reference_cnn_layers(4, 4)
+        out = {f"Q{idx}": Q for idx, Q in Qr.items()}
+        out["pred"] = q.quantized_net.predict(x).argmax(-1)
+        save("ref_network_cnn", **out)
+    finally:
+        os.chdir(cwd)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "network":
+        network_goldens()
+    else:
+        main()
+        network_goldens()
