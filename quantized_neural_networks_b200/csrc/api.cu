@@ -56,6 +56,7 @@ int gpfq_ws(gpfq_ctx *ctx, int slot, size_t bytes, void **out) {
             // pending kernels may still read the old buffer
             CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
             CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
+            for (auto &s : ctx->aux_stream) if (s) CUDA_TRY(ctx, cudaStreamSynchronize(s));
             CUDA_TRY(ctx, cudaFree(b.p));
             b.p = nullptr;
             b.cap = 0;
@@ -121,6 +122,8 @@ extern "C" int gpfq_create(int device, gpfq_ctx **out) {
         for (int i = 0; ok && i < 8; ++i) ok = cudaEventCreate(&r.e[i]) == cudaSuccess;
     ctx->cur = &ctx->ring[0];
     for (int i = 0; ok && i < 4; ++i) ok = cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; ok && i < 4; ++i) ok = cudaEventCreateWithFlags(&ctx->ev_chain[i], cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; ok && i < 2; ++i) ok = cudaStreamCreateWithFlags(&ctx->aux_stream[i], cudaStreamNonBlocking) == cudaSuccess;
     if (!ok) {
         delete ctx;
         return GPFQ_ERR_CUDA;
@@ -141,6 +144,7 @@ extern "C" int gpfq_trim(gpfq_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->copy_stream);
+    for (auto &s : ctx->aux_stream) if (s) cudaStreamSynchronize(s);
     for (auto &b : ctx->ws) {
         if (b.p) cudaFree(b.p);
         b.p = nullptr;
@@ -163,6 +167,8 @@ extern "C" void gpfq_destroy(gpfq_ctx *ctx) {
     for (auto &r : ctx->ring)
         for (auto &e : r.e) if (e) cudaEventDestroy(e);
     for (auto &e : ctx->ev_copy) if (e) cudaEventDestroy(e);
+    for (auto &e : ctx->ev_chain) if (e) cudaEventDestroy(e);
+    for (auto &s : ctx->aux_stream) if (s) cudaStreamDestroy(s);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
@@ -197,8 +203,9 @@ extern "C" int gpfq_set_option(gpfq_ctx *ctx, const char *key, int64_t value) {
     } else if (!strcmp(key, "sweep_i8")) {      // residual-form sweep contractions: 0 auto, 1 int8 slices on tcgen05, 2 fp64 DMMA
         if (value < 0 || value > 2) return gpfq_fail(ctx, GPFQ_ERR_ARG, "sweep_i8 must be 0, 1 or 2");
         ctx->sweep_i8 = (int)value;
-    } else if (!strcmp(key, "sweep_kernel")) {  // 0 persistent neuron-tile kernel, 1 one launch pair per block
-        if (value < 0 || value > 1) return gpfq_fail(ctx, GPFQ_ERR_ARG, "sweep_kernel must be 0 or 1");
+    } else if (!strcmp(key, "sweep_kernel")) {  // 0 pipelined range walk where it applies, else the neuron-tile kernel;
+                                                 // 1 one launch pair per block; 2 always the (unpipelined) neuron-tile kernel
+        if (value < 0 || value > 2) return gpfq_fail(ctx, GPFQ_ERR_ARG, "sweep_kernel must be 0, 1 or 2");
         ctx->sweep_variant = (int)value;
     } else {
         return gpfq_fail(ctx, GPFQ_ERR_ARG, "unknown option '%s'", key);

@@ -50,6 +50,8 @@ struct gpfq_ctx {
     int64_t calls = 0;          // API calls begun so far
     CallRecord *cur = nullptr;  // record of the call in progress
     cudaEvent_t ev_copy[4] = {};
+    cudaStream_t aux_stream[2] = {};   // residual-form sweep: the W part of the residual update of each neuron group
+    cudaEvent_t ev_chain[4] = {};      // ... [2 g] residuals sliced (main -> aux), [2 g + 1] W part landed (aux -> main)
     std::string err = "";
     int launches = 0;
     int conv_variant = 0;         // 3x3 patch-Gram kernel: 0 TMA-staged / correlation form (default), 1 direct LDG, 2 generic,

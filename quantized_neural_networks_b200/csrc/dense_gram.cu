@@ -140,7 +140,10 @@ sweep_tile_kernel(const double *__restrict__ G1, const double *__restrict__ G2, 
                   const double *__restrict__ Wt, double *__restrict__ Qt, int64_t nj,
                   const double *__restrict__ alphabets, const int *__restrict__ Koff,
                   const int *__restrict__ Flags, int64_t t_begin, int64_t t_end, const double *__restrict__ Dt,
-                  int64_t ldd) {
+                  int64_t ldd, int8_t *__restrict__ Kq, int64_t krows, int64_t krow0, double inv_h) {
+    // Kq (nullable): the decisions also go out as int8 level indices k' = q / h (one digit slice of the int8 contractions
+    // of the residual-form sweep, slgemm_i8.cu) in its K-block-tiled layout (sl_offset): krows rows, this launch's neuron 0 is
+    // row krow0.
     // Directions [t_begin, t_end) (t_begin a multiple of 32).  Dt (nullable): (n_alph, nj, ldd) contributions of the
     // directions before t_begin, from one large NT contraction on the host side (two-level blocking).
     using Cfg = SweepCfg<NT>;
@@ -350,16 +353,296 @@ sweep_tile_kernel(const double *__restrict__ G1, const double *__restrict__ G2, 
         __syncthreads();
         for (int e = tid; e < NT * B; e += THREADS) {
             const int j = e / B, t = e % B;
-            if (jt + j < nj && t < nb) Qa[(jt + j) * N0 + t0 + t] = qblk[j * (B + 1) + t];
+            if (jt + j < nj && t < nb) {
+                const double q = qblk[j * (B + 1) + t];
+                Qa[(jt + j) * N0 + t0 + t] = q;
+                if (Kq) Kq[sl_offset(t0 + t, 0, krow0 + jt + j, krows, 1)] = (int8_t)__double2int_rn(q * inv_h);
+            }
         }
         __syncthreads();  // Q block visible to this CTA's later panel loads
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Pipelined range walk: the same work as sweep_tile_kernel, but the panel of block b + 1 is contracted WHILE block b is being
+// walked.  In sweep_tile_kernel a block costs panel + walk back to back (measured 12.9 us per block of 32 directions, of
+// which the serial walk is 6 us); here four warps (the "contractors") prepare block b + 1 -- the contributions of every
+// direction whose decision is already known, i.e. the W terms of all earlier directions of the range and the Q terms of
+// blocks <= b - 1 -- underneath the walk of block b by the walker warps (4 lanes per neuron, as before), and only ONE
+// 32-direction chunk, G2[block b + 1, block b] x Q_b, remains between two walks.  Two working sets (block operands, prior
+// dots, decisions) alternate between the roles; named barriers hand them over:
+//   READY[s]      contractors -> walkers: set s holds block b's operands and residual dots
+//   WALK_DONE[s]  walkers -> contractors: the decisions of block b are in set s (and in Qt / the int8 index slice)
+// One CTA per SM (up to 200 KB of shared memory); the host uses it when every CTA of the launch is resident at once.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(count) : "memory"); }
+
+template <int NT>
+struct PipeCfg {
+    static constexpr int B = SWEEP_B, KC = 64, LD = KC + 4, STAGES = 3, THREADS = 256, CT = 128;
+    static constexpr int SET = 2 * B * (B + 1) + 2 * NT * (B + 1) + B * (NT + 1) + 3 * B;   // doubles per working set
+    static constexpr size_t SMEM = sizeof(double) * ((size_t)STAGES * (B + NT) * LD + 2 * SET + GPFQ_MAX_K);
+};
+
+template <int NT>
+__global__ void __launch_bounds__(256, 1)
+sweep_pipe_kernel(const double *__restrict__ G1, const double *__restrict__ G2, int64_t ldg, int64_t N0,
+                  const double *__restrict__ Wt, double *__restrict__ Qt, int64_t nj, const double *__restrict__ alphabets,
+                  const int *__restrict__ Koff, const int *__restrict__ Flags, int64_t t_begin, int64_t t_end,
+                  const double *__restrict__ Dt, int64_t ldd, int8_t *__restrict__ Kq, int64_t krows, int64_t krow0, double inv_h) {
+    using Cfg = PipeCfg<NT>;
+    constexpr int B = Cfg::B, KC = Cfg::KC, LD = Cfg::LD, STAGES = Cfg::STAGES, CT = Cfg::CT, NA = NT / 8, NW = 4 * NT;
+    constexpr int BAR_C = 1, BAR_READY = 2, BAR_WALK_DONE = 4, HANDOVER = NW + CT;
+    extern __shared__ __align__(16) unsigned char sweep_smem[];
+    double *gst = reinterpret_cast<double *>(sweep_smem);   // STAGES x B x LD   (Gram rows of the block being prepared)
+    double *wst = gst + STAGES * B * LD;                    // STAGES x NT x LD  (W or Q panel of the tile)
+    double *sets = wst + STAGES * NT * LD;                  // 2 working sets
+    double *alph = sets + 2 * Cfg::SET;
+    auto g2d_of = [&](int s) { return sets + s * Cfg::SET; };                  // 2B x (B+1): G2 diagonal tile, then B rows of zeros
+    auto wblk_of = [&](int s) { return g2d_of(s) + 2 * B * (B + 1); };         // NT x (B+1)
+    auto qblk_of = [&](int s) { return wblk_of(s) + NT * (B + 1); };           // NT x (B+1): prior dots in, decisions out
+    auto dsm_of = [&](int s) { return qblk_of(s) + NT * (B + 1); };            // B x (NT+1): this range's part of the dots
+    auto nrm_of = [&](int s) { return dsm_of(s) + B * (NT + 1); };             // B, then rinv (B), then G1[t][t] (B)
+
+    const int a = blockIdx.y;
+    const int K = Koff[a + 1] - Koff[a];
+    const int64_t jt = (int64_t)blockIdx.x * NT;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    double *Qa = Qt + (int64_t)a * nj * N0;
+    for (int e = tid; e < K; e += 256) alph[e] = alphabets[Koff[a] + e];
+    for (int e = tid; e < 2 * B * (B + 1); e += 256) g2d_of(e / (B * (B + 1)))[B * (B + 1) + e % (B * (B + 1))] = 0.0;
+    __syncthreads();
+    const double inv_step = gpfq_inv_step(alph, K, Flags[a]);
+    const int nblk = (int)((t_end - t_begin + B - 1) / B);
+    const double *Da = Dt ? Dt + (int64_t)a * nj * ldd : nullptr;
+
+    if (warp >= 4) {
+        // =============================== contractors ===============================
+        const int ct = tid - 128, cw = warp - 4, grp = lane >> 2, tig = lane & 3;
+        constexpr int GCH = B * (KC / 2) / CT;                      // 16-byte pieces of a Gram chunk per thread (8)
+        constexpr int WCH = (NT * (KC / 2) + CT - 1) / CT;          // ... of a W / Q chunk per thread (2, 4, 8)
+        constexpr int DPT = B * B / CT;                             // diagonal-tile entries per thread (8)
+        constexpr int WPT = (NT * B + CT - 1) / CT;                 // W-block entries per thread (2, 4, 8)
+        int w_off[WCH], w_bytes[WCH];
+        const double *w_src[WCH], *q_src[WCH];
+#pragma unroll
+        for (int i = 0; i < WCH; ++i) {
+            const int idx = ct + i * CT, r = idx / (KC / 2), c = idx % (KC / 2);
+            const bool in_tile = idx < NT * (KC / 2);
+            const bool ok = in_tile && (jt + r < nj);
+            w_off[i] = in_tile ? r * LD + c * 2 : -1;
+            w_src[i] = Wt + (ok ? (jt + r) * N0 + c * 2 : 0);
+            q_src[i] = Qa + (ok ? (jt + r) * N0 + c * 2 : 0);
+            w_bytes[i] = ok ? 16 : 0;
+        }
+        for (int b = 0; b < nblk; ++b) {
+            const int s = b & 1;
+            const int64_t t0 = t_begin + (int64_t)b * B;
+            const int nb = (int)((t_end - t0) < B ? (t_end - t0) : B);
+            if (b > 0) named_bar_sync(BAR_C, CT);   // every contractor is done with ring slots 0 / 1 of the previous block
+            // ---- the block's own operands and its G2 tile against the previous block: requested now, parked in registers
+            double pg1[DPT], pg2[DPT], pgp[DPT], pw[WPT], pd[WPT];
+#pragma unroll
+            for (int i = 0; i < DPT; ++i) {
+                const int e = ct + i * CT, r = e / B, c = e % B;
+                const bool ok = r < nb && c <= r;
+                pg1[i] = ok ? __ldg(G1 + (t0 + r) * ldg + t0 + c) : 0.0;
+                pg2[i] = ok ? __ldg(G2 + (t0 + r) * ldg + t0 + c) : 0.0;
+                pgp[i] = (b > 0 && r < nb) ? __ldg(G2 + (t0 + r) * ldg + t0 - B + c) : 0.0;
+            }
+#pragma unroll
+            for (int i = 0; i < WPT; ++i) {
+                const int e = ct + i * CT, j = e / B, t = e % B;
+                const bool ok = e < NT * B && jt + j < nj && t < nb;
+                pw[i] = ok ? __ldg(Wt + (jt + j) * N0 + t0 + t) : 0.0;
+                pd[i] = (ok && Da) ? __ldg(Da + (jt + j) * ldd + (t0 - t_begin) + t) : 0.0;  // prior ranges
+            }
+            // ---- early panel: W terms of blocks 0 .. b-1, Q terms of blocks 0 .. b-2 (block b-1 is being walked right now)
+            int g_off[GCH], g_bytes[GCH];
+            const double *g1_src[GCH], *g2_src[GCH];
+#pragma unroll
+            for (int i = 0; i < GCH; ++i) {
+                const int idx = ct + i * CT, r = idx / (KC / 2), c = idx % (KC / 2);
+                const bool ok = t0 + r < N0;
+                g_off[i] = r * LD + c * 2;
+                g1_src[i] = G1 + (ok ? (t0 + r) * ldg + c * 2 : 0);
+                g2_src[i] = G2 + (ok ? (t0 + r) * ldg + c * 2 : 0);
+                g_bytes[i] = ok ? 16 : 0;
+            }
+            double acc[NA][2];
+#pragma unroll
+            for (int i = 0; i < NA; ++i) acc[i][0] = acc[i][1] = 0.0;
+            const int n1 = b * B, n2 = b > 0 ? (b - 1) * B : 0;
+            const int nck1 = (n1 + KC - 1) / KC, nck2 = (n2 + KC - 1) / KC, total = nck1 + nck2;
+            auto issue = [&](int it) {
+                if (it < total) {
+                    const int seg = it >= nck1;
+                    const int krel = (seg ? it - nck1 : it) * KC;
+                    const int64_t k0 = t_begin + krel;
+                    const int kleft = (seg ? n2 : n1) - krel;      // directions of the chunk that exist (a multiple of 32)
+                    const int st = it % STAGES;
+#pragma unroll
+                    for (int i = 0; i < GCH; ++i) {
+                        const bool in = ((ct + i * CT) % (KC / 2)) * 2 < kleft;
+                        cp_async16(gst + st * B * LD + g_off[i], in ? (seg ? g2_src[i] : g1_src[i]) + k0 : G1, in ? g_bytes[i] : 0);
+                    }
+#pragma unroll
+                    for (int i = 0; i < WCH; ++i)
+                        if (w_off[i] >= 0) {
+                            const bool in = ((ct + i * CT) % (KC / 2)) * 2 < kleft;
+                            cp_async16(wst + st * NT * LD + w_off[i], in ? (seg ? q_src[i] : w_src[i]) + k0 : Wt, in ? w_bytes[i] : 0);
+                        }
+                }
+                cp_async_commit();
+            };
+            auto contract = [&](const double *gs, const double *ws, bool neg, int kmax) {
+                const double *as = gs + (cw * 8 + grp) * LD + tig;
+                const double *bs = ws + grp * LD + tig;
+#pragma unroll 4
+                for (int kk = 0; kk < kmax; kk += 4) {
+                    const double av = neg ? -as[kk] : as[kk];
+#pragma unroll
+                    for (int i = 0; i < NA; ++i) dmma_m8n8k4(acc[i][0], acc[i][1], av, bs[i * 8 * LD + kk]);
+                }
+            };
+            issue(0);
+            issue(1);
+            for (int it = 0; it < total; ++it) {
+                cp_async_wait<1>();
+                named_bar_sync(BAR_C, CT);  // chunk `it` landed for every contractor; chunk it-1 fully consumed
+                issue(it + 2);
+                const int st = it % STAGES;
+                contract(gst + st * B * LD, wst + st * NT * LD, it >= nck1, KC);
+            }
+            cp_async_wait<0>();
+            named_bar_sync(BAR_C, CT);      // the ring is idle: slot 0 takes the block's own (masked) tile, slot 1 the tile
+                                            // against the previous block
+            // ---- working set s (its last reader, the walk of block b-2, is over: WALK_DONE of b-2 was awaited while
+            //      preparing block b-1) and the two register-parked tiles
+            double *g2d = g2d_of(s), *wblk = wblk_of(s), *qblk = qblk_of(s), *nrm = nrm_of(s), *rinv = nrm + B, *g1dd = rinv + B;
+            double *gst1 = gst + B * LD, *wst1 = wst + NT * LD;
+#pragma unroll
+            for (int i = 0; i < DPT; ++i) {
+                const int e = ct + i * CT, r = e / B, c = e % B;
+                g2d[r * (B + 1) + c] = pg2[i];
+                gst[r * LD + c] = c < r ? pg1[i] : 0.0;   // strictly lower: what w_s (s < t, same block) adds to d_t
+                gst1[r * LD + c] = pgp[i];
+                if (c == r) {
+                    const double nv = r < nb ? (double)(float)sqrt(pg2[i]) : 0.0;
+                    nrm[r] = nv;
+                    rinv[r] = nv < GPFQ_DEAD_NORM ? 0.0 : 1.0 / (nv * nv);
+                    g1dd[r] = pg1[i];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < WPT; ++i) {
+                const int e = ct + i * CT, j = e / B, t = e % B;
+                if (e < NT * B) {
+                    wblk[j * (B + 1) + t] = pw[i];
+                    qblk[j * (B + 1) + t] = pd[i];
+                    wst[j * LD + t] = pw[i];
+                }
+            }
+            named_bar_sync(BAR_C, CT);
+            contract(gst, wst, false, B);
+            if (b > 0) {
+                named_bar_sync(BAR_WALK_DONE + (s ^ 1), HANDOVER);   // block b-1 is walked: its decisions sit in the other set
+                const double *qprev = qblk_of(s ^ 1);
+#pragma unroll
+                for (int i = 0; i < WPT; ++i) {
+                    const int e = ct + i * CT, j = e / B, t = e % B;
+                    if (e < NT * B) wst1[j * LD + t] = qprev[j * (B + 1) + t];
+                }
+                named_bar_sync(BAR_C, CT);
+                contract(gst1, wst1, true, B);
+            }
+            double *dsm = dsm_of(s);
+#pragma unroll
+            for (int i = 0; i < NA; ++i) {
+                double *dp = dsm + (cw * 8 + grp) * (NT + 1) + i * 8 + tig * 2;
+                dp[0] = acc[i][0];
+                dp[1] = acc[i][1];
+            }
+            __threadfence_block();
+            named_bar_arrive(BAR_READY + s, HANDOVER);
+        }
+    } else if (tid < NW) {
+        // =============================== walkers: FOUR lanes per neuron (lane = 4 j + r) ===============================
+        const int j = tid >> 2, r = tid & 3;
+        for (int b = 0; b < nblk; ++b) {
+            const int s = b & 1;
+            const int64_t t0 = t_begin + (int64_t)b * B;
+            const int nb = (int)((t_end - t0) < B ? (t_end - t0) : B);
+            named_bar_sync(BAR_READY + s, HANDOVER);
+            const double *g2d = g2d_of(s), *wrow = wblk_of(s) + j * (B + 1), *dsm = dsm_of(s), *nrm = nrm_of(s), *rinv = nrm + B, *g1dd = rinv + B;
+            double *qrow = qblk_of(s) + j * (B + 1);
+            double d[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {  // prior ranges + this range's panel
+                const int t = 4 * i + r;
+                d[i] = qrow[t] + dsm[t * (NT + 1) + j];
+            }
+            __syncwarp();  // every lane has read its prior-range values before the first q lands in qblk
+            const int ngrp = (nb + 3) >> 2;
+#pragma unroll 1
+            for (int g4 = 0; g4 < ngrp; ++g4) {
+                const double *gbase = g2d + (4 * g4 + r) * (B + 1) + 4 * g4;  // G2[4 (g4 + i) + r][4 g4 + rr] at gbase[4 i (B+1) + rr]
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {
+                    const int tt = 4 * g4 + rr;
+                    const double d0 = __shfl_sync(0xffffffffu, d[0], (lane & ~3) + rr);
+                    const double wv = wrow[tt];
+                    const double num = fma(wv, g1dd[tt], d0);
+                    double q = gpfq_decide_rcp_inl(nrm[tt], rinv[tt], d0, num, wv, alph, K, inv_step);
+                    if (tt >= nb) q = 0.0;  // past the end of a partial block: no decision, no update
+                    if (r == rr && tt < nb) qrow[tt] = q;
+                    if (rr < 3) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) d[i] = fma(-gbase[4 * i * (B + 1) + rr], q, d[i]);
+                    } else {  // last step of the group: slot 0 is spent in every lane, shift down while updating
+#pragma unroll
+                        for (int i = 0; i < 7; ++i) d[i] = fma(-gbase[4 * (i + 1) * (B + 1) + rr], q, d[i + 1]);
+                        d[7] = 0.0;
+                    }
+                }
+            }
+            // ---- this lane's own decisions (directions = r mod 4) go out: Qt for later ranges / the result, and the int8 index
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int tt = 4 * i + r;
+                if (jt + j < nj && tt < nb) {
+                    const double q = qrow[tt];
+                    Qa[(jt + j) * N0 + t0 + tt] = q;
+                    if (Kq) Kq[sl_offset(t0 + tt, 0, krow0 + jt + j, krows, 1)] = (int8_t)__double2int_rn(q * inv_h);
+                }
+            }
+            __threadfence_block();
+            named_bar_arrive(BAR_WALK_DONE + s, HANDOVER);
+        }
+    }
+}
+
+template <int NT>
+static int launch_sweep_pipe(gpfq_ctx *ctx, const double *G1, const double *G2, int64_t ldg, int64_t N0, const double *Wt,
+                             double *Qt, int64_t nj, const double *d_alph, const int *d_koff, const int *d_flags,
+                             int n_alph, int64_t t_begin, int64_t t_end, const double *Dt, int64_t ldd, int8_t *Kq,
+                             int64_t krows, int64_t krow0, double inv_h) {
+    const size_t smem = PipeCfg<NT>::SMEM;
+    dim3 grid((unsigned)ceil_div64(nj, NT), (unsigned)n_alph);
+    auto k = sweep_pipe_kernel<NT>;
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, 256, smem, ctx->stream>>>(G1, G2, ldg, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, t_begin, t_end, Dt, ldd, Kq, krows,
+                                        krow0, inv_h);
+    KERNEL_CHECK(ctx);
+    return GPFQ_OK;
+}
+
 template <int NT>
 static int launch_sweep_tile(gpfq_ctx *ctx, const double *G1, const double *G2, int64_t ldg, int64_t N0, const double *Wt,
                              double *Qt, int64_t nj, const double *d_alph, const int *d_koff, const int *d_flags,
-                             int n_alph, int64_t t_begin, int64_t t_end, const double *Dt, int64_t ldd) {
+                             int n_alph, int64_t t_begin, int64_t t_end, const double *Dt, int64_t ldd, int8_t *Kq = nullptr,
+                             int64_t krows = 0, int64_t krow0 = 0, double inv_h = 0.0) {
     const size_t smem = SweepCfg<NT>::SMEM;
     dim3 grid((unsigned)ceil_div64(nj, NT), (unsigned)n_alph);
     const bool aligned = (N0 % 2 == 0) && (ldg % 2 == 0) && ((uintptr_t)G1 % 16 == 0) && ((uintptr_t)G2 % 16 == 0) &&
@@ -367,11 +650,11 @@ static int launch_sweep_tile(gpfq_ctx *ctx, const double *G1, const double *G2, 
     if (aligned) {
         auto k = sweep_tile_kernel<NT, true>;
         CUDA_TRY(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, 256, smem, ctx->stream>>>(G1, G2, ldg, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, t_begin, t_end, Dt, ldd);
+        k<<<grid, 256, smem, ctx->stream>>>(G1, G2, ldg, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, t_begin, t_end, Dt, ldd, Kq, krows, krow0, inv_h);
     } else {
         auto k = sweep_tile_kernel<NT, false>;
         CUDA_TRY(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, 256, smem, ctx->stream>>>(G1, G2, ldg, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, t_begin, t_end, Dt, ldd);
+        k<<<grid, 256, smem, ctx->stream>>>(G1, G2, ldg, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, t_begin, t_end, Dt, ldd, Kq, krows, krow0, inv_h);
     }
     KERNEL_CHECK(ctx);
     return GPFQ_OK;
@@ -482,7 +765,7 @@ __global__ void widen_transpose_kernel(const float *__restrict__ X, int64_t ldx,
 }
 
 static bool dense_uses_lowrank(gpfq_ctx *ctx, int64_t N0, int64_t m, int64_t nj, int n_alph, bool same, bool i8_ok) {
-    if (ctx->sweep_variant != 0 || ctx->lowrank_variant == 1) return false;
+    if (ctx->sweep_variant == 1 || ctx->lowrank_variant == 1) return false;
     if (ctx->lowrank_variant >= 2) return N0 > 64;
     if (!i8_ok) return 3 * m < N0 && N0 >= 4096 && nj >= 256;   // fp64 (DMMA) contractions: the measured rule of round 1
     // int8-slice contractions (slgemm_i8.cu): 39 slice-pair products of nj x m x N0 at ~2e15 int8 op/s plus the block-diagonal
@@ -511,10 +794,24 @@ static int64_t pick_range_length(gpfq_ctx *ctx, int64_t nj, int n_alph) {
 
 static int dispatch_sweep_tile(gpfq_ctx *ctx, int NT, const double *G1, const double *G2, int64_t ldg, int64_t N0,
                                const double *Wt, double *Qt, int64_t nj, const double *d_alph, const int *d_koff,
-                               const int *d_flags, int n_alph, int64_t tb, int64_t te, const double *Dp, int64_t R) {
-    if (NT == 32) return launch_sweep_tile<32>(ctx, G1, G2, ldg, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph, tb, te, Dp, R);
-    if (NT == 16) return launch_sweep_tile<16>(ctx, G1, G2, ldg, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph, tb, te, Dp, R);
-    return launch_sweep_tile<8>(ctx, G1, G2, ldg, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph, tb, te, Dp, R);
+                               const int *d_flags, int n_alph, int64_t tb, int64_t te, const double *Dp, int64_t R,
+                               int8_t *Kq = nullptr, int64_t krows = 0, int64_t krow0 = 0, double inv_h = 0.0) {
+    // The pipelined walk (one CTA per SM) when its 16-byte copies are possible and every CTA of the launch is resident at
+    // once; the narrowest neuron tile that allows it.  ctx->sweep_variant == 2 keeps the unpipelined tile kernel (A/B).
+    const bool aligned = (N0 % 2 == 0) && (ldg % 2 == 0) && ((uintptr_t)G1 % 16 == 0) && ((uintptr_t)G2 % 16 == 0) &&
+                         ((uintptr_t)Wt % 16 == 0) && ((uintptr_t)Qt % 16 == 0) && ((nj * N0) % 2 == 0);
+    if (aligned && ctx->sweep_variant != 2) {
+        const int64_t sms = ctx->sm_count;
+        if (ceil_div64(nj, 8) * n_alph <= sms)
+            return launch_sweep_pipe<8>(ctx, G1, G2, ldg, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph, tb, te, Dp, R, Kq, krows, krow0, inv_h);
+        if (ceil_div64(nj, 16) * n_alph <= sms)
+            return launch_sweep_pipe<16>(ctx, G1, G2, ldg, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph, tb, te, Dp, R, Kq, krows, krow0, inv_h);
+        if (ceil_div64(nj, 32) * n_alph <= sms)
+            return launch_sweep_pipe<32>(ctx, G1, G2, ldg, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph, tb, te, Dp, R, Kq, krows, krow0, inv_h);
+    }
+    if (NT == 32) return launch_sweep_tile<32>(ctx, G1, G2, ldg, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph, tb, te, Dp, R, Kq, krows, krow0, inv_h);
+    if (NT == 16) return launch_sweep_tile<16>(ctx, G1, G2, ldg, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph, tb, te, Dp, R, Kq, krows, krow0, inv_h);
+    return launch_sweep_tile<8>(ctx, G1, G2, ldg, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph, tb, te, Dp, R, Kq, krows, krow0, inv_h);
 }
 
 // Sweep with the low-rank outer level.  Wt (nj, N0) is ready; Qt (n_alph, nj, N0) receives the result.
@@ -767,8 +1064,8 @@ static int dense_lowrank_sweep_i8(gpfq_ctx *ctx, const float *X, const float *Xq
     GPFQ_TRY(gpfq_ws(ctx, WS_SL_U, (size_t)S * njP * mP, (void **)&sU));
     GPFQ_TRY(gpfq_ws(ctx, WS_SL_KQ, (size_t)njP * N0P, (void **)&sKq));
     GPFQ_TRY(gpfq_ws(ctx, WS_SL_E, (size_t)(2 * njP + N0P + 3 * mP + 16) * sizeof(int32_t), (void **)&e));
-    int32_t *eW = e, *eU = eW + njP, *eXq = eU + njP, *eXT = eXq + N0P, *eXqT = same ? eXT : eXT + mP;
-    int *scratch = eXT + 2 * mP;
+    int32_t *eW = e, *eU = eW + njP, *eXq = eU + njP, *eXT = eXq + N0P;   // X^T and X~^T share their per-sample exponents
+    int *scratch = eXT + mP;
     GPFQ_TRY(gpfq_ws(ctx, WS_LR_U, (size_t)nj * m * sizeof(double), (void **)&Ut));
     GPFQ_TRY(gpfq_ws(ctx, WS_G2, (size_t)N0 * R * sizeof(double), (void **)&Gc2));
     if (same) Gc1 = Gc2;
@@ -777,10 +1074,9 @@ static int dense_lowrank_sweep_i8(gpfq_ctx *ctx, const float *X, const float *Xq
 
     CUDA_TRY(ctx, gpfq_record(ctx, 2, st));
     // slicing, once per layer
-    GPFQ_TRY(sl_rowsplit<float>(ctx, Xq, ldx, N0, m, eXq, sXq, N0P, mP, N0P));
-    GPFQ_TRY(sl_transsplit(ctx, X, ldx, N0, m, eXT, scratch, sXT, mP, N0P));
-    if (!same) GPFQ_TRY(sl_transsplit(ctx, Xq, ldx, N0, m, eXqT, scratch, sXqT, mP, N0P));
-    GPFQ_TRY(sl_rowsplit<double>(ctx, Wt, N0, nj, N0, eW, sW, njP, N0P, njP));
+    GPFQ_TRY(sl_rowsplit<float>(ctx, Xq, ldx, N0, m, eXq, sXq, N0P, mP, 0, N0P));
+    GPFQ_TRY(sl_transsplit(ctx, X, same ? nullptr : Xq, ldx, N0, m, eXT, scratch, sXT, sXqT, mP, N0P));
+    GPFQ_TRY(sl_rowsplit<double>(ctx, Wt, N0, nj, N0, eW, sW, njP, N0P, 0, njP));
     // block-diagonal Gram tiles, compact: Gc[t][s - tb(t)], row stride R (exact fp32 x fp32 products, fp64 sums)
     const int64_t nfull = N0 / R;
     for (int which = 0; which < (same ? 1 : 2); ++which) {
@@ -814,37 +1110,57 @@ static int dense_lowrank_sweep_i8(gpfq_ctx *ctx, const float *X, const float *Xq
     }
     CUDA_TRY(ctx, gpfq_record(ctx, 3, st));
     CUDA_TRY(ctx, cudaMemsetAsync(Ut, 0, (size_t)nj * m * sizeof(double), st));
+    CUDA_TRY(ctx, cudaMemsetAsync(sKq, 0, (size_t)njP * N0P, st));   // padding rows / directions of the index slice stay zero
     SlOperand oW, oXT, oXqT, oXq, oU, oKq;
-    GPFQ_TRY(sl_make_operand(ctx, &oW, sW, njP, N0P, S, eW, 0));
-    GPFQ_TRY(sl_make_operand(ctx, &oXT, sXT, mP, N0P, S, eXT, 0));
-    GPFQ_TRY(sl_make_operand(ctx, &oXqT, sXqT, mP, N0P, S, eXqT, 0));
-    GPFQ_TRY(sl_make_operand(ctx, &oXq, sXq, N0P, mP, S, eXq, 0));
-    GPFQ_TRY(sl_make_operand(ctx, &oU, sU, njP, mP, S, eU, 0));
-    GPFQ_TRY(sl_make_operand(ctx, &oKq, sKq, njP, N0P, 1, nullptr, 6));   // single digit b: value = b 2^(e - 6) = b
+    GPFQ_TRY(sl_make_operand(ctx, &oW, sW, njP, N0P, S, eW, 0, false));
+    GPFQ_TRY(sl_make_operand(ctx, &oXT, sXT, mP, N0P, S, eXT, 0, true));
+    GPFQ_TRY(sl_make_operand(ctx, &oXqT, sXqT, mP, N0P, S, eXT, 0, true));
+    GPFQ_TRY(sl_make_operand(ctx, &oXq, sXq, N0P, mP, S, eXq, 0, true));
+    GPFQ_TRY(sl_make_operand(ctx, &oU, sU, njP, mP, S, eU, 0, false));
+    GPFQ_TRY(sl_make_operand(ctx, &oKq, sKq, njP, N0P, 1, nullptr, 6, false));   // single digit b: value = b 2^(e - 6) = b
     const int D_UPDATE = 7, D_DOTS = 6;
 
-    auto chain = [&](cudaStream_t on, int64_t j_lo, int64_t njh) -> int {
-        cudaStream_t keep = ctx->stream;
-        ctx->stream = on;
+    // One chain per group of neurons.  On the critical path of a range stay only what needs the previous range's decisions:
+    // the Q part of the residual update (5 exact slice pairs), the re-slicing of U, the residual dots D_r and the walk.  The W
+    // part of the update, U += W_r X_r (19 pairs), depends on no decision: it runs on the group's aux stream as soon as U has
+    // been sliced for D_r, underneath D_r and the walk of range r.  Order on U (fixed, so the fp64 sums are reproducible):
+    //   slice(r) | W part of r (aux) | Q part of r (main, after the walk and after the W part) | slice(r + 1) ...
+    auto chain = [&](int g, cudaStream_t on, int64_t j_lo, int64_t njh) -> int {
+        cudaStream_t keep = ctx->stream, aux = ctx->aux_stream[g];
+        cudaEvent_t ev_sliced = ctx->ev_chain[2 * g], ev_wpart = ctx->ev_chain[2 * g + 1];
         int rc = GPFQ_OK;
         const int64_t rows_h = ceil_div64(njh, 128) * 128;
+        auto cu = [&](cudaError_t e) { if (e != cudaSuccess && rc == GPFQ_OK) rc = gpfq_fail(ctx, GPFQ_ERR_CUDA, "%s", cudaGetErrorString(e)); };
         for (int64_t tb = 0, pb = 0; tb < N0 && rc == GPFQ_OK; pb = tb, tb += R) {
             const int64_t te = tb + R < N0 ? tb + R : N0;
+            ctx->stream = on;
             if (tb > 0) {
-                const int64_t Kp = ceil_div64(tb - pb, 128) * 128;
-                rc = sl_qindex(ctx, Qt + j_lo * N0, N0, njh, pb, tb, 1.0 / h, sKq + j_lo * N0P, rows_h, N0P, Kp);
+                const int64_t Kp = ceil_div64(tb - pb, 128) * 128;   // the walk of [pb, tb) left its level indices in sKq
+                cu(cudaStreamWaitEvent(on, ev_wpart, 0));
+                SlProduct qp = {&oKq, &oXqT, j_lo, 0, pb, Kp, 6, -h};
+                rc = slgemm_i8(ctx, &qp, 1, Ut + j_lo * m, m, njh, m, true);          // U -= h K'_r X~_r
                 if (rc != GPFQ_OK) break;
-                SlProduct up[2] = {{&oW, &oXT, j_lo, 0, pb, Kp, D_UPDATE, 1.0}, {&oKq, &oXqT, j_lo, 0, pb, Kp, 6, -h}};
-                rc = slgemm_i8(ctx, up, 2, Ut + j_lo * m, m, njh, m, true);        // U += W_r X_r - h K'_r X~_r
+                rc = sl_rowsplit<double>(ctx, Ut + j_lo * m, m, njh, m, eU, sU, njP, mP, j_lo, rows_h);
                 if (rc != GPFQ_OK) break;
-                rc = sl_rowsplit<double>(ctx, Ut + j_lo * m, m, njh, m, eU + j_lo, sU + j_lo * mP, njP, mP, rows_h);
-                if (rc != GPFQ_OK) break;
+            }
+            cu(cudaEventRecord(ev_sliced, on));
+            if (tb > 0) {
                 SlProduct dp = {&oU, &oXq, j_lo, tb, 0, mP, D_DOTS, 1.0};
                 rc = slgemm_i8(ctx, &dp, 1, Do + j_lo * R, R, njh, te - tb, false);   // D_r = U X~_r^T
                 if (rc != GPFQ_OK) break;
             }
+            if (te < N0) {   // the W part of THIS range, for the ranges after it
+                const int64_t Kp = ceil_div64(te - tb, 128) * 128;
+                cu(cudaStreamWaitEvent(aux, ev_sliced, 0));
+                ctx->stream = aux;
+                SlProduct wp = {&oW, &oXT, j_lo, 0, tb, Kp, D_UPDATE, 1.0};
+                rc = slgemm_i8(ctx, &wp, 1, Ut + j_lo * m, m, njh, m, true);          // U += W_r X_r
+                cu(cudaEventRecord(ev_wpart, aux));
+                ctx->stream = on;
+                if (rc != GPFQ_OK) break;
+            }
             rc = dispatch_sweep_tile(ctx, NT, Gc1 - tb, Gc2 - tb, R, N0, Wt + j_lo * N0, Qt + j_lo * N0, njh, d_alph, d_koff,
-                                     d_flags, 1, tb, te, tb > 0 ? Do + j_lo * R : nullptr, R);
+                                     d_flags, 1, tb, te, tb > 0 ? Do + j_lo * R : nullptr, R, sKq, njP, j_lo, 1.0 / h);
         }
         ctx->stream = keep;
         return rc;
@@ -859,13 +1175,13 @@ static int dense_lowrank_sweep_i8(gpfq_ctx *ctx, const float *X, const float *Xq
         const int64_t half = ceil_div64(ceil_div64(nj, 2), 128) * 128;
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev_copy[0], st));
         CUDA_TRY(ctx, cudaStreamWaitEvent(side, ctx->ev_copy[0], 0));
-        GPFQ_TRY(chain(st, 0, half));
-        GPFQ_TRY(chain(side, half, nj - half));
+        GPFQ_TRY(chain(0, st, 0, half));
+        GPFQ_TRY(chain(1, side, half, nj - half));
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev_copy[1], side));
         CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_copy[1], 0));
         return GPFQ_OK;
     }
-    return chain(st, 0, nj);
+    return chain(0, st, 0, nj);
 }
 
 // Dense layer by Gram + sweep.  All pointers are device pointers.
@@ -922,7 +1238,7 @@ int dense_gram_path(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx,
         if (same) G1 = G2;
         else GPFQ_TRY(gpfq_ws(ctx, WS_G1, (size_t)N0 * N0 * sizeof(double), (void **)&G1));
     }
-    if (ctx->sweep_variant != 0)
+    if (ctx->sweep_variant == 1)
         GPFQ_TRY(gpfq_ws(ctx, WS_DT, (size_t)n_alph * nj * SWEEP_B * sizeof(double), (void **)&Dt));
 
     CUDA_TRY(ctx, gpfq_record(ctx, 2, ctx->stream));
@@ -930,7 +1246,7 @@ int dense_gram_path(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx,
     else ctx->last_gram_kernel = 0;
     CUDA_TRY(ctx, gpfq_record(ctx, 3, ctx->stream));
 
-    if (ctx->sweep_variant == 0) {
+    if (ctx->sweep_variant != 1) {
         // Two-level blocking: directions in ranges of R; what the earlier ranges contribute to a range is ONE large NT
         // contraction (all SMs, split over neurons x directions, and over K when that is too few tiles), the
         // persistent neuron-tile kernel then walks the range.

@@ -8,51 +8,82 @@
 //
 // Operands are stored as S signed base-256 digit slices per value with one exponent per ROW (row = output row or column,
 // K contiguous):   x[r][k] * 2^-e_r = sum_{s=1..S} b_s[r][k] 2^(2 - 8 s)   (b in [-128, 127]; rounding at 2^-(8S-2) of 2^e_r).
-// A "phase" is one (segment, d): every slice pair with s_a + s_b = d accumulates EXACTLY into one s32 TMEM accumulator
-// (<= 5 pairs x K <= 26112), then the epilogue folds it into the tile's fp64 accumulators with the scale
-// alpha 2^(4 - 8 d + eA_i + eB_j).  Unlike gram_i8.cu (K = all samples, few phases per byte of output) these products have a
-// short K, so a read-modify-write of the fp64 tile in global memory per phase would dominate: the fp64 accumulators live in
-// TENSOR MEMORY instead (tcgen05.ld / tcgen05.st by the epilogue warps; 128 x 128 tile = 256 columns of lo / hi words, next
-// to two 128-column s32 MMA accumulators: all 512 columns), and C is touched once per tile.
+// Every slice pair with s_a + s_b = d accumulates EXACTLY into the s32 TMEM accumulator of its d (<= 5 pairs x K <= 26112);
+// ALL d of a product are open at once -- a 128 x 64 output tile leaves room for eight 64-column accumulators in the 512 TMEM
+// columns -- so a K block of every A slice and every B slice is fetched ONCE (two TMA boxes of 5 slices each per stage) and
+// feeds all 15-19 pair MMAs, and the fp64 combination  sum_d S_d alpha 2^(4 - 8 d + eA_i + eB_j)  happens once per product,
+// in registers (one output row per epilogue thread), in a fixed order: bit-reproducible.  C is touched once per tile.
 //
-// Kernel anatomy (one CTA per 128 x 128 output tile, one CTA per SM):
-//   warp 0    TMA producer: 128 x 128 B boxes of one A slice and one B slice per stage (128B swizzle), 6-stage mbarrier ring
-//   warp 1    TMEM allocator + single-thread MMA issuer: 4 x tcgen05.mma.cta_group::1.kind::i8 (M128 N128 K32) per stage
-//   warps 2-5 epilogue: per phase tcgen05.ld (s32) -> fp64 scale -> fma into the TMEM-resident fp64 tile (tcgen05.ld/st);
-//             after the last phase the tile is written (or added) to C, one row per thread
+// Kernel anatomy (one CTA per 128 x 64 output tile, one CTA per SM):
+//   warp 0    TMA producer: boxes of 64 B x 128 rows x SA slices (A) and 64 B x 64 rows x SB slices (B) per stage, 64B swizzle,
+//             3-stage mbarrier ring
+//   warp 1    TMEM allocator + single-thread MMA issuer: 2 x tcgen05.mma.cta_group::1.kind::i8 (M128 N64 K32) per slice pair
+//             and K block
+//   warps 2-5 epilogue: per product tcgen05.ld of every accumulator -> fp64 fma into 64 register sums per thread; after the
+//             last product the row is scaled by 2^eB and written (or added) to C
 #include <algorithm>
 
 #include "slgemm_i8.cuh"
 
 namespace slg {
-constexpr int TM = 128, TN = 128, BK = 128;
-constexpr int STAGES = 6;
-constexpr int A_BYTES = TM * BK, B_BYTES = TN * BK, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int THREADS = 192;
-constexpr int S = 5;                 // digit slices per sliced value
+constexpr int TM = 128, TN = 64, BK = 64;    // output tile, K bytes per stage
+constexpr int STAGES = 3;
+constexpr int S = 5;                         // digit slices per sliced value
 constexpr int P_BITS = 8 * S - 2;
-constexpr int KB_MAX = 204;          // K blocks per call: 5 pairs * 204 * 128 * 128^2 < 2^31
-constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */ + 2 * TN * sizeof(double);
+constexpr int A_SLICE = TM * BK, B_SLICE = TN * BK;
+constexpr int STAGE_BYTES = S * (A_SLICE + B_SLICE);
+constexpr int THREADS = 192;
+constexpr int MAX_PHASES = 8;                // 512 TMEM columns / TN
+constexpr int OUT_PITCH = TN + 1;            // doubles: the epilogue's transposing tile (conflict-free row writes)
+constexpr int KB_MAX = 408;                  // K blocks per call: 5 pairs * 408 * 64 * 128^2 < 2^31
+constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */ + TN * sizeof(double);
 }  // namespace slg
 
 struct SlSeg {
     int SA, SB, D;          // slices of A / B; slice pairs with s_a + s_b <= D
     int a_row0, b_row0;     // first row of this product inside the A / B slice tensors (the tile offset is added)
-    int k0, kblocks;        // first K byte (both operands) and K blocks of 128 bytes
+    int k0, kblocks;        // first K byte (both operands) and K blocks of 64 bytes
     double alpha;
     const int32_t *eA;      // row exponents, indexed like the slice rows (nullptr: eA_const)
-    const int32_t *eB;
-    int eA_const, eB_const;
+    int eA_const;
 };
 
 struct SlArgs {
     SlSeg seg[2];
     int nseg, tiles_n;
+    const int32_t *eB;      // exponents of the B rows (= output columns), shared by the segments (nullptr: eB_const)
+    int eB_const, b_row0;
     double *C;
     int64_t ldc;
     int M, N;               // valid rows / columns of C
     int accumulate, vec2;
 };
+
+// K-major operand tile with 64-byte rows, SWIZZLE_64B: 8-row atoms of 512 B (SBO), LBO unused (1), descriptor version 1
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)4 << 61);
+}
+
+// Every slice pair (k, l), k + l = d <= D, of one K block, fully unrolled: descriptors are base + constant (the start address
+// field holds bytes >> 4 and a stage never crosses the 14-bit field), the accumulator of d sits at TMEM column (d - 2) TN.
+template <int SA, int SB, int D>
+__device__ __forceinline__ void sl_issue_kblock(uint32_t tmem_base, uint64_t da, uint64_t db, uint32_t idesc, bool first) {
+    using namespace slg;
+#pragma unroll
+    for (int d = 2; d <= D; ++d) {
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int k_lo = (d - SB) > 1 ? (d - SB) : 1, k_hi = SA < (d - 1) ? SA : (d - 1);
+#pragma unroll
+        for (int k = k_lo; k <= k_hi; ++k)
+#pragma unroll
+            for (int ks = 0; ks < BK / 32; ++ks)
+                i8g::umma_i8(tmem_base + (uint32_t)((d - 2) * TN), da + (uint64_t)(((k - 1) * A_SLICE + ks * 32) >> 4),
+                             db + (uint64_t)(((d - k - 1) * B_SLICE + ks * 32) >> 4), idesc,
+                             (k == k_lo && ks == 0) ? (first ? 0u : 1u) : 1u);
+    }
+}
 
 __global__ void __launch_bounds__(slg::THREADS, 1)
 slgemm_i8_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapB0,
@@ -63,30 +94,27 @@ slgemm_i8_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)sl_smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)STAGES * STAGE_BYTES);
     uint64_t *empty = full + STAGES;
-    uint64_t *acc_full = empty + STAGES;    // [2]
-    uint64_t *acc_empty = acc_full + 2;     // [2]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
-    double *colscale = reinterpret_cast<double *>(smem + (size_t)STAGES * STAGE_BYTES + 256);   // [2][TN]: 2^eB of the tile's columns
+    uint64_t *seg_full = empty + STAGES;    // the accumulators of the current segment are complete
+    uint64_t *seg_empty = seg_full + 1;     // ... have been drained by the epilogue
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(seg_empty + 1);
+    double *colscale = reinterpret_cast<double *>(smem + (size_t)STAGES * STAGE_BYTES + 256);   // [TN]: 2^eB of the tile's columns
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ti = blockIdx.x / args.tiles_n, tj = blockIdx.x % args.tiles_n;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+        mbar_init(seg_full, 1);
+        mbar_init(seg_empty, 4);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
     }
-    if (warp >= 2) {
-        const int c = threadIdx.x - 64;     // 0..127: one column of the tile per epilogue thread
-        for (int s = 0; s < args.nseg; ++s) {
-            const SlSeg &g = args.seg[s];
-            const int e = g.eB ? g.eB[g.b_row0 + tj * TN + c] : g.eB_const;
-            colscale[s * TN + c] = ldexp(1.0, e);
-        }
+    if (warp >= 2 && threadIdx.x - 64 < TN) {
+        const int c = threadIdx.x - 64;     // one column of the tile
+        colscale[c] = ldexp(1.0, args.eB ? args.eB[args.b_row0 + tj * TN + c] : args.eB_const);
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
@@ -94,124 +122,116 @@ slgemm_i8_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ---- TMA producer
+        // ---- TMA producer: every slice of the A rows and of the B rows of one K block per stage (two boxes)
         if (lane == 0) {
             int iter = 0;
             for (int sg = 0; sg < args.nseg; ++sg) {
                 const SlSeg &g = args.seg[sg];
                 const CUtensorMap *ma = sg ? &mapA1 : &mapA0, *mb = sg ? &mapB1 : &mapB0;
-                for (int d = 2; d <= g.D; ++d) {
-                    const int k_lo = max(1, d - g.SB), k_hi = min(g.SA, d - 1);
-                    for (int k = k_lo; k <= k_hi; ++k) {
-                        const int l = d - k;
-                        for (int kb = 0; kb < g.kblocks; ++kb, ++iter) {
-                            const int s = iter % STAGES;
-                            if (iter >= STAGES) mbar_wait(&empty[s], ((iter / STAGES) - 1) & 1);
-                            unsigned char *a = smem + (size_t)s * STAGE_BYTES, *b = a + A_BYTES;
-                            mbar_expect_tx(&full[s], STAGE_BYTES);
-                            tma_load_3d(a, ma, &full[s], g.k0 + kb * BK, g.a_row0 + ti * TM, k - 1);
-                            tma_load_3d(b, mb, &full[s], g.k0 + kb * BK, g.b_row0 + tj * TN, l - 1);
-                        }
-                    }
+                const uint32_t bytes = (uint32_t)(g.SA * A_SLICE + g.SB * B_SLICE);
+                for (int kb = 0; kb < g.kblocks; ++kb, ++iter) {
+                    const int s = iter % STAGES;
+                    if (iter >= STAGES) mbar_wait(&empty[s], ((iter / STAGES) - 1) & 1);
+                    unsigned char *a = smem + (size_t)s * STAGE_BYTES, *b = a + S * A_SLICE;
+                    mbar_expect_tx(&full[s], bytes);
+                    tma_load_4d(a, ma, &full[s], 0, g.a_row0 + ti * TM, 0, g.k0 / BK + kb);
+                    tma_load_4d(b, mb, &full[s], 0, g.b_row0 + tj * TN, 0, g.k0 / BK + kb);
                 }
             }
         }
     } else if (warp == 1) {
-        // ---- MMA issuer
+        // ---- MMA issuer: per K block every slice pair (k, l), k + l = d, into the accumulator of its d
         if (lane == 0) {
-            // instruction descriptor: D = s32, A = B = signed 8-bit, both K-major, N = 128, M = 128
+            // instruction descriptor: D = s32, A = B = signed 8-bit, both K-major, N = 64, M = 128
             const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-            int iter = 0, p = 0;
+            int iter = 0;
             for (int sg = 0; sg < args.nseg; ++sg) {
                 const SlSeg &g = args.seg[sg];
-                for (int d = 2; d <= g.D; ++d, ++p) {
-                    const int buf = p & 1;
-                    if (p >= 2) {  // the epilogue must have drained this accumulator
-                        mbar_wait(&acc_empty[buf], ((p >> 1) - 1) & 1);
-                        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                    }
-                    const uint32_t tmem_d = tmem_base + (uint32_t)(buf * TN);
-                    const int n_it = (min(g.SA, d - 1) - max(1, d - g.SB) + 1) * g.kblocks;
-                    for (int it = 0; it < n_it; ++it, ++iter) {
-                        const int s = iter % STAGES;
-                        mbar_wait(&full[s], (iter / STAGES) & 1);
-                        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                        const uint32_t a = smem_u32(smem + (size_t)s * STAGE_BYTES), b = a + A_BYTES;
-#pragma unroll
-                        for (int ks = 0; ks < BK / 32; ++ks)
-                            umma_i8(tmem_d, umma_desc_sw128(a + ks * 32), umma_desc_sw128(b + ks * 32), idesc, (it | ks) ? 1u : 0u);
-                        umma_commit(&empty[s]);  // the stage may be refilled once these MMAs have read it
-                    }
-                    umma_commit(&acc_full[buf]);
+                if (sg > 0) {   // the epilogue must have drained the previous segment's accumulators
+                    mbar_wait(seg_empty, (sg - 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 }
+                for (int kb = 0; kb < g.kblocks; ++kb, ++iter) {
+                    const int s = iter % STAGES;
+                    mbar_wait(&full[s], (iter / STAGES) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                    const uint32_t a = smem_u32(smem + (size_t)s * STAGE_BYTES), b = a + S * A_SLICE;
+                    const uint64_t da = umma_desc_sw64(a), db = umma_desc_sw64(b);
+                    // the usual slice-pair sets as straight-line code (one thread issues every MMA: at 32 tensor-core cycles per
+                    // M128 N64 K32 instruction the loop overhead of the generic form would be the bottleneck)
+                    if (g.SA == 5 && g.SB == 5 && g.D == 6) sl_issue_kblock<5, 5, 6>(tmem_base, da, db, idesc, kb == 0);
+                    else if (g.SA == 5 && g.SB == 5 && g.D == 7) sl_issue_kblock<5, 5, 7>(tmem_base, da, db, idesc, kb == 0);
+                    else if (g.SA == 1 && g.SB == 5 && g.D == 6) sl_issue_kblock<1, 5, 6>(tmem_base, da, db, idesc, kb == 0);
+                    else
+                        for (int d = 2; d <= g.D; ++d) {
+                            const uint32_t tmem_d = tmem_base + (uint32_t)((d - 2) * TN);
+                            const int k_lo = max(1, d - g.SB), k_hi = min(g.SA, d - 1);
+                            for (int k = k_lo; k <= k_hi; ++k) {
+                                const uint32_t ak = a + (k - 1) * A_SLICE, bl = b + (d - k - 1) * B_SLICE;
+#pragma unroll
+                                for (int ks = 0; ks < BK / 32; ++ks)
+                                    umma_i8(tmem_d, umma_desc_sw64(ak + ks * 32), umma_desc_sw64(bl + ks * 32), idesc,
+                                            (kb | (k - k_lo) | ks) ? 1u : 0u);
+                            }
+                        }
+                    umma_commit(&empty[s]);  // the stage may be refilled once these MMAs have read it
+                }
+                umma_commit(seg_full);
             }
         }
     } else {
-        // ---- epilogue: TMEM lanes 32 * (warp % 4) .. + 31 are this warp's tile rows; one thread = one row.
+        // ---- epilogue: TMEM lanes 32 * (warp % 4) .. + 31 are this warp's tile rows; one thread = one row, whose 64 fp64
+        // sums stay in registers over all segments and phases:  sum_seg sum_d  S_d * alpha 2^(4 - 8 d + eA_row),  then 2^eB_col.
         const int quad = warp & 3;
-        const int row_t = quad * 32 + lane;                          // row inside the tile
+        const int row_t = quad * 32 + lane;
         const uint32_t lane_field = (uint32_t)(quad * 32) << 16;
-        const uint32_t acc64 = tmem_base + lane_field + 2 * TN;      // fp64 tile: column c at words 2 c (lo), 2 c + 1 (hi)
-        int p = 0;
+        double acc[TN];
+#pragma unroll
+        for (int i = 0; i < TN; ++i) acc[i] = 0.0;
         for (int sg = 0; sg < args.nseg; ++sg) {
             const SlSeg &g = args.seg[sg];
             const int ea = g.eA ? g.eA[g.a_row0 + ti * TM + row_t] : g.eA_const;
-            const double *cs = colscale + sg * TN;
-            for (int d = 2; d <= g.D; ++d, ++p) {
-                const int buf = p & 1;
-                mbar_wait(&acc_full[buf], (p >> 1) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            mbar_wait(seg_full, sg & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+#pragma unroll 1
+            for (int d = 2; d <= g.D; ++d) {
                 const double rs = ldexp(g.alpha, 4 - 8 * d + ea);
-#pragma unroll 1
-                for (int cc = 0; cc < TN / 32; ++cc) {
-                    uint32_t v[32], a[64];
-                    tmem_ld32(tmem_base + lane_field + (uint32_t)(buf * TN + cc * 32), v);
-                    if (p > 0) tmem_ld64(acc64 + cc * 64, a);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const double prev = p > 0 ? __hiloint2double((int)a[2 * i + 1], (int)a[2 * i]) : 0.0;
-                        const double r = fma((double)(int)v[i] * cs[cc * 32 + i], rs, prev);
-                        a[2 * i] = (uint32_t)__double2loint(r);
-                        a[2 * i + 1] = (uint32_t)__double2hiint(r);
-                    }
-                    tmem_st64(acc64 + cc * 64, a);
-                }
-                asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[buf]);
-            }
-        }
-        // ---- the finished tile: one row per thread, 32 consecutive doubles per chunk
-        const int64_t row = (int64_t)ti * TM + row_t;
-#pragma unroll 1
-        for (int cc = 0; cc < TN / 32; ++cc) {
-            uint32_t a[64];
-            tmem_ld64(acc64 + cc * 64, a);
-            const int64_t col0 = (int64_t)tj * TN + cc * 32;
-            if (row < args.M && col0 < args.N) {
-                double *o = args.C + row * args.ldc + col0;
-                if (args.vec2 && col0 + 32 <= args.N) {
+                for (int hf = 0; hf < TN / 32; ++hf) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + lane_field + (uint32_t)((d - 2) * TN + hf * 32), v);
 #pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        double2 r = make_double2(__hiloint2double((int)a[2 * i + 1], (int)a[2 * i]),
-                                                 __hiloint2double((int)a[2 * i + 3], (int)a[2 * i + 2]));
-                        if (args.accumulate) {
-                            const double2 old = *reinterpret_cast<const double2 *>(o + i);
-                            r.x += old.x;
-                            r.y += old.y;
-                        }
-                        *reinterpret_cast<double2 *>(o + i) = r;
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (col0 + i < args.N) {
-                            const double r = __hiloint2double((int)a[2 * i + 1], (int)a[2 * i]);
-                            o[i] = args.accumulate ? o[i] + r : r;
-                        }
+                    for (int i = 0; i < 32; ++i) acc[hf * 32 + i] = fma((double)(int)v[i], rs, acc[hf * 32 + i]);
                 }
             }
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(seg_empty);
         }
+        // ---- the finished tile.  A thread holds one ROW; written straight out that is 32 scattered 16-byte accesses per
+        // instruction (measured: 300 us per call on the read-modify-write of U).  The operand ring is idle by now (every MMA
+        // of the CTA has completed), so each warp transposes its 32 rows through it and touches C in whole 256-byte runs.
+        double *tr = reinterpret_cast<double *>(smem) + (size_t)quad * 32 * OUT_PITCH;
+#pragma unroll
+        for (int i = 0; i < TN; ++i) tr[lane * OUT_PITCH + i] = acc[i] * colscale[i];
+        __syncwarp();
+        const int64_t row0 = (int64_t)ti * TM + quad * 32, col0 = (int64_t)tj * TN;
+        // all loads of the read-modify-write first (64 independent requests in flight per lane), then the stores
+        double old[32][TN / 32];
+#pragma unroll
+        for (int r = 0; r < 32; ++r)
+#pragma unroll
+            for (int hf = 0; hf < TN / 32; ++hf) {
+                const int c = hf * 32 + lane;
+                old[r][hf] = (args.accumulate && row0 + r < args.M && col0 + c < args.N) ? args.C[(row0 + r) * args.ldc + col0 + c] : 0.0;
+            }
+#pragma unroll
+        for (int r = 0; r < 32; ++r)
+#pragma unroll
+            for (int hf = 0; hf < TN / 32; ++hf) {
+                const int c = hf * 32 + lane;
+                if (row0 + r < args.M && col0 + c < args.N) args.C[(row0 + r) * args.ldc + col0 + c] = old[r][hf] + tr[r * OUT_PITCH + c];
+            }
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
@@ -227,7 +247,7 @@ slgemm_i8_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
 template <typename T>
 __global__ void __launch_bounds__(256) sl_rowsplit_kernel(const T *__restrict__ X, int64_t ldx, int64_t rows, int64_t cols,
                                                           int32_t *__restrict__ e, int8_t *__restrict__ slices, int64_t rowsP,
-                                                          int64_t colsP) {
+                                                          int64_t colsP, int64_t row0) {
     using namespace slg;
     __shared__ double red[8];
     __shared__ int ex_s;
@@ -244,7 +264,7 @@ __global__ void __launch_bounds__(256) sl_rowsplit_kernel(const T *__restrict__ 
         for (int w = 1; w < 8; ++w) mx = fmax(mx, red[w]);
         int ex = 0;
         if (mx > 0.0 && isfinite(mx)) frexp(mx, &ex);   // mx = f 2^ex, f in [0.5, 1)  =>  |x| < 2^ex
-        e[r] = ex;
+        e[row0 + r] = ex;
         ex_s = ex;
     }
     __syncthreads();
@@ -268,7 +288,60 @@ __global__ void __launch_bounds__(256) sl_rowsplit_kernel(const T *__restrict__ 
         }
 #pragma unroll
         for (int k = 0; k < S; ++k)
-            *reinterpret_cast<uint4 *>(slices + ((int64_t)k * rowsP + r) * colsP + i0) =
+            *reinterpret_cast<uint4 *>(slices + sl_offset(i0, k, row0 + r, rowsP, S)) =
+                make_uint4(packed[k][0], packed[k][1], packed[k][2], packed[k][3]);
+    }
+}
+
+// The same for short rows (colsP <= 32 * 16 * CH): one WARP per row, the row held in registers -- one pass over the data.
+// (The residuals U are re-sliced after every range of the sweep: 2048 rows of 1504 doubles.)
+template <typename T, int CH>
+__global__ void __launch_bounds__(256) sl_rowsplit_warp_kernel(const T *__restrict__ X, int64_t ldx, int64_t rows, int64_t cols,
+                                                               int32_t *__restrict__ e, int8_t *__restrict__ slices, int64_t rowsP,
+                                                               int64_t colsP, int64_t row0, int64_t grid_rows) {
+    using namespace slg;
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= grid_rows) return;
+    const T *row = X + r * ldx;
+    double v[CH][16];
+    double mx = 0.0;
+#pragma unroll
+    for (int ch = 0; ch < CH; ++ch) {
+        const int64_t c0 = (int64_t)(ch * 32 + lane) * 16;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const double x = (r < rows && c0 + i < cols) ? (double)row[c0 + i] : 0.0;
+            v[ch][i] = x;
+            mx = fmax(mx, fabs(x));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    int ex = 0;
+    if (mx > 0.0 && isfinite(mx)) frexp(mx, &ex);
+    if (lane == 0) e[row0 + r] = ex;
+    const double scale = ldexp(1.0, P_BITS - ex);
+#pragma unroll
+    for (int ch = 0; ch < CH; ++ch) {
+        const int64_t c0 = (int64_t)(ch * 32 + lane) * 16;
+        if (c0 >= colsP) continue;
+        uint32_t packed[S][4];
+#pragma unroll
+        for (int k = 0; k < S; ++k) packed[k][0] = packed[k][1] = packed[k][2] = packed[k][3] = 0u;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            long long q = __double2ll_rn(v[ch][c] * scale);
+#pragma unroll
+            for (int k = S - 1; k >= 0; --k) {
+                const int dg = (int)((q + 128) & 255) - 128;
+                q = (q - dg) >> 8;
+                packed[k][c >> 2] |= ((uint32_t)(dg & 0xff)) << (8 * (c & 3));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < S; ++k)
+            *reinterpret_cast<uint4 *>(slices + sl_offset(c0, k, row0 + r, rowsP, S)) =
                 make_uint4(packed[k][0], packed[k][1], packed[k][2], packed[k][3]);
     }
 }
@@ -328,42 +401,35 @@ __global__ void __launch_bounds__(128) sl_transsplit_kernel(const float *__restr
     }
 #pragma unroll
     for (int k = 0; k < S; ++k)
-        *reinterpret_cast<uint4 *>(slices + ((int64_t)k * mP + i) * N0P + t0 + tg * 16) =
+        *reinterpret_cast<uint4 *>(slices + sl_offset(t0 + tg * 16, k, i, mP, S)) =
             make_uint4(packed[k][0], packed[k][1], packed[k][2], packed[k][3]);
-}
-
-// Level indices of a range of decisions: q = h k', k' in [-(K-1), K-1] (symmetric equispaced alphabet; the literal 0 of a dead
-// direction is k' = 0)  ->  one int8 "slice" (rows, N0P) of the whole decision matrix, byte columns [tb, tb + width) written
-// (zeros for neurons >= nj and directions >= te).
-__global__ void __launch_bounds__(256) sl_qindex_kernel(const double *__restrict__ Qt, int64_t N0, int64_t nj, int64_t tb, int64_t te,
-                                                        double inv_h, int8_t *__restrict__ out, int64_t grid_rows, int64_t N0P,
-                                                        int64_t width) {
-    const int64_t per_row = width / 16;
-    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (idx >= grid_rows * per_row) return;
-    const int64_t j = idx / per_row, c0 = (idx % per_row) * 16;
-    uint32_t w[4] = {0u, 0u, 0u, 0u};
-    if (j < nj) {
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-            const int64_t t = tb + c0 + c;
-            const int kq = t < te ? __double2int_rn(Qt[j * N0 + t] * inv_h) : 0;
-            w[c >> 2] |= ((uint32_t)(kq & 0xff)) << (8 * (c & 3));
-        }
-    }
-    *reinterpret_cast<uint4 *>(out + j * N0P + tb + c0) = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
 // ---- host side -------------------------------------------------------------------------------------------------
 int sl_make_operand(gpfq_ctx *ctx, SlOperand *op, const int8_t *slices, int64_t rowsP, int64_t kbytes, int n_slices, const int32_t *e,
-                    int e_const) {
+                    int e_const, bool is_b) {
+    using namespace slg;
     op->slices = slices;
     op->rowsP = rowsP;
     op->kbytes = kbytes;
     op->n_slices = n_slices;
     op->e = e;
     op->e_const = e_const;
-    return make_i8_slice_map(ctx, &op->map, slices, rowsP, kbytes, n_slices);
+    op->is_b = is_b;
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return gpfq_fail(ctx, GPFQ_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available from this driver");
+    // one box = BK bytes x (TN | TM) rows x EVERY slice of one K block: lands slice-major in the stage, 64B-swizzled rows;
+    // in the K-block-tiled layout (sl_offset) that is n_slices contiguous runs of 4 / 8 KB
+    const cuuint64_t dims[4] = {(cuuint64_t)BK, (cuuint64_t)rowsP, (cuuint64_t)n_slices, (cuuint64_t)(kbytes / BK)};
+    const cuuint64_t strides[3] = {(cuuint64_t)BK, (cuuint64_t)BK * (cuuint64_t)rowsP, (cuuint64_t)BK * (cuuint64_t)rowsP * (cuuint64_t)n_slices};
+    const cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(is_b ? TN : TM), (cuuint32_t)n_slices, 1u};
+    const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    if (kbytes % BK) return gpfq_fail(ctx, GPFQ_ERR_ARG, "slice tensors are padded to whole K blocks");
+    const CUresult rc = enc(&op->map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<int8_t *>(slices), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) return gpfq_fail(ctx, GPFQ_ERR_CUDA, "cuTensorMapEncodeTiled failed with code %d", (int)rc);
+    return GPFQ_OK;
 }
 
 // C[M x N] (ldc) = or += sum of the products.  M, N: valid extents; the slice tensors are zero-padded to tile multiples.
@@ -374,26 +440,31 @@ int slgemm_i8(gpfq_ctx *ctx, const SlProduct *prod, int nprod, double *C, int64_
     a.nseg = nprod;
     for (int s = 0; s < nprod; ++s) {
         const SlProduct &p = prod[s];
-        if (p.K % BK || p.k0 % 16 || p.K / BK > KB_MAX || p.K < BK)
-            return gpfq_fail(ctx, GPFQ_ERR_ARG, "slgemm_i8: K = %lld (offset %lld) must be a multiple of 128 (16), at most %d",
+        if (p.K % BK || p.k0 % BK || p.K / BK > KB_MAX || p.K < BK)
+            return gpfq_fail(ctx, GPFQ_ERR_ARG, "slgemm_i8: K = %lld (offset %lld) must be multiples of 64, at most %d",
                              (long long)p.K, (long long)p.k0, KB_MAX * BK);
+        if (p.A->is_b || !p.B->is_b || p.A->n_slices > S || p.B->n_slices > S)
+            return gpfq_fail(ctx, GPFQ_ERR_ARG, "slgemm_i8: operand roles / slice counts");
         if (p.a_row0 + ceil_div64(M, TM) * TM > p.A->rowsP || p.b_row0 + ceil_div64(N, TN) * TN > p.B->rowsP ||
             p.k0 + p.K > p.A->kbytes || p.k0 + p.K > p.B->kbytes)
             return gpfq_fail(ctx, GPFQ_ERR_ARG, "slgemm_i8: operand slices are not padded to the tile grid");
+        if (s > 0 && (p.B->e != prod[0].B->e || p.B->e_const != prod[0].B->e_const || p.b_row0 != prod[0].b_row0))
+            return gpfq_fail(ctx, GPFQ_ERR_ARG, "slgemm_i8: the products of one call must share the exponents of their B rows");
         SlSeg &g = a.seg[s];
         g.SA = p.A->n_slices;
         g.SB = p.B->n_slices;
-        g.D = std::min(p.D, g.SA + g.SB);
+        g.D = std::min(std::min(p.D, g.SA + g.SB), MAX_PHASES + 1);
         g.a_row0 = (int)p.a_row0;
         g.b_row0 = (int)p.b_row0;
         g.k0 = (int)p.k0;
         g.kblocks = (int)(p.K / BK);
         g.alpha = p.alpha;
         g.eA = p.A->e;
-        g.eB = p.B->e;
         g.eA_const = p.A->e_const;
-        g.eB_const = p.B->e_const;
     }
+    a.eB = prod[0].B->e;
+    a.eB_const = prod[0].B->e_const;
+    a.b_row0 = (int)prod[0].b_row0;
     a.tiles_n = (int)ceil_div64(N, TN);
     a.C = C;
     a.ldc = ldc;
@@ -412,36 +483,43 @@ int slgemm_i8(gpfq_ctx *ctx, const SlProduct *prod, int nprod, double *C, int64_
 // slices of a row-major fp64 / fp32 matrix (rows x cols, row = output row, K = cols); e: rowsP exponents
 template <typename T>
 int sl_rowsplit(gpfq_ctx *ctx, const T *X, int64_t ldx, int64_t rows, int64_t cols, int32_t *e, int8_t *slices, int64_t rowsP,
-                int64_t colsP, int64_t grid_rows) {
-    sl_rowsplit_kernel<T><<<(unsigned)grid_rows, 256, 0, ctx->stream>>>(X, ldx, rows, cols, e, slices, rowsP, colsP);
+                int64_t colsP, int64_t row0, int64_t grid_rows) {
+    const unsigned wgrid = (unsigned)ceil_div64(grid_rows, 8);
+    if (colsP <= 32 * 16 * 2)
+        sl_rowsplit_warp_kernel<T, 2><<<wgrid, 256, 0, ctx->stream>>>(X, ldx, rows, cols, e, slices, rowsP, colsP, row0, grid_rows);
+    else if (colsP <= 32 * 16 * 4)
+        sl_rowsplit_warp_kernel<T, 4><<<wgrid, 256, 0, ctx->stream>>>(X, ldx, rows, cols, e, slices, rowsP, colsP, row0, grid_rows);
+    else
+        sl_rowsplit_kernel<T><<<(unsigned)grid_rows, 256, 0, ctx->stream>>>(X, ldx, rows, cols, e, slices, rowsP, colsP, row0);
     KERNEL_CHECK(ctx);
     return GPFQ_OK;
 }
-template int sl_rowsplit<double>(gpfq_ctx *, const double *, int64_t, int64_t, int64_t, int32_t *, int8_t *, int64_t, int64_t, int64_t);
-template int sl_rowsplit<float>(gpfq_ctx *, const float *, int64_t, int64_t, int64_t, int32_t *, int8_t *, int64_t, int64_t, int64_t);
+template int sl_rowsplit<double>(gpfq_ctx *, const double *, int64_t, int64_t, int64_t, int32_t *, int8_t *, int64_t, int64_t, int64_t, int64_t);
+template int sl_rowsplit<float>(gpfq_ctx *, const float *, int64_t, int64_t, int64_t, int32_t *, int8_t *, int64_t, int64_t, int64_t, int64_t);
 
-// slices of X^T for X (N0, m) fp32: (S, mP, N0P), exponent per sample; scratch: mP ints
-int sl_transsplit(gpfq_ctx *ctx, const float *X, int64_t ldx, int64_t N0, int64_t m, int32_t *e, int *scratch, int8_t *slices,
-                  int64_t mP, int64_t N0P) {
+// slices of X^T (and, unless Xq is null, of Xq^T with the SAME per-sample exponents: max over both matrices) for X, Xq
+// (N0, m) fp32: (S, mP, N0P) each; scratch: mP ints
+int sl_transsplit(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx, int64_t N0, int64_t m, int32_t *e, int *scratch,
+                  int8_t *slices, int8_t *slices_q, int64_t mP, int64_t N0P) {
     cudaStream_t st = ctx->stream;
     CUDA_TRY(ctx, cudaMemsetAsync(scratch, 0, (size_t)mP * sizeof(int), st));
     const int rows_per_cta = 256;
     dim3 g1((unsigned)ceil_div64(m, 256), (unsigned)ceil_div64(N0, rows_per_cta));
     sl_colmax_kernel<<<g1, 256, 0, st>>>(X, ldx, N0, m, scratch, rows_per_cta);
     KERNEL_CHECK(ctx);
+    if (Xq) {
+        sl_colmax_kernel<<<g1, 256, 0, st>>>(Xq, ldx, N0, m, scratch, rows_per_cta);
+        KERNEL_CHECK(ctx);
+    }
     sl_exp_from_max_kernel<<<(unsigned)ceil_div64(mP, 256), 256, 0, st>>>(scratch, m, mP, e);
     KERNEL_CHECK(ctx);
     dim3 g2((unsigned)(N0P / 64), (unsigned)(mP / 32));
     sl_transsplit_kernel<<<g2, 128, 0, st>>>(X, ldx, N0, m, e, slices, mP, N0P);
     KERNEL_CHECK(ctx);
-    return GPFQ_OK;
-}
-
-int sl_qindex(gpfq_ctx *ctx, const double *Qt, int64_t N0, int64_t nj, int64_t tb, int64_t te, double inv_h, int8_t *out,
-              int64_t grid_rows, int64_t N0P, int64_t width) {
-    const int64_t n = grid_rows * (width / 16);
-    sl_qindex_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, ctx->stream>>>(Qt, N0, nj, tb, te, inv_h, out, grid_rows, N0P, width);
-    KERNEL_CHECK(ctx);
+    if (Xq) {
+        sl_transsplit_kernel<<<g2, 128, 0, st>>>(Xq, ldx, N0, m, e, slices_q, mP, N0P);
+        KERNEL_CHECK(ctx);
+    }
     return GPFQ_OK;
 }
 
@@ -455,7 +533,7 @@ extern "C" int gpfq_debug_slgemm(gpfq_ctx *ctx, const double *A, const float *B,
     if (!A || !B || !C_out || M < 1 || N < 1 || K < 1) return gpfq_fail(ctx, GPFQ_ERR_ARG, "bad arguments");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    const int64_t MP = ceil_div64(M, TM) * TM, NP = ceil_div64(N, TN) * TN, KP = ceil_div64(K, BK) * BK;
+    const int64_t MP = ceil_div64(M, 128) * 128, NP = ceil_div64(N, 128) * 128, KP = ceil_div64(K, 128) * 128;
     double *dA = nullptr, *dC = nullptr;
     float *dB = nullptr;
     int8_t *sA = nullptr, *sB = nullptr;
@@ -468,12 +546,12 @@ extern "C" int gpfq_debug_slgemm(gpfq_ctx *ctx, const double *A, const float *B,
     GPFQ_TRY(gpfq_ws(ctx, WS_I8_E, (size_t)(MP + 2 * NP + 8) * sizeof(int32_t), (void **)&e));
     CUDA_TRY(ctx, cudaMemcpyAsync(dA, A, (size_t)M * K * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(ctx, cudaMemcpyAsync(dB, B, (size_t)N * K * sizeof(float), cudaMemcpyHostToDevice, st));
-    GPFQ_TRY(sl_rowsplit<double>(ctx, dA, K, M, K, e, sA, MP, KP, MP));
-    if (transposed_b) GPFQ_TRY(sl_transsplit(ctx, dB, N, K, N, e + MP, reinterpret_cast<int *>(e + MP + NP), sB, NP, KP));
-    else GPFQ_TRY(sl_rowsplit<float>(ctx, dB, K, N, K, e + MP, sB, NP, KP, NP));
+    GPFQ_TRY(sl_rowsplit<double>(ctx, dA, K, M, K, e, sA, MP, KP, 0, MP));
+    if (transposed_b) GPFQ_TRY(sl_transsplit(ctx, dB, nullptr, N, K, N, e + MP, reinterpret_cast<int *>(e + MP + NP), sB, nullptr, NP, KP));
+    else GPFQ_TRY(sl_rowsplit<float>(ctx, dB, K, N, K, e + MP, sB, NP, KP, 0, NP));
     SlOperand oa, ob;
-    GPFQ_TRY(sl_make_operand(ctx, &oa, sA, MP, KP, S, e, 0));
-    GPFQ_TRY(sl_make_operand(ctx, &ob, sB, NP, KP, S, e + MP, 0));
+    GPFQ_TRY(sl_make_operand(ctx, &oa, sA, MP, KP, S, e, 0, false));
+    GPFQ_TRY(sl_make_operand(ctx, &ob, sB, NP, KP, S, e + MP, 0, true));
     int64_t done = 0;
     bool first = true;
     while (done < KP) {     // K chunks of at most KB_MAX blocks: the s32 accumulators cannot overflow

@@ -2,12 +2,20 @@
 #pragma once
 #include "i8_common.cuh"
 
-struct SlOperand {          // a sliced matrix on the device: (n_slices, rowsP, kbytes) int8 + row exponents
+// Layout of a sliced operand in HBM: K-BLOCK TILED, so that everything one pipeline stage fetches is a handful of contiguous
+// 4-8 KB runs (a TMA box over rows that lie 25 KB apart is served one 64-byte request at a time: measured 10x slower):
+//   byte (slice s, row r, K position c)  at  ((c / 64 * n_slices + s) * rowsP + r) * 64 + c % 64
+__host__ __device__ __forceinline__ int64_t sl_offset(int64_t c, int s, int64_t r, int64_t rowsP, int n_slices) {
+    return (((c >> 6) * n_slices + s) * rowsP + r) * 64 + (c & 63);
+}
+
+struct SlOperand {          // a sliced matrix on the device: n_slices x rowsP x kbytes int8 (K-block tiled, sl_offset) + row exponents
     const int8_t *slices = nullptr;
     int64_t rowsP = 0, kbytes = 0;
     int n_slices = 0;
     const int32_t *e = nullptr;   // nullptr: e_const for every row
     int e_const = 0;
+    bool is_b = false;            // tensor-map box: 64 rows (a B operand: output columns) or 128 rows (an A operand)
     CUtensorMap map;
 };
 
@@ -19,16 +27,14 @@ struct SlProduct {          // one segment: alpha * A[a_row0 : a_row0 + M, k0 : 
 };
 
 int sl_make_operand(gpfq_ctx *ctx, SlOperand *op, const int8_t *slices, int64_t rowsP, int64_t kbytes, int n_slices, const int32_t *e,
-                    int e_const);
-// C[M x N] (ldc) = or += sum of the products.  M, N: valid extents; the slice tensors are zero-padded to 128-row / 128-byte tiles.
+                    int e_const, bool is_b);
+// C[M x N] (ldc) = or += sum of the products (at most two, sharing the exponents of their B rows).  M, N: valid extents; the
+// slice tensors are zero-padded to the 128-row / 64-column / 64-byte tile grid.
 int slgemm_i8(gpfq_ctx *ctx, const SlProduct *prod, int nprod, double *C, int64_t ldc, int64_t M, int64_t N, bool accumulate);
-// 5 digit slices + row exponents of `grid_rows` rows (rows >= `rows` and columns >= cols are zeros) of a row-major matrix;
-// `slices` / `e` point at the first of these rows inside a (5, rowsP, colsP) slice tensor
+// 5 digit slices + row exponents of `grid_rows` rows (rows >= `rows` and columns >= cols are zeros) of a row-major matrix,
+// written as rows row0 .. row0 + grid_rows - 1 of a 5 x rowsP x colsP slice tensor (e: exponent of row row0 + r at e[row0 + r])
 template <typename T>
 int sl_rowsplit(gpfq_ctx *ctx, const T *X, int64_t ldx, int64_t rows, int64_t cols, int32_t *e, int8_t *slices, int64_t rowsP,
-                int64_t colsP, int64_t grid_rows);
-int sl_transsplit(gpfq_ctx *ctx, const float *X, int64_t ldx, int64_t N0, int64_t m, int32_t *e, int *scratch, int8_t *slices,
-                  int64_t mP, int64_t N0P);
-// int8 level indices k' = q / h of decisions [tb, te) of `grid_rows` neurons, written at byte columns tb.. of a (rowsP, N0P) tensor
-int sl_qindex(gpfq_ctx *ctx, const double *Qt, int64_t N0, int64_t nj, int64_t tb, int64_t te, double inv_h, int8_t *out,
-              int64_t grid_rows, int64_t N0P, int64_t width);
+                int64_t colsP, int64_t row0, int64_t grid_rows);
+int sl_transsplit(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx, int64_t N0, int64_t m, int32_t *e, int *scratch,
+                  int8_t *slices, int8_t *slices_q, int64_t mP, int64_t N0P);
