@@ -200,6 +200,9 @@ extern "C" int gpfq_set_option(gpfq_ctx *ctx, const char *key, int64_t value) {
         // 3 carried residuals as ONE chain (no two-stream split of the neurons)
         if (value < 0 || value > 3) return gpfq_fail(ctx, GPFQ_ERR_ARG, "sweep_outer must be 0, 1, 2 or 3");
         ctx->lowrank_variant = (int)value;
+    } else if (!strcmp(key, "sweep_nt")) {      // pipelined range walk: neurons per CTA (0 auto)
+        if (value != 0 && value != 8 && value != 16 && value != 32) return gpfq_fail(ctx, GPFQ_ERR_ARG, "sweep_nt must be 0, 8, 16 or 32");
+        ctx->sweep_nt = (int)value;
     } else if (!strcmp(key, "sweep_i8")) {      // residual-form sweep contractions: 0 auto, 1 int8 slices on tcgen05, 2 fp64 DMMA
         if (value < 0 || value > 2) return gpfq_fail(ctx, GPFQ_ERR_ARG, "sweep_i8 must be 0, 1 or 2");
         ctx->sweep_i8 = (int)value;

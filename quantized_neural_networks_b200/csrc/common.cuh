@@ -63,6 +63,7 @@ struct gpfq_ctx {
     bool stream_literal = false;  // streaming walk: reproduce the reference's fp32-rounded w*X products (set per call)
     int gram_variant = 0;         // Dense Gram stage: 0 auto, 1 fp64 DMMA (mma.sync), 2 int8 slices on tcgen05 (gram_i8.cu)
     int lowrank_variant = 0;      // sweep outer level: 0 auto, 1 Gram rows, 2 residual (low-rank) form
+    int sweep_nt = 0;             // pipelined range walk: neurons per CTA (0 auto, 8 / 16 / 32)
     int sweep_i8 = 0;             // sweep contractions of the residual form: 0 auto, 1 int8 slices on tcgen05, 2 fp64 DMMA
     int i8_pairs_d = 0;           // int8 Gram: keep slice pairs with k + l <= this (0: the default of gram_i8.cu)
     const double *h_alph = nullptr;  // host copy of the current call's alphabets (levels back to back) and their offsets

@@ -802,7 +802,14 @@ static int dispatch_sweep_tile(gpfq_ctx *ctx, int NT, const double *G1, const do
                          ((uintptr_t)Wt % 16 == 0) && ((uintptr_t)Qt % 16 == 0) && ((nj * N0) % 2 == 0);
     if (aligned && ctx->sweep_variant != 2) {
         const int64_t sms = ctx->sm_count;
-        if (ceil_div64(nj, 8) * n_alph <= sms)
+        const int force = ctx->sweep_nt;
+        if (force == 32 || (force == 0 && false)) {
+            if (ceil_div64(nj, 32) * n_alph <= sms)
+                return launch_sweep_pipe<32>(ctx, G1, G2, ldg, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph, tb, te, Dp, R, Kq, krows, krow0, inv_h);
+        } else if (force == 16) {
+            if (ceil_div64(nj, 16) * n_alph <= sms)
+                return launch_sweep_pipe<16>(ctx, G1, G2, ldg, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph, tb, te, Dp, R, Kq, krows, krow0, inv_h);
+        } else if (ceil_div64(nj, 8) * n_alph <= sms)
             return launch_sweep_pipe<8>(ctx, G1, G2, ldg, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph, tb, te, Dp, R, Kq, krows, krow0, inv_h);
         if (ceil_div64(nj, 16) * n_alph <= sms)
             return launch_sweep_pipe<16>(ctx, G1, G2, ldg, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph, tb, te, Dp, R, Kq, krows, krow0, inv_h);
@@ -1051,7 +1058,7 @@ static int dense_lowrank_sweep_i8(gpfq_ctx *ctx, const float *X, const float *Xq
     cudaStream_t st = ctx->stream, side = ctx->copy_stream;
     int64_t R = pick_range_length(ctx, nj, 1);
     R = std::max<int64_t>(128, R / 128 * 128);      // K blocks of the update are 128 directions
-    const int64_t N0P = ceil_div64(N0, 128) * 128, mP = ceil_div64(m, 128) * 128, njP = ceil_div64(nj, 128) * 128;
+    const int64_t N0P = ceil_div64(N0, R) * R, mP = ceil_div64(m, 128) * 128, njP = ceil_div64(nj, 128) * 128;   // whole ranges
     constexpr int S = 5;
     int8_t *sW = nullptr, *sXT = nullptr, *sXqT = nullptr, *sXq = nullptr, *sU = nullptr, *sKq = nullptr;
     int32_t *e = nullptr;
@@ -1067,45 +1074,38 @@ static int dense_lowrank_sweep_i8(gpfq_ctx *ctx, const float *X, const float *Xq
     int32_t *eW = e, *eU = eW + njP, *eXq = eU + njP, *eXT = eXq + N0P;   // X^T and X~^T share their per-sample exponents
     int *scratch = eXT + mP;
     GPFQ_TRY(gpfq_ws(ctx, WS_LR_U, (size_t)nj * m * sizeof(double), (void **)&Ut));
-    GPFQ_TRY(gpfq_ws(ctx, WS_G2, (size_t)N0 * R * sizeof(double), (void **)&Gc2));
+    const size_t gc_bytes = (size_t)ceil_div64(N0, R) * R * R * sizeof(double);
+    GPFQ_TRY(gpfq_ws(ctx, WS_G2, gc_bytes, (void **)&Gc2));
     if (same) Gc1 = Gc2;
-    else GPFQ_TRY(gpfq_ws(ctx, WS_G1, (size_t)N0 * R * sizeof(double), (void **)&Gc1));
+    else GPFQ_TRY(gpfq_ws(ctx, WS_G1, gc_bytes, (void **)&Gc1));
     GPFQ_TRY(gpfq_ws(ctx, WS_DT, (size_t)nj * R * sizeof(double), (void **)&Do));
+    constexpr int D_DOTS_GRAM = 6;
 
     CUDA_TRY(ctx, gpfq_record(ctx, 2, st));
     // slicing, once per layer
     GPFQ_TRY(sl_rowsplit<float>(ctx, Xq, ldx, N0, m, eXq, sXq, N0P, mP, 0, N0P));
+    SlOperand oXqB;
+    GPFQ_TRY(sl_make_operand(ctx, &oXqB, sXq, N0P, mP, S, eXq, 0, true));
     GPFQ_TRY(sl_transsplit(ctx, X, same ? nullptr : Xq, ldx, N0, m, eXT, scratch, sXT, sXqT, mP, N0P));
     GPFQ_TRY(sl_rowsplit<double>(ctx, Wt, N0, nj, N0, eW, sW, njP, N0P, 0, njP));
-    // block-diagonal Gram tiles, compact: Gc[t][s - tb(t)], row stride R (exact fp32 x fp32 products, fp64 sums)
-    const int64_t nfull = N0 / R;
-    for (int which = 0; which < (same ? 1 : 2); ++which) {
-        for (int64_t b0 = 0; b0 < nfull; b0 += 65535) {
-            const int64_t nb = std::min<int64_t>(65535, nfull - b0), tb = b0 * R;
-            GemmArgs g = {};
-            g.seg[0] = {Xq + tb * ldx, (which ? X : Xq) + tb * ldx, ldx, ldx, m, 1.0};
-            g.nseg = 1;
-            g.M = g.N = R;
-            g.C = (which ? Gc1 : Gc2) + tb * R;
-            g.ldc = R;
-            g.nsplit = 1;
-            g.lower_only = 1;
-            g.batch_strideA0 = R * ldx;
-            g.batch_strideB = R * ldx;
-            g.batch_strideC = R * R;
-            GPFQ_TRY((launch_gemm_nt<float, 128, 64, 32>(ctx, g, (int)nb)));
+    // block-diagonal Gram tiles, compact: Gc[t][s - tb(t)], row stride R -- on tcgen05 as well (15 slice pairs over the m
+    // samples, as the Dense Gram stage of gram_i8.cu: dropped terms ~2e-11 of |X~_t||X_s|): every range is one batch of one launch
+    {
+        int8_t *sXr = nullptr, *sXqA = sXq;
+        int32_t *eXr = eXq;
+        if (!same) {
+            GPFQ_TRY(gpfq_ws(ctx, WS_I8_SX, (size_t)S * N0P * mP, (void **)&sXr));
+            GPFQ_TRY(gpfq_ws(ctx, WS_I8_E, (size_t)N0P * sizeof(int32_t), (void **)&eXr));
+            GPFQ_TRY(sl_rowsplit<float>(ctx, X, ldx, N0, m, eXr, sXr, N0P, mP, 0, N0P));
         }
-        if (nfull * R < N0) {
-            const int64_t tb = nfull * R;
-            GemmArgs g = {};
-            g.seg[0] = {Xq + tb * ldx, (which ? X : Xq) + tb * ldx, ldx, ldx, m, 1.0};
-            g.nseg = 1;
-            g.M = g.N = N0 - tb;
-            g.C = (which ? Gc1 : Gc2) + tb * R;
-            g.ldc = R;
-            g.nsplit = 1;
-            g.lower_only = 1;
-            GPFQ_TRY((launch_gemm_nt<float, 128, 64, 32>(ctx, g, 1)));
+        SlOperand oXqA, oXrB;
+        GPFQ_TRY(sl_make_operand(ctx, &oXqA, sXqA, N0P, mP, S, eXq, 0, false));
+        GPFQ_TRY(sl_make_operand(ctx, &oXrB, same ? sXq : sXr, N0P, mP, S, eXr, 0, true));
+        const int nrange = (int)ceil_div64(N0, R);
+        // rows / columns beyond N0 of the last range are zero slices: their (unused) outputs are zeros; Gc holds nrange * R rows
+        for (int which = 0; which < (same ? 1 : 2); ++which) {
+            SlProduct gp = {&oXqA, which ? &oXrB : &oXqB, 0, 0, 0, mP, D_DOTS_GRAM, 1.0};
+            GPFQ_TRY(slgemm_i8(ctx, &gp, 1, which ? Gc1 : Gc2, R, R, R, false, nrange, R, R * R, true));
         }
     }
     CUDA_TRY(ctx, gpfq_record(ctx, 3, st));

@@ -57,6 +57,9 @@ struct SlArgs {
     int64_t ldc;
     int M, N;               // valid rows / columns of C
     int accumulate, vec2;
+    int batch_rows;         // blockIdx.y batches: A rows, B rows (and their exponents) advance by batch_rows, C by batch_c
+    int64_t batch_c;
+    int lower_only;         // skip tiles entirely above the diagonal (block-diagonal Gram tiles)
 };
 
 // K-major operand tile with 64-byte rows, SWIZZLE_64B: 8-row atoms of 512 B (SBO), LBO unused (1), descriptor version 1
@@ -101,6 +104,8 @@ slgemm_i8_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ti = blockIdx.x / args.tiles_n, tj = blockIdx.x % args.tiles_n;
+    if (args.lower_only && tj * TN > ti * TM + TM - 1) return;
+    const int brow = (int)blockIdx.y * args.batch_rows;     // batch offset of the A and B rows
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -114,7 +119,7 @@ slgemm_i8_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     }
     if (warp >= 2 && threadIdx.x - 64 < TN) {
         const int c = threadIdx.x - 64;     // one column of the tile
-        colscale[c] = ldexp(1.0, args.eB ? args.eB[args.b_row0 + tj * TN + c] : args.eB_const);
+        colscale[c] = ldexp(1.0, args.eB ? args.eB[args.b_row0 + brow + tj * TN + c] : args.eB_const);
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
@@ -134,8 +139,8 @@ slgemm_i8_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                     if (iter >= STAGES) mbar_wait(&empty[s], ((iter / STAGES) - 1) & 1);
                     unsigned char *a = smem + (size_t)s * STAGE_BYTES, *b = a + S * A_SLICE;
                     mbar_expect_tx(&full[s], bytes);
-                    tma_load_4d(a, ma, &full[s], 0, g.a_row0 + ti * TM, 0, g.k0 / BK + kb);
-                    tma_load_4d(b, mb, &full[s], 0, g.b_row0 + tj * TN, 0, g.k0 / BK + kb);
+                    tma_load_4d(a, ma, &full[s], 0, g.a_row0 + brow + ti * TM, 0, g.k0 / BK + kb);
+                    tma_load_4d(b, mb, &full[s], 0, g.b_row0 + brow + tj * TN, 0, g.k0 / BK + kb);
                 }
             }
         }
@@ -190,7 +195,7 @@ slgemm_i8_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         for (int i = 0; i < TN; ++i) acc[i] = 0.0;
         for (int sg = 0; sg < args.nseg; ++sg) {
             const SlSeg &g = args.seg[sg];
-            const int ea = g.eA ? g.eA[g.a_row0 + ti * TM + row_t] : g.eA_const;
+            const int ea = g.eA ? g.eA[g.a_row0 + brow + ti * TM + row_t] : g.eA_const;
             mbar_wait(seg_full, sg & 1);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 #pragma unroll 1
@@ -216,6 +221,7 @@ slgemm_i8_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         for (int i = 0; i < TN; ++i) tr[lane * OUT_PITCH + i] = acc[i] * colscale[i];
         __syncwarp();
         const int64_t row0 = (int64_t)ti * TM + quad * 32, col0 = (int64_t)tj * TN;
+        double *Cb = args.C + (int64_t)blockIdx.y * args.batch_c;
         // all loads of the read-modify-write first (64 independent requests in flight per lane), then the stores
         double old[32][TN / 32];
 #pragma unroll
@@ -223,14 +229,14 @@ slgemm_i8_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
 #pragma unroll
             for (int hf = 0; hf < TN / 32; ++hf) {
                 const int c = hf * 32 + lane;
-                old[r][hf] = (args.accumulate && row0 + r < args.M && col0 + c < args.N) ? args.C[(row0 + r) * args.ldc + col0 + c] : 0.0;
+                old[r][hf] = (args.accumulate && row0 + r < args.M && col0 + c < args.N) ? Cb[(row0 + r) * args.ldc + col0 + c] : 0.0;
             }
 #pragma unroll
         for (int r = 0; r < 32; ++r)
 #pragma unroll
             for (int hf = 0; hf < TN / 32; ++hf) {
                 const int c = hf * 32 + lane;
-                if (row0 + r < args.M && col0 + c < args.N) args.C[(row0 + r) * args.ldc + col0 + c] = old[r][hf] + tr[r * OUT_PITCH + c];
+                if (row0 + r < args.M && col0 + c < args.N) Cb[(row0 + r) * args.ldc + col0 + c] = old[r][hf] + tr[r * OUT_PITCH + c];
             }
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -433,7 +439,8 @@ int sl_make_operand(gpfq_ctx *ctx, SlOperand *op, const int8_t *slices, int64_t 
 }
 
 // C[M x N] (ldc) = or += sum of the products.  M, N: valid extents; the slice tensors are zero-padded to tile multiples.
-int slgemm_i8(gpfq_ctx *ctx, const SlProduct *prod, int nprod, double *C, int64_t ldc, int64_t M, int64_t N, bool accumulate) {
+int slgemm_i8(gpfq_ctx *ctx, const SlProduct *prod, int nprod, double *C, int64_t ldc, int64_t M, int64_t N, bool accumulate,
+              int nbatch, int64_t batch_rows, int64_t batch_c, bool lower_only) {
     using namespace slg;
     if (nprod < 1 || nprod > 2) return gpfq_fail(ctx, GPFQ_ERR_ARG, "slgemm_i8: 1 or 2 products");
     SlArgs a = {};
@@ -445,7 +452,8 @@ int slgemm_i8(gpfq_ctx *ctx, const SlProduct *prod, int nprod, double *C, int64_
                              (long long)p.K, (long long)p.k0, KB_MAX * BK);
         if (p.A->is_b || !p.B->is_b || p.A->n_slices > S || p.B->n_slices > S)
             return gpfq_fail(ctx, GPFQ_ERR_ARG, "slgemm_i8: operand roles / slice counts");
-        if (p.a_row0 + ceil_div64(M, TM) * TM > p.A->rowsP || p.b_row0 + ceil_div64(N, TN) * TN > p.B->rowsP ||
+        if (p.a_row0 + (nbatch - 1) * batch_rows + ceil_div64(M, TM) * TM > p.A->rowsP ||
+            p.b_row0 + (nbatch - 1) * batch_rows + ceil_div64(N, TN) * TN > p.B->rowsP ||
             p.k0 + p.K > p.A->kbytes || p.k0 + p.K > p.B->kbytes)
             return gpfq_fail(ctx, GPFQ_ERR_ARG, "slgemm_i8: operand slices are not padded to the tile grid");
         if (s > 0 && (p.B->e != prod[0].B->e || p.B->e_const != prod[0].B->e_const || p.b_row0 != prod[0].b_row0))
@@ -472,8 +480,12 @@ int slgemm_i8(gpfq_ctx *ctx, const SlProduct *prod, int nprod, double *C, int64_
     a.N = (int)N;
     a.accumulate = accumulate ? 1 : 0;
     a.vec2 = (ldc % 2 == 0) && ((uintptr_t)C % 16 == 0);
+    a.batch_rows = (int)batch_rows;
+    a.batch_c = batch_c;
+    a.lower_only = lower_only ? 1 : 0;
+    if (nbatch < 1 || nbatch > 65535) return gpfq_fail(ctx, GPFQ_ERR_ARG, "slgemm_i8: 1..65535 batches");
     CUDA_TRY(ctx, cudaFuncSetAttribute(slgemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    const unsigned grid = (unsigned)(ceil_div64(M, TM) * a.tiles_n);
+    const dim3 grid((unsigned)(ceil_div64(M, TM) * a.tiles_n), (unsigned)nbatch);
     const SlProduct &p1 = prod[nprod - 1];
     slgemm_i8_kernel<<<grid, THREADS, SMEM, ctx->stream>>>(prod[0].A->map, prod[0].B->map, p1.A->map, p1.B->map, a);
     KERNEL_CHECK(ctx);

@@ -30,7 +30,10 @@ int sl_make_operand(gpfq_ctx *ctx, SlOperand *op, const int8_t *slices, int64_t 
                     int e_const, bool is_b);
 // C[M x N] (ldc) = or += sum of the products (at most two, sharing the exponents of their B rows).  M, N: valid extents; the
 // slice tensors are zero-padded to the 128-row / 64-column / 64-byte tile grid.
-int slgemm_i8(gpfq_ctx *ctx, const SlProduct *prod, int nprod, double *C, int64_t ldc, int64_t M, int64_t N, bool accumulate);
+// nbatch > 1: blockIdx.y batches whose A and B rows advance by batch_rows and whose C advances by batch_c elements (the
+// block-diagonal Gram tiles of the residual-form sweep); lower_only skips tiles entirely above the diagonal.
+int slgemm_i8(gpfq_ctx *ctx, const SlProduct *prod, int nprod, double *C, int64_t ldc, int64_t M, int64_t N, bool accumulate,
+              int nbatch = 1, int64_t batch_rows = 0, int64_t batch_c = 0, bool lower_only = false);
 // 5 digit slices + row exponents of `grid_rows` rows (rows >= `rows` and columns >= cols are zeros) of a row-major matrix,
 // written as rows row0 .. row0 + grid_rows - 1 of a 5 x rowsP x colsP slice tensor (e: exponent of row row0 + r at e[row0 + r])
 template <typename T>

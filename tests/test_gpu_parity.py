@@ -656,3 +656,21 @@ def test_slgemm_i8_matches_fp64(engine, M, N, K, tb):
     Bi = rng.integers(0, 255, (N, K)).astype(np.float32)
     Ci = engine.debug_slgemm(Ai, np.ascontiguousarray(Bi.T) if tb else Bi, D=10, transposed_b=tb)
     assert np.array_equal(Ci, Ai @ Bi.astype(np.float64).T)
+
+
+# ---- streaming vs Gram vs carried residuals: picked by measurement -------------------------------------------------------
+def test_auto_picks_a_measured_best_method(engine):
+    """BASELINE north_star: the streaming variant "is benchmarked against it per layer shape, and the faster one is picked by
+    measurement".  On Dense shapes of configs 1-4 `auto` must stay within 10 % (+ 50 us) of the fastest method measured here
+    (tools/dense_methods.py; the full table is profiles/dense_methods_r2.md), and every method must give the same layer."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import dense_methods as DM
+    for shape in DM.SHAPES:
+        if shape[1] * shape[2] > 4096 * 4096 or shape[1] > 8192:     # the two largest shapes: table only
+            continue
+        res = DM.measure(engine, shape, reps=2)
+        best = min(v["ms"] for k, v in res.items() if k != "auto")
+        assert res["auto"]["ms"] <= 1.10 * best + 0.05, (shape, res)
+        assert min(v["agreement"] for v in res.values()) >= AGREE, (shape, res)

@@ -23,11 +23,14 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--first", action="store_true", help="X == Xq (first layer)")
     ap.add_argument("--bits", type=float, default=np.log2(3))
+    ap.add_argument("--opt", default="", help="comma-separated key=value engine options (gpfq_set_option)")
     args = ap.parse_args()
     import torch
     from quantized_neural_networks_b200 import get_engine
     eng = get_engine(0)
     dev = torch.device("cuda", 0)
+    for kv in [v for v in args.opt.split(",") if v]:
+        eng.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     for shp in args.shapes.split(","):
         N0, N1, m = (int(v) for v in shp.split("x"))
         g = torch.Generator(device=dev).manual_seed(N0 + N1 + m)
