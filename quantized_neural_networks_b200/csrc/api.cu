@@ -122,8 +122,8 @@ extern "C" int gpfq_create(int device, gpfq_ctx **out) {
         for (int i = 0; ok && i < 8; ++i) ok = cudaEventCreate(&r.e[i]) == cudaSuccess;
     ctx->cur = &ctx->ring[0];
     for (int i = 0; ok && i < 4; ++i) ok = cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming) == cudaSuccess;
-    for (int i = 0; ok && i < 4; ++i) ok = cudaEventCreateWithFlags(&ctx->ev_chain[i], cudaEventDisableTiming) == cudaSuccess;
-    for (int i = 0; ok && i < 2; ++i) ok = cudaStreamCreateWithFlags(&ctx->aux_stream[i], cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; ok && i < 12; ++i) ok = cudaEventCreateWithFlags(&ctx->ev_chain[i], cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; ok && i < 8; ++i) ok = cudaStreamCreateWithFlags(&ctx->aux_stream[i], cudaStreamNonBlocking) == cudaSuccess;
     if (!ok) {
         delete ctx;
         return GPFQ_ERR_CUDA;
@@ -200,6 +200,12 @@ extern "C" int gpfq_set_option(gpfq_ctx *ctx, const char *key, int64_t value) {
         // 3 carried residuals as ONE chain (no two-stream split of the neurons)
         if (value < 0 || value > 3) return gpfq_fail(ctx, GPFQ_ERR_ARG, "sweep_outer must be 0, 1, 2 or 3");
         ctx->lowrank_variant = (int)value;
+    } else if (!strcmp(key, "sweep_range")) {   // residual-form sweep on tcgen05: directions per range (0 auto)
+        if (value < 0 || value > 8192 || value % 128) return gpfq_fail(ctx, GPFQ_ERR_ARG, "sweep_range must be 0 or a multiple of 128 up to 8192");
+        ctx->sweep_range = (int)value;
+    } else if (!strcmp(key, "sweep_groups")) {  // residual-form sweep: independent neuron groups in flight (0 auto)
+        if (value != 0 && value != 1 && value != 2 && value != 4) return gpfq_fail(ctx, GPFQ_ERR_ARG, "sweep_groups must be 0, 1, 2 or 4");
+        ctx->sweep_groups = (int)value;
     } else if (!strcmp(key, "sweep_nt")) {      // pipelined range walk: neurons per CTA (0 auto)
         if (value != 0 && value != 8 && value != 16 && value != 32) return gpfq_fail(ctx, GPFQ_ERR_ARG, "sweep_nt must be 0, 8, 16 or 32");
         ctx->sweep_nt = (int)value;

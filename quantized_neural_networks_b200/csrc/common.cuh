@@ -50,14 +50,18 @@ struct gpfq_ctx {
     int64_t calls = 0;          // API calls begun so far
     CallRecord *cur = nullptr;  // record of the call in progress
     cudaEvent_t ev_copy[4] = {};
-    cudaStream_t aux_stream[2] = {};   // residual-form sweep: the W part of the residual update of each neuron group
-    cudaEvent_t ev_chain[4] = {};      // ... [2 g] residuals sliced (main -> aux), [2 g + 1] W part landed (aux -> main)
+    cudaStream_t aux_stream[8] = {};   // residual-form sweep, up to 4 neuron groups: [g] the W part of group g's residual update,
+                                       // [4 + g] the main chain of group g >= 1 (group 0 runs on `stream`)
+    cudaEvent_t ev_chain[12] = {};     // ... [3 g] residuals sliced (main -> aux), [3 g + 1] W part landed (aux -> main), [3 g + 2] done
+    int sweep_range = 0;               // ... directions per range (0 auto; a multiple of 128)
+    int sweep_groups = 0;              // ... neuron groups (0 auto, 1 / 2 / 4)
     std::string err = "";
     int launches = 0;
     int conv_variant = 0;         // 3x3 patch-Gram kernel: 0 TMA-staged / correlation form (default), 1 direct LDG, 2 generic,
                                   // 3 NHWC entry point: shared-memory planes kernel instead of the correlation form
     int corr_pack = 0;            // correlation form, images packed as virtual channels: 0 by shape, 1 always (tests), 2 never
     bool corr_direct_small = false;  // correlation form also on images below 128 pixels (tests)
+    int corr_occ[2][9] = {};      // correlation-form kernels: resident CTAs per SM by [X~ == X][rows per band] (0: not queried yet)
     int corr_rb = 0;              // correlation-form conv Grams: rows per band (0: chosen per image height)
     int sweep_variant = 0;        // triangular sweep: 0 persistent neuron-tile kernel (default), 1 one launch pair per block
     bool stream_literal = false;  // streaming walk: reproduce the reference's fp32-rounded w*X products (set per call)
@@ -156,6 +160,22 @@ __device__ __forceinline__ double gpfq_bit_round_eq(double v, const double *__re
     if (d1 < bd) { bd = d1; best = a1; }
     if (d2 < bd) best = a2;
     return best;
+}
+
+// The same quantizer for the ternary alphabet {-a, 0, a} (bits = log2 3: the VGG16 and MNIST configurations): the literal
+// three-level scan itself -- the same subtractions, absolute values and strict comparisons in ascending order, so every tie goes
+// where _bit_round_parallel sends it -- with the levels in registers: no index arithmetic, no shared-memory loads on the
+// serial chain of the walk (the windowed form above costs ~115 dependent cycles per step, this one ~25).
+__device__ __forceinline__ double gpfq_bit_round_ternary(double v, double a) {
+    const double dl = fabs(__dsub_rn(-a, v)), dm = fabs(__dsub_rn(0.0, v)), dh = fabs(__dsub_rn(a, v));
+    double best = -a, bd = dl;
+    if (dm < bd) { bd = dm; best = 0.0; }
+    if (dh < bd) best = a;
+    return best;
+}
+// a > 0 when the alphabet staged at `alph` is exactly {-a, 0, a}, else 0
+__device__ __forceinline__ double gpfq_ternary_radius(const double *alph, int K) {
+    return (K == 3 && alph[1] == 0.0 && alph[2] > 0.0 && alph[0] == -alph[2]) ? alph[2] : 0.0;
 }
 
 // inv_step of an alphabet staged in shared memory (flag from the host: 1 = ascending and equispaced)

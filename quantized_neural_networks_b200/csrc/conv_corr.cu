@@ -438,27 +438,35 @@ int corr9_pack_stage(gpfq_ctx *ctx, const float *act, int64_t n_img, int H, int 
 template <int RB>
 static int corr9_resident_ctas(bool same) {
     using namespace corr9;
+    // a failed query only costs launch geometry (the caller plans for one CTA per SM): its error is consumed HERE, where it
+    // arose, so that it can neither leak into the next launch check nor swallow an unrelated pending error
     int a = 0, b = 0;
-    cudaFuncSetAttribute(conv_corr9_tma_kernel<RB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Ring<RB, false>::SMEM);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, conv_corr9_tma_kernel<RB, false>, WARPS * 32, Ring<RB, false>::SMEM);
-    if (same) return a > 0 ? a : 1;
-    cudaFuncSetAttribute(conv_corr9_tma_kernel<RB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Ring<RB, true>::SMEM);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, conv_corr9_tma_kernel<RB, true>, WARPS * 32, Ring<RB, true>::SMEM);
-    a = a < b ? a : b;
-    return a > 0 ? a : 1;
+    if (cudaFuncSetAttribute(conv_corr9_tma_kernel<RB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Ring<RB, false>::SMEM) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, conv_corr9_tma_kernel<RB, false>, WARPS * 32, Ring<RB, false>::SMEM) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    if (same) return a;
+    if (cudaFuncSetAttribute(conv_corr9_tma_kernel<RB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Ring<RB, true>::SMEM) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, conv_corr9_tma_kernel<RB, true>, WARPS * 32, Ring<RB, true>::SMEM) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return a < b ? a : b;
 }
 
 // Slots (warps per channel group) that fill every SM with as many CTAs of four warps as stay resident.
 int corr9_pick_slots(gpfq_ctx *ctx, int RB, bool same, int64_t c_first, int n_ch, int64_t ntasks) {
     using namespace corr9;
-    static int occ[2][9] = {};
     if (RB < 1 || RB > 8) return WARPS;
-    if (!occ[same][RB])
-        occ[same][RB] = RB == 8 ? corr9_resident_ctas<8>(same) : RB == 6 ? corr9_resident_ctas<6>(same)
-                       : RB == 4 ? corr9_resident_ctas<4>(same) : corr9_resident_ctas<1>(same);
-    cudaGetLastError();
+    int &occ = ctx->corr_occ[same ? 1 : 0][RB];      // per context (= per device): no state shared between engines / threads
+    if (!occ) {
+        occ = RB == 8 ? corr9_resident_ctas<8>(same) : RB == 6 ? corr9_resident_ctas<6>(same)
+              : RB == 4 ? corr9_resident_ctas<4>(same) : corr9_resident_ctas<1>(same);
+        if (occ < 1) occ = 1;                        // the occupancy query failed: plan for one CTA per SM
+    }
     const int64_t groups = ceil_div64(n_ch + (c_first & 3), 32);
-    int64_t per = ceil_div64((int64_t)ctx->sm_count * occ[same][RB] * WARPS, groups);
+    int64_t per = ceil_div64((int64_t)ctx->sm_count * occ * WARPS, groups);
     per = std::min<int64_t>(per, std::max<int64_t>(1, ntasks));
     return (int)(ceil_div64(per, WARPS) * WARPS);
 }

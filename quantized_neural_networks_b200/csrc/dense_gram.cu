@@ -111,7 +111,7 @@ sweep_inblock_kernel(const double *__restrict__ G1, const double *__restrict__ G
 //   Q block -> shared memory -> Qt (neuron-major), read back by the later panels of this same CTA.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double gpfq_decide_rcp_inl(double nrm, double rinv, double d, double num, double w,
-                                                      const double *__restrict__ alph, int K, double inv_step) {
+                                                      const double *__restrict__ alph, int K, double inv_step, double tern = 0.0) {
     if (nrm < GPFQ_DEAD_NORM) return 0.0;
     double v = w;
     if (!(fabs(d) < GPFQ_PERP_DOT)) {
@@ -120,6 +120,7 @@ __device__ __forceinline__ double gpfq_decide_rcp_inl(double nrm, double rinv, d
         const double e = fma(-q0, den, num);
         v = fma(e, rinv, q0);
     }
+    if (tern > 0.0) return gpfq_bit_round_ternary(v, tern);   // CTA-uniform: {-a, 0, a} with the levels in registers
     return gpfq_bit_round_eq(v, alph, K, inv_step);
 }
 
@@ -174,6 +175,7 @@ sweep_tile_kernel(const double *__restrict__ G1, const double *__restrict__ G2, 
     for (int e = tid; e < B * (B + 1); e += THREADS) g2d[B * (B + 1) + e] = 0.0;
     __syncthreads();
     const double inv_step = gpfq_inv_step(alph, K, Flags[a]);
+    const double tern = gpfq_ternary_radius(alph, K);
 
     // this thread's 16-byte chunks of every W / Q tile (fixed for the whole walk)
     int w_off[WCH];
@@ -336,7 +338,7 @@ sweep_tile_kernel(const double *__restrict__ G1, const double *__restrict__ G2, 
                     const double d0 = __shfl_sync(0xffffffffu, d[0], (lane & ~3) + rr);
                     const double wv = wrow[tt];
                     const double num = fma(wv, g1dd[tt], d0);
-                    double q = gpfq_decide_rcp_inl(nrm[tt], rinv[tt], d0, num, wv, alph, K, inv_step);
+                    double q = gpfq_decide_rcp_inl(nrm[tt], rinv[tt], d0, num, wv, alph, K, inv_step, tern);
                     if (tt >= nb) q = 0.0;  // past the end of a partial block: no decision, no update
                     if (r == rr && tt < nb) qrow[tt] = q;
                     if (rr < 3) {
@@ -380,7 +382,10 @@ __device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volati
 
 template <int NT>
 struct PipeCfg {
-    static constexpr int B = SWEEP_B, KC = 64, LD = KC + 4, STAGES = 3, THREADS = 256, CT = 128;
+    // K chunks of 64 directions through a cp.async ring, four deep where shared memory allows (three chunks in flight: the
+    // contractors are bound by the L2 latency of their chunk loads, and late blocks of a range have up to 15 chunks to get through
+    // while one block is walked)
+    static constexpr int B = SWEEP_B, KC = 64, LD = KC + 4, STAGES = NT == 32 ? 3 : 4, THREADS = 256, CT = 128;
     static constexpr int SET = 2 * B * (B + 1) + 2 * NT * (B + 1) + B * (NT + 1) + 3 * B;   // doubles per working set
     static constexpr size_t SMEM = sizeof(double) * ((size_t)STAGES * (B + NT) * LD + 2 * SET + GPFQ_MAX_K);
 };
@@ -414,6 +419,7 @@ sweep_pipe_kernel(const double *__restrict__ G1, const double *__restrict__ G2, 
     for (int e = tid; e < 2 * B * (B + 1); e += 256) g2d_of(e / (B * (B + 1)))[B * (B + 1) + e % (B * (B + 1))] = 0.0;
     __syncthreads();
     const double inv_step = gpfq_inv_step(alph, K, Flags[a]);
+    const double tern = gpfq_ternary_radius(alph, K);
     const int nblk = (int)((t_end - t_begin + B - 1) / B);
     const double *Da = Dt ? Dt + (int64_t)a * nj * ldd : nullptr;
 
@@ -506,12 +512,12 @@ sweep_pipe_kernel(const double *__restrict__ G1, const double *__restrict__ G2, 
                     for (int i = 0; i < NA; ++i) dmma_m8n8k4(acc[i][0], acc[i][1], av, bs[i * 8 * LD + kk]);
                 }
             };
-            issue(0);
-            issue(1);
+#pragma unroll
+            for (int p = 0; p < STAGES - 1; ++p) issue(p);
             for (int it = 0; it < total; ++it) {
-                cp_async_wait<1>();
+                cp_async_wait<STAGES - 2>();
                 named_bar_sync(BAR_C, CT);  // chunk `it` landed for every contractor; chunk it-1 fully consumed
-                issue(it + 2);
+                issue(it + STAGES - 1);
                 const int st = it % STAGES;
                 contract(gst + st * B * LD, wst + st * NT * LD, it >= nck1, KC);
             }
@@ -594,7 +600,7 @@ sweep_pipe_kernel(const double *__restrict__ G1, const double *__restrict__ G2, 
                     const double d0 = __shfl_sync(0xffffffffu, d[0], (lane & ~3) + rr);
                     const double wv = wrow[tt];
                     const double num = fma(wv, g1dd[tt], d0);
-                    double q = gpfq_decide_rcp_inl(nrm[tt], rinv[tt], d0, num, wv, alph, K, inv_step);
+                    double q = gpfq_decide_rcp_inl(nrm[tt], rinv[tt], d0, num, wv, alph, K, inv_step, tern);
                     if (tt >= nb) q = 0.0;  // past the end of a partial block: no decision, no update
                     if (r == rr && tt < nb) qrow[tt] = q;
                     if (rr < 3) {
@@ -1058,6 +1064,7 @@ static int dense_lowrank_sweep_i8(gpfq_ctx *ctx, const float *X, const float *Xq
     cudaStream_t st = ctx->stream, side = ctx->copy_stream;
     int64_t R = pick_range_length(ctx, nj, 1);
     R = std::max<int64_t>(128, R / 128 * 128);      // K blocks of the update are 128 directions
+    if (ctx->sweep_range) R = ctx->sweep_range;
     const int64_t N0P = ceil_div64(N0, R) * R, mP = ceil_div64(m, 128) * 128, njP = ceil_div64(nj, 128) * 128;   // whole ranges
     constexpr int S = 5;
     int8_t *sW = nullptr, *sXT = nullptr, *sXqT = nullptr, *sXq = nullptr, *sU = nullptr, *sKq = nullptr;
@@ -1127,7 +1134,7 @@ static int dense_lowrank_sweep_i8(gpfq_ctx *ctx, const float *X, const float *Xq
     //   slice(r) | W part of r (aux) | Q part of r (main, after the walk and after the W part) | slice(r + 1) ...
     auto chain = [&](int g, cudaStream_t on, int64_t j_lo, int64_t njh) -> int {
         cudaStream_t keep = ctx->stream, aux = ctx->aux_stream[g];
-        cudaEvent_t ev_sliced = ctx->ev_chain[2 * g], ev_wpart = ctx->ev_chain[2 * g + 1];
+        cudaEvent_t ev_sliced = ctx->ev_chain[3 * g], ev_wpart = ctx->ev_chain[3 * g + 1];
         int rc = GPFQ_OK;
         const int64_t rows_h = ceil_div64(njh, 128) * 128;
         auto cu = [&](cudaError_t e) { if (e != cudaSuccess && rc == GPFQ_OK) rc = gpfq_fail(ctx, GPFQ_ERR_CUDA, "%s", cudaGetErrorString(e)); };
@@ -1170,16 +1177,30 @@ static int dense_lowrank_sweep_i8(gpfq_ctx *ctx, const float *X, const float *Xq
         stats->reserved |= 1;
     }
     ctx->last_sweep_i8 = 1;
-    if (nj >= 2048 && ctx->lowrank_variant != 3) {
-        // two independent halves of the neurons on two streams: one half's contractions fill the other half's serial walk
-        const int64_t half = ceil_div64(ceil_div64(nj, 2), 128) * 128;
+    int G = ctx->sweep_groups ? ctx->sweep_groups : (nj >= 4096 ? 4 : (nj >= 2048 ? 2 : 1));
+    if (ctx->lowrank_variant == 3) G = 1;
+    while (G > 1 && ceil_div64(nj, G) < 256) G >>= 1;
+    if (G > 1) {
+        // Independent groups of neurons, one chain each on its own stream: while one group sits in the latency-bound walk of a
+        // range (which is given few SMs: 32 neurons per CTA) the contractions of the other groups have the rest of the chip.
+        const int64_t gs = ceil_div64(ceil_div64(nj, G), 128) * 128;
+        const int keep_nt = ctx->sweep_nt;
+        if (!keep_nt) ctx->sweep_nt = 32;
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev_copy[0], st));
-        CUDA_TRY(ctx, cudaStreamWaitEvent(side, ctx->ev_copy[0], 0));
-        GPFQ_TRY(chain(0, st, 0, half));
-        GPFQ_TRY(chain(1, side, half, nj - half));
-        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_copy[1], side));
-        CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_copy[1], 0));
-        return GPFQ_OK;
+        int rc = GPFQ_OK;
+        for (int g = 0; g < G && rc == GPFQ_OK; ++g) {
+            const int64_t j_lo = g * gs, njh = std::min<int64_t>(gs, nj - j_lo);
+            if (njh <= 0) break;
+            cudaStream_t on = g ? ctx->aux_stream[4 + g] : st;
+            if (g) CUDA_TRY(ctx, cudaStreamWaitEvent(on, ctx->ev_copy[0], 0));
+            rc = chain(g, on, j_lo, njh);
+            if (g) {
+                CUDA_TRY(ctx, cudaEventRecord(ctx->ev_chain[3 * g + 2], on));
+                CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_chain[3 * g + 2], 0));
+            }
+        }
+        ctx->sweep_nt = keep_nt;
+        return rc;
     }
     return chain(0, st, 0, nj);
 }

@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(256) i8_row_exponent_kernel(const float *__res
         for (int w = 1; w < 8; ++w) { mx = fmaxf(mx, red_mx[w]); sum += red_s[w]; nnz += red_n[w]; }
         int ex = 0;
         if (mx > 0.f && isfinite(mx)) frexpf(mx, &ex);  // mx = f * 2^ex, f in [0.5, 1)  =>  |x| <= mx < 2^ex
+        if (!isfinite(mx) || !isfinite(sum)) atomicMax(wide, 3);  // Inf / NaN in the inputs: the digit slices would be garbage
         e[blockIdx.x] = ex;
         if (nnz > 0) {
             const double top = ldexp(1.0, ex) * (double)nnz;
@@ -302,14 +303,17 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 
 // G[t][s] (s <= t) = (sum of the K-split partials, in index order) * 2^(eA_t + eB_s)
 // (part may alias G when there is a single split: every element is read and written by the same thread)
+// Non-finite inputs (level 3 from the slicing kernels: a diverged activation collection) give an all-NaN Gram, which is what
+// the fp64 contraction and the streaming walk make of them too -- never finite garbage from meaningless digits.
 __global__ void i8_finish_kernel(const double *part, int nsplit, int64_t split_stride, const int32_t *__restrict__ eA,
-                                 const int32_t *__restrict__ eB, int64_t N0, double *G) {
+                                 const int32_t *__restrict__ eB, int64_t N0, double *G, const int *__restrict__ wide) {
     const int64_t t = blockIdx.y;
     const int et = eA[t];
+    const bool poisoned = *wide >= 3;
     for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s <= t; s += (int64_t)gridDim.x * blockDim.x) {
         double tot = part[t * N0 + s];
         for (int k = 1; k < nsplit; ++k) tot += part[(int64_t)k * split_stride + t * N0 + s];
-        G[t * N0 + s] = ldexp(tot, et + eB[s]);
+        G[t * N0 + s] = poisoned ? __longlong_as_double(0x7ff8000000000000LL) : ldexp(tot, et + eB[s]);
     }
 }
 
@@ -419,10 +423,10 @@ int gram_i8_stage(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx, i
     gram_i8_kernel<<<grid, THREADS, SMEM, st>>>(map_q, map_x, a);
     KERNEL_CHECK(ctx);
     dim3 cgrid((unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(N0, 256), 64)), (unsigned)N0);
-    i8_finish_kernel<<<cgrid, 256, 0, st>>>(part2, pl.nsplit, N0 * N0, e_q, e_q, N0, G2);
+    i8_finish_kernel<<<cgrid, 256, 0, st>>>(part2, pl.nsplit, N0 * N0, e_q, e_q, N0, G2, wide);
     KERNEL_CHECK(ctx);
     if (!same) {
-        i8_finish_kernel<<<cgrid, 256, 0, st>>>(part1, pl.nsplit, N0 * N0, e_q, e_x, N0, G1);
+        i8_finish_kernel<<<cgrid, 256, 0, st>>>(part1, pl.nsplit, N0 * N0, e_q, e_x, N0, G1, wide);
         KERNEL_CHECK(ctx);
     }
     return GPFQ_OK;

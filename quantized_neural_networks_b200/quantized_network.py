@@ -133,6 +133,9 @@ class QuantizedNeuralNetwork:
         self._init_device(device, method, shard, gram_split)
 
     def _init_device(self, device, method, shard, gram_split="auto"):
+        if int(round(2 ** self.bits)) > 64:   # GPFQ_MAX_K of include/gpfq.h: the kernels keep an alphabet in shared memory
+            raise ValueError(f"bits={self.bits}: the CUDA path supports alphabets of up to 64 levels (bits <= 6); the reference "
+                             "accepts any `bits`, see INTEGRATION.md")
         if gram_split not in ("auto", "samples", "replicate"):
             raise ValueError(f"gram_split must be 'auto', 'samples' or 'replicate', not {gram_split!r}")
         self.device, self.method, self.gram_split = device, method, gram_split

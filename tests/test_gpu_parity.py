@@ -674,3 +674,16 @@ def test_auto_picks_a_measured_best_method(engine):
         best = min(v["ms"] for k, v in res.items() if k != "auto")
         assert res["auto"]["ms"] <= 1.10 * best + 0.05, (shape, res)
         assert min(v["agreement"] for v in res.values()) >= AGREE, (shape, res)
+
+
+def test_gram_i8_non_finite_inputs_give_nan_not_garbage(engine):
+    """An Inf / NaN in the layer inputs (a diverged activation collection) must not be sliced into finite digits: the tcgen05
+    Gram comes back all-NaN, like the fp64 contraction makes of the affected rows."""
+    rng = np.random.default_rng(3)
+    X = np.maximum(rng.standard_normal((300, 2048)), 0).astype(np.float32)
+    for bad in (np.inf, np.nan):
+        Xb = X.copy()
+        Xb[17, 100] = bad
+        with _gram_kernel(engine, 2):
+            G1, G2 = engine.gram_matrices(Xb)
+        assert np.isnan(np.tril(G2)).all()

@@ -315,3 +315,16 @@ def test_grid_runner_host_logic_and_level_packing():
     assert lev.tolist() == [[0, 3, -1], [2, 1, 1]] and np.array_equal(unpack_levels(lev, A2), Q)
     with pytest.raises(ValueError):
         pack_levels(np.array([0.123]), A)
+
+
+def test_alphabets_above_64_levels_are_rejected_in_the_constructor():
+    """GPFQ_MAX_K (include/gpfq.h): bits > 6 cannot run on the CUDA path; the mirror classes say so up front instead of
+    failing at the first layer (the reference accepts any `bits`)."""
+    import pytest
+    from quantized_neural_networks_b200 import QuantizedCNN, QuantizedNeuralNetwork, hostnet
+    net = hostnet.mnist_mlp(seed=0, widths=(8,), n_in=16, n_out=4)
+    seq = hostnet.ArraySequence(np.zeros((4, 4, 4), np.float32), np.zeros(4, int), 2)
+    for cls in (QuantizedNeuralNetwork, QuantizedCNN):
+        with pytest.raises(ValueError, match="64 levels"):
+            cls(net, 2, seq, bits=8)
+        cls(net, 2, seq, bits=6)     # 64 levels: accepted

@@ -197,3 +197,55 @@ def test_gpu_cnn_matches_reference_host_code(conv_path):
             n += 1
     assert n == 6
     assert np.array_equal(q.quantized_net.predict(x).argmax(-1), z["pred"])
+
+
+# ---- GPU: the reference-side binding of INTEGRATION.md section 1, executed verbatim --------------------------------------
+@pytest.mark.gpu
+def test_integration_md_stub_runs_as_written(tmp_path, monkeypatch):
+    """INTEGRATION.md shows the ~40-line ctypes stub a maintainer of the reference would drop into scripts/gpfq_cuda.py.  This
+    test extracts that code block from the document, executes it unchanged (h5py -> the in-memory stand-in of ref_shim, the
+    bare "libgpfq.so" resolved to the in-tree build) and drives both of its functions on hand-off files written the way the
+    reference writes them (`layer{idx}_data.h5` :471-500, `channel{c}_patch_array.h5` :756-797)."""
+    import ctypes
+    import re
+    import sys
+    import types
+    from quantized_neural_networks_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    code = re.search(r"## 1\. The stub.*?```python\n(.*?)```", text, re.S).group(1)
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setitem(sys.modules, "h5py", types.SimpleNamespace(File=ref_shim._MemFile))
+    real_cdll = ctypes.CDLL
+    monkeypatch.setattr(ctypes, "CDLL", lambda name, *a, **k: real_cdll(_lib.LIB_PATH if name == "libgpfq.so" else name, *a, **k))
+    stub = {}
+    exec(compile(code, "INTEGRATION.md#stub", "exec"), stub)
+
+    rng = np.random.default_rng(77)
+    N0, N1, m = 300, 12, 640
+    Z = rng.standard_normal((N0, m))
+    wX = np.maximum(Z, 0).astype(np.float32)
+    qX = np.maximum(Z + 0.05 * rng.standard_normal((N0, m)), 0).astype(np.float32)
+    W = (rng.uniform(-1, 1, (N0, N1)) * 0.2).astype(np.float32)
+    A = O.layer_alphabet(W, 3, O.unit_alphabet(np.log2(3)))
+    with ref_shim._MemFile("layer3_data.h5", "w") as hf:
+        hf.create_dataset("wX", shape=(N0, m))
+        hf.create_dataset("qX", shape=(N0, m))
+        hf["wX"][...] = wX
+        hf["qX"][...] = qX
+    assert np.array_equal(stub["dense_layer"](W, "layer3_data.h5", A), c_oracle.quantize_layer(W, wX, qX, A))
+
+    act = np.maximum(rng.standard_normal((6, 10, 10, 3)), 0).astype(np.float32)
+    actq = np.maximum(act + 0.05 * rng.standard_normal(act.shape), 0).astype(np.float32)
+    Wc = (rng.uniform(-1, 1, (3, 3, 3, 5)) * 0.3).astype(np.float32)
+    Ac = O.layer_alphabet(Wc, 4, O.unit_alphabet(4))
+    files, pm = [], []
+    for c in range(3):
+        Xp = O.channel_patches(act, c, (3, 3), (1, 1), "SAME")
+        Xqp = O.channel_patches(actq, c, (3, 3), (1, 1), "SAME")
+        pm.append((Xp, Xqp))
+        with ref_shim._MemFile(f"channel{c}_patch_array.h5", "w") as hf:
+            hf.create_dataset(f"wX_channel{c}", data=Xp, chunks=True, maxshape=(None, None))
+            hf.create_dataset(f"qX_channel{c}", data=Xqp, chunks=True, maxshape=(None, None))
+        files.append(f"channel{c}_patch_array.h5")
+    assert np.array_equal(stub["conv_channels"](Wc, files, Ac), c_oracle.quantize_conv_layer(Wc, lambda c: pm[c], Ac))
