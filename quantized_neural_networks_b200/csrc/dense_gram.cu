@@ -774,12 +774,17 @@ static bool dense_uses_lowrank(gpfq_ctx *ctx, int64_t N0, int64_t m, int64_t nj,
     if (ctx->sweep_variant == 1 || ctx->lowrank_variant == 1) return false;
     if (ctx->lowrank_variant >= 2) return N0 > 64;
     if (!i8_ok) return 3 * m < N0 && N0 >= 4096 && nj >= 256;   // fp64 (DMMA) contractions: the measured rule of round 1
-    // int8-slice contractions (slgemm_i8.cu): 39 slice-pair products of nj x m x N0 at ~2e15 int8 op/s plus the block-diagonal
-    // Gram tiles, against N0^2 nj fp64 MACs at ~1e13 /s plus the full tcgen05 Gram stage (15 pairs per Gram)
+    // int8-slice contractions (slgemm_i8.cu).  Both forms calibrated on this pool's B200 (tools/dense_methods.py,
+    // profiles/dense_methods_r2.md):
+    //   carried residuals  39 slice-pair products of nj x m x N0 at an effective 9.8e14 int8 op/s (the kernels are bound by their
+    //                      operand stream from L2 and per-CTA latency, not by the tensor pipe) + 0.6 us per direction and 4096
+    //                      neurons for the chain slicing -> dots -> walk of every range
+    //   Gram rows          N0^2 nj fp64 MACs at 1.05e13 /s (DMMA contraction) + 0.3 us per direction (walk) + the full tcgen05
+    //                      Gram stage (15 pairs)
     if (N0 < 1024 || nj < 256) return false;
     const double grams = same ? 1.0 : 2.0;
-    const double t_lr = 78.0 * nj * (double)m * N0 / 2.0e15 + grams * (double)m * N0 * 512.0 / 1.3e13;
-    const double t_gr = (double)N0 * N0 * nj / 1.0e13 + grams * 15.0 * (double)N0 * N0 * m / 2.0e15;
+    const double t_lr = 8.0e-14 * nj * (double)m * N0 + 0.6e-6 * N0 * std::max(1.0, (double)nj / 4096.0);
+    const double t_gr = (double)N0 * N0 * nj / 1.05e13 + 0.3e-6 * N0 + grams * 15.0 * (double)N0 * N0 * m / 2.2e15;
     return t_lr < t_gr;
 }
 
