@@ -390,11 +390,10 @@ def layer_roofline(d, sts, ms, hbm_peak, i8_peak):
 
 
 def load_traffic(kernel):
-    """Per-launch DRAM bytes of `kernel` from the committed ncu --set full capture of this round (profiles/r2_traffic.json,
-    written by tools/ncu_summary.py --traffic); None when no capture is committed."""
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) against algorithmic bytes of `kernel` from the committed
+    `ncu --set full` capture of this round (profiles/r2_traffic.json); None when no capture is committed."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
-        return t.get(kernel)
+        return json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json"))).get(kernel)
     except Exception:
         return None
 
@@ -511,12 +510,17 @@ def main():
     conv_bytes = sum(stage[d["name"]][0]["bytes_algorithmic"] for d in data if d["kind"] == "conv" and stage[d["name"]][0].get("gram_kernel") in (4, 5))
     conv_dfma = sum(stage[d["name"]][0]["flops_algorithmic"] / 2 for d in data if d["kind"] == "conv" and stage[d["name"]][0].get("gram_kernel") in (4, 5))
     roofline = None
+    traffic = load_traffic("conv_corr9_tma_kernel")
     if conv_ms > 0:
         ach = conv_bytes / (conv_ms * 1e-3) / 1e9
         roofline = {"kernel": "conv_corr9_tma_kernel (3x3 per-channel Grams as 13 displacement sums straight from the NHWC activations: "
                               "TMA 4-D boxes -> per-warp mbarrier ring -> fp64 register window, DFMA)",
                     "share_of_step": round(conv_ms / ms_per_step, 3), "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": ach / hbm_peak, "traffic": load_traffic("conv_corr9_tma_kernel"),
+                    "frac": ach / hbm_peak,
+                    "traffic": None if traffic is None else traffic["ratio"] * conv_bytes,
+                    "traffic_note": None if traffic is None else
+                    f"DRAM bytes of the same launches = {traffic['ratio']:.3f} x their algorithmic bytes, the ratio ncu measured on "
+                    f"{traffic['layer']}: {traffic['note']} ({traffic['capture']})",
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy)" if peaks else "fallback (B200_PROFILING.md)",
                     "algorithmic_bytes": "4 B per pixel and channel per tensor (X and Xq activations, each read once) over the CUDA-event "
                                          "time of the Gram stage of every conv call of the last step",

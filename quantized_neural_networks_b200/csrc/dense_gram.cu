@@ -398,7 +398,7 @@ sweep_pipe_kernel(const double *__restrict__ G1, const double *__restrict__ G2, 
                   const double *__restrict__ Dt, int64_t ldd, int8_t *__restrict__ Kq, int64_t krows, int64_t krow0, double inv_h) {
     using Cfg = PipeCfg<NT>;
     constexpr int B = Cfg::B, KC = Cfg::KC, LD = Cfg::LD, STAGES = Cfg::STAGES, CT = Cfg::CT, NA = NT / 8, NW = 4 * NT;
-    constexpr int BAR_C = 1, BAR_READY = 2, BAR_WALK_DONE = 4, HANDOVER = NW + CT;
+    constexpr int BAR_C = 1, BAR_READY = 2, BAR_WALK_DONE = 4, BAR_Q_STORED = 6, HANDOVER = NW + CT;
     extern __shared__ __align__(16) unsigned char sweep_smem[];
     double *gst = reinterpret_cast<double *>(sweep_smem);   // STAGES x B x LD   (Gram rows of the block being prepared)
     double *wst = gst + STAGES * B * LD;                    // STAGES x NT x LD  (W or Q panel of the tile)
@@ -447,6 +447,9 @@ sweep_pipe_kernel(const double *__restrict__ G1, const double *__restrict__ G2, 
             const int64_t t0 = t_begin + (int64_t)b * B;
             const int nb = (int)((t_end - t0) < B ? (t_end - t0) : B);
             if (b > 0) named_bar_sync(BAR_C, CT);   // every contractor is done with ring slots 0 / 1 of the previous block
+            // the early panel reads the decisions of blocks <= b-2 from Qt: block b-2's have been stored (long ago: its walk ended
+            // before block b-1 was even handed over)
+            if (b >= 2) named_bar_sync(BAR_Q_STORED + (s & 1), HANDOVER);
             // ---- the block's own operands and its G2 tile against the previous block: requested now, parked in registers
             double pg1[DPT], pg2[DPT], pgp[DPT], pw[WPT], pd[WPT];
 #pragma unroll
@@ -613,7 +616,12 @@ sweep_pipe_kernel(const double *__restrict__ G1, const double *__restrict__ G2, 
                     }
                 }
             }
-            // ---- this lane's own decisions (directions = r mod 4) go out: Qt for later ranges / the result, and the int8 index
+            // ---- hand the decisions over (they sit in qblk of this set) before anything else: the contractors only need them in
+            // shared memory for the one chunk that separates this walk from the next
+            __threadfence_block();
+            named_bar_arrive(BAR_WALK_DONE + s, HANDOVER);
+            // ---- this lane's own decisions (directions = r mod 4) go out: Qt for later ranges / the result, and the int8 index.
+            // qblk of this set is rewritten only after the contractors have seen Q_STORED of this block (two blocks on).
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int tt = 4 * i + r;
@@ -623,8 +631,10 @@ sweep_pipe_kernel(const double *__restrict__ G1, const double *__restrict__ G2, 
                     if (Kq) Kq[sl_offset(t0 + tt, 0, krow0 + jt + j, krows, 1)] = (int8_t)__double2int_rn(q * inv_h);
                 }
             }
-            __threadfence_block();
-            named_bar_arrive(BAR_WALK_DONE + s, HANDOVER);
+            if (b + 2 < nblk) {   // somebody will wait for it
+                __threadfence_block();
+                named_bar_arrive(BAR_Q_STORED + s, HANDOVER);
+            }
         }
     }
 }
@@ -777,14 +787,15 @@ static bool dense_uses_lowrank(gpfq_ctx *ctx, int64_t N0, int64_t m, int64_t nj,
     // int8-slice contractions (slgemm_i8.cu).  Both forms calibrated on this pool's B200 (tools/dense_methods.py,
     // profiles/dense_methods_r2.md):
     //   carried residuals  39 slice-pair products of nj x m x N0 at an effective 9.8e14 int8 op/s (the kernels are bound by their
-    //                      operand stream from L2 and per-CTA latency, not by the tensor pipe) + 0.6 us per direction and 4096
-    //                      neurons for the chain slicing -> dots -> walk of every range
+    //                      operand stream from L2 and per-CTA latency, not by the tensor pipe) + 0.3 us per direction for the
+    //                      chain slicing -> dots -> walk of every range + another 0.3 us per direction and 4096 neurons
     //   Gram rows          N0^2 nj fp64 MACs at 1.05e13 /s (DMMA contraction) + 0.3 us per direction (walk) + the full tcgen05
     //                      Gram stage (15 pairs)
-    if (N0 < 1024 || nj < 256) return false;
+    //                      (the chain costs 0.3 us per direction even for a handful of neurons: one rank of a multi-GPU job)
+    if (N0 < 1024 || nj < 64 || m > N0) return false;
     const double grams = same ? 1.0 : 2.0;
-    const double t_lr = 8.0e-14 * nj * (double)m * N0 + 0.6e-6 * N0 * std::max(1.0, (double)nj / 4096.0);
-    const double t_gr = (double)N0 * N0 * nj / 1.05e13 + 0.3e-6 * N0 + grams * 15.0 * (double)N0 * N0 * m / 2.2e15;
+    const double t_lr = 8.0e-14 * nj * (double)m * N0 + N0 * (0.3e-6 + 0.3e-6 * (double)nj / 4096.0) + 0.35e-3;
+    const double t_gr = (double)N0 * N0 * nj / 1.05e13 + 0.3e-6 * N0 + grams * 15.0 * (double)N0 * N0 * m / 2.2e15 + 0.35e-3;
     return t_lr < t_gr;
 }
 

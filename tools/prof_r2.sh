@@ -1,0 +1,17 @@
+#!/bin/bash
+# Round-2 profiling evidence (run under gpurun, one GPU).  Outputs under gpurun_out/, summarised into profiles/ by
+# tools/launch_summary.py / tools/ncu_summary.py.
+set -x
+mkdir -p gpurun_out
+# 1. launch list of the VGG16 value leg (3 warm-up passes + 1 timed), full size
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_bench_launches.csv \
+    python bench.py --profile --steps 1 --warmup 3 > gpurun_out/r2_bench_launches.log 2>&1
+# 2. the dominant kernel (correlation-form conv Grams), ncu --set full, 376 images (ncu saves / restores device memory per replay)
+ncu --set full --clock-control none --import-source on -k regex:conv_corr9_tma -s 2 -c 4 -o gpurun_out/r2_corr9_vgg \
+    python bench.py --profile --steps 1 --warmup 3 --n-img 376 > gpurun_out/r2_corr9_vgg.log 2>&1
+# 3. the tcgen05 contraction and the pipelined walk of the residual-form sweep on VGG16 fc1
+ncu --set full --clock-control none --import-source on -k regex:slgemm_i8 -s 40 -c 3 -o gpurun_out/r2_slgemm_fc1 \
+    python tools/dense_bench.py --shapes 25088x4096x1504 --methods auto --reps 0 > gpurun_out/r2_slgemm_fc1.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:sweep_pipe -s 20 -c 1 -o gpurun_out/r2_pipe_fc1 \
+    python tools/dense_bench.py --shapes 25088x4096x1504 --methods auto --reps 0 > gpurun_out/r2_pipe_fc1.log 2>&1
+ls -la gpurun_out/*.ncu-rep
