@@ -10,13 +10,13 @@
 // K contiguous):   x[r][k] * 2^-e_r = sum_{s=1..S} b_s[r][k] 2^(2 - 8 s)   (b in [-128, 127]; rounding at 2^-(8S-2) of 2^e_r).
 // Every slice pair with s_a + s_b = d accumulates EXACTLY into the s32 TMEM accumulator of its d (<= 5 pairs x K <= 26112);
 // ALL d of a product are open at once -- a 128 x 64 output tile leaves room for eight 64-column accumulators in the 512 TMEM
-// columns -- so a K block of every A slice and every B slice is fetched ONCE (two TMA boxes of 5 slices each per stage) and
-// feeds all 15-19 pair MMAs, and the fp64 combination  sum_d S_d alpha 2^(4 - 8 d + eA_i + eB_j)  happens once per product,
+// columns -- so a K block of every A slice and every B slice is fetched ONCE per stage and feeds all 15-19 pair MMAs, and the fp64 combination  sum_d S_d alpha 2^(4 - 8 d + eA_i + eB_j)  happens once per product,
 // in registers (one output row per epilogue thread), in a fixed order: bit-reproducible.  C is touched once per tile.
 //
 // Kernel anatomy (one CTA per 128 x 64 output tile, one CTA per SM):
-//   warp 0    TMA producer: boxes of 64 B x 128 rows x SA slices (A) and 64 B x 64 rows x SB slices (B) per stage, 64B swizzle,
-//             3-stage mbarrier ring
+//   warp 0    producer: per stage one bulk copy (cp.async.bulk, UBLKCP) of 128 rows x 64 B per A slice and of 64 rows x 64 B per
+//             B slice -- the slice tensors are stored K-block tiled and already 64B-swizzled (slgemm_i8.cuh), so a tile IS its
+//             shared-memory image -- into a 3-stage mbarrier ring
 //   warp 1    TMEM allocator + single-thread MMA issuer: 2 x tcgen05.mma.cta_group::1.kind::i8 (M128 N64 K32) per slice pair
 //             and K block
 //   warps 2-5 epilogue: per product tcgen05.ld of every accumulator -> fp64 fma into 64 register sums per thread; after the
@@ -46,6 +46,8 @@ struct SlSeg {
     double alpha;
     const int32_t *eA;      // row exponents, indexed like the slice rows (nullptr: eA_const)
     int eA_const;
+    const int8_t *A, *B;    // slice tensors (K-block tiled, pre-swizzled: sl_offset)
+    int64_t rowsA, rowsB;   // their padded row counts
 };
 
 struct SlArgs {
@@ -89,8 +91,7 @@ __device__ __forceinline__ void sl_issue_kblock(uint32_t tmem_base, uint64_t da,
 }
 
 __global__ void __launch_bounds__(slg::THREADS, 1)
-slgemm_i8_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapB0,
-                 const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapB1, const SlArgs args) {
+slgemm_i8_kernel(const SlArgs args) {
     using namespace i8g;
     using namespace slg;
     extern __shared__ unsigned char sl_smem_raw[];
@@ -127,20 +128,23 @@ slgemm_i8_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ---- TMA producer: every slice of the A rows and of the B rows of one K block per stage (two boxes)
+        // ---- producer: every slice of the A rows and of the B rows of one K block per stage, one bulk copy per slice
         if (lane == 0) {
             int iter = 0;
             for (int sg = 0; sg < args.nseg; ++sg) {
                 const SlSeg &g = args.seg[sg];
-                const CUtensorMap *ma = sg ? &mapA1 : &mapA0, *mb = sg ? &mapB1 : &mapB0;
                 const uint32_t bytes = (uint32_t)(g.SA * A_SLICE + g.SB * B_SLICE);
+                // slice s of K block kb of rows row0.. is ONE contiguous run of 128 (64) rows x 64 bytes
+                const int8_t *pa = g.A + ((int64_t)(g.k0 / BK) * g.SA * g.rowsA + g.a_row0 + brow + ti * TM) * BK;
+                const int8_t *pb = g.B + ((int64_t)(g.k0 / BK) * g.SB * g.rowsB + g.b_row0 + brow + tj * TN) * BK;
+                const int64_t a_slice = g.rowsA * BK, b_slice = g.rowsB * BK;
                 for (int kb = 0; kb < g.kblocks; ++kb, ++iter) {
                     const int s = iter % STAGES;
                     if (iter >= STAGES) mbar_wait(&empty[s], ((iter / STAGES) - 1) & 1);
                     unsigned char *a = smem + (size_t)s * STAGE_BYTES, *b = a + S * A_SLICE;
                     mbar_expect_tx(&full[s], bytes);
-                    tma_load_4d(a, ma, &full[s], 0, g.a_row0 + brow + ti * TM, 0, g.k0 / BK + kb);
-                    tma_load_4d(b, mb, &full[s], 0, g.b_row0 + brow + tj * TN, 0, g.k0 / BK + kb);
+                    for (int sl = 0; sl < g.SA; ++sl) bulk_load(a + sl * A_SLICE, pa + ((int64_t)kb * g.SA + sl) * a_slice, A_SLICE, &full[s]);
+                    for (int sl = 0; sl < g.SB; ++sl) bulk_load(b + sl * B_SLICE, pb + ((int64_t)kb * g.SB + sl) * b_slice, B_SLICE, &full[s]);
                 }
             }
         }
@@ -415,6 +419,8 @@ __global__ void __launch_bounds__(128) sl_transsplit_kernel(const float *__restr
 int sl_make_operand(gpfq_ctx *ctx, SlOperand *op, const int8_t *slices, int64_t rowsP, int64_t kbytes, int n_slices, const int32_t *e,
                     int e_const, bool is_b) {
     using namespace slg;
+    if (kbytes % BK || rowsP % TM || ((uintptr_t)slices & 15))
+        return gpfq_fail(ctx, GPFQ_ERR_ARG, "slice tensors are padded to whole K blocks and 128-row tiles, 16-byte aligned");
     op->slices = slices;
     op->rowsP = rowsP;
     op->kbytes = kbytes;
@@ -422,19 +428,6 @@ int sl_make_operand(gpfq_ctx *ctx, SlOperand *op, const int8_t *slices, int64_t 
     op->e = e;
     op->e_const = e_const;
     op->is_b = is_b;
-    EncodeTiledFn enc = encode_tiled_fn();
-    if (!enc) return gpfq_fail(ctx, GPFQ_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available from this driver");
-    // one box = BK bytes x (TN | TM) rows x EVERY slice of one K block: lands slice-major in the stage, 64B-swizzled rows;
-    // in the K-block-tiled layout (sl_offset) that is n_slices contiguous runs of 4 / 8 KB
-    const cuuint64_t dims[4] = {(cuuint64_t)BK, (cuuint64_t)rowsP, (cuuint64_t)n_slices, (cuuint64_t)(kbytes / BK)};
-    const cuuint64_t strides[3] = {(cuuint64_t)BK, (cuuint64_t)BK * (cuuint64_t)rowsP, (cuuint64_t)BK * (cuuint64_t)rowsP * (cuuint64_t)n_slices};
-    const cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(is_b ? TN : TM), (cuuint32_t)n_slices, 1u};
-    const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
-    if (kbytes % BK) return gpfq_fail(ctx, GPFQ_ERR_ARG, "slice tensors are padded to whole K blocks");
-    const CUresult rc = enc(&op->map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<int8_t *>(slices), dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (rc != CUDA_SUCCESS) return gpfq_fail(ctx, GPFQ_ERR_CUDA, "cuTensorMapEncodeTiled failed with code %d", (int)rc);
     return GPFQ_OK;
 }
 
@@ -469,6 +462,10 @@ int slgemm_i8(gpfq_ctx *ctx, const SlProduct *prod, int nprod, double *C, int64_
         g.alpha = p.alpha;
         g.eA = p.A->e;
         g.eA_const = p.A->e_const;
+        g.A = p.A->slices;
+        g.B = p.B->slices;
+        g.rowsA = p.A->rowsP;
+        g.rowsB = p.B->rowsP;
     }
     a.eB = prod[0].B->e;
     a.eB_const = prod[0].B->e_const;
@@ -486,8 +483,7 @@ int slgemm_i8(gpfq_ctx *ctx, const SlProduct *prod, int nprod, double *C, int64_
     if (nbatch < 1 || nbatch > 65535) return gpfq_fail(ctx, GPFQ_ERR_ARG, "slgemm_i8: 1..65535 batches");
     CUDA_TRY(ctx, cudaFuncSetAttribute(slgemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     const dim3 grid((unsigned)(ceil_div64(M, TM) * a.tiles_n), (unsigned)nbatch);
-    const SlProduct &p1 = prod[nprod - 1];
-    slgemm_i8_kernel<<<grid, THREADS, SMEM, ctx->stream>>>(prod[0].A->map, prod[0].B->map, p1.A->map, p1.B->map, a);
+    slgemm_i8_kernel<<<grid, THREADS, SMEM, ctx->stream>>>(a);
     KERNEL_CHECK(ctx);
     return GPFQ_OK;
 }

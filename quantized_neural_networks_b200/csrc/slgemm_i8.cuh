@@ -2,11 +2,14 @@
 #pragma once
 #include "i8_common.cuh"
 
-// Layout of a sliced operand in HBM: K-BLOCK TILED, so that everything one pipeline stage fetches is a handful of contiguous
-// 4-8 KB runs (a TMA box over rows that lie 25 KB apart is served one 64-byte request at a time: measured 10x slower):
-//   byte (slice s, row r, K position c)  at  ((c / 64 * n_slices + s) * rowsP + r) * 64 + c % 64
+// Layout of a sliced operand in HBM: the SHARED-MEMORY IMAGE of its tiles.  K-block tiled -- everything one pipeline stage
+// fetches is a handful of contiguous 4-8 KB runs -- and already 64B-swizzled (16-byte chunk c of row r sits at chunk
+// c ^ ((r >> 1) & 3), the pattern UMMA's SWIZZLE_64B descriptors expect), so a stage is filled by plain 1-D bulk copies
+// (cp.async.bulk: one request per 4-8 KB; the same boxes through a tensor map cost one 64-byte request per row and capped an
+// SM at ~40 GB/s):
+//   byte (slice s, row r, K position c)  at  ((c / 64 * n_slices + s) * rowsP + r) * 64 + ((c / 16 % 4) ^ (r / 2 % 4)) * 16 + c % 16
 __host__ __device__ __forceinline__ int64_t sl_offset(int64_t c, int s, int64_t r, int64_t rowsP, int n_slices) {
-    return (((c >> 6) * n_slices + s) * rowsP + r) * 64 + (c & 63);
+    return (((c >> 6) * n_slices + s) * rowsP + r) * 64 + ((((c >> 4) & 3) ^ ((r >> 1) & 3)) << 4) + (c & 15);
 }
 
 struct SlOperand {          // a sliced matrix on the device: n_slices x rowsP x kbytes int8 (K-block tiled, sl_offset) + row exponents
@@ -15,8 +18,7 @@ struct SlOperand {          // a sliced matrix on the device: n_slices x rowsP x
     int n_slices = 0;
     const int32_t *e = nullptr;   // nullptr: e_const for every row
     int e_const = 0;
-    bool is_b = false;            // tensor-map box: 64 rows (a B operand: output columns) or 128 rows (an A operand)
-    CUtensorMap map;
+    bool is_b = false;            // used as the B operand (output columns: 64-row tiles) or as the A operand (128-row tiles)
 };
 
 struct SlProduct {          // one segment: alpha * A[a_row0 : a_row0 + M, k0 : k0 + K] B[b_row0 : b_row0 + N, k0 : k0 + K]^T
