@@ -223,8 +223,8 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             }
         }
     } else if (warp == 1) {
-        // ---- MMA issuer
-        if (lane == 0) {
+        // ---- MMA issuer: the whole warp runs the (uniform) loops and waits, one elected lane issues (i8_common.cuh: elect_one)
+        {
             // instruction descriptor: D = s32, A = B = signed 8-bit, both K-major, N = 256, M = 128
             const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
             int iter = 0, p = 0;
@@ -243,12 +243,16 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                         mbar_wait(&full[s], (iter / STAGES) & 1);
                         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                         const uint32_t a = smem_u32(smem + (size_t)s * STAGE_BYTES), b = a + A_BYTES;
+                        if (elect_one()) {
 #pragma unroll
-                        for (int ks = 0; ks < BK / 32; ++ks)
-                            umma_i8(tmem_d, umma_desc_sw128(a + ks * 32), umma_desc_sw128(b + ks * 32), idesc, (it | ks) ? 1u : 0u);
-                        umma_commit(&empty[s]);  // the stage may be refilled once these MMAs have read it
+                            for (int ks = 0; ks < BK / 32; ++ks)
+                                umma_i8(tmem_d, umma_desc_sw128(a + ks * 32), umma_desc_sw128(b + ks * 32), idesc, (it | ks) ? 1u : 0u);
+                            umma_commit(&empty[s]);  // the stage may be refilled once these MMAs have read it
+                        }
+                        __syncwarp();
                     }
-                    umma_commit(&acc_full[buf]);
+                    if (elect_one()) umma_commit(&acc_full[buf]);
+                    __syncwarp();
                 }
             }
         }

@@ -34,6 +34,14 @@ __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, u
             smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+// One lane of a converged warp (elect.sync): the single-thread tcgen05 instructions are issued under it while the surrounding
+// loops stay warp-uniform -- under a plain `if (lane == 0)` the compiler treats descriptors and TMEM addresses as divergent
+// values and wraps EVERY tcgen05.mma in an ELECT / R2UR.BROADCAST retry loop (~10 extra instructions per MMA).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
 // 1-D bulk copy global -> shared (UBLKCP), completion on an mbarrier; 16-byte aligned, size a multiple of 16
 __device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)),

@@ -149,8 +149,9 @@ slgemm_i8_kernel(const SlArgs args) {
             }
         }
     } else if (warp == 1) {
-        // ---- MMA issuer: per K block every slice pair (k, l), k + l = d, into the accumulator of its d
-        if (lane == 0) {
+        // ---- MMA issuer: per K block every slice pair (k, l), k + l = d, into the accumulator of its d.  The whole warp runs the
+        // (uniform) loops and waits; one elected lane issues.
+        {
             // instruction descriptor: D = s32, A = B = signed 8-bit, both K-major, N = 64, M = 128
             const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
             int iter = 0;
@@ -160,32 +161,38 @@ slgemm_i8_kernel(const SlArgs args) {
                     mbar_wait(seg_empty, (sg - 1) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 }
+                const int mode = (g.SA == 5 && g.SB == 5 && g.D == 6) ? 1 : (g.SA == 5 && g.SB == 5 && g.D == 7) ? 2
+                                 : (g.SA == 1 && g.SB == 5 && g.D == 6) ? 3 : 0;
                 for (int kb = 0; kb < g.kblocks; ++kb, ++iter) {
                     const int s = iter % STAGES;
                     mbar_wait(&full[s], (iter / STAGES) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                     const uint32_t a = smem_u32(smem + (size_t)s * STAGE_BYTES), b = a + S * A_SLICE;
                     const uint64_t da = umma_desc_sw64(a), db = umma_desc_sw64(b);
-                    // the usual slice-pair sets as straight-line code (one thread issues every MMA: at 32 tensor-core cycles per
-                    // M128 N64 K32 instruction the loop overhead of the generic form would be the bottleneck)
-                    if (g.SA == 5 && g.SB == 5 && g.D == 6) sl_issue_kblock<5, 5, 6>(tmem_base, da, db, idesc, kb == 0);
-                    else if (g.SA == 5 && g.SB == 5 && g.D == 7) sl_issue_kblock<5, 5, 7>(tmem_base, da, db, idesc, kb == 0);
-                    else if (g.SA == 1 && g.SB == 5 && g.D == 6) sl_issue_kblock<1, 5, 6>(tmem_base, da, db, idesc, kb == 0);
-                    else
-                        for (int d = 2; d <= g.D; ++d) {
-                            const uint32_t tmem_d = tmem_base + (uint32_t)((d - 2) * TN);
-                            const int k_lo = max(1, d - g.SB), k_hi = min(g.SA, d - 1);
-                            for (int k = k_lo; k <= k_hi; ++k) {
-                                const uint32_t ak = a + (k - 1) * A_SLICE, bl = b + (d - k - 1) * B_SLICE;
+                    if (elect_one()) {
+                        // the usual slice-pair sets as straight-line code (at 32 tensor-core cycles per M128 N64 K32 instruction the
+                        // loop overhead of the generic form would be the bottleneck)
+                        if (mode == 1) sl_issue_kblock<5, 5, 6>(tmem_base, da, db, idesc, kb == 0);
+                        else if (mode == 2) sl_issue_kblock<5, 5, 7>(tmem_base, da, db, idesc, kb == 0);
+                        else if (mode == 3) sl_issue_kblock<1, 5, 6>(tmem_base, da, db, idesc, kb == 0);
+                        else
+                            for (int d = 2; d <= g.D; ++d) {
+                                const uint32_t tmem_d = tmem_base + (uint32_t)((d - 2) * TN);
+                                const int k_lo = max(1, d - g.SB), k_hi = min(g.SA, d - 1);
+                                for (int k = k_lo; k <= k_hi; ++k) {
+                                    const uint32_t ak = a + (k - 1) * A_SLICE, bl = b + (d - k - 1) * B_SLICE;
 #pragma unroll
-                                for (int ks = 0; ks < BK / 32; ++ks)
-                                    umma_i8(tmem_d, umma_desc_sw64(ak + ks * 32), umma_desc_sw64(bl + ks * 32), idesc,
-                                            (kb | (k - k_lo) | ks) ? 1u : 0u);
+                                    for (int ks = 0; ks < BK / 32; ++ks)
+                                        umma_i8(tmem_d, umma_desc_sw64(ak + ks * 32), umma_desc_sw64(bl + ks * 32), idesc,
+                                                (kb | (k - k_lo) | ks) ? 1u : 0u);
+                                }
                             }
-                        }
-                    umma_commit(&empty[s]);  // the stage may be refilled once these MMAs have read it
+                        umma_commit(&empty[s]);  // the stage may be refilled once these MMAs have read it
+                    }
+                    __syncwarp();
                 }
-                umma_commit(seg_full);
+                if (elect_one()) umma_commit(seg_full);
+                __syncwarp();
             }
         }
     } else {
