@@ -93,6 +93,9 @@ int gpfq_set_stream(gpfq_ctx *ctx, void *cuda_stream);
  *   "corr_rows"    correlation form: image rows per band (0 auto by image height, or 4 / 6 / 8)
  *   "sweep_kernel"  0 pipelined range walk (panel of block b+1 contracted during the walk of block b) when every CTA is
  *                  resident, else the persistent tile kernel; 1 one launch pair per block; 2 always the persistent tile kernel
+ *   "sweep_wq"     residual-form sweep on tcgen05: 0 auto, 1 W part of the residual update on an aux stream underneath the walk,
+ *                  2 W and Q part as one two-product launch
+ *   "sweep_range"  residual-form sweep on tcgen05: directions per range (0 auto, else a multiple of 128)
  *   "sweep_groups" residual-form sweep on tcgen05: independent neuron groups in flight (0 auto, 1, 2 or 4)
  *   "sweep_nt"     pipelined range walk: neurons per CTA (0 auto, 8, 16 or 32)
  *   "sweep_i8"     contractions of the residual-form sweep: 0 auto, 1 int8 slices on tcgen05, 2 fp64 DMMA

@@ -200,6 +200,10 @@ extern "C" int gpfq_set_option(gpfq_ctx *ctx, const char *key, int64_t value) {
         // 3 carried residuals as ONE chain (no two-stream split of the neurons)
         if (value < 0 || value > 3) return gpfq_fail(ctx, GPFQ_ERR_ARG, "sweep_outer must be 0, 1, 2 or 3");
         ctx->lowrank_variant = (int)value;
+    } else if (!strcmp(key, "sweep_wq")) {      // residual-form sweep on tcgen05: W part of the update on the aux stream (1) or
+                                                 // together with the Q part as one two-product launch (2); 0 auto
+        if (value < 0 || value > 2) return gpfq_fail(ctx, GPFQ_ERR_ARG, "sweep_wq must be 0, 1 or 2");
+        ctx->sweep_wq = (int)value;
     } else if (!strcmp(key, "sweep_range")) {   // residual-form sweep on tcgen05: directions per range (0 auto)
         if (value < 0 || value > 8192 || value % 128) return gpfq_fail(ctx, GPFQ_ERR_ARG, "sweep_range must be 0 or a multiple of 128 up to 8192");
         ctx->sweep_range = (int)value;

@@ -53,6 +53,7 @@ struct gpfq_ctx {
     cudaStream_t aux_stream[8] = {};   // residual-form sweep, up to 4 neuron groups: [g] the W part of group g's residual update,
                                        // [4 + g] the main chain of group g >= 1 (group 0 runs on `stream`)
     cudaEvent_t ev_chain[12] = {};     // ... [3 g] residuals sliced (main -> aux), [3 g + 1] W part landed (aux -> main), [3 g + 2] done
+    int sweep_wq = 0;                  // ... 0 auto, 1 W part of the update on the aux stream, 2 W and Q parts as one two-product launch
     int sweep_range = 0;               // ... directions per range (0 auto; a multiple of 128)
     int sweep_groups = 0;              // ... neuron groups (0 auto, 1 / 2 / 4)
     std::string err = "";

@@ -1153,26 +1153,35 @@ static int dense_lowrank_sweep_i8(gpfq_ctx *ctx, const float *X, const float *Xq
         cudaEvent_t ev_sliced = ctx->ev_chain[3 * g], ev_wpart = ctx->ev_chain[3 * g + 1];
         int rc = GPFQ_OK;
         const int64_t rows_h = ceil_div64(njh, 128) * 128;
+        // measured (VGG16 fc1 / fc2): with thousands of neurons the sweep is bound by the SUM of its contraction launches -- W and Q
+        // part as ONE two-product launch (25.5 vs 27.3 ms); a shard of a few hundred neurons is bound by the LATENCY of the
+        // chain -- W part off it, on the aux stream (11.0 vs 11.6 ms)
+        const bool merged = ctx->sweep_wq == 2 || (ctx->sweep_wq == 0 && nj >= 2048);
         auto cu = [&](cudaError_t e) { if (e != cudaSuccess && rc == GPFQ_OK) rc = gpfq_fail(ctx, GPFQ_ERR_CUDA, "%s", cudaGetErrorString(e)); };
         for (int64_t tb = 0, pb = 0; tb < N0 && rc == GPFQ_OK; pb = tb, tb += R) {
             const int64_t te = tb + R < N0 ? tb + R : N0;
             ctx->stream = on;
             if (tb > 0) {
                 const int64_t Kp = ceil_div64(tb - pb, 128) * 128;   // the walk of [pb, tb) left its level indices in sKq
-                cu(cudaStreamWaitEvent(on, ev_wpart, 0));
-                SlProduct qp = {&oKq, &oXqT, j_lo, 0, pb, Kp, 6, -h};
-                rc = slgemm_i8(ctx, &qp, 1, Ut + j_lo * m, m, njh, m, true);          // U -= h K'_r X~_r
+                if (merged) {   // U += W_r X_r - h K'_r X~_r as ONE launch of two products (same B-row exponents)
+                    SlProduct up[2] = {{&oW, &oXT, j_lo, 0, pb, Kp, D_UPDATE, 1.0}, {&oKq, &oXqT, j_lo, 0, pb, Kp, 6, -h}};
+                    rc = slgemm_i8(ctx, up, 2, Ut + j_lo * m, m, njh, m, true);
+                } else {
+                    cu(cudaStreamWaitEvent(on, ev_wpart, 0));
+                    SlProduct qp = {&oKq, &oXqT, j_lo, 0, pb, Kp, 6, -h};
+                    rc = slgemm_i8(ctx, &qp, 1, Ut + j_lo * m, m, njh, m, true);          // U -= h K'_r X~_r
+                }
                 if (rc != GPFQ_OK) break;
                 rc = sl_rowsplit<double>(ctx, Ut + j_lo * m, m, njh, m, eU, sU, njP, mP, j_lo, rows_h);
                 if (rc != GPFQ_OK) break;
             }
-            cu(cudaEventRecord(ev_sliced, on));
+            if (!merged) cu(cudaEventRecord(ev_sliced, on));
             if (tb > 0) {
                 SlProduct dp = {&oU, &oXq, j_lo, tb, 0, mP, D_DOTS, 1.0};
                 rc = slgemm_i8(ctx, &dp, 1, Do + j_lo * R, R, njh, te - tb, false);   // D_r = U X~_r^T
                 if (rc != GPFQ_OK) break;
             }
-            if (te < N0) {   // the W part of THIS range, for the ranges after it
+            if (te < N0 && !merged) {   // the W part of THIS range, for the ranges after it
                 const int64_t Kp = ceil_div64(te - tb, 128) * 128;
                 cu(cudaStreamWaitEvent(aux, ev_sliced, 0));
                 ctx->stream = aux;
