@@ -213,6 +213,10 @@ extern "C" int gpfq_set_option(gpfq_ctx *ctx, const char *key, int64_t value) {
     } else if (!strcmp(key, "sweep_nt")) {      // pipelined range walk: neurons per CTA (0 auto)
         if (value != 0 && value != 8 && value != 16 && value != 32) return gpfq_fail(ctx, GPFQ_ERR_ARG, "sweep_nt must be 0, 8, 16 or 32");
         ctx->sweep_nt = (int)value;
+    } else if (!strcmp(key, "sweep_walk")) {    // range walk of the residual-form sweep (ternary alphabets): 0 auto, 1 tensor-core
+                                                 // walk (sweep_tc.cu), 2 sweep_pipe / sweep_tile kernels
+        if (value < 0 || value > 2) return gpfq_fail(ctx, GPFQ_ERR_ARG, "sweep_walk must be 0, 1 or 2");
+        ctx->sweep_walk = (int)value;
     } else if (!strcmp(key, "sweep_i8")) {      // residual-form sweep contractions: 0 auto, 1 int8 slices on tcgen05, 2 fp64 DMMA
         if (value < 0 || value > 2) return gpfq_fail(ctx, GPFQ_ERR_ARG, "sweep_i8 must be 0, 1 or 2");
         ctx->sweep_i8 = (int)value;

@@ -69,6 +69,8 @@ struct gpfq_ctx {
     int gram_variant = 0;         // Dense Gram stage: 0 auto, 1 fp64 DMMA (mma.sync), 2 int8 slices on tcgen05 (gram_i8.cu)
     int lowrank_variant = 0;      // sweep outer level: 0 auto, 1 Gram rows, 2 residual (low-rank) form
     int sweep_nt = 0;             // pipelined range walk: neurons per CTA (0 auto, 8 / 16 / 32)
+    int sweep_walk = 0;           // range walk of the residual-form sweep: 0 auto, 1 tensor-core walk (sweep_tc.cu), 2 sweep_pipe / sweep_tile
+    int last_sweep_tc = 0;        // the last residual-form sweep walked its ranges with sweep_tc_kernel
     int sweep_i8 = 0;             // sweep contractions of the residual form: 0 auto, 1 int8 slices on tcgen05, 2 fp64 DMMA
     int i8_pairs_d = 0;           // int8 Gram: keep slice pairs with k + l <= this (0: the default of gram_i8.cu)
     const double *h_alph = nullptr;  // host copy of the current call's alphabets (levels back to back) and their offsets
@@ -89,7 +91,8 @@ enum WsSlot {
     WS_X = 0, WS_XQ, WS_W, WS_Q, WS_WT, WS_QT, WS_G1, WS_G2, WS_PART, WS_DT, WS_NRM, WS_ALPH,
     WS_U, WS_PTRS, WS_CG, WS_CPART, WS_PATCH_A, WS_PATCH_B, WS_ACT_A, WS_ACT_B, WS_QIDX, WS_MISC,
     WS_I8_SQ, WS_I8_SX, WS_I8_E, WS_I8_TILES, WS_LR_XD, WS_LR_XT, WS_LR_U, WS_CORR_B,
-    WS_SL_W, WS_SL_XT, WS_SL_XQT, WS_SL_XQ, WS_SL_U, WS_SL_KQ, WS_SL_E
+    WS_SL_W, WS_SL_XT, WS_SL_XQT, WS_SL_XQ, WS_SL_U, WS_SL_KQ, WS_SL_E,
+    WS_TC_TAB, WS_TC_G2S, WS_TC_G1S, WS_TC_E, WS_TC_P, WS_TC_W
 };
 
 int gpfq_fail(gpfq_ctx *ctx, int code, const char *fmt, ...);

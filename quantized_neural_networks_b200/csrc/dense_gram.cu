@@ -12,6 +12,7 @@
 
 #include "gemm_nt.cuh"
 #include "slgemm_i8.cuh"
+#include "sweep_tc.cuh"
 
 static constexpr int SWEEP_B = 32;
 static constexpr int64_t SWEEP_OUTER = 512;  // directions per range of the two-level sweep
@@ -1075,12 +1076,18 @@ static bool dense_lowrank_uses_i8(gpfq_ctx *ctx, int64_t N0, int64_t m, int64_t 
 
 static int dense_lowrank_sweep_i8(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx, int64_t N0, int64_t m,
                                   const double *Wt, double *Qt, int64_t nj, const double *d_alph, const int *d_koff,
-                                  const int *d_flags, int NT, double h, gpfq_stats *stats) {
+                                  const int *d_flags, int NT, double h, gpfq_stats *stats, const float *W, int64_t ldw, int64_t j0,
+                                  double *Qd, int64_t ldq, int64_t col0) {
     const bool same = (Xq == X);
     cudaStream_t st = ctx->stream, side = ctx->copy_stream;
     int64_t R = pick_range_length(ctx, nj, 1);
     R = std::max<int64_t>(128, R / 128 * 128);      // K blocks of the update are 128 directions
     if (ctx->sweep_range) R = ctx->sweep_range;
+    // Ternary alphabets: the tensor-core range walk (sweep_tc.cu) -- the W terms of every range as ONE batched product before the
+    // sweep, the Q terms inside the walk kernel, one thread per neuron
+    const bool ternary = ctx->h_koff[1] - ctx->h_koff[0] == 3;
+    const bool use_tc = ternary && ctx->sweep_walk != 2 && R <= stc::MAX_R;
+    ctx->last_sweep_tc = use_tc ? 1 : 0;
     const int64_t N0P = ceil_div64(N0, R) * R, mP = ceil_div64(m, 128) * 128, njP = ceil_div64(nj, 128) * 128;   // whole ranges
     constexpr int S = 5;
     int8_t *sW = nullptr, *sXT = nullptr, *sXqT = nullptr, *sXq = nullptr, *sU = nullptr, *sKq = nullptr;
@@ -1136,6 +1143,33 @@ static int dense_lowrank_sweep_i8(gpfq_ctx *ctx, const float *X, const float *Xq
     CUDA_TRY(ctx, cudaMemsetAsync(sKq, 0, (size_t)njP * N0P, st));   // padding rows / directions of the index slice stay zero
     SlOperand oW, oXT, oXqT, oXq, oU, oKq;
     GPFQ_TRY(sl_make_operand(ctx, &oW, sW, njP, N0P, S, eW, 0, false));
+    TcTables tct;
+    double *Pd = nullptr;   // (nj, N0P): per range the W terms of the range itself, then + D_r (what the earlier ranges contribute)
+    float *Wn = nullptr;    // (nj, N0P): the weights neuron-major, fp32
+    if (use_tc) {
+        GPFQ_TRY(gpfq_ws(ctx, WS_TC_W, (size_t)njP * N0P * sizeof(float), (void **)&Wn));   // (rows >= nj: never written, never used)
+        GPFQ_TRY(sweep_tc_weights(ctx, W, ldw, j0, N0, N0P, nj, Wn));
+        int8_t *sG1 = nullptr;
+        int32_t *eG1 = nullptr;
+        GPFQ_TRY(gpfq_ws(ctx, WS_TC_G1S, (size_t)S * N0P * R, (void **)&sG1));
+        GPFQ_TRY(gpfq_ws(ctx, WS_TC_E, (size_t)N0P * sizeof(int32_t), (void **)&eG1));
+        GPFQ_TRY(gpfq_ws(ctx, WS_TC_P, (size_t)njP * N0P * sizeof(double), (void **)&Pd));
+        GPFQ_TRY(sweep_tc_prepare(ctx, Gc1, Gc2, R, true, N0, N0P, R, h, &tct));
+        GPFQ_TRY(sweep_tc_bind(ctx, &tct, Pd, Wn, njP, N0P));
+        GPFQ_TRY(sweep_tc_slice_g1_lower(ctx, Gc1, R, true, N0, N0P, R, eG1, sG1));
+        SlOperand oG1;
+        GPFQ_TRY(sl_make_operand(ctx, &oG1, sG1, N0P, R, S, eG1, 0, true));
+        // P[:, range r] = W[:, range r] strict_lower(G1_rr)^T for every range: the batches of one launch (19 slice pairs; column
+        // tile tj of a range needs the K blocks 0 .. tj only)
+        SlProduct pp = {&oW, &oG1, 0, 0, 0, R, 7, 1.0, 0};
+        SlBatch pb;
+        pb.n = (int)(N0P / R);
+        pb.a_k = R;
+        pb.b_rows = R;
+        pb.c = R;
+        pb.ktri = true;
+        GPFQ_TRY(slgemm_i8_ex(ctx, &pp, 1, Pd, N0P, nj, R, false, pb));
+    }
     GPFQ_TRY(sl_make_operand(ctx, &oXT, sXT, mP, N0P, S, eXT, 0, true));
     GPFQ_TRY(sl_make_operand(ctx, &oXqT, sXqT, mP, N0P, S, eXT, 0, true));
     GPFQ_TRY(sl_make_operand(ctx, &oXq, sXq, N0P, mP, S, eXq, 0, true));
@@ -1178,7 +1212,8 @@ static int dense_lowrank_sweep_i8(gpfq_ctx *ctx, const float *X, const float *Xq
             if (!merged) cu(cudaEventRecord(ev_sliced, on));
             if (tb > 0) {
                 SlProduct dp = {&oU, &oXq, j_lo, tb, 0, mP, D_DOTS, 1.0};
-                rc = slgemm_i8(ctx, &dp, 1, Do + j_lo * R, R, njh, te - tb, false);   // D_r = U X~_r^T
+                if (use_tc) rc = slgemm_i8(ctx, &dp, 1, Pd + j_lo * N0P + tb, N0P, njh, te - tb, true);   // P_r += U X~_r^T
+                else rc = slgemm_i8(ctx, &dp, 1, Do + j_lo * R, R, njh, te - tb, false);   // D_r = U X~_r^T
                 if (rc != GPFQ_OK) break;
             }
             if (te < N0 && !merged) {   // the W part of THIS range, for the ranges after it
@@ -1191,8 +1226,11 @@ static int dense_lowrank_sweep_i8(gpfq_ctx *ctx, const float *X, const float *Xq
                 ctx->stream = on;
                 if (rc != GPFQ_OK) break;
             }
-            rc = dispatch_sweep_tile(ctx, NT, Gc1 - tb, Gc2 - tb, R, N0, Wt + j_lo * N0, Qt + j_lo * N0, njh, d_alph, d_koff,
-                                     d_flags, 1, tb, te, tb > 0 ? Do + j_lo * R : nullptr, R, sKq, njP, j_lo, 1.0 / h);
+            if (use_tc)
+                rc = sweep_tc_range(ctx, tct, tb, te, j_lo, njh, sKq, njP, j_lo, 2.0 * h);   // {-a, 0, a}: h = a / 2
+            else
+                rc = dispatch_sweep_tile(ctx, NT, Gc1 - tb, Gc2 - tb, R, N0, Wt + j_lo * N0, Qt + j_lo * N0, njh, d_alph, d_koff,
+                                         d_flags, 1, tb, te, tb > 0 ? Do + j_lo * R : nullptr, R, sKq, njP, j_lo, 1.0 / h);
         }
         ctx->stream = keep;
         return rc;
@@ -1225,9 +1263,13 @@ static int dense_lowrank_sweep_i8(gpfq_ctx *ctx, const float *X, const float *Xq
             }
         }
         ctx->sweep_nt = keep_nt;
-        return rc;
+        if (rc != GPFQ_OK) return rc;
+    } else {
+        GPFQ_TRY(chain(0, st, 0, nj));
     }
-    return chain(0, st, 0, nj);
+    // the tensor-core walk leaves level indices only: the layer's fp64 values are made from them here
+    if (use_tc) GPFQ_TRY(sweep_tc_q_from_kq(ctx, sKq, njP, N0, nj, 2.0 * h, Qd, ldq, col0));
+    return GPFQ_OK;
 }
 
 // Dense layer by Gram + sweep.  All pointers are device pointers.
@@ -1258,10 +1300,11 @@ int dense_gram_path(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx,
     if (lowrank) {
         ctx->last_sweep_i8 = 0;
         if (i8_sweep)
-            GPFQ_TRY(dense_lowrank_sweep_i8(ctx, X, Xq, ldx, N0, m, Wt, Qt, nj, d_alph, d_koff, d_flags, NT, h_step, st));
+            GPFQ_TRY(dense_lowrank_sweep_i8(ctx, X, Xq, ldx, N0, m, Wt, Qt, nj, d_alph, d_koff, d_flags, NT, h_step, st, W, ldw, j0, Qd, ldq,
+                                            col0));
         else
             GPFQ_TRY(dense_lowrank_sweep(ctx, X, Xq, ldx, N0, m, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph, NT));
-        for (int a = 0; a < n_alph; ++a) {
+        for (int a = 0; a < n_alph && !(i8_sweep && ctx->last_sweep_tc); ++a) {
             dim3 grid((unsigned)ceil_div64(N0, 32), (unsigned)ceil_div64(nj, 32));
             transpose_q_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(Qt + (int64_t)a * nj * N0, N0, nj,
                                                                       Qd + (int64_t)a * N0 * ldq, ldq, col0);

@@ -42,7 +42,7 @@ constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /* alignment slack *
 struct SlSeg {
     int SA, SB, D;          // slices of A / B; slice pairs with s_a + s_b <= D
     int a_row0, b_row0;     // first row of this product inside the A / B slice tensors (the tile offset is added)
-    int k0, kblocks;        // first K byte (both operands) and K blocks of 64 bytes
+    int k0, k0b, kblocks;   // first K byte of A / of B and K blocks of 64 bytes
     double alpha;
     const int32_t *eA;      // row exponents, indexed like the slice rows (nullptr: eA_const)
     int eA_const;
@@ -59,9 +59,10 @@ struct SlArgs {
     int64_t ldc;
     int M, N;               // valid rows / columns of C
     int accumulate, vec2;
-    int batch_rows;         // blockIdx.y batches: A rows, B rows (and their exponents) advance by batch_rows, C by batch_c
-    int64_t batch_c;
+    int batch_rows_a, batch_rows_b, batch_k0a;   // blockIdx.y batches: A rows / B rows (and their exponents) / A's first K byte advance
+    int64_t batch_c;        // ... and C by batch_c elements
     int lower_only;         // skip tiles entirely above the diagonal (block-diagonal Gram tiles)
+    int ktri;               // B strictly lower triangular in (row, K): column tile tj stops after K block tj
 };
 
 // K-major operand tile with 64-byte rows, SWIZZLE_64B: 8-row atoms of 512 B (SBO), LBO unused (1), descriptor version 1
@@ -106,7 +107,9 @@ slgemm_i8_kernel(const SlArgs args) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ti = blockIdx.x / args.tiles_n, tj = blockIdx.x % args.tiles_n;
     if (args.lower_only && tj * TN > ti * TM + TM - 1) return;
-    const int brow = (int)blockIdx.y * args.batch_rows;     // batch offset of the A and B rows
+    const int brow_a = (int)blockIdx.y * args.batch_rows_a, brow_b = (int)blockIdx.y * args.batch_rows_b;   // batch offsets of the rows
+    const int bk0a = (int)blockIdx.y * args.batch_k0a;
+    const int kcap = args.ktri ? tj + 1 : (1 << 30);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -120,7 +123,7 @@ slgemm_i8_kernel(const SlArgs args) {
     }
     if (warp >= 2 && threadIdx.x - 64 < TN) {
         const int c = threadIdx.x - 64;     // one column of the tile
-        colscale[c] = ldexp(1.0, args.eB ? args.eB[args.b_row0 + brow + tj * TN + c] : args.eB_const);
+        colscale[c] = ldexp(1.0, args.eB ? args.eB[args.b_row0 + brow_b + tj * TN + c] : args.eB_const);
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
@@ -135,10 +138,11 @@ slgemm_i8_kernel(const SlArgs args) {
                 const SlSeg &g = args.seg[sg];
                 const uint32_t bytes = (uint32_t)(g.SA * A_SLICE + g.SB * B_SLICE);
                 // slice s of K block kb of rows row0.. is ONE contiguous run of 128 (64) rows x 64 bytes
-                const int8_t *pa = g.A + ((int64_t)(g.k0 / BK) * g.SA * g.rowsA + g.a_row0 + brow + ti * TM) * BK;
-                const int8_t *pb = g.B + ((int64_t)(g.k0 / BK) * g.SB * g.rowsB + g.b_row0 + brow + tj * TN) * BK;
+                const int8_t *pa = g.A + ((int64_t)((g.k0 + bk0a) / BK) * g.SA * g.rowsA + g.a_row0 + brow_a + ti * TM) * BK;
+                const int8_t *pb = g.B + ((int64_t)(g.k0b / BK) * g.SB * g.rowsB + g.b_row0 + brow_b + tj * TN) * BK;
+                const int kblocks = min(g.kblocks, kcap);
                 const int64_t a_slice = g.rowsA * BK, b_slice = g.rowsB * BK;
-                for (int kb = 0; kb < g.kblocks; ++kb, ++iter) {
+                for (int kb = 0; kb < kblocks; ++kb, ++iter) {
                     const int s = iter % STAGES;
                     if (iter >= STAGES) mbar_wait(&empty[s], ((iter / STAGES) - 1) & 1);
                     unsigned char *a = smem + (size_t)s * STAGE_BYTES, *b = a + S * A_SLICE;
@@ -163,7 +167,8 @@ slgemm_i8_kernel(const SlArgs args) {
                 }
                 const int mode = (g.SA == 5 && g.SB == 5 && g.D == 6) ? 1 : (g.SA == 5 && g.SB == 5 && g.D == 7) ? 2
                                  : (g.SA == 1 && g.SB == 5 && g.D == 6) ? 3 : 0;
-                for (int kb = 0; kb < g.kblocks; ++kb, ++iter) {
+                const int kblocks = min(g.kblocks, kcap);
+                for (int kb = 0; kb < kblocks; ++kb, ++iter) {
                     const int s = iter % STAGES;
                     mbar_wait(&full[s], (iter / STAGES) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -206,7 +211,7 @@ slgemm_i8_kernel(const SlArgs args) {
         for (int i = 0; i < TN; ++i) acc[i] = 0.0;
         for (int sg = 0; sg < args.nseg; ++sg) {
             const SlSeg &g = args.seg[sg];
-            const int ea = g.eA ? g.eA[g.a_row0 + brow + ti * TM + row_t] : g.eA_const;
+            const int ea = g.eA ? g.eA[g.a_row0 + brow_a + ti * TM + row_t] : g.eA_const;
             mbar_wait(seg_full, sg & 1);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 #pragma unroll 1
@@ -441,20 +446,32 @@ int sl_make_operand(gpfq_ctx *ctx, SlOperand *op, const int8_t *slices, int64_t 
 // C[M x N] (ldc) = or += sum of the products.  M, N: valid extents; the slice tensors are zero-padded to tile multiples.
 int slgemm_i8(gpfq_ctx *ctx, const SlProduct *prod, int nprod, double *C, int64_t ldc, int64_t M, int64_t N, bool accumulate,
               int nbatch, int64_t batch_rows, int64_t batch_c, bool lower_only) {
+    SlBatch b;
+    b.n = nbatch;
+    b.a_rows = b.b_rows = batch_rows;
+    b.c = batch_c;
+    b.lower_only = lower_only;
+    return slgemm_i8_ex(ctx, prod, nprod, C, ldc, M, N, accumulate, b);
+}
+
+int slgemm_i8_ex(gpfq_ctx *ctx, const SlProduct *prod, int nprod, double *C, int64_t ldc, int64_t M, int64_t N, bool accumulate,
+                 const SlBatch &batch) {
     using namespace slg;
+    const int nbatch = batch.n;
     if (nprod < 1 || nprod > 2) return gpfq_fail(ctx, GPFQ_ERR_ARG, "slgemm_i8: 1 or 2 products");
     SlArgs a = {};
     a.nseg = nprod;
     for (int s = 0; s < nprod; ++s) {
         const SlProduct &p = prod[s];
-        if (p.K % BK || p.k0 % BK || p.K / BK > KB_MAX || p.K < BK)
+        const int64_t k0b = p.k0b < 0 ? p.k0 : p.k0b;
+        if (p.K % BK || p.k0 % BK || k0b % BK || batch.a_k % BK || p.K / BK > KB_MAX || p.K < BK)
             return gpfq_fail(ctx, GPFQ_ERR_ARG, "slgemm_i8: K = %lld (offset %lld) must be multiples of 64, at most %d",
                              (long long)p.K, (long long)p.k0, KB_MAX * BK);
         if (p.A->is_b || !p.B->is_b || p.A->n_slices > S || p.B->n_slices > S)
             return gpfq_fail(ctx, GPFQ_ERR_ARG, "slgemm_i8: operand roles / slice counts");
-        if (p.a_row0 + (nbatch - 1) * batch_rows + ceil_div64(M, TM) * TM > p.A->rowsP ||
-            p.b_row0 + (nbatch - 1) * batch_rows + ceil_div64(N, TN) * TN > p.B->rowsP ||
-            p.k0 + p.K > p.A->kbytes || p.k0 + p.K > p.B->kbytes)
+        if (p.a_row0 + (nbatch - 1) * batch.a_rows + ceil_div64(M, TM) * TM > p.A->rowsP ||
+            p.b_row0 + (nbatch - 1) * batch.b_rows + ceil_div64(N, TN) * TN > p.B->rowsP ||
+            p.k0 + (nbatch - 1) * batch.a_k + p.K > p.A->kbytes || k0b + p.K > p.B->kbytes)
             return gpfq_fail(ctx, GPFQ_ERR_ARG, "slgemm_i8: operand slices are not padded to the tile grid");
         if (s > 0 && (p.B->e != prod[0].B->e || p.B->e_const != prod[0].B->e_const || p.b_row0 != prod[0].b_row0))
             return gpfq_fail(ctx, GPFQ_ERR_ARG, "slgemm_i8: the products of one call must share the exponents of their B rows");
@@ -465,6 +482,7 @@ int slgemm_i8(gpfq_ctx *ctx, const SlProduct *prod, int nprod, double *C, int64_
         g.a_row0 = (int)p.a_row0;
         g.b_row0 = (int)p.b_row0;
         g.k0 = (int)p.k0;
+        g.k0b = (int)k0b;
         g.kblocks = (int)(p.K / BK);
         g.alpha = p.alpha;
         g.eA = p.A->e;
@@ -484,9 +502,12 @@ int slgemm_i8(gpfq_ctx *ctx, const SlProduct *prod, int nprod, double *C, int64_
     a.N = (int)N;
     a.accumulate = accumulate ? 1 : 0;
     a.vec2 = (ldc % 2 == 0) && ((uintptr_t)C % 16 == 0);
-    a.batch_rows = (int)batch_rows;
-    a.batch_c = batch_c;
-    a.lower_only = lower_only ? 1 : 0;
+    a.batch_rows_a = (int)batch.a_rows;
+    a.batch_rows_b = (int)batch.b_rows;
+    a.batch_k0a = (int)batch.a_k;
+    a.batch_c = batch.c;
+    a.lower_only = batch.lower_only ? 1 : 0;
+    a.ktri = batch.ktri ? 1 : 0;
     if (nbatch < 1 || nbatch > 65535) return gpfq_fail(ctx, GPFQ_ERR_ARG, "slgemm_i8: 1..65535 batches");
     CUDA_TRY(ctx, cudaFuncSetAttribute(slgemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     const dim3 grid((unsigned)(ceil_div64(M, TM) * a.tiles_n), (unsigned)nbatch);

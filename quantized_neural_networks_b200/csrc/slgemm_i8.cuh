@@ -26,6 +26,14 @@ struct SlProduct {          // one segment: alpha * A[a_row0 : a_row0 + M, k0 : 
     int64_t a_row0, b_row0, k0, K;
     int D;
     double alpha;
+    int64_t k0b = -1;       // first K byte of the B operand when it differs from A's (-1: k0)
+};
+
+struct SlBatch {            // blockIdx.y batches: per batch the A rows advance by a_rows, the B rows (and the exponents of both) by
+    int n = 1;              // b_rows, A's first K byte by a_k and C by c elements
+    int64_t a_rows = 0, b_rows = 0, a_k = 0, c = 0;
+    bool lower_only = false;   // skip tiles entirely above the diagonal (block-diagonal Gram tiles)
+    bool ktri = false;         // B is strictly lower triangular in (row, K): column tile tj only needs the K blocks 0 .. tj
 };
 
 int sl_make_operand(gpfq_ctx *ctx, SlOperand *op, const int8_t *slices, int64_t rowsP, int64_t kbytes, int n_slices, const int32_t *e,
@@ -36,6 +44,8 @@ int sl_make_operand(gpfq_ctx *ctx, SlOperand *op, const int8_t *slices, int64_t 
 // block-diagonal Gram tiles of the residual-form sweep); lower_only skips tiles entirely above the diagonal.
 int slgemm_i8(gpfq_ctx *ctx, const SlProduct *prod, int nprod, double *C, int64_t ldc, int64_t M, int64_t N, bool accumulate,
               int nbatch = 1, int64_t batch_rows = 0, int64_t batch_c = 0, bool lower_only = false);
+int slgemm_i8_ex(gpfq_ctx *ctx, const SlProduct *prod, int nprod, double *C, int64_t ldc, int64_t M, int64_t N, bool accumulate,
+                 const SlBatch &batch);
 // 5 digit slices + row exponents of `grid_rows` rows (rows >= `rows` and columns >= cols are zeros) of a row-major matrix,
 // written as rows row0 .. row0 + grid_rows - 1 of a 5 x rowsP x colsP slice tensor (e: exponent of row row0 + r at e[row0 + r])
 template <typename T>

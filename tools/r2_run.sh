@@ -1,10 +1,6 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fullsize.py tests/test_gpu_network.py tests/test_gpu_sample_split.py -x -q -m gpu -k "conv or corr or cnn or vgg or gram_i8_non_finite" 2>&1 | tail -5
-timeout 900 python bench.py --steps 5 --warmup 3 --no-e2e > gpurun_out/r2q_bench_vgg.json 2> gpurun_out/r2q_bench_vgg.err; tail -3 gpurun_out/r2q_bench_vgg.err
-python - <<'PY'
-import json
-l=json.loads(open('gpurun_out/r2q_bench_vgg.json').read().strip().splitlines()[-1])
-print({k:l[k] for k in ('value','ms_per_step','gpu_launches')})
-print({k:(v['ms'], v.get('frac')) for k,v in l['per_layer'].items()})
-PY
+timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "sweep_lowrank or slgemm" 2>&1 | tail -15
+timeout 300 python tools/dense_bench.py --shapes 25088x4096x1504,25088x512x1504,4096x4096x1504,4096x1000x1504 --methods auto --reps 2 2>&1 | grep shape | cut -c1-200
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_tc_fc1_launches.csv \
+    python tools/dense_bench.py --shapes 25088x512x1504 --methods auto --reps 0 > /dev/null 2>&1
