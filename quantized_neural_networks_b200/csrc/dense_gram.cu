@@ -785,18 +785,19 @@ static bool dense_uses_lowrank(gpfq_ctx *ctx, int64_t N0, int64_t m, int64_t nj,
     if (ctx->sweep_variant == 1 || ctx->lowrank_variant == 1) return false;
     if (ctx->lowrank_variant >= 2) return N0 > 64;
     if (!i8_ok) return 3 * m < N0 && N0 >= 4096 && nj >= 256;   // fp64 (DMMA) contractions: the measured rule of round 1
-    // int8-slice contractions (slgemm_i8.cu).  Both forms calibrated on this pool's B200 (tools/dense_methods.py,
-    // profiles/dense_methods_r2.md):
-    //   carried residuals  39 slice-pair products of nj x m x N0 at an effective 9.8e14 int8 op/s (the kernels are bound by their
-    //                      operand stream from L2 and per-CTA latency, not by the tensor pipe) + 0.3 us per direction for the
-    //                      chain slicing -> dots -> walk of every range + another 0.3 us per direction and 4096 neurons
-    //   Gram rows          N0^2 nj fp64 MACs at 1.05e13 /s (DMMA contraction) + 0.3 us per direction (walk) + the full tcgen05
+    // int8-slice contractions (slgemm_i8.cu) and the tensor-core range walk (sweep_tc.cu).  Both forms calibrated on this pool's B200
+    // (tools/dense_methods.py, profiles/dense_methods_r2.md):
+    //   carried residuals  39 slice-pair products of nj x m x N0 at an effective 1.08e15 int8 op/s (the kernels are bound by their
+    //                      operand stream from L2 and per-CTA latency, not by the tensor pipe) + 0.265 us per direction for the
+    //                      chain update -> slicing -> dots -> walk of every range (~135 us per 512 directions, whatever nj)
+    //   Gram rows          N0^2 nj fp64 MACs at 1.2e13 /s (DMMA contraction) + 0.1 us per direction (walk) + the full tcgen05
     //                      Gram stage (15 pairs)
-    //                      (the chain costs 0.3 us per direction even for a handful of neurons: one rank of a multi-GPU job)
-    if (N0 < 1024 || nj < 64 || m > N0) return false;
+    // m > N0 (config 4's 4096 x 4096 at m = 5000: 6.9 against 8.5 ms) only with thousands of neurons to amortise the chain.
+    if (N0 < 1024 || nj < 64) return false;
+    if (m > N0 && (nj < 2048 || m > 2 * N0)) return false;
     const double grams = same ? 1.0 : 2.0;
-    const double t_lr = 8.0e-14 * nj * (double)m * N0 + N0 * (0.3e-6 + 0.3e-6 * (double)nj / 4096.0) + 0.35e-3;
-    const double t_gr = (double)N0 * N0 * nj / 1.05e13 + 0.3e-6 * N0 + grams * 15.0 * (double)N0 * N0 * m / 2.2e15 + 0.35e-3;
+    const double t_lr = 7.2e-14 * nj * (double)m * N0 + 0.265e-6 * N0 + 0.1e-3;
+    const double t_gr = (double)N0 * N0 * nj / 1.2e13 + 0.1e-6 * N0 + grams * 15.0 * (double)N0 * N0 * m / 2.2e15 + 0.3e-3;
     return t_lr < t_gr;
 }
 
@@ -1085,8 +1086,10 @@ static int dense_lowrank_sweep_i8(gpfq_ctx *ctx, const float *X, const float *Xq
     if (ctx->sweep_range) R = ctx->sweep_range;
     // Ternary alphabets: the tensor-core range walk (sweep_tc.cu) -- the W terms of every range as ONE batched product before the
     // sweep, the Q terms inside the walk kernel, one thread per neuron
-    const bool ternary = ctx->h_koff[1] - ctx->h_koff[0] == 3;
-    const bool use_tc = ternary && ctx->sweep_walk != 2 && R <= stc::MAX_R;
+    const int K_levels = ctx->h_koff[1] - ctx->h_koff[0];
+    const double a_top = ctx->h_alph[ctx->h_koff[0] + K_levels - 1];
+    const double *d_levels = d_alph;   // one alphabet per call on this path: its levels start the device array
+    const bool use_tc = ctx->sweep_walk != 2 && R <= stc::MAX_R;
     ctx->last_sweep_tc = use_tc ? 1 : 0;
     const int64_t N0P = ceil_div64(N0, R) * R, mP = ceil_div64(m, 128) * 128, njP = ceil_div64(nj, 128) * 128;   // whole ranges
     constexpr int S = 5;
@@ -1227,7 +1230,7 @@ static int dense_lowrank_sweep_i8(gpfq_ctx *ctx, const float *X, const float *Xq
                 if (rc != GPFQ_OK) break;
             }
             if (use_tc)
-                rc = sweep_tc_range(ctx, tct, tb, te, j_lo, njh, sKq, njP, j_lo, 2.0 * h);   // {-a, 0, a}: h = a / 2
+                rc = sweep_tc_range(ctx, tct, tb, te, j_lo, njh, sKq, njP, j_lo, a_top, d_levels, K_levels);   // {-a, 0, a}: h = a / 2
             else
                 rc = dispatch_sweep_tile(ctx, NT, Gc1 - tb, Gc2 - tb, R, N0, Wt + j_lo * N0, Qt + j_lo * N0, njh, d_alph, d_koff,
                                          d_flags, 1, tb, te, tb > 0 ? Do + j_lo * R : nullptr, R, sKq, njP, j_lo, 1.0 / h);
@@ -1268,7 +1271,7 @@ static int dense_lowrank_sweep_i8(gpfq_ctx *ctx, const float *X, const float *Xq
         GPFQ_TRY(chain(0, st, 0, nj));
     }
     // the tensor-core walk leaves level indices only: the layer's fp64 values are made from them here
-    if (use_tc) GPFQ_TRY(sweep_tc_q_from_kq(ctx, sKq, njP, N0, nj, 2.0 * h, Qd, ldq, col0));
+    if (use_tc) GPFQ_TRY(sweep_tc_q_from_kq(ctx, sKq, njP, N0, nj, d_levels, K_levels, Qd, ldq, col0));
     return GPFQ_OK;
 }
 
@@ -1340,8 +1343,65 @@ int dense_gram_path(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx,
         // contraction (all SMs, split over neurons x directions, and over K when that is too few tiles), the
         // persistent neuron-tile kernel then walks the range.
         const int64_t tiles_m = ceil_div64(nj, 128) * n_alph;
-        const int64_t R = pick_range_length(ctx, nj, n_alph);
+        int64_t R = pick_range_length(ctx, nj, n_alph);
         double *Do = nullptr, *Dpart = nullptr;
+        // One symmetric equispaced alphabet: the tensor-core range walk (sweep_tc.cu).  P = (what the earlier ranges contribute:
+        // the Gram-row contraction below) + (the W terms of the range itself: one batched product on the fp64 pipe up front).
+        double h_tc = 0.0;
+        // (measured, profiles/dense_methods_r2.md: below ~2048 directions the few extra launches of the preparation cost more than the
+        //  walk saves -- MNIST's layers 0.65 -> 0.73 ms -- so those keep sweep_pipe_kernel; sweep_walk = 1 forces the new walk)
+        const bool use_tc = n_alph == 1 && ctx->sweep_walk != 2 && (N0 >= 2048 || ctx->sweep_walk == 1) && ctx->h_alph && ctx->h_koff &&
+                            ctx->h_flags && N0 < ((int64_t)1 << 30) &&
+                            alphabet_symmetric_equispaced(ctx->h_alph + ctx->h_koff[0], ctx->h_koff[1] - ctx->h_koff[0], ctx->h_flags[0], &h_tc);
+        ctx->last_sweep_tc = use_tc ? 1 : 0;
+        TcTables tct;
+        double *Pd = nullptr, *G1m = nullptr;
+        float *Wn = nullptr;
+        int8_t *sKq = nullptr;
+        int64_t N0P = 0, njP = 0;
+        const int K_levels = use_tc ? ctx->h_koff[1] - ctx->h_koff[0] : 0;
+        const double a_top = use_tc ? ctx->h_alph[ctx->h_koff[0] + K_levels - 1] : 0.0;
+        if (use_tc) {
+            R = std::min<int64_t>(R, stc::MAX_R);
+            N0P = ceil_div64(N0, R) * R;
+            njP = ceil_div64(nj, 128) * 128;
+            GPFQ_TRY(gpfq_ws(ctx, WS_TC_P, (size_t)njP * N0P * sizeof(double), (void **)&Pd));
+            GPFQ_TRY(gpfq_ws(ctx, WS_TC_W, (size_t)njP * N0P * sizeof(float), (void **)&Wn));
+            GPFQ_TRY(gpfq_ws(ctx, WS_TC_G1M, (size_t)N0P * R * sizeof(double), (void **)&G1m));
+            GPFQ_TRY(gpfq_ws(ctx, WS_SL_KQ, (size_t)njP * N0P, (void **)&sKq));
+            CUDA_TRY(ctx, cudaMemsetAsync(Pd, 0, (size_t)njP * N0P * sizeof(double), ctx->stream));
+            GPFQ_TRY(sweep_tc_weights(ctx, W, ldw, j0, N0, N0P, nj, Wn));
+            GPFQ_TRY(sweep_tc_prepare(ctx, G1, G2, N0, false, N0, N0P, R, h_tc, &tct));
+            GPFQ_TRY(sweep_tc_bind(ctx, &tct, Pd, Wn, njP, N0P));
+            GPFQ_TRY(sweep_tc_mask_g1_lower(ctx, G1, N0, N0, N0P, R, G1m));
+            const int64_t nfull = N0 / R;
+            GemmArgs g = {};   // P[:, range] = Wt[:, range] strict_lower(G1[range, range])^T, every full range a batch
+            g.seg[0] = {Wt, G1m, N0, R, R, 1.0};
+            g.nseg = 1;
+            g.M = nj;
+            g.N = R;
+            g.C = Pd;
+            g.ldc = N0P;
+            g.nsplit = 1;
+            g.batch_strideA0 = R;
+            g.batch_strideB = R * R;
+            g.batch_strideC = R;
+            for (int64_t b0 = 0; b0 < nfull; b0 += 65535) {
+                GemmArgs gb = g;
+                gb.seg[0].A = Wt + b0 * R;
+                gb.seg[0].B = G1m + b0 * R * R;
+                gb.C = Pd + b0 * R;
+                GPFQ_TRY((launch_gemm_nt<double, 128, 64, 16>(ctx, gb, (int)std::min<int64_t>(65535, nfull - b0))));
+            }
+            if (nfull * R < N0) {   // the ragged last range
+                const int64_t tb = nfull * R;
+                GemmArgs gl = g;
+                gl.seg[0] = {Wt + tb, G1m + tb * R, N0, R, N0 - tb, 1.0};
+                gl.N = N0 - tb;
+                gl.C = Pd + tb;
+                GPFQ_TRY((launch_gemm_nt<double, 128, 64, 16>(ctx, gl, 1)));
+            }
+        }
         if (N0 > R) GPFQ_TRY(gpfq_ws(ctx, WS_DT, (size_t)n_alph * nj * R * sizeof(double), (void **)&Do));
         for (int64_t tb = 0; tb < N0; tb += R) {
             const int64_t te = tb + R < N0 ? tb + R : N0;
@@ -1375,8 +1435,14 @@ int dense_gram_path(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx,
                     GPFQ_TRY((launch_gemm_nt<double, 128, 64, 16>(ctx, g, n_alph)));
                 }
             }
-            GPFQ_TRY(dispatch_sweep_tile(ctx, NT, G1, G2, N0, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph, tb, te,
-                                         tb > 0 ? Do : nullptr, R));
+            if (use_tc) {
+                if (tb > 0) GPFQ_TRY(sweep_tc_add_outer(ctx, Pd + tb, N0P, Do, R, nj, te - tb));
+                GPFQ_TRY(sweep_tc_range(ctx, tct, tb, te, 0, nj, sKq, njP, 0, a_top, d_alph, K_levels));
+                GPFQ_TRY(sweep_tc_qt_from_kq(ctx, sKq, njP, tb, te, nj, d_alph, K_levels, Qt, N0));
+            } else {
+                GPFQ_TRY(dispatch_sweep_tile(ctx, NT, G1, G2, N0, N0, Wt, Qt, nj, d_alph, d_koff, d_flags, n_alph, tb, te,
+                                             tb > 0 ? Do : nullptr, R));
+            }
         }
     } else {
         // multi-launch reference: one NT contraction + one in-block kernel per 32 directions

@@ -45,7 +45,8 @@ constexpr int OFF_D = OFF_B + NST * B_STAGE;          // 2 sets x 2 TMA boxes (1
 constexpr int OFF_W = OFF_D + 2 * D_BYTES;            // 2 sets x 1 TMA box (32 directions x 128 neurons, fp32, 128B swizzle)
 constexpr int OFF_TAB = OFF_W + 2 * W_BYTES;
 constexpr int OFF_Q = OFF_TAB + 2 * TAB_BYTES;
-constexpr int OFF_BAR = OFF_Q + NB * NT;
+constexpr int OFF_ALPH = OFF_Q + NB * NT;              // the alphabet's levels (replay path of alphabets with more than 3 levels)
+constexpr int OFF_BAR = OFF_ALPH + 128 * 8;
 constexpr int IN_BYTES = D_BYTES + W_BYTES + TAB_BYTES;   // what one block's inputs add up to (one mbarrier transaction count)
 constexpr size_t SMEM = (size_t)OFF_BAR + 256 + 1024 /* alignment slack */;
 constexpr int ACC_COLS = S * NB;                       // TMEM columns of one accumulator set
@@ -90,7 +91,9 @@ __device__ __forceinline__ void tmem_ld_5x16(uint32_t taddr, uint32_t (&v)[S][16
 // The literal walk of one block from the saved residual dots (own shared-memory column), for a warp that raised a flag:
 // gpfq_decide_rcp_inl of dense_gram.cu with the ternary scan.  Rolled loops; decisions go out as level indices.
 static __device__ __noinline__ void replay_block(unsigned char *dset, const unsigned char *wset, int j, const TabA *tab, double a,
-                                                 int8_t *qcol) {
+                                                 int8_t *qcol, const double *alph, int K) {
+    // K == 3: the ternary scan with the levels in registers; else the windowed scan of the equispaced levels (common.cuh)
+    const double inv_step = 0.5 * (double)(K - 1) / a, inv_h = (double)(K - 1) / a;
     auto dptr = [&](int t) { return reinterpret_cast<double *>(dset + (t >> 4) * (D_BYTES / 2) + sw128(j, (t & 15) >> 1)) + (t & 1); };
     for (int t = 0; t < NB; ++t) {
         const double d0 = *dptr(t);
@@ -105,9 +108,9 @@ static __device__ __noinline__ void replay_block(unsigned char *dset, const unsi
                 const double e = fma(-q0, tab->den[t], num);
                 v = fma(e, rinv, q0);
             }
-            q = gpfq_bit_round_ternary(v, a);
+            q = K == 3 ? gpfq_bit_round_ternary(v, a) : gpfq_bit_round_eq(v, alph, K, inv_step);
         }
-        qcol[t * NT] = (int8_t)(q > 0.0 ? 2 : (q < 0.0 ? -2 : 0));
+        qcol[t * NT] = (int8_t)__double2int_rn(q * inv_h);   // level index k' = q / h, h = a / (K - 1); the literal 0 of a dead direction is 0
         for (int u = t + 1; u < NB; ++u) {
             double *du = dptr(u);
             *du = fma(-tab->g2c[t * NB + u], q, *du);
@@ -115,10 +118,11 @@ static __device__ __noinline__ void replay_block(unsigned char *dset, const unsi
     }
 }
 
+template <bool TERN>
 __global__ void __launch_bounds__(THREADS, 1)
 sweep_tc_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapW, const TabA *__restrict__ tabs,
                 const int8_t *__restrict__ g2s, int kbr, int64_t tb, int64_t te, int row0, int64_t nj, int8_t *__restrict__ Kq,
-                int64_t krows, int64_t krow0, double a) {
+                int64_t krows, int64_t krow0, double a, const double *__restrict__ levels, int K) {
     using namespace i8g;
     extern __shared__ unsigned char stc_smem_raw[];
     // (offset arithmetic on the array itself: the compiler keeps the shared address space, LDS / STS instead of generic accesses)
@@ -143,6 +147,8 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
         mbar_init(walk_done, NT);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
+    double *alph = reinterpret_cast<double *>(smem + OFF_ALPH);
+    if (!TERN && tid < K) alph[tid] = levels[tid];
     if (warp == 4) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
@@ -158,6 +164,8 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
         const int64_t jg = (int64_t)blockIdx.x * NT + j;
         const bool valid = jg < nj;   // (rows beyond nj exist in P / Wn -- allocation padding -- and hold whatever they hold)
         const double hh = 0.5 * a, tol = hh * 0x1p-45, big = a * 0x1p40;
+        // more than three levels a_k = -a + k s, s = 2 a / (K - 1): grid position kr = (p + a) / s, nearest level by the 1.5 * 2^52 trick
+        const double km1 = (double)(K - 1), step = 2.0 * a / km1, cmid = 0.5 * km1, magic = 6755399441055744.0;
         const uint32_t lane_field = (uint32_t)(warp * 32) << 16;
         for (int b = 0; b < nblk; ++b) {
             const int buf = b & 1;
@@ -211,12 +219,25 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
                 const double wv = (double)((t & 3) == 0 ? w4.x : (t & 3) == 1 ? w4.y : (t & 3) == 2 ? w4.z : w4.w);
                 const double ri = tab->rinv[t];
                 const double num = fma(wv, tab->g1dd[t], d[t]);
-                const double p = num * ri;
-                const bool up = p > hh, dn = p <= -hh;
-                const double q = up ? a : (dn ? -a : 0.0);
-                const double ap = fabs(p);
-                flag |= (int)!(fabs(ap - hh) > tol) | (int)!(ap < big) | ((int)(fabs(d[t]) < GPFQ_PERP_DOT) & (int)(ri != 0.0));
-                pk[t >> 2] |= (up ? 2u : (dn ? 0xfeu : 0u)) << (8 * (t & 3));   // level index k' = q / h = +-2 (h = a / 2)
+                double q;
+                if (TERN) {
+                    const double p = num * ri;
+                    const bool up = p > hh, dn = p <= -hh;
+                    q = up ? a : (dn ? -a : 0.0);
+                    const double ap = fabs(p);
+                    flag |= (int)!(fabs(ap - hh) > tol) | (int)!(ap < big) | ((int)(fabs(d[t]) < GPFQ_PERP_DOT) & (int)(ri != 0.0));
+                    pk[t >> 2] |= (up ? 2u : (dn ? 0xfeu : 0u)) << (8 * (t & 3));   // level index k' = q / h = +-2 (h = a / 2)
+                } else {
+                    const double kr = fma(num, tab->ris[t], cmid);          // ris = rinv / s
+                    const double r0 = (kr + magic) - magic;                  // rint(kr)
+                    const double r = fmin(fmax(r0, 0.0), km1);
+                    const bool live = ri != 0.0;
+                    q = live ? fma(r, step, -a) : 0.0;                       // a dead direction: the literal 0 (:83-84), index 0
+                    // a tie between two levels (or anything within 2^-30 of a step of one), a non-finite / huge argument, the :86 guard
+                    flag |= ((int)!(fabs(kr - r0) < 0.5 - 0x1p-30) | (int)!(fabs(kr) < 0x1p40) | (int)(fabs(d[t]) < GPFQ_PERP_DOT)) & (int)live;
+                    const int kq = live ? __double2int_rn(fma(r, 2.0, -km1)) : 0;   // k' = 2 k - (K - 1)
+                    pk[t >> 2] |= ((uint32_t)kq & 0xffu) << (8 * (t & 3));
+                }
 #pragma unroll
                 for (int pp = (t + 1) >> 1; pp < NB / 2; ++pp) {
                     const double2 g = g2[t * (NB / 2) + pp];
@@ -230,7 +251,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
             }
             if (__any_sync(0xffffffffu, flag != 0 && valid)) {   // (rows beyond nj hold zeros: they would trip the :86 guard at every step)
                 int8_t *qcol = reinterpret_cast<int8_t *>(smem + OFF_Q) + j;
-                replay_block(dset, wset, j, tab, a, qcol);
+                replay_block(dset, wset, j, tab, a, qcol, alph, K);
 #pragma unroll
                 for (int i = 0; i < NB / 4; ++i) {
                     uint32_t w4 = 0u;
@@ -399,6 +420,7 @@ stc_prepare_kernel(const double *__restrict__ G1, const double *__restrict__ G2,
         tab->nrm[tt] = nv;
         tab->rinv[tt] = nv < GPFQ_DEAD_NORM ? 0.0 : 1.0 / (nv * nv);
         tab->den[tt] = nv * nv;
+        tab->ris[tt] = nv < GPFQ_DEAD_NORM ? 0.0 : (1.0 / (nv * nv)) / (2.0 * h);   // h = a / (K - 1): one step is 2 h
         tab->sc[tt] = bad_s[tt] ? __longlong_as_double(0x7ff8000000000000LL) : ldexp(h, ex_s[tt] - (8 * S - 2));
     }
 }
@@ -444,6 +466,34 @@ stc_slice_g1_lower_kernel(const double *__restrict__ G1, int64_t ldg, int compac
     }
 }
 
+// G1m[t][c] = G1[t][tb(t) + c] for c < t - tb(t), else 0: the strictly lower part of every range's G1 tile, compact (row stride R), fp64
+// -- the B operand of the same product on the fp64 pipe (Gram-row form of the sweep, gemm_nt.cuh)
+__global__ void stc_mask_g1_lower_kernel(const double *__restrict__ G1, int64_t ldg, int64_t N0, int64_t N0P, int64_t R,
+                                         double *__restrict__ G1m) {
+    const int64_t t = blockIdx.x;
+    const int64_t tbr = (t / R) * R;
+    const int lo = t < N0 ? (int)(t - tbr) : 0;
+    for (int c = threadIdx.x; c < (int)R; c += blockDim.x) G1m[t * R + c] = c < lo ? G1[t * ldg + tbr + c] : 0.0;
+}
+
+// P[j][tb + c] += Do[j][c] (what the earlier ranges contribute, from the Gram-row contraction) for c < n
+__global__ void stc_add_outer_kernel(double *__restrict__ P, int64_t ldp, const double *__restrict__ Do, int64_t ldd, int64_t nj, int n) {
+    const int64_t j = blockIdx.x;
+    if (j >= nj) return;
+    for (int c = threadIdx.x; c < n; c += blockDim.x) P[j * ldp + c] += Do[j * ldd + c];
+}
+
+// Qt[j][t] = the level of index Kq[j][t] for the directions [tb, te): the neuron-major fp64 decisions the Gram-row contraction of the
+// later ranges reads
+__global__ void stc_qt_from_kq_kernel(const int8_t *__restrict__ Kq, int64_t krows, int64_t tb, int64_t te, int64_t nj,
+                                      const double *__restrict__ levels, int K, double *__restrict__ Qt, int64_t ldq) {
+    const int64_t j = blockIdx.x;
+    for (int64_t t = tb + threadIdx.x; t < te; t += blockDim.x) {
+        const int k = Kq[sl_offset(t, 0, j, krows, 1)];
+        Qt[j * ldq + t] = k == 0 ? 0.0 : levels[(k + K - 1) >> 1];
+    }
+}
+
 // Wn[j][t] = W[t * ldw + wcol0 + j] (fp32, neuron-major, N0P columns, zeros beyond N0): what a walker thread copies per block
 __global__ void stc_weights_kernel(const float *__restrict__ W, int64_t ldw, int64_t wcol0, int64_t N0, int64_t N0P, int64_t nj,
                                    float *__restrict__ Wn) {
@@ -460,9 +510,10 @@ __global__ void stc_weights_kernel(const float *__restrict__ W, int64_t ldw, int
     }
 }
 
-// Q[t * ldq + col0 + j] = (a / 2) Kq[j][t]: the layer's quantized weights from the level indices of the walk
-__global__ void stc_q_from_kq_kernel(const int8_t *__restrict__ Kq, int64_t krows, int64_t N0, int64_t nj, double a,
-                                     double *__restrict__ Q, int64_t ldq, int64_t col0) {
+// Q[t * ldq + col0 + j] = level of index Kq[j][t] (k' = 2 k - (K - 1); the literal 0 for k' = 0): the layer's quantized weights from
+// the level indices of the walk -- the stored levels themselves, bit for bit
+__global__ void stc_q_from_kq_kernel(const int8_t *__restrict__ Kq, int64_t krows, int64_t N0, int64_t nj, const double *__restrict__ levels,
+                                     int K, double *__restrict__ Q, int64_t ldq, int64_t col0) {
     __shared__ int8_t tile[32][33];
     const int64_t tb = (int64_t)blockIdx.x * 32, jb = (int64_t)blockIdx.y * 32;
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
@@ -474,7 +525,7 @@ __global__ void stc_q_from_kq_kernel(const int8_t *__restrict__ Kq, int64_t krow
         const int64_t t = tb + r, j = jb + threadIdx.x;
         if (t < N0 && j < nj) {
             const int k = tile[threadIdx.x][r];
-            Q[t * ldq + col0 + j] = k > 0 ? a : (k < 0 ? -a : 0.0);
+            Q[t * ldq + col0 + j] = k == 0 ? 0.0 : levels[(k + K - 1) >> 1];
         }
     }
 }
@@ -512,10 +563,29 @@ int sweep_tc_weights(gpfq_ctx *ctx, const float *W, int64_t ldw, int64_t wcol0, 
     return GPFQ_OK;
 }
 
-int sweep_tc_q_from_kq(gpfq_ctx *ctx, const int8_t *Kq, int64_t krows, int64_t N0, int64_t nj, double a, double *Q, int64_t ldq,
-                       int64_t col0) {
+int sweep_tc_mask_g1_lower(gpfq_ctx *ctx, const double *G1, int64_t ldg, int64_t N0, int64_t N0P, int64_t R, double *G1m) {
+    stc::stc_mask_g1_lower_kernel<<<(unsigned)N0P, 128, 0, ctx->stream>>>(G1, ldg, N0, N0P, R, G1m);
+    KERNEL_CHECK(ctx);
+    return GPFQ_OK;
+}
+
+int sweep_tc_add_outer(gpfq_ctx *ctx, double *P, int64_t ldp, const double *Do, int64_t ldd, int64_t nj, int64_t n) {
+    stc::stc_add_outer_kernel<<<(unsigned)nj, 128, 0, ctx->stream>>>(P, ldp, Do, ldd, nj, (int)n);
+    KERNEL_CHECK(ctx);
+    return GPFQ_OK;
+}
+
+int sweep_tc_qt_from_kq(gpfq_ctx *ctx, const int8_t *Kq, int64_t krows, int64_t tb, int64_t te, int64_t nj, const double *levels, int K,
+                        double *Qt, int64_t ldq) {
+    stc::stc_qt_from_kq_kernel<<<(unsigned)nj, 128, 0, ctx->stream>>>(Kq, krows, tb, te, nj, levels, K, Qt, ldq);
+    KERNEL_CHECK(ctx);
+    return GPFQ_OK;
+}
+
+int sweep_tc_q_from_kq(gpfq_ctx *ctx, const int8_t *Kq, int64_t krows, int64_t N0, int64_t nj, const double *levels, int K, double *Q,
+                       int64_t ldq, int64_t col0) {
     dim3 grid((unsigned)ceil_div64(N0, 32), (unsigned)ceil_div64(nj, 32));
-    stc::stc_q_from_kq_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(Kq, krows, N0, nj, a, Q, ldq, col0);
+    stc::stc_q_from_kq_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(Kq, krows, N0, nj, levels, K, Q, ldq, col0);
     KERNEL_CHECK(ctx);
     return GPFQ_OK;
 }
@@ -549,13 +619,20 @@ int sweep_tc_bind(gpfq_ctx *ctx, TcTables *tab, const double *P, const float *Wn
 }
 
 int sweep_tc_range(gpfq_ctx *ctx, const TcTables &tab, int64_t tb, int64_t te, int64_t row0, int64_t nj, int8_t *Kq, int64_t krows,
-                   int64_t krow0, double a) {
+                   int64_t krow0, double a, const double *levels, int K) {
     using namespace stc;
-    if (tb % tab.R || te - tb > tab.R || te <= tb || row0 % NT || row0 + ceil_div64(nj, NT) * NT > tab.rowsP || !Kq)
+    if (tb % tab.R || te - tb > tab.R || te <= tb || row0 % NT || row0 + ceil_div64(nj, NT) * NT > tab.rowsP || !Kq || K < 2 || K > 128)
         return gpfq_fail(ctx, GPFQ_ERR_ARG, "sweep_tc: a range starts at a multiple of %lld directions", (long long)tab.R);
-    CUDA_TRY(ctx, cudaFuncSetAttribute(sweep_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    sweep_tc_kernel<<<(unsigned)ceil_div64(nj, NT), THREADS, SMEM, ctx->stream>>>(tab.mapP, tab.mapW, tab.tabs, tab.g2s, (int)(tab.R / KB), tb, te,
-                                                                               (int)row0, nj, Kq, krows, krow0, a);
+    const dim3 grid((unsigned)ceil_div64(nj, NT));
+    if (K == 3) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(sweep_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        sweep_tc_kernel<true><<<grid, THREADS, SMEM, ctx->stream>>>(tab.mapP, tab.mapW, tab.tabs, tab.g2s, (int)(tab.R / KB), tb, te, (int)row0, nj,
+                                                                    Kq, krows, krow0, a, levels, K);
+    } else {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(sweep_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        sweep_tc_kernel<false><<<grid, THREADS, SMEM, ctx->stream>>>(tab.mapP, tab.mapW, tab.tabs, tab.g2s, (int)(tab.R / KB), tb, te, (int)row0, nj,
+                                                                     Kq, krows, krow0, a, levels, K);
+    }
     KERNEL_CHECK(ctx);
     return GPFQ_OK;
 }

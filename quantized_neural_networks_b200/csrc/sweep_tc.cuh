@@ -20,6 +20,7 @@ struct TabA {
     double g1dd[NB];       // G1[t][t]
     double rinv[NB];       // RN(1 / nrm^2), 0 for a dead direction (and for the padding beyond N0)
     double den[NB];        // nrm^2
+    double ris[NB];        // rinv / (2 h): the decision argument in units of the alphabet's step
     double nrm[NB];        // (double)(float)sqrt(G2[t][t])   (the snrm2 result of quantized_network.py:83)
     double sc[NB];         // h 2^(e_t - 38): scale of the integer Q-term sums of direction t
 };
@@ -49,10 +50,17 @@ int sweep_tc_slice_g1_lower(gpfq_ctx *ctx, const double *G1, int64_t ldg, bool c
 //       both bound once per layer (sweep_tc_bind: rowsP x ldp allocations, rowsP a multiple of 128); this launch's neuron 0 is row row0
 //   Kq  out: the decisions as int8 level indices k' = q / (a / 2) (sl_offset layout, krows rows, neuron 0 at row krow0)
 int sweep_tc_bind(gpfq_ctx *ctx, TcTables *tab, const double *P, const float *Wn, int64_t rowsP, int64_t ldp);
+//   a, levels, K: the symmetric equispaced alphabet (device levels, a = levels[K - 1]); K == 3 runs the ternary specialisation
 int sweep_tc_range(gpfq_ctx *ctx, const TcTables &tab, int64_t tb, int64_t te, int64_t row0, int64_t nj, int8_t *Kq, int64_t krows,
-                   int64_t krow0, double a);
+                   int64_t krow0, double a, const double *levels, int K);
 // Wn[j][t] = W[t * ldw + wcol0 + j], (nj, N0P) fp32, zeros beyond N0
 int sweep_tc_weights(gpfq_ctx *ctx, const float *W, int64_t ldw, int64_t wcol0, int64_t N0, int64_t N0P, int64_t nj, float *Wn);
-// Q[t * ldq + col0 + j] = (a / 2) Kq[j][t] for t < N0, j < nj
-int sweep_tc_q_from_kq(gpfq_ctx *ctx, const int8_t *Kq, int64_t krows, int64_t N0, int64_t nj, double a, double *Q, int64_t ldq,
-                       int64_t col0);
+// Q[t * ldq + col0 + j] = the level of index Kq[j][t] for t < N0, j < nj
+int sweep_tc_q_from_kq(gpfq_ctx *ctx, const int8_t *Kq, int64_t krows, int64_t N0, int64_t nj, const double *levels, int K, double *Q,
+                       int64_t ldq, int64_t col0);
+// Gram-row form of the sweep (full G1 / G2 in HBM): the strictly lower part of every range's G1 tile as a compact fp64 matrix
+// (N0P, R) for the in-range W terms on the fp64 pipe; P[:, tb : tb + n] += Do; Qt[:, tb : te] from the level indices
+int sweep_tc_mask_g1_lower(gpfq_ctx *ctx, const double *G1, int64_t ldg, int64_t N0, int64_t N0P, int64_t R, double *G1m);
+int sweep_tc_add_outer(gpfq_ctx *ctx, double *P, int64_t ldp, const double *Do, int64_t ldd, int64_t nj, int64_t n);
+int sweep_tc_qt_from_kq(gpfq_ctx *ctx, const int8_t *Kq, int64_t krows, int64_t tb, int64_t te, int64_t nj, const double *levels, int K,
+                        double *Qt, int64_t ldq);

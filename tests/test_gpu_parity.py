@@ -617,8 +617,24 @@ def test_sweep_lowrank_outer_level_matches_the_oracle(engine, N0, N1, m, first):
         assert np.array_equal(Q, Qf)
         A2 = O.layer_alphabet(W, 4, O.unit_alphabet(3))
         Qm = engine.dense_layer(X, None if first else Xq, W, [A, A2], method="gram", j0=1, j1=N1 - 1)
+        # alphabets with more than three levels through the tensor-core walk (even K: no zero level; the 16 levels of 4 bits)
+        Q16 = {bits: engine.dense_layer(X, None if first else Xq, W, O.layer_alphabet(W, 3, O.unit_alphabet(bits)), method="gram")
+               for bits in (2, 4)}
+        engine.set_option("sweep_walk", 2)                                          # the same walks by sweep_pipe / sweep_tile
+        try:
+            assert np.array_equal(engine.dense_layer(X, None if first else Xq, W, A, method="gram"), Q)
+            for bits, Qb in Q16.items():
+                Ab = O.layer_alphabet(W, 3, O.unit_alphabet(bits))
+                assert np.array_equal(engine.dense_layer(X, None if first else Xq, W, Ab, method="gram"), Qb)
+        finally:
+            engine.set_option("sweep_walk", 0)
     finally:
         engine.set_option("sweep_outer", 0)
+    for bits, Qb in Q16.items():
+        # (520, 2048, m = 48) with 16 levels: ONE neuron meets a tie at the 1e-9 level of the Gram form and leaves the oracle's path
+        # there (132 of 1 064 960 entries) -- every walk kernel alike
+        Ab = O.layer_alphabet(W, 3, O.unit_alphabet(bits))
+        assert O.agreement(Qb, c_oracle.quantize_layer(W, X, Xq, Ab)) >= 0.9998
     check(Q, Qref, W, X, Xq, exact=True)
     engine.set_option("sweep_outer", 1)
     try:
@@ -634,6 +650,37 @@ def test_sweep_lowrank_outer_level_matches_the_oracle(engine, N0, N1, m, first):
         finally:
             engine.set_option("sweep_outer", 0)
     assert np.array_equal(Qm[1][:, 1:N1 - 1], c_oracle.quantize_layer(W, X, Xq, A2)[:, 1:N1 - 1])
+
+
+# ---- the tensor-core range walk under the Gram-row form of the sweep (sweep_tc.cu; default from 2048 directions) -----------
+@pytest.mark.parametrize("N0,N1,m,first,bits", [(1100, 130, 1500, False, np.log2(3)), (700, 40, 2000, True, 4), (2304, 200, 2600, False, 4),
+                                                 (1030, 257, 1200, False, 2)])
+def test_tensor_core_walk_gram_rows(engine, N0, N1, m, first, bits):
+    """`sweep_walk = 1` with `sweep_outer = 1`: what the earlier ranges contribute comes from the Gram-row contraction, the range itself
+    is walked by sweep_tc_kernel (ragged last range, neuron counts off the 128 grid, dead directions, 3 / 4 / 16 levels).  Same layer as
+    the oracle's literal walk and as sweep_pipe / sweep_tile."""
+    rng = np.random.default_rng(N0 + N1 + m)
+    if first:
+        X = (rng.uniform(0, 1, (N0, m)) * (rng.uniform(0, 1, (N0, m)) < 0.5)).astype(np.float32)
+        X[5:25] = 0
+        Xq = X
+    else:
+        X, Xq = hidden_pair(rng, N0, m)
+    W = glorot(rng, N0, N1)
+    A = O.layer_alphabet(W, 3, O.unit_alphabet(bits))
+    engine.set_option("sweep_outer", 1)
+    try:
+        engine.set_option("sweep_walk", 1)
+        Q = engine.dense_layer(X, None if first else Xq, W, A, method="gram")
+        Qs = engine.dense_layer(X, None if first else Xq, W, A, method="gram", j0=3, j1=N1 - 2)
+        engine.set_option("sweep_walk", 2)
+        Qo = engine.dense_layer(X, None if first else Xq, W, A, method="gram")
+    finally:
+        engine.set_option("sweep_walk", 0)
+        engine.set_option("sweep_outer", 0)
+    assert np.array_equal(Q, Qo)
+    assert np.array_equal(Qs[:, 3:N1 - 2], Q[:, 3:N1 - 2])
+    check(Q, c_oracle.quantize_layer(W, X, Xq, A), W, X, Xq, exact=True)
 
 
 # ---- the int8-slice tcgen05 contraction of the residual-form sweep (slgemm_i8.cu) ---------------------------------------

@@ -1,6 +1,15 @@
 set -x
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "sweep_lowrank or slgemm" 2>&1 | tail -15
-timeout 300 python tools/dense_bench.py --shapes 25088x4096x1504,25088x512x1504,4096x4096x1504,4096x1000x1504 --methods auto --reps 2 2>&1 | grep shape | cut -c1-200
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_tc_fc1_launches.csv \
-    python tools/dense_bench.py --shapes 25088x512x1504 --methods auto --reps 0 > /dev/null 2>&1
+timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -8
+timeout 900 python bench.py --steps 5 --warmup 3 --no-e2e > gpurun_out/r2r_bench_vgg.json 2> gpurun_out/r2r_bench_vgg.err; tail -3 gpurun_out/r2r_bench_vgg.err
+for w in cifar10_cnn mnist_mlp; do timeout 600 python bench.py --workload $w --steps 5 --warmup 3 --no-e2e > gpurun_out/r2r_bench_$w.json 2> gpurun_out/r2r_bench_$w.err; tail -3 gpurun_out/r2r_bench_$w.err; done
+python - <<'PY'
+import json
+for n in ('vgg','cifar10_cnn','mnist_mlp'):
+    try:
+        l=json.loads(open(f'gpurun_out/r2r_bench_{n}.json').read().strip().splitlines()[-1])
+        print(n, {k:l[k] for k in ('value','ms_per_step','gpu_launches')})
+        print({k:(round(v['ms'],3), v.get('frac')) for k,v in l['per_layer'].items()})
+        print('parity', {k:v.get('agreement') for k,v in l.get('parity',{}).items()} if isinstance(l.get('parity'),dict) else l.get('parity'))
+    except Exception as e: print(n, 'ERR', e)
+PY
