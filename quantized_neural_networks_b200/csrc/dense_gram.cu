@@ -795,6 +795,9 @@ static bool dense_uses_lowrank(gpfq_ctx *ctx, int64_t N0, int64_t m, int64_t nj,
     // m > N0 (config 4's 4096 x 4096 at m = 5000: 6.9 against 8.5 ms) only with thousands of neurons to amortise the chain.
     if (N0 < 1024 || nj < 64) return false;
     if (m > N0 && (nj < 2048 || m > 2 * N0)) return false;
+    // few samples against many directions (VGG16's fc layers, also one rank's shard of them: 125 neurons of fc3 measured 2.26 ms by
+    // Gram rows -- the full Gram stage at m = 1504 runs far below the rate assumed here -- against ~1.4 ms in the residual form)
+    if (2 * m <= N0 && N0 >= 4096) return true;
     const double grams = same ? 1.0 : 2.0;
     const double t_lr = 7.2e-14 * nj * (double)m * N0 + 0.265e-6 * N0 + 0.1e-3;
     const double t_gr = (double)N0 * N0 * nj / 1.2e13 + 0.1e-6 * N0 + grams * 15.0 * (double)N0 * N0 * m / 2.2e15 + 0.3e-3;
