@@ -1150,6 +1150,8 @@ static int dense_lowrank_sweep_i8(gpfq_ctx *ctx, const float *X, const float *Xq
     SlOperand oW, oXT, oXqT, oXq, oU, oKq;
     GPFQ_TRY(sl_make_operand(ctx, &oW, sW, njP, N0P, S, eW, 0, false));
     TcTables tct;
+    double *Dsplit = nullptr;   // K-split partials of the residual dots (few neurons)
+    if (use_tc && ceil_div64(nj, 128) * (R / 64) * 2 <= ctx->sm_count) GPFQ_TRY(gpfq_ws(ctx, WS_PART, (size_t)6 * njP * R * sizeof(double), (void **)&Dsplit));
     double *Pd = nullptr;   // (nj, N0P): per range the W terms of the range itself, then + D_r (what the earlier ranges contribute)
     float *Wn = nullptr;    // (nj, N0P): the weights neuron-major, fp32
     if (use_tc) {
@@ -1218,7 +1220,22 @@ static int dense_lowrank_sweep_i8(gpfq_ctx *ctx, const float *X, const float *Xq
             if (!merged) cu(cudaEventRecord(ev_sliced, on));
             if (tb > 0) {
                 SlProduct dp = {&oU, &oXq, j_lo, tb, 0, mP, D_DOTS, 1.0};
-                if (use_tc) rc = slgemm_i8(ctx, &dp, 1, Pd + j_lo * N0P + tb, N0P, njh, te - tb, true);   // P_r += U X~_r^T
+                // few neurons (one rank's shard): the residual dots are a handful of tiles with a long K loop -- split the samples
+                // over batches so that every SM gets a tile, fixed-order sum of the partials afterwards
+                const int64_t dtiles = ceil_div64(njh, 128) * ceil_div64(te - tb, 64);
+                int ns = 1;
+                for (int c : {6, 4, 3, 2})
+                    if (ns == 1 && dtiles * c <= ctx->sm_count && (mP / 64) % c == 0 && mP / c >= 256) ns = c;
+                if (use_tc && ns > 1 && Dsplit) {
+                    SlBatch sb;
+                    sb.n = ns;
+                    sb.a_k = sb.b_k = mP / ns;
+                    sb.c = njP * R;
+                    SlProduct dps = {&oU, &oXq, j_lo, tb, 0, mP / ns, D_DOTS, 1.0, 0};
+                    rc = slgemm_i8_ex(ctx, &dps, 1, Dsplit + j_lo * R, R, njh, te - tb, false, sb);
+                    if (rc == GPFQ_OK)
+                        rc = sweep_tc_add_partials(ctx, Pd + j_lo * N0P + tb, N0P, Dsplit + j_lo * R, ns, njP * R, R, njh, te - tb);
+                } else if (use_tc) rc = slgemm_i8(ctx, &dp, 1, Pd + j_lo * N0P + tb, N0P, njh, te - tb, true);   // P_r += U X~_r^T
                 else rc = slgemm_i8(ctx, &dp, 1, Do + j_lo * R, R, njh, te - tb, false);   // D_r = U X~_r^T
                 if (rc != GPFQ_OK) break;
             }

@@ -59,7 +59,7 @@ struct SlArgs {
     int64_t ldc;
     int M, N;               // valid rows / columns of C
     int accumulate, vec2;
-    int batch_rows_a, batch_rows_b, batch_k0a;   // blockIdx.y batches: A rows / B rows (and their exponents) / A's first K byte advance
+    int batch_rows_a, batch_rows_b, batch_k0a, batch_k0b;   // blockIdx.y batches: A rows / B rows (and their exponents) / first K bytes advance
     int64_t batch_c;        // ... and C by batch_c elements
     int lower_only;         // skip tiles entirely above the diagonal (block-diagonal Gram tiles)
     int ktri;               // B strictly lower triangular in (row, K): column tile tj stops after K block tj
@@ -108,7 +108,7 @@ slgemm_i8_kernel(const SlArgs args) {
     const int ti = blockIdx.x / args.tiles_n, tj = blockIdx.x % args.tiles_n;
     if (args.lower_only && tj * TN > ti * TM + TM - 1) return;
     const int brow_a = (int)blockIdx.y * args.batch_rows_a, brow_b = (int)blockIdx.y * args.batch_rows_b;   // batch offsets of the rows
-    const int bk0a = (int)blockIdx.y * args.batch_k0a;
+    const int bk0a = (int)blockIdx.y * args.batch_k0a, bk0b = (int)blockIdx.y * args.batch_k0b;
     const int kcap = args.ktri ? tj + 1 : (1 << 30);
 
     if (threadIdx.x == 0) {
@@ -139,7 +139,7 @@ slgemm_i8_kernel(const SlArgs args) {
                 const uint32_t bytes = (uint32_t)(g.SA * A_SLICE + g.SB * B_SLICE);
                 // slice s of K block kb of rows row0.. is ONE contiguous run of 128 (64) rows x 64 bytes
                 const int8_t *pa = g.A + ((int64_t)((g.k0 + bk0a) / BK) * g.SA * g.rowsA + g.a_row0 + brow_a + ti * TM) * BK;
-                const int8_t *pb = g.B + ((int64_t)(g.k0b / BK) * g.SB * g.rowsB + g.b_row0 + brow_b + tj * TN) * BK;
+                const int8_t *pb = g.B + ((int64_t)((g.k0b + bk0b) / BK) * g.SB * g.rowsB + g.b_row0 + brow_b + tj * TN) * BK;
                 const int kblocks = min(g.kblocks, kcap);
                 const int64_t a_slice = g.rowsA * BK, b_slice = g.rowsB * BK;
                 for (int kb = 0; kb < kblocks; ++kb, ++iter) {
@@ -464,14 +464,14 @@ int slgemm_i8_ex(gpfq_ctx *ctx, const SlProduct *prod, int nprod, double *C, int
     for (int s = 0; s < nprod; ++s) {
         const SlProduct &p = prod[s];
         const int64_t k0b = p.k0b < 0 ? p.k0 : p.k0b;
-        if (p.K % BK || p.k0 % BK || k0b % BK || batch.a_k % BK || p.K / BK > KB_MAX || p.K < BK)
+        if (p.K % BK || p.k0 % BK || k0b % BK || batch.a_k % BK || batch.b_k % BK || p.K / BK > KB_MAX || p.K < BK)
             return gpfq_fail(ctx, GPFQ_ERR_ARG, "slgemm_i8: K = %lld (offset %lld) must be multiples of 64, at most %d",
                              (long long)p.K, (long long)p.k0, KB_MAX * BK);
         if (p.A->is_b || !p.B->is_b || p.A->n_slices > S || p.B->n_slices > S)
             return gpfq_fail(ctx, GPFQ_ERR_ARG, "slgemm_i8: operand roles / slice counts");
         if (p.a_row0 + (nbatch - 1) * batch.a_rows + ceil_div64(M, TM) * TM > p.A->rowsP ||
             p.b_row0 + (nbatch - 1) * batch.b_rows + ceil_div64(N, TN) * TN > p.B->rowsP ||
-            p.k0 + (nbatch - 1) * batch.a_k + p.K > p.A->kbytes || k0b + p.K > p.B->kbytes)
+            p.k0 + (nbatch - 1) * batch.a_k + p.K > p.A->kbytes || k0b + (nbatch - 1) * batch.b_k + p.K > p.B->kbytes)
             return gpfq_fail(ctx, GPFQ_ERR_ARG, "slgemm_i8: operand slices are not padded to the tile grid");
         if (s > 0 && (p.B->e != prod[0].B->e || p.B->e_const != prod[0].B->e_const || p.b_row0 != prod[0].b_row0))
             return gpfq_fail(ctx, GPFQ_ERR_ARG, "slgemm_i8: the products of one call must share the exponents of their B rows");
@@ -505,6 +505,7 @@ int slgemm_i8_ex(gpfq_ctx *ctx, const SlProduct *prod, int nprod, double *C, int
     a.batch_rows_a = (int)batch.a_rows;
     a.batch_rows_b = (int)batch.b_rows;
     a.batch_k0a = (int)batch.a_k;
+    a.batch_k0b = (int)batch.b_k;
     a.batch_c = batch.c;
     a.lower_only = batch.lower_only ? 1 : 0;
     a.ktri = batch.ktri ? 1 : 0;

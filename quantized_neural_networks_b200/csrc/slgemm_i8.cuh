@@ -32,6 +32,7 @@ struct SlProduct {          // one segment: alpha * A[a_row0 : a_row0 + M, k0 : 
 struct SlBatch {            // blockIdx.y batches: per batch the A rows advance by a_rows, the B rows (and the exponents of both) by
     int n = 1;              // b_rows, A's first K byte by a_k and C by c elements
     int64_t a_rows = 0, b_rows = 0, a_k = 0, c = 0;
+    int64_t b_k = 0;           // ... and B's first K byte by b_k (K split over batches: a_k = b_k = the chunk, c = one partial result)
     bool lower_only = false;   // skip tiles entirely above the diagonal (block-diagonal Gram tiles)
     bool ktri = false;         // B is strictly lower triangular in (row, K): column tile tj only needs the K blocks 0 .. tj
 };

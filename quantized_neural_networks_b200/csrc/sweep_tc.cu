@@ -163,7 +163,11 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
         const int j = tid;
         const int64_t jg = (int64_t)blockIdx.x * NT + j;
         const bool valid = jg < nj;   // (rows beyond nj exist in P / Wn -- allocation padding -- and hold whatever they hold)
-        const double hh = 0.5 * a, tol = hh * 0x1p-45, big = a * 0x1p40;
+        const double hh = 0.5 * a;
+        // flags of the ternary walk, compared as high words: [hi(a / 2) - 1, hi(a / 2) + 1] around the thresholds (a window of ~2^-20
+        // relative: one warp-block in ~300 replays), a * 2^40 and above (NaN / Inf included), 1e-10 and below (:86)
+        const uint32_t near_lo = (uint32_t)__double2hiint(hh) - 1u, big_hi = (uint32_t)__double2hiint(a * 0x1p40),
+                       perp_hi = (uint32_t)__double2hiint(GPFQ_PERP_DOT);
         // more than three levels a_k = -a + k s, s = 2 a / (K - 1): grid position kr = (p + a) / s, nearest level by the 1.5 * 2^52 trick
         const double km1 = (double)(K - 1), step = 2.0 * a / km1, cmid = 0.5 * km1, magic = 6755399441055744.0;
         const uint32_t lane_field = (uint32_t)(warp * 32) << 16;
@@ -212,6 +216,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
 #pragma unroll
             for (int i = 0; i < NB / 4; ++i) pk[i] = 0u;
             int flag = 0;
+            uint32_t m_near = 0xffffffffu, m_big = 0u, m_perp = 0xffffffffu;
 #pragma unroll
             for (int t = 0; t < NB; ++t) {
                 float4 w4;
@@ -224,8 +229,12 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
                     const double p = num * ri;
                     const bool up = p > hh, dn = p <= -hh;
                     q = up ? a : (dn ? -a : 0.0);
-                    const double ap = fabs(p);
-                    flag |= (int)!(fabs(ap - hh) > tol) | (int)!(ap < big) | ((int)(fabs(d[t]) < GPFQ_PERP_DOT) & (int)(ri != 0.0));
+                    // the flags on the integer pipe (the fp64 pipe carries the chain): |p| within a few 2^-20 of the threshold,
+                    // |p| huge / not finite, and the :86 guard on |d| (dead directions masked out by the table)
+                    const uint32_t hp = (uint32_t)__double2hiint(p) & 0x7fffffffu;
+                    m_near = min(m_near, hp - near_lo);
+                    m_big = max(m_big, hp);
+                    m_perp = min(m_perp, ((uint32_t)__double2hiint(d[t]) & 0x7fffffffu) | (uint32_t)tab->deadm[t]);
                     pk[t >> 2] |= (up ? 2u : (dn ? 0xfeu : 0u)) << (8 * (t & 3));   // level index k' = q / h = +-2 (h = a / 2)
                 } else {
                     const double kr = fma(num, tab->ris[t], cmid);          // ris = rinv / s
@@ -249,6 +258,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
                 // late steps, 2.4 us per block instead of ~1.)
                 if (kbr == -1 - t) asm volatile("trap;\n");
             }
+            if (TERN) flag = (int)(m_near <= 2u) | (int)(m_big >= big_hi) | (int)(m_perp <= perp_hi);
             if (__any_sync(0xffffffffu, flag != 0 && valid)) {   // (rows beyond nj hold zeros: they would trip the :86 guard at every step)
                 int8_t *qcol = reinterpret_cast<int8_t *>(smem + OFF_Q) + j;
                 replay_block(dset, wset, j, tab, a, qcol, alph, K);
@@ -420,6 +430,7 @@ stc_prepare_kernel(const double *__restrict__ G1, const double *__restrict__ G2,
         tab->nrm[tt] = nv;
         tab->rinv[tt] = nv < GPFQ_DEAD_NORM ? 0.0 : 1.0 / (nv * nv);
         tab->den[tt] = nv * nv;
+        tab->deadm[tt] = nv < GPFQ_DEAD_NORM ? 0x7ff00000 : 0;
         tab->ris[tt] = nv < GPFQ_DEAD_NORM ? 0.0 : (1.0 / (nv * nv)) / (2.0 * h);   // h = a / (K - 1): one step is 2 h
         tab->sc[tt] = bad_s[tt] ? __longlong_as_double(0x7ff8000000000000LL) : ldexp(h, ex_s[tt] - (8 * S - 2));
     }
@@ -481,6 +492,17 @@ __global__ void stc_add_outer_kernel(double *__restrict__ P, int64_t ldp, const 
     const int64_t j = blockIdx.x;
     if (j >= nj) return;
     for (int c = threadIdx.x; c < n; c += blockDim.x) P[j * ldp + c] += Do[j * ldd + c];
+}
+
+// P[j][c] += sum of ns partial results part[k][j][c] (K split of the residual dots over batches), in index order
+__global__ void stc_add_partials_kernel(double *__restrict__ P, int64_t ldp, const double *__restrict__ part, int ns, int64_t stride,
+                                        int64_t ldd, int64_t nj, int n) {
+    const int64_t j = blockIdx.x;
+    for (int c = threadIdx.x; c < n; c += blockDim.x) {
+        double s = part[j * ldd + c];
+        for (int k = 1; k < ns; ++k) s += part[(int64_t)k * stride + j * ldd + c];
+        P[j * ldp + c] += s;
+    }
 }
 
 // Qt[j][t] = the level of index Kq[j][t] for the directions [tb, te): the neuron-major fp64 decisions the Gram-row contraction of the
@@ -571,6 +593,13 @@ int sweep_tc_mask_g1_lower(gpfq_ctx *ctx, const double *G1, int64_t ldg, int64_t
 
 int sweep_tc_add_outer(gpfq_ctx *ctx, double *P, int64_t ldp, const double *Do, int64_t ldd, int64_t nj, int64_t n) {
     stc::stc_add_outer_kernel<<<(unsigned)nj, 128, 0, ctx->stream>>>(P, ldp, Do, ldd, nj, (int)n);
+    KERNEL_CHECK(ctx);
+    return GPFQ_OK;
+}
+
+int sweep_tc_add_partials(gpfq_ctx *ctx, double *P, int64_t ldp, const double *part, int ns, int64_t stride, int64_t ldd, int64_t nj,
+                          int64_t n) {
+    stc::stc_add_partials_kernel<<<(unsigned)nj, 128, 0, ctx->stream>>>(P, ldp, part, ns, stride, ldd, nj, (int)n);
     KERNEL_CHECK(ctx);
     return GPFQ_OK;
 }

@@ -23,6 +23,7 @@ struct TabA {
     double ris[NB];        // rinv / (2 h): the decision argument in units of the alphabet's step
     double nrm[NB];        // (double)(float)sqrt(G2[t][t])   (the snrm2 result of quantized_network.py:83)
     double sc[NB];         // h 2^(e_t - 38): scale of the integer Q-term sums of direction t
+    int32_t deadm[NB];     // 0x7ff00000 for a dead direction (masks the perpendicularity flag), else 0
 };
 }  // namespace stc
 
@@ -64,3 +65,6 @@ int sweep_tc_mask_g1_lower(gpfq_ctx *ctx, const double *G1, int64_t ldg, int64_t
 int sweep_tc_add_outer(gpfq_ctx *ctx, double *P, int64_t ldp, const double *Do, int64_t ldd, int64_t nj, int64_t n);
 int sweep_tc_qt_from_kq(gpfq_ctx *ctx, const int8_t *Kq, int64_t krows, int64_t tb, int64_t te, int64_t nj, const double *levels, int K,
                         double *Qt, int64_t ldq);
+// P[:, 0 : n] += part[0] + ... + part[ns - 1] (partials `stride` elements apart, row stride ldd): the K-split residual dots
+int sweep_tc_add_partials(gpfq_ctx *ctx, double *P, int64_t ldp, const double *part, int ns, int64_t stride, int64_t ldd, int64_t nj,
+                          int64_t n);
