@@ -1151,7 +1151,7 @@ static int dense_lowrank_sweep_i8(gpfq_ctx *ctx, const float *X, const float *Xq
     GPFQ_TRY(sl_make_operand(ctx, &oW, sW, njP, N0P, S, eW, 0, false));
     TcTables tct;
     double *Dsplit = nullptr;   // K-split partials of the residual dots (few neurons)
-    if (use_tc && ceil_div64(nj, 128) * (R / 64) * 2 <= ctx->sm_count) GPFQ_TRY(gpfq_ws(ctx, WS_PART, (size_t)6 * njP * R * sizeof(double), (void **)&Dsplit));
+    if (use_tc && ceil_div64(nj, 128) * (R / 64) * 3 <= ctx->sm_count) GPFQ_TRY(gpfq_ws(ctx, WS_PART, (size_t)6 * njP * R * sizeof(double), (void **)&Dsplit));
     double *Pd = nullptr;   // (nj, N0P): per range the W terms of the range itself, then + D_r (what the earlier ranges contribute)
     float *Wn = nullptr;    // (nj, N0P): the weights neuron-major, fp32
     if (use_tc) {
@@ -1224,7 +1224,7 @@ static int dense_lowrank_sweep_i8(gpfq_ctx *ctx, const float *X, const float *Xq
                 // over batches so that every SM gets a tile, fixed-order sum of the partials afterwards
                 const int64_t dtiles = ceil_div64(njh, 128) * ceil_div64(te - tb, 64);
                 int ns = 1;
-                for (int c : {6, 4, 3, 2})
+                for (int c : {6, 4, 3})   // (two-way splits measured slower than none: fc3's 1000 neurons 1.64 -> 1.76 ms)
                     if (ns == 1 && dtiles * c <= ctx->sm_count && (mP / 64) % c == 0 && mP / c >= 256) ns = c;
                 if (use_tc && ns > 1 && Dsplit) {
                     SlBatch sb;

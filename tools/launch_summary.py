@@ -18,10 +18,13 @@ def main():
     ap.add_argument("--out")
     ap.add_argument("--title", default="launch list")
     ap.add_argument("--note", default="")
+    ap.add_argument("--ours", action="store_true", help="drop torch's own kernels (input synthesis of the profiled script)")
     a = ap.parse_args()
     rows = list(csv.reader(l for l in open(a.csv) if l.startswith('"')))
     hdr = rows[0]
     ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    if a.ours:
+        rows = [hdr] + [r for r in rows[1:] if not any(t in r[ki] for t in ("native::", "at_cuda_detail", "at::", "cub::"))]
     n = len(rows) - 1
     per = n // a.passes
     agg, tot = collections.OrderedDict(), 0.0

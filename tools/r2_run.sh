@@ -1,4 +1,5 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fullsize.py -x -q -m gpu -k "sweep or lowrank or tensor_core or fc1 or fc2 or auto or dense" 2>&1 | tail -6
-timeout 300 python tools/dense_bench.py --shapes 25088x4096x1504,25088x512x1504,4096x512x1504,4096x125x1504,4096x4096x1504 --methods auto --reps 2 2>&1 | grep shape | cut -c1-200
+N=8
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r2_bench_vgg16_n$N.json 2> gpurun_out/r2_bench_vgg16_n$N.err; tail -3 gpurun_out/r2_bench_vgg16_n$N.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --workload cifar10_cnn --steps 10 --warmup 3 > gpurun_out/r2_bench_cifar10_cnn_n$N.json 2> /dev/null
