@@ -98,6 +98,8 @@ int gpfq_set_stream(gpfq_ctx *ctx, void *cuda_stream);
  *   "sweep_range"  residual-form sweep on tcgen05: directions per range (0 auto, else a multiple of 128)
  *   "sweep_groups" residual-form sweep on tcgen05: independent neuron groups in flight (0 auto, 1, 2 or 4)
  *   "sweep_nt"     pipelined range walk: neurons per CTA (0 auto, 8, 16 or 32)
+ *   "sweep_walk"   range walk of the sweep for one symmetric equispaced alphabet: 0 auto (the tensor-core walk sweep_tc_kernel in the
+ *                  residual form and for Gram-row sweeps from 2048 directions), 1 always the tensor-core walk, 2 sweep_pipe / sweep_tile
  *   "sweep_i8"     contractions of the residual-form sweep: 0 auto, 1 int8 slices on tcgen05, 2 fp64 DMMA
  *   "sweep_outer"  0 auto, 1 Gram rows of all earlier directions, 2 carried residuals (3 m N0 N1 MACs: wins when m << N0),
  *                  3 carried residuals as one chain (default: two halves of the neurons on two streams, so that one half's
