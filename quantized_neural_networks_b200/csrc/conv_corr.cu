@@ -277,6 +277,164 @@ conv_corr9_tma_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_con
     }
 }
 
+
+// ---- strip variant for small images (W in {8, 14, 16, 28, 32}) -------------------------------------------------------
+// The band walk above pays per band: a window reset, two edge stages of the four to six 5-column stages, reductions to global
+// memory for the first / last pixel column -- on 28 x 28 images it runs at 0.27-0.34 of the DFMA rate, on 14 x 14 at 0.17
+// (profiles/r1l_conv_corr9_vgg_conv10.md).  Here a task is a band of RB rows x a STRIP of SW <= 16 columns, fetched whole (one
+// TMA box of (RB + 2) x (SW + 4) pixels x 32 channels, zero fill outside the image = the padding, plus the RB x SW centre pixels
+// of xq for the xq x x pass) and walked as straight-line code: the column index is a compile-time constant, so the rotating
+// register window, the column class (first / between / last pixel column) and every shared-memory offset are static, there are
+// no edge stages and the three column classes are three register accumulator sets stored once per warp.  W = 28 / 32 are two
+// strips (the inner strip boundary is an ordinary "between" column: the halo columns hold real pixels).  Same records as the
+// band kernel (conv_corr9_assemble_kernel reads both), same exact products, fixed summation order.
+namespace corr9s {
+using corr9::ND;
+using corr9::REC;
+constexpr int WARPS = 4;      // warps per CTA
+constexpr int NS = 1;         // boxes per warp: ONE -- a strip box is 15-24 KB, and two to three warps per SM sub-partition that take
+                              // turns (one waits for its box while another multiplies) measured faster than one warp that double-buffers
+template <int SW, int RB, bool CROSS>
+struct Cfg {
+    static constexpr int BW = SW + 4;                                  // box columns: the strip and two halo columns either side
+    static constexpr int WIN_FLOATS = (RB + 2) * BW * 32;
+    static constexpr int CTR_FLOATS = CROSS ? RB * SW * 32 : 0;
+    static constexpr int STAGE_FLOATS = WIN_FLOATS + CTR_FLOATS;
+    static constexpr size_t WARP_BYTES = (size_t)NS * STAGE_FLOATS * sizeof(float);
+    static constexpr size_t SMEM = WARPS * WARP_BYTES + WARPS * NS * sizeof(uint64_t);
+};
+}  // namespace corr9s
+
+template <int SW, int RB, bool CROSS>
+__global__ void __launch_bounds__(corr9s::WARPS * 32)
+conv_corr9_strip_kernel(const __grid_constant__ CUtensorMap mapWin, const __grid_constant__ CUtensorMap mapCtr, Corr9Geom gm,
+                        double *__restrict__ partial, int slot_stride, int slot0) {
+    using namespace corr9s;
+    using corr9::mbar_expect_tx;
+    using corr9::mbar_init;
+    using corr9::mbar_wait;
+    using corr9::tma_load_4d;
+    using C = Cfg<SW, RB, CROSS>;
+    constexpr int BW = C::BW;
+    extern __shared__ __align__(128) unsigned char corr9_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = blockIdx.x * WARPS + warp;
+    const int c0 = (int)(gm.c_first & ~(int64_t)3) + (int)blockIdx.y * 32;
+    const int chl = c0 + lane - (int)gm.c_first;
+    const bool chok = chl >= 0 && chl < gm.n_ch;
+    float *ring = reinterpret_cast<float *>(corr9_smem + warp * C::WARP_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(corr9_smem + WARPS * C::WARP_BYTES) + warp * NS;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncwarp();
+    const int nstrips = gm.W / SW;
+    const int nrows = gm.y_last - gm.y_first + 1;
+    const int nbands = gm.two_rows ? 1 : (nrows + RB - 1) / RB;
+    const int per_img = nbands * nstrips;                    // tasks of an image: (band, strip) pairs, strip fastest
+    const int64_t ntasks = gm.n_img * per_img;               // two_rows: the (image, strip) pairs of this slot's row
+    const int64_t t_first = gm.two_rows ? slot / 2 : slot, t_step = gm.two_rows ? gm.slots / 2 : gm.slots;
+    const int row_fixed = (slot & 1) ? gm.y_last : gm.y_first;
+    // (image, position inside the image) of a task advance by a fixed step from one task of this warp to its next: no division in
+    // the loop
+    const int step_img = (int)(t_step / per_img), step_in = (int)(t_step % per_img);
+    auto fetch = [&](int img, int in, uint32_t pos) {        // lane 0: the box(es) of task (img, in) into ring position pos
+        const int band = in / nstrips, strip = in - band * nstrips;   // small 32-bit division
+        const int y0 = gm.two_rows ? row_fixed : gm.y_first + band * RB, x0 = strip * SW;
+        const int s = (int)(pos % NS);
+        float *dst = ring + s * C::STAGE_FLOATS;
+        mbar_expect_tx(&bars[s], (uint32_t)(C::STAGE_FLOATS * sizeof(float)));
+        tma_load_4d(dst, &mapWin, &bars[s], c0, x0 - 2, y0 - 2, img);
+        if (CROSS) tma_load_4d(dst + C::WIN_FLOATS, &mapCtr, &bars[s], c0, x0, y0, img);
+    };
+    double acc[ND], accF[ND], accL[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) acc[d] = accF[d] = accL[d] = 0.0;
+    int img = (int)(gm.img0 + t_first / per_img), in = (int)(t_first % per_img);
+    if (t_first < ntasks && lane == 0) fetch(img, in, 0);
+    uint32_t pos = 0;
+    for (int64_t task = t_first; task < ntasks; task += t_step, ++pos) {
+        int nimg = img + step_img, nin = in + step_in;       // this warp's next task
+        if (nin >= per_img) { nin -= per_img; ++nimg; }
+        if (NS > 1) {
+            __syncwarp();      // the box consumed two tasks ago is free again
+            if (task + t_step < ntasks && lane == 0) fetch(nimg, nin, pos + 1);
+        }
+        const int band = in / nstrips, strip = in - band * nstrips;
+        const int y0 = gm.two_rows ? row_fixed : gm.y_first + band * RB;
+        const bool left_edge = strip == 0, right_edge = strip == nstrips - 1;
+        unsigned rowmask = 0;
+#pragma unroll
+        for (int i = 0; i < RB; ++i) rowmask |= (y0 + i <= gm.y_last) ? (1u << i) : 0u;
+        const int s = (int)(pos % NS);
+        mbar_wait(&bars[s], (pos / NS) & 1u);
+        const float *tb = ring + s * C::STAGE_FLOATS + lane;
+        const float *ta = tb + C::WIN_FLOATS;
+        double win[RB + 2][5];
+#pragma unroll
+        for (int bc = 0; bc < 4; ++bc)
+#pragma unroll
+            for (int r = 0; r < RB + 2; ++r) win[r][bc] = (double)tb[(r * BW + bc) * 32];
+#pragma unroll
+        for (int p = 0; p < SW; ++p) {   // pixel column x0 + p: window = box columns p .. p + 4, physical slots (p + k) % 5
+#pragma unroll
+            for (int r = 0; r < RB + 2; ++r) win[r][(p + 4) % 5] = (double)tb[(r * BW + p + 4) * 32];
+            const bool edge = p == 0 || p == SW - 1;
+            double e[ND];
+            if (edge) {
+#pragma unroll
+                for (int d = 0; d < ND; ++d) e[d] = 0.0;
+            }
+#pragma unroll
+            for (int i = 0; i < RB; ++i) {
+                double a = CROSS ? (double)ta[(i * SW + p) * 32] : win[i + 2][(p + 2) % 5];
+                a = (rowmask >> i) & 1u ? a : 0.0;
+                if (edge) {
+#pragma unroll
+                    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                        for (int dx = 0; dx < 5; ++dx) e[dy * 5 + dx] = fma(a, win[i + dy][(p + dx) % 5], e[dy * 5 + dx]);
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) e[10 + dx] = fma(a, win[i + 2][(p + dx) % 5], e[10 + dx]);
+                } else {
+#pragma unroll
+                    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                        for (int dx = 0; dx < 5; ++dx) acc[dy * 5 + dx] = fma(a, win[i + dy][(p + dx) % 5], acc[dy * 5 + dx]);
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) acc[10 + dx] = fma(a, win[i + 2][(p + dx) % 5], acc[10 + dx]);
+                }
+            }
+            if (edge) {   // the image's first / last pixel column has its own class; a strip boundary inside the image does not
+                const bool first = p == 0 && left_edge, last = p == SW - 1 && right_edge;
+#pragma unroll
+                for (int d = 0; d < ND; ++d) {
+                    accF[d] += first ? e[d] : 0.0;
+                    accL[d] += last ? e[d] : 0.0;
+                    acc[d] += (first || last) ? 0.0 : e[d];
+                }
+            }
+        }
+        if (NS == 1) {
+            __syncwarp();      // every lane has read the box: fetch the next one into it
+            if (task + t_step < ntasks && lane == 0) fetch(nimg, nin, pos + 1);
+        }
+        img = nimg;
+        in = nin;
+    }
+    if (chok) {
+        double *rec = partial + ((size_t)chl * slot_stride + slot0 + slot) * REC + (CROSS ? 0 : 3 * ND);
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            rec[d] = accF[d];
+            rec[ND + d] = acc[d];
+            rec[2 * ND + d] = accL[d];
+        }
+    }
+}
+
 // gram: (n_channels, 2 * 81): [G1 | G2], lower triangle + diagonal valid, zeros above (conv_finalize_kernel's layout).
 // partial: records of the launch over rows 1 .. H-2 (left column, interior, right column); rpartial: records of the
 // top / bottom row launch (even slots: top-left corner, top row, top-right corner; odd slots: the bottom ones).
@@ -491,13 +649,14 @@ int corr9_tensor_ok(const float *act, const float *actq) {
     return corr9_encode_fn() != nullptr && ((uintptr_t)act & 15) == 0 && ((uintptr_t)actq & 15) == 0;
 }
 
-// (C, W, H, N) fp32 tensor map with a 32-channel x 5-column x `rows`-row box
-static bool corr9_make_map(CUtensorMap *map, const float *act, int64_t n_img_total, int H, int W, int64_t C, int rows) {
+// (C, W, H, N) fp32 tensor map with a 32-channel x `cols`-column x `rows`-row box
+static bool corr9_make_map(CUtensorMap *map, const float *act, int64_t n_img_total, int H, int W, int64_t C, int rows,
+                           int cols = corr9::WC) {
     Corr9EncodeFn enc = corr9_encode_fn();
     if (!enc) return false;
     const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img_total};
     const cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};  // bytes, dims 1..3
-    const cuuint32_t box[4] = {32u, (cuuint32_t)corr9::WC, (cuuint32_t)rows, 1u};
+    const cuuint32_t box[4] = {32u, (cuuint32_t)cols, (cuuint32_t)rows, 1u};
     const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(act), dims, strides, box, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -530,6 +689,49 @@ static int launch_corr9(gpfq_ctx *ctx, const float *actq, const float *actx, boo
     return GPFQ_OK;
 }
 
+
+template <int SW, int RB>
+static int launch_corr9_strip(gpfq_ctx *ctx, const float *actq, const float *actx, bool same, const Corr9Geom &gm, int64_t C,
+                              int64_t n_img_total, double *partial, int slot_stride, int slot0) {
+    using namespace corr9s;
+    cudaStream_t st = ctx->stream;
+    dim3 grid((unsigned)(gm.slots / WARPS), (unsigned)ceil_div64(gm.n_ch + (gm.c_first & 3), 32));
+    CUtensorMap mq_win, mq_ctr, mx_win;
+    bool ok = corr9_make_map(&mq_win, actq, n_img_total, gm.H, gm.W, C, RB + 2, SW + 4);
+    if (ok && !same)
+        ok = corr9_make_map(&mq_ctr, actq, n_img_total, gm.H, gm.W, C, RB, SW) &&
+             corr9_make_map(&mx_win, actx, n_img_total, gm.H, gm.W, C, RB + 2, SW + 4);
+    if (!ok) return gpfq_fail(ctx, GPFQ_ERR_CUDA, "cuTensorMapEncodeTiled failed for the (%lld, %d, %d, %lld) activations",
+                              (long long)n_img_total, gm.H, gm.W, (long long)C);
+    CUDA_TRY(ctx, cudaFuncSetAttribute(conv_corr9_strip_kernel<SW, RB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)Cfg<SW, RB, false>::SMEM));
+    conv_corr9_strip_kernel<SW, RB, false><<<grid, WARPS * 32, Cfg<SW, RB, false>::SMEM, st>>>(mq_win, mq_win, gm, partial, slot_stride, slot0);
+    KERNEL_CHECK(ctx);
+    if (!same) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(conv_corr9_strip_kernel<SW, RB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)Cfg<SW, RB, true>::SMEM));
+        conv_corr9_strip_kernel<SW, RB, true><<<grid, WARPS * 32, Cfg<SW, RB, true>::SMEM, st>>>(mx_win, mq_ctr, gm, partial, slot_stride, slot0);
+        KERNEL_CHECK(ctx);
+    }
+    return GPFQ_OK;
+}
+
+// strip width of the small-image variant for an image width (0: none)
+static int corr9_strip_width(int Wd) { return Wd == 8 ? 8 : (Wd == 14 || Wd == 28) ? 14 : (Wd == 16 || Wd == 32) ? 16 : 0; }
+
+template <int SW>
+static int corr9_strip_stage(gpfq_ctx *ctx, const float *actq, const float *act, bool same, Corr9Geom gm, int64_t C, int64_t n_img_total,
+                             double *partial, int slot_stride, int slot0, int slots, double *rpartial, int rslot_stride, int rslot0,
+                             int rslots) {
+    if (gm.H > 2) {
+        gm.slots = slots; gm.y_first = 1; gm.y_last = gm.H - 2; gm.two_rows = 0;
+        GPFQ_TRY((launch_corr9_strip<SW, 4>(ctx, actq, act, same, gm, C, n_img_total, partial, slot_stride, slot0)));
+    }
+    gm.slots = rslots; gm.y_first = 0; gm.y_last = gm.H - 1; gm.two_rows = 1;
+    GPFQ_TRY((launch_corr9_strip<SW, 1>(ctx, actq, act, same, gm, C, n_img_total, rpartial, rslot_stride, rslot0)));
+    return GPFQ_OK;
+}
+
 // Correlation sums of channels [c_first, c_first + n_ch) over images [img0, img0 + n_img) of a tensor of n_img_total
 // images: fills slots [slot0, slot0 + slots) of `partial` (rows 1 .. H-2) and [rslot0, rslot0 + rslots) of `rpartial`
 // (top / bottom row) of every channel.  Both record arrays must be zeroed by the caller.
@@ -542,6 +744,12 @@ int conv_corr9_stage(gpfq_ctx *ctx, const float *act, const float *actq, bool sa
     if (n_img_total >= ((int64_t)1 << 31)) return gpfq_fail(ctx, GPFQ_ERR_ARG, "corr9: too many images");
     Corr9Geom gm;
     gm.H = H; gm.W = Wd; gm.c_first = c_first; gm.n_ch = n_ch; gm.img0 = img0; gm.n_img = n_img;
+    if (const int sw = ctx->corr_strip == 2 ? 0 : corr9_strip_width(Wd)) {   // small images: whole strips as straight-line code
+        gm.slots = 0; gm.y_first = gm.y_last = gm.two_rows = 0;
+        if (sw == 8) return corr9_strip_stage<8>(ctx, actq, act, same, gm, C, n_img_total, partial, slot_stride, slot0, slots, rpartial, rslot_stride, rslot0, rslots);
+        if (sw == 14) return corr9_strip_stage<14>(ctx, actq, act, same, gm, C, n_img_total, partial, slot_stride, slot0, slots, rpartial, rslot_stride, rslot0, rslots);
+        return corr9_strip_stage<16>(ctx, actq, act, same, gm, C, n_img_total, partial, slot_stride, slot0, slots, rpartial, rslot_stride, rslot0, rslots);
+    }
     if (H > 2) {
         gm.slots = slots; gm.y_first = 1; gm.y_last = H - 2; gm.two_rows = 0;
         switch (RB) {

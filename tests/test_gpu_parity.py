@@ -450,6 +450,8 @@ def test_conv_corr9_matches_patch_form(engine, n_img, H, Wd, C, F):
     runs = {"planner": (dict(), {0, 4, 5}), "planes": (dict(conv_kernel=3), {0})}
     if geom and mappable:
         runs["direct"] = (dict(corr_small=1, corr_pack=2), {4})
+        if Wd in (8, 14, 16, 28, 32):   # these widths take the strip kernel by default: the band kernel on the same images
+            runs["direct, band kernel"] = (dict(corr_small=1, corr_pack=2, corr_strip=2), {4})
     if geom:
         runs["packed"] = (dict(corr_pack=1), {5})
     out = {}
