@@ -29,7 +29,7 @@ int msq_stage(gpfq_ctx *, const void *, int, int64_t, const double *, int, int, 
 int nhwc9_plan(int, int, int, int, int, int, int, int, int *, int *);
 int corr9_plan(int, int, int, int, int, int, int, int, int, int);
 int corr9_pack_stage(gpfq_ctx *, const float *, int64_t, int, int, int64_t, int64_t, int, int, int64_t, int64_t, float *);
-int corr9_pick_slots(gpfq_ctx *, int, bool, int64_t, int, int64_t);
+int corr9_pick_slots(gpfq_ctx *, int, bool, int64_t, int, int64_t, int);
 int corr9_tensor_ok(const float *, const float *);
 int conv_corr9_stage(gpfq_ctx *, const float *, const float *, bool, int64_t, int64_t, int64_t, int, int, int64_t, int64_t, int,
                      int, double *, int, int, int, double *, int, int, int);
@@ -895,8 +895,8 @@ extern "C" int gpfq_conv_layer_nhwc(gpfq_ctx *ctx, const float *act, const float
         const int64_t units_per_chunk = pack ? cipc / corr_G : cipc;      // tensor "images" per chunk
         const int64_t units_total = pack ? ceil_div64(n_img, corr_G) : n_img;
         const int nbands = (int)ceil_div64(H - 2, corr_rb);                        // rows 1 .. H-2 in bands
-        const int per_ic = corr9_pick_slots(ctx, corr_rb, same, vc0, vch, units_per_chunk * nbands);
-        const int bper_ic = corr9_pick_slots(ctx, 1, same, vc0, vch, 2 * units_per_chunk);   // top and bottom row of every image
+        const int per_ic = corr9_pick_slots(ctx, corr_rb, same, vc0, vch, units_per_chunk * nbands, (int)Wd);
+        const int bper_ic = corr9_pick_slots(ctx, 1, same, vc0, vch, 2 * units_per_chunk, (int)Wd);   // top and bottom row of every image
         const int slots = cn_ic * per_ic, bslots = cn_ic * bper_ic;
         double *partial = nullptr, *bpartial = nullptr, *gram = nullptr;
         float *pkA = nullptr, *pkQ = nullptr;

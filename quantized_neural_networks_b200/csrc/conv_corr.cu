@@ -372,15 +372,24 @@ conv_corr9_strip_kernel(const __grid_constant__ CUtensorMap mapWin, const __grid
         mbar_wait(&bars[s], (pos / NS) & 1u);
         const float *tb = ring + s * C::STAGE_FLOATS + lane;
         const float *ta = tb + C::WIN_FLOATS;
-        double win[RB + 2][5];
+        // The fp32 -> fp64 conversions run on the XU pipe at a quarter of the DFMA rate (8 cycles per warp instruction) and a warp issues
+        // in order: converted right where they are needed they come in bursts that stall the DFMAs behind them (ncu: fp64 pipe 49 %,
+        // XU 43 % active, not overlapping).  So the operands of column p + 1 are converted DURING column p, one or two per row of 13
+        // DFMAs: a window of SIX physical columns (box column p + 5 goes to slot (p + 5) % 6 while slots p .. p + 4 are in use).
+        double win[RB + 2][6];
+        double ctr[RB], ctr_n[RB];
+        (void)ctr;
+        (void)ctr_n;
 #pragma unroll
-        for (int bc = 0; bc < 4; ++bc)
+        for (int bc = 0; bc < 5; ++bc)
 #pragma unroll
             for (int r = 0; r < RB + 2; ++r) win[r][bc] = (double)tb[(r * BW + bc) * 32];
+        if (CROSS) {
 #pragma unroll
-        for (int p = 0; p < SW; ++p) {   // pixel column x0 + p: window = box columns p .. p + 4, physical slots (p + k) % 5
+            for (int i = 0; i < RB; ++i) ctr[i] = (double)ta[(i * SW) * 32];
+        }
 #pragma unroll
-            for (int r = 0; r < RB + 2; ++r) win[r][(p + 4) % 5] = (double)tb[(r * BW + p + 4) * 32];
+        for (int p = 0; p < SW; ++p) {   // pixel column x0 + p: window = box columns p .. p + 4, physical slots (p + k) % 6
             const bool edge = p == 0 || p == SW - 1;
             double e[ND];
             if (edge) {
@@ -389,23 +398,34 @@ conv_corr9_strip_kernel(const __grid_constant__ CUtensorMap mapWin, const __grid
             }
 #pragma unroll
             for (int i = 0; i < RB; ++i) {
-                double a = CROSS ? (double)ta[(i * SW + p) * 32] : win[i + 2][(p + 2) % 5];
+                double a = CROSS ? ctr[i] : win[i + 2][(p + 2) % 6];
                 a = (rowmask >> i) & 1u ? a : 0.0;
                 if (edge) {
 #pragma unroll
                     for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
-                        for (int dx = 0; dx < 5; ++dx) e[dy * 5 + dx] = fma(a, win[i + dy][(p + dx) % 5], e[dy * 5 + dx]);
+                        for (int dx = 0; dx < 5; ++dx) e[dy * 5 + dx] = fma(a, win[i + dy][(p + dx) % 6], e[dy * 5 + dx]);
 #pragma unroll
-                    for (int dx = 0; dx < 3; ++dx) e[10 + dx] = fma(a, win[i + 2][(p + dx) % 5], e[10 + dx]);
+                    for (int dx = 0; dx < 3; ++dx) e[10 + dx] = fma(a, win[i + 2][(p + dx) % 6], e[10 + dx]);
                 } else {
 #pragma unroll
                     for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
-                        for (int dx = 0; dx < 5; ++dx) acc[dy * 5 + dx] = fma(a, win[i + dy][(p + dx) % 5], acc[dy * 5 + dx]);
+                        for (int dx = 0; dx < 5; ++dx) acc[dy * 5 + dx] = fma(a, win[i + dy][(p + dx) % 6], acc[dy * 5 + dx]);
 #pragma unroll
-                    for (int dx = 0; dx < 3; ++dx) acc[10 + dx] = fma(a, win[i + 2][(p + dx) % 5], acc[10 + dx]);
+                    for (int dx = 0; dx < 3; ++dx) acc[10 + dx] = fma(a, win[i + 2][(p + dx) % 6], acc[10 + dx]);
                 }
+                // the next column's operands: window rows i and i + RB (the latter for i < 2), centre pixel of row i
+                if (p + 5 < BW) {
+                    win[i][(p + 5) % 6] = (double)tb[(i * BW + p + 5) * 32];
+                    if (i + RB < RB + 2) win[i + RB][(p + 5) % 6] = (double)tb[((i + RB) * BW + p + 5) * 32];
+                    if (RB == 1) win[2][(p + 5) % 6] = (double)tb[(2 * BW + p + 5) * 32];
+                }
+                if (CROSS && p + 1 < SW) ctr_n[i] = (double)ta[(i * SW + p + 1) * 32];
+            }
+            if (CROSS) {
+#pragma unroll
+                for (int i = 0; i < RB; ++i) ctr[i] = ctr_n[i];
             }
             if (edge) {   // the image's first / last pixel column has its own class; a strip boundary inside the image does not
                 const bool first = p == 0 && left_edge, last = p == SW - 1 && right_edge;
@@ -613,10 +633,44 @@ static int corr9_resident_ctas(bool same) {
     return a < b ? a : b;
 }
 
-// Slots (warps per channel group) that fill every SM with as many CTAs of four warps as stay resident.
-int corr9_pick_slots(gpfq_ctx *ctx, int RB, bool same, int64_t c_first, int n_ch, int64_t ntasks) {
+static int corr9_strip_width(int Wd);
+template <int SW, int RB>
+static int corr9_strip_resident_ctas(bool same) {
+    using namespace corr9s;
+    int a = 0, b = 0;
+    if (cudaFuncSetAttribute(conv_corr9_strip_kernel<SW, RB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<SW, RB, false>::SMEM) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, conv_corr9_strip_kernel<SW, RB, false>, WARPS * 32, Cfg<SW, RB, false>::SMEM) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    if (same) return a;
+    if (cudaFuncSetAttribute(conv_corr9_strip_kernel<SW, RB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<SW, RB, true>::SMEM) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, conv_corr9_strip_kernel<SW, RB, true>, WARPS * 32, Cfg<SW, RB, true>::SMEM) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return a < b ? a : b;
+}
+
+// Slots (warps per channel group) that fill every SM with as many CTAs of four warps as stay resident.  Wd: the image width (the
+// strip kernel of small images has its own occupancy; there the slot count is rounded DOWN to whole CTAs so that the launch is one
+// wave -- every warp gets the same number of tasks, and 1.5 waves cost two: measured on VGG16's 28 x 28 layers).
+int corr9_pick_slots(gpfq_ctx *ctx, int RB, bool same, int64_t c_first, int n_ch, int64_t ntasks, int Wd) {
     using namespace corr9;
     if (RB < 1 || RB > 8) return WARPS;
+    if (const int sw = ctx->corr_strip == 2 ? 0 : corr9_strip_width(Wd)) {
+        const int rb = RB == 1 ? 1 : 4, wi = sw == 8 ? 0 : sw == 14 ? 1 : 2;
+        int &socc = ctx->corr_strip_occ[same ? 1 : 0][rb == 1 ? 0 : 1][wi];
+        if (!socc) {
+            socc = rb == 1 ? (sw == 8 ? corr9_strip_resident_ctas<8, 1>(same) : sw == 14 ? corr9_strip_resident_ctas<14, 1>(same) : corr9_strip_resident_ctas<16, 1>(same))
+                           : (sw == 8 ? corr9_strip_resident_ctas<8, 4>(same) : sw == 14 ? corr9_strip_resident_ctas<14, 4>(same) : corr9_strip_resident_ctas<16, 4>(same));
+            if (socc < 1) socc = 1;
+        }
+        const int64_t groups = ceil_div64(n_ch + (c_first & 3), 32);
+        int64_t ctas = std::max<int64_t>(1, (int64_t)ctx->sm_count * socc / groups);    // CTAs per channel group: one wave, rounded down
+        ctas = std::min<int64_t>(ctas, std::max<int64_t>(1, ceil_div64(ntasks, corr9s::WARPS)));
+        return (int)(ctas * corr9s::WARPS);
+    }
     int &occ = ctx->corr_occ[same ? 1 : 0][RB];      // per context (= per device): no state shared between engines / threads
     if (!occ) {
         occ = RB == 8 ? corr9_resident_ctas<8>(same) : RB == 6 ? corr9_resident_ctas<6>(same)
