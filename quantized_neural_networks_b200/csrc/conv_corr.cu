@@ -292,14 +292,17 @@ namespace corr9s {
 using corr9::ND;
 using corr9::REC;
 constexpr int WARPS = 4;      // warps per CTA
-constexpr int NS = 1;         // boxes per warp: ONE -- a strip box is 15-24 KB, and two to three warps per SM sub-partition that take
-                              // turns (one waits for its box while another multiplies) measured faster than one warp that double-buffers
+// boxes per warp: ONE for the bands of four rows -- a strip box is 15-24 KB, and two to three warps per SM sub-partition that take turns
+// (one waits for its box while another multiplies) measured faster than one warp that double-buffers; the one-row tasks of the top /
+// bottom rows (7-9 KB boxes, 182-208 DFMAs each) keep two in flight
+template <int RB> struct Boxes { static constexpr int NS = RB == 1 ? 2 : 1; };
 template <int SW, int RB, bool CROSS>
 struct Cfg {
     static constexpr int BW = SW + 4;                                  // box columns: the strip and two halo columns either side
     static constexpr int WIN_FLOATS = (RB + 2) * BW * 32;
     static constexpr int CTR_FLOATS = CROSS ? RB * SW * 32 : 0;
     static constexpr int STAGE_FLOATS = WIN_FLOATS + CTR_FLOATS;
+    static constexpr int NS = Boxes<RB>::NS;
     static constexpr size_t WARP_BYTES = (size_t)NS * STAGE_FLOATS * sizeof(float);
     static constexpr size_t SMEM = WARPS * WARP_BYTES + WARPS * NS * sizeof(uint64_t);
 };
@@ -315,7 +318,7 @@ conv_corr9_strip_kernel(const __grid_constant__ CUtensorMap mapWin, const __grid
     using corr9::mbar_wait;
     using corr9::tma_load_4d;
     using C = Cfg<SW, RB, CROSS>;
-    constexpr int BW = C::BW;
+    constexpr int BW = C::BW, NS = C::NS;
     extern __shared__ __align__(128) unsigned char corr9_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot = blockIdx.x * WARPS + warp;
