@@ -30,6 +30,7 @@ int nhwc9_plan(int, int, int, int, int, int, int, int, int *, int *);
 int corr9_plan(int, int, int, int, int, int, int, int, int, int);
 int corr9_pack_stage(gpfq_ctx *, const float *, int64_t, int, int, int64_t, int64_t, int, int, int64_t, int64_t, float *);
 int corr9_pick_slots(gpfq_ctx *, int, bool, int64_t, int, int64_t, int);
+int corr9_uses_strips(gpfq_ctx *, int);
 int corr9_tensor_ok(const float *, const float *);
 int conv_corr9_stage(gpfq_ctx *, const float *, const float *, bool, int64_t, int64_t, int64_t, int, int, int64_t, int64_t, int,
                      int, double *, int, int, int, double *, int, int, int);
@@ -867,7 +868,7 @@ extern "C" int gpfq_conv_layer_nhwc(gpfq_ctx *ctx, const float *act, const float
     // fewer MACs and the shared-memory planes kernel wins; packing pays for itself only on large images whose channel
     // count cannot be mapped directly (VGG's first layer: 7.0 -> 3.6 ms); channel shards of 8-16 channels run faster
     // unpacked with idle lanes.
-    const bool corr_direct = C >= 32 && C % 4 == 0 && n_ch >= 8 && H * Wd >= 128;
+    const bool corr_direct = C >= 32 && C % 4 == 0 && n_ch >= 8 && (H * Wd >= 128 || (H * Wd >= 64 && corr9_uses_strips(ctx, (int)Wd)));
     int corr_G = 1;
     if (corr_rb && !(C >= 32 && C % 4 == 0) && H * Wd >= 4096 && ctx->corr_pack != 2) {
         int g = 32, a = (int)(n_ch % 32);

@@ -789,6 +789,9 @@ static int corr9_strip_stage(gpfq_ctx *ctx, const float *actq, const float *act,
     return GPFQ_OK;
 }
 
+// does the correlation form of images of this width use the strip kernel
+int corr9_uses_strips(gpfq_ctx *ctx, int Wd) { return ctx->corr_strip != 2 && corr9_strip_width(Wd) != 0; }
+
 // Correlation sums of channels [c_first, c_first + n_ch) over images [img0, img0 + n_img) of a tensor of n_img_total
 // images: fills slots [slot0, slot0 + slots) of `partial` (rows 1 .. H-2) and [rslot0, rslot0 + rslots) of `rpartial`
 // (top / bottom row) of every channel.  Both record arrays must be zeroed by the caller.
