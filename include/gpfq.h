@@ -91,7 +91,7 @@ int gpfq_set_stream(gpfq_ctx *ctx, void *cuda_stream);
  *                  mapped (C < 32 or C % 4 != 0) and the images are large, 1 always, 2 never
  *   "corr_small"   1: correlation form also on images below 128 pixels (default: the planes kernel is faster there)
  *   "corr_rows"    correlation form: image rows per band (0 auto by image height, or 4 / 6 / 8)
- *   "corr_strip"   correlation form on small images (widths 8, 14, 16, 28, 32): 0 the strip kernel (whole strips of <= 16 columns as
+ *   "corr_strip"   correlation form on small images (widths 8, 14, 16, 28, 32, 56, 64): 0 the strip kernel (whole strips of <= 16 columns as
  *                  straight-line code), 2 the band kernel
  *   "sweep_kernel"  0 pipelined range walk (panel of block b+1 contracted during the walk of block b) when every CTA is
  *                  resident, else the persistent tile kernel; 1 one launch pair per block; 2 always the persistent tile kernel

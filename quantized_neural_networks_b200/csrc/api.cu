@@ -194,7 +194,7 @@ extern "C" int gpfq_set_option(gpfq_ctx *ctx, const char *key, int64_t value) {
     } else if (!strcmp(key, "corr_rows")) {   // correlation form: rows per band (0 auto, 4, 6 or 8)
         if (value != 0 && value != 4 && value != 6 && value != 8) return gpfq_fail(ctx, GPFQ_ERR_ARG, "corr_rows must be 0, 4, 6 or 8");
         ctx->corr_rb = (int)value;
-    } else if (!strcmp(key, "corr_strip")) {    // correlation form on small images: 0 strip kernel (W in {8, 14, 16, 28, 32}), 2 band kernel
+    } else if (!strcmp(key, "corr_strip")) {    // correlation form on small images: 0 strip kernel (W in {8, 14, 16, 28, 32, 56, 64}), 2 band kernel
         if (value != 0 && value != 2) return gpfq_fail(ctx, GPFQ_ERR_ARG, "corr_strip must be 0 or 2");
         ctx->corr_strip = (int)value;
     } else if (!strcmp(key, "conv_kernel")) {   // 0 TMA-staged / correlation form, 1 direct LDG, 2 generic, 3 NHWC planes kernel

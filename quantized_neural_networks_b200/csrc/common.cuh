@@ -65,7 +65,7 @@ struct gpfq_ctx {
     int corr_occ[2][9] = {};      // correlation-form kernels: resident CTAs per SM by [X~ == X][rows per band] (0: not queried yet)
     int corr_rb = 0;              // correlation-form conv Grams: rows per band (0: chosen per image height)
     int corr_strip_occ[2][2][3] = {};  // strip kernel: resident CTAs per SM by [X~ == X][rows per band 1 / 4][strip width 8 / 14 / 16]
-    int corr_strip = 0;           // ... small images (W in {8, 14, 16, 28, 32}): 0 the strip kernel, 2 the band kernel
+    int corr_strip = 0;           // ... small images (W in {8, 14, 16, 28, 32, 56, 64}): 0 the strip kernel, 2 the band kernel
     int sweep_variant = 0;        // triangular sweep: 0 persistent neuron-tile kernel (default), 1 one launch pair per block
     bool stream_literal = false;  // streaming walk: reproduce the reference's fp32-rounded w*X products (set per call)
     int gram_variant = 0;         // Dense Gram stage: 0 auto, 1 fp64 DMMA (mma.sync), 2 int8 slices on tcgen05 (gram_i8.cu)
