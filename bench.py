@@ -513,8 +513,9 @@ def main():
     traffic = load_traffic("conv_corr9_tma_kernel")
     if conv_ms > 0:
         ach = conv_bytes / (conv_ms * 1e-3) / 1e9
-        roofline = {"kernel": "conv_corr9_tma_kernel (3x3 per-channel Grams as 13 displacement sums straight from the NHWC activations: "
-                              "TMA 4-D boxes -> per-warp mbarrier ring -> fp64 register window, DFMA)",
+        roofline = {"kernel": "conv_corr9_tma_kernel / conv_corr9_strip_kernel (3x3 per-channel Grams as 13 displacement sums straight from "
+                              "the NHWC activations: TMA 4-D boxes -> per-warp mbarrier ring -> fp64 register window, DFMA; bands of "
+                              "5-column boxes on 224 / 112-pixel images, whole strips of <= 16 columns as straight-line code below)",
                     "share_of_step": round(conv_ms / ms_per_step, 3), "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                     "frac": ach / hbm_peak,
                     "traffic": None if traffic is None else traffic["ratio"] * conv_bytes,

@@ -13,6 +13,9 @@ ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpuru
 # 2. the dominant kernel (correlation-form conv Grams), ncu --set full, 376 images (ncu saves / restores device memory per replay)
 ncu --set full --clock-control none --import-source on -k regex:conv_corr9_tma -s 2 -c 4 -o gpurun_out/r2_corr9_vgg -f \
     python bench.py --profile --steps 1 --warmup 3 --n-img 376 > gpurun_out/r2_corr9_vgg.log 2>&1
+# 2b. the strip kernel of the small images on VGG16's 28 x 28 x 512 layer (the xq x x pass of conv8)
+ncu --set full --warp-sampling-interval 0 --clock-control none --import-source on -k regex:conv_corr9_strip_kernel -s 33 -c 2 -o gpurun_out/r2_strip_conv8 -f \
+    python bench.py --profile --steps 1 --warmup 1 --n-img 376 > gpurun_out/r2_strip_conv8.log 2>&1
 # 3. the tcgen05 contraction and the tensor-core range walk of the residual-form sweep on VGG16 fc1
 ncu --set full --clock-control none --import-source on -k regex:slgemm_i8 -s 60 -c 3 -o gpurun_out/r2_slgemm_fc1 -f \
     python tools/dense_bench.py --shapes 25088x4096x1504 --methods auto --reps 0 > gpurun_out/r2_slgemm_fc1.log 2>&1
