@@ -1,5 +1,5 @@
 // sweep_tc.cu -- the range walk of the Dense sweep with one THREAD per neuron and the range's Q terms on the 5th-generation
-// tensor cores (ternary alphabets: the VGG16 / MNIST configurations).
+// tensor cores (symmetric equispaced alphabets; the ternary one of the VGG16 / MNIST configurations has its own specialisation).
 //
 // What a range of R <= 512 directions [tb, te) has to do for every neuron (quantized_network.py:83-89, :117-119 in Gram form):
 //     d_t = P[t] - sum_{tb <= s < t} q_s G2[t][s],   q_t = Q( (d_t + w_t G1[t][t]) / nrm_t^2 )        (guards of :83-87)
@@ -18,9 +18,13 @@
 //       on the chain (~40 dependent cycles per step; the 4-lanes-per-neuron walk of sweep_pipe_kernel measured ~360).
 // Exactness of the short chain: with p = RN(num * rinv) and v = RN(num / den) (what the reference rounds), |p - v| <= 3 ulp, so
 // the ternary decision of p (thresholds +- a / 2, ties as _bit_round_parallel breaks them: v = a / 2 -> 0, v = -a / 2 -> -a) is
-// the decision of v unless p lies within 2^-45 of a threshold, is not finite or huge, or the perpendicularity guard (:86) fires.
-// Those steps raise a flag; a warp with a flag replays its block from the saved residual dots with the literal arithmetic
-// (Markstein-corrected division, the three-level scan).  Random data replays one block per neuron (u_0 = 0 at the first step).
+// the decision of v unless p lies within a few 2^-20 of a threshold (compared as high words, on the integer pipe), is not finite or
+// huge, or the perpendicularity guard (:86) fires on a live direction.  Those steps raise a flag; a warp with a flag replays its
+// block from the saved residual dots with the literal arithmetic (Markstein-corrected division, the three-level scan).  Random data
+// replays one block per neuron (u_0 = 0 at the first step) and about one warp-block in 300 for a near-threshold value.  Alphabets
+// with more than three levels round the grid position kr = (p + a) / step with the 1.5 * 2^52 trick; a value within 2^-30 of a step
+// of a tie between two levels flags the same way.  The results are level INDICES; the fp64 values of the layer are looked up from
+// the stored levels afterwards (stc_q_from_kq_kernel), bit for bit the alphabet's entries.
 //
 // Kernel anatomy (one CTA per 128 neurons, one CTA per SM, 224 threads):
 //   warps 0-3  walkers: thread = neuron = TMEM lane
