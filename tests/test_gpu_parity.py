@@ -54,6 +54,31 @@ def test_golden_dense(engine, method, name, xq, tags):
         assert np.all(np.isin(Q, np.concatenate([A, [0.0]])))
 
 
+@pytest.mark.parametrize("outer", [1, 2])
+@pytest.mark.parametrize("name,xq,tags", [("dense_first_ternary", None, ["c1", "c2", "c3", "c6"]),
+                                          ("dense_hidden_grid", "Xq", ["k3", "k4", "k8", "k16"]),
+                                          ("dense_int_pixels", None, [""]), ("dense_wide_short", "Xq", [""]), ("ties_and_dead", None, ["3", "4"])])
+def test_golden_dense_tensor_core_walk(engine, name, xq, tags, outer):
+    """The reference's own outputs through the tensor-core range walk (`sweep_walk = 1`; by default it only takes layers of 2048
+    directions and more): Gram-row form (`sweep_outer = 1`) and carried residuals (`sweep_outer = 2`, more than 64 directions),
+    3 / 4 / 8 / 16 levels, exact ties (integer pixels, the 4 x 4 tie fixture), dead directions -- the flagged steps replay with the
+    literal arithmetic, so every entry must match."""
+    z = golden(name)
+    X = z["X"]
+    Xq = z[xq] if xq else None
+    engine.set_option("sweep_walk", 1)
+    engine.set_option("sweep_outer", outer)
+    try:
+        for tag in tags:
+            A = z["A" + tag] if name == "ties_and_dead" else (z["A_" + tag] if tag else z["A"])
+            Qref = z["Q" + tag] if name == "ties_and_dead" else (z["Q_" + tag] if tag else z["Q"])
+            Q = engine.dense_layer(X, Xq, z["W"], A, method="gram")
+            check(Q, Qref, z["W"], X, X if Xq is None else Xq, exact=True)
+    finally:
+        engine.set_option("sweep_walk", 0)
+        engine.set_option("sweep_outer", 0)
+
+
 def test_golden_multi_alphabet_batch(engine):
     """Several (bits, c) grid points over the same X, Xq, W in ONE call (config 5)."""
     z = golden("dense_hidden_grid")
@@ -669,6 +694,7 @@ def test_tensor_core_walk_gram_rows(engine, N0, N1, m, first, bits):
     else:
         X, Xq = hidden_pair(rng, N0, m)
     W = glorot(rng, N0, N1)
+    W[:, 5] = 0          # a pruned neuron: its residual stays 0, the :86 guard fires at every step (every block of its warp replays)
     A = O.layer_alphabet(W, 3, O.unit_alphabet(bits))
     engine.set_option("sweep_outer", 1)
     try:
