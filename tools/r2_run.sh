@@ -1,2 +1,3 @@
 set -x
-timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "tensor_core" 2>&1 | tail -15
+mkdir -p gpurun_out
+bash tools/sanitize.sh 2>&1 | tail -24
