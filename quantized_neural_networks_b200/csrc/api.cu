@@ -866,11 +866,11 @@ extern "C" int gpfq_conv_layer_nhwc(gpfq_ctx *ctx, const float *act, const float
     // full warp of channels.  Otherwise G images are packed side by side as virtual channels first (conv_corr.cu).
     // Measured (tools/vgg_bench.py --net cifar / --conv-kernel 3): on 8 x 8 images the per-band start-up outweighs the 6.5x
     // fewer MACs and the shared-memory planes kernel wins; packing pays for itself only on large images whose channel
-    // count cannot be mapped directly (VGG's first layer: 7.0 -> 3.6 ms); channel shards of 8-16 channels run faster
-    // unpacked with idle lanes.
+    // count cannot be mapped directly (VGG's first layer: 7.0 -> 3.6 ms; with the strip kernel also on images from 1024 pixels:
+    // CIFAR10's 32 x 32 x 3 first layer 0.50 -> 0.23 ms); channel shards of 8-16 channels run faster unpacked with idle lanes.
     const bool corr_direct = C >= 32 && C % 4 == 0 && n_ch >= 8 && (H * Wd >= 128 || (H * Wd >= 64 && corr9_uses_strips(ctx, (int)Wd)));
     int corr_G = 1;
-    if (corr_rb && !(C >= 32 && C % 4 == 0) && H * Wd >= 4096 && ctx->corr_pack != 2) {
+    if (corr_rb && !(C >= 32 && C % 4 == 0) && (H * Wd >= 4096 || (H * Wd >= 1024 && corr9_uses_strips(ctx, (int)Wd))) && ctx->corr_pack != 2) {
         int g = 32, a = (int)(n_ch % 32);
         while (a) { const int t = g % a; g = a; a = t; }   // g = gcd(n_ch, 32)
         corr_G = 32 / g;

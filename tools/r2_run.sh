@@ -1,5 +1,2 @@
 set -x
-mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
-timeout 600 python bench.py --impl reference --gpus 1 --steps 2 --warmup 1 > gpurun_out/r2_bench_reference.json 2> gpurun_out/r2_bench_reference.err; tail -2 gpurun_out/r2_bench_reference.err; cut -c1-600 gpurun_out/r2_bench_reference.json
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_network.py tests/test_gpu_fullsize.py -x -q -m gpu -k "conv or corr or cnn" 2>&1 | tail -4
