@@ -373,6 +373,7 @@ def layer_roofline(d, sts, ms, hbm_peak, i8_peak):
         if st["method"] == 2:
             macs = 3.0 * m * N0 * nj if st.get("gram_kernel") == 3 else float(N0) * N0 * nj
             i8 = st.get("reserved", 0)
+            rec["walk"] = "sweep_tc_kernel (tensor-core range walk)" if i8 & 2 else "sweep_pipe_kernel / sweep_tile_kernel"
             if i8 & 1:      # sweep contractions on tcgen05 (int8 slices): reported against the int8 tensor peak
                 ops = float(st["flops_algorithmic"])
                 rec.update(bound="tensor (int8 slices on tcgen05)", frac=round(ops / (st["ms_sweep"] * 1e-3) / 1e12 / i8_peak, 3),

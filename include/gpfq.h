@@ -69,7 +69,8 @@ typedef struct gpfq_stats {
                                 3 block-diagonal tiles only (residual form of the sweep's outer level);
                                 conv NHWC entry point: 4 = correlation form (13 displacement sums per Gram),
                                 5 = correlation form on images packed side by side as virtual channels */
-    int32_t reserved;
+    int32_t reserved;        /* bit 0: contractions of the residual-form sweep ran on tcgen05 (int8 slices); bit 1: the sweep's ranges were
+                                walked by the tensor-core walk (sweep_tc_kernel) */
 } gpfq_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------

@@ -1261,6 +1261,7 @@ static int dense_lowrank_sweep_i8(gpfq_ctx *ctx, const float *X, const float *Xq
     if (stats) {
         stats->flops_algorithmic = 2LL * (19 + 5 + 15) * nj * m * N0;   // int8 operations of the 39 slice-pair products
         stats->reserved |= 1;
+        if (use_tc) stats->reserved |= 2;   // ... and the ranges were walked by sweep_tc_kernel
     }
     ctx->last_sweep_i8 = 1;
     int G = ctx->sweep_groups ? ctx->sweep_groups : (nj >= 4096 ? 4 : (nj >= 2048 ? 2 : 1));
@@ -1499,6 +1500,7 @@ int dense_gram_path(gpfq_ctx *ctx, const float *X, const float *Xq, int64_t ldx,
     if (st) {
         st->method = GPFQ_METHOD_GRAM >> 4;
         st->gram_kernel = ctx->last_gram_kernel;
+        if (ctx->sweep_variant != 1 && ctx->last_sweep_tc) st->reserved |= 2;   // ranges walked by sweep_tc_kernel
         st->flops_algorithmic = pre ? 2 * N0 * N0 * nj * n_alph : (same ? 1 : 2) * m * N0 * (N0 + 1);  // lower triangles
         st->bytes_algorithmic = (pre ? 0 : (same ? 1 : 2) * 4 * N0 * m) + (same ? 1 : 2) * 8 * N0 * N0;
     }
