@@ -1086,6 +1086,7 @@ static int dense_lowrank_sweep_i8(gpfq_ctx *ctx, const float *X, const float *Xq
     cudaStream_t st = ctx->stream, side = ctx->copy_stream;
     int64_t R = pick_range_length(ctx, nj, 1);
     R = std::max<int64_t>(128, R / 128 * 128);      // K blocks of the update are 128 directions
+    if (ctx->sweep_walk != 2) R = std::min<int64_t>(R, stc::MAX_R);   // the tensor-core walk keeps a range's level indices in shared memory
     if (ctx->sweep_range) R = ctx->sweep_range;
     // Ternary alphabets: the tensor-core range walk (sweep_tc.cu) -- the W terms of every range as ONE batched product before the
     // sweep, the Q terms inside the walk kernel, one thread per neuron

@@ -1,5 +1,3 @@
 set -x
-for o in "" "sweep_nt=16"; do
-  echo "== opt: $o"
-  timeout 300 python tools/dense_bench.py --shapes 25088x4096x1504,4096x4096x1504 --methods auto --reps 2 --opt "$o" 2>&1 | grep shape | cut -c1-150
-done
+timeout 300 python tools/dense_bench.py --shapes 4096x3000x1504,25088x3000x1504 --methods auto --reps 2 2>&1 | grep shape | cut -c1-200
+timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "lowrank or auto" 2>&1 | tail -3
