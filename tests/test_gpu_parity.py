@@ -445,7 +445,7 @@ class _conv_options:
                                             (2, 28, 28, 96, 2), (2, 16, 16, 32, 3), (1, 45, 37, 36, 2), (70, 8, 8, 44, 2),
                                             (3, 6, 5, 32, 2), (2, 9, 23, 72, 2), (5, 10, 6, 40, 3), (2, 5, 12, 32, 2),
                                             (5, 9, 11, 3, 4), (40, 12, 12, 8, 2), (7, 8, 8, 12, 2), (3, 10, 10, 33, 2),
-                                            (33, 6, 7, 16, 2), (2, 70, 66, 3, 2), (2, 19, 56, 32, 2)])
+                                            (33, 6, 7, 16, 2), (2, 70, 66, 3, 2), (2, 19, 56, 32, 2), (2, 32, 32, 40, 2), (1, 9, 64, 32, 2)])
 def test_conv_corr9_matches_patch_form(engine, n_img, H, Wd, C, F):
     """Correlation form of the 3x3 / stride 1 / SAME Grams (conv_corr.cu: 13 displacement sums per pixel region, added per
     tap) against the oracle and against the patch-form kernel (shared-memory planes), with the planner's choice and with
